@@ -1,0 +1,165 @@
+/*
+ * gatk.h -- C ABI of libgatk.so: the B200 (sm_100a) GAT-layer kernels.
+ *
+ * Drop-in boundary for the hot path of ArielleRosinski/pyGAT (reference files under
+ * /root/reference).  Every entry point takes plain device pointers, sizes and a
+ * cudaStream_t (passed as void*); no torch types.  All buffers are allocated by the
+ * caller (PyTorch on the host side), the library keeps no reference after return.
+ * Calls are stream-ordered and never synchronise the device.
+ *
+ * Return value: 0 on success, non-zero on error; gatk_last_error() returns the
+ * message of the last failure on the calling thread.
+ *
+ * Common layout conventions
+ *   N        nodes (rows = destination i, columns = source j;  layers.py:141-150)
+ *   E        stored entries of the adjacency pattern, in adj.nonzero() order (layers.py:129)
+ *   H        heads of one layer (models.py:17-27 builds them as separate modules)
+ *   Dp       per-head width padded to 4 * 2^k floats (D = out_features, layers.py:15)
+ *   "rows"   fp32 [N, H*Dp] with an explicit leading dimension (floats), head h at
+ *            columns [h*Dp, (h+1)*Dp) -- this IS torch.cat(heads, dim=1) (models.py:32)
+ *   rowptr   int64 [N+1];  col / trow / perm  int32 [E]  (E < 2^31 per graph shard)
+ */
+#ifndef GATK_H
+#define GATK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GATK_VERSION 100
+#if defined(__GNUC__)
+#define GATK_API __attribute__((visibility("default")))
+#else
+#define GATK_API
+#endif
+
+GATK_API int gatk_version(void);
+GATK_API const char* gatk_last_error(void);
+/* Number of SMs of the current device (grid sizing), <0 on error. */
+GATK_API int gatk_sm_count(void);
+
+/* ------------------------------------------------------------------ K0: graph build
+ * Replaces `adj.nonzero().t()` (layers.py:129, rule 0: entry != 0) and the `adj > 0`
+ * mask (layers.py:41, rule 1: entry > 0).  adj is a dense [n, n] fp32 matrix with
+ * arbitrary element strides (utils.py:55 yields column-major, load_data_ppi.py:86
+ * row-major).  Step 1 writes rowptr (inclusive scan of per-row counts, rowptr[0]=0);
+ * the caller reads E = rowptr[n], allocates col, and runs step 2. */
+GATK_API size_t gatk_scan_workspace_bytes(int64_t n);
+GATK_API int gatk_csr_from_dense_rowptr(const float* adj, int64_t n, int64_t row_stride, int64_t col_stride,
+                               int rule, int64_t* rowptr, void* ws, size_t ws_bytes, void* stream);
+GATK_API int gatk_csr_from_dense_fill(const float* adj, int64_t n, int64_t row_stride, int64_t col_stride,
+                             int rule, const int64_t* rowptr, int32_t* col, void* stream);
+/* COO (row-major sorted, as adj.nonzero() returns it) -> rowptr; col is coo_col cast. */
+GATK_API int gatk_csr_from_coo(const int64_t* coo_row, const int64_t* coo_col, int64_t e, int64_t n,
+                      int64_t* rowptr, int32_t* col, void* ws, size_t ws_bytes, void* stream);
+/* Transposed pattern (source-major) with the permutation back into CSR edge ids; stable,
+ * so destinations appear ascending within a source.  n_rows/n_cols: CSR shape. */
+GATK_API size_t gatk_transpose_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t e);
+GATK_API int gatk_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t e, const int64_t* rowptr,
+                       const int32_t* col, int64_t* tptr, int32_t* trow, int32_t* perm,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ dropout (F.dropout, layers.py:34,37,43 / :132,136,153)
+ * keep[i] = 1 with probability 1-p (Philox4x32-10 keyed by seed, counter = offset + i/4). */
+GATK_API int gatk_dropout_keep_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+/* y = keep ? x * scale : 0  (rows x cols with leading dims; keep dense rows*cols). */
+GATK_API int gatk_mask_scale(const float* x, int64_t ldx, const uint8_t* keep, float scale, float* y, int64_t ldy,
+                    int64_t rows, int64_t cols, void* stream);
+
+/* ------------------------------------------------------------------ K1/K5: projection GEMMs
+ * Row-major fp32 C[M,N] = op(A)[M,K] * op(B)[K,N] (+ C if accumulate), fp32-accurate.
+ * Replaces torch.mm(h, W) / mm(h, skip_projection) (layers.py:35,48,134,166) and their
+ * autograd (dW = h^T dWh, dh = dWh W^T).  transA: A stored [K,M]; transB: B stored [N,K].
+ * ws: split-K scratch (gatk_gemm_workspace_bytes). */
+GATK_API size_t gatk_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K);
+GATK_API int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+              const float* B, int64_t ldb, float* C, int64_t ldc, int accumulate,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* Attention-logit halves f_i = Wh_i . a[:D], g_j = Wh_j . a[D:] (layers.py:60-61, :141-144),
+ * after the post-projection dropout (layers.py:37,136) applied IN PLACE to wh when
+ * keep_wh != NULL (keep_wh is [n, H*Dp] dense).  a_src / a_dst are [H, Dp]. */
+GATK_API int gatk_logits_fwd(int64_t n, int H, int Dp, float* wh, int64_t ldw, const uint8_t* keep_wh,
+                    float inv_keep, const float* a_src, const float* a_dst, float* f, float* g,
+                    void* stream);
+
+/* ------------------------------------------------------------------ K2: fused attention forward
+ * One pass per destination row over its CSR edges: LeakyReLU(f_i + g_j), online
+ * max-subtracted softmax, attention dropout, weighted aggregation of Wh_j, division by the
+ * row sum, optional skip add and ELU.  Replaces layers.py:40-51 and :141-170 including
+ * torch_scatter.scatter_max (:145) and both SpecialSpmm calls (:150,:156).
+ *
+ * Rows are local [0, n_dst); col indexes wh / g (global sources).  Rows longer than
+ * seg_len are listed in hub_rows and processed as segments (hub_seg_ptr: int32
+ * [n_hub+1], exclusive scan of per-hub segment counts) with partial softmax states in
+ * hub_scratch (floats: n_hub_seg * (H*Dp + 2*H)) merged by a second kernel.
+ * keep_att: [E, H] or NULL.  hagg (pre-skip, pre-ELU aggregation) and lse
+ * (m + log l per row/head) are saved for backward; either may be NULL.
+ * counter: one int32 of scratch (dynamic row scheduler). */
+GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp,
+                  const float* wh, int64_t ldw, const float* f, const float* g,
+                  const uint8_t* keep_att, float inv_keep, float alpha,
+                  const float* skipv, int64_t lds, int act_elu,
+                  float* hagg, float* out, int64_t ldo, float* lse,
+                  int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr,
+                  int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream);
+
+/* ------------------------------------------------------------------ K3: backward, destination-row pass
+ * From gout = dL/d(out): dhp = dL/dh' (ELU' applied), c_i = dhp_i . hagg_i, and per edge
+ * dz_ij = alpha_ij * (keep/(1-p) * (dhp_i . Wh_j) - c_i) * LeakyReLU'(f_i+g_j); writes
+ * edge_alpha (post-dropout attention), edge_dz, df_i = sum_j dz_ij.  O(E*D): replaces the
+ * dense N x N SpecialSpmmFunction.backward (layers.py:81-90).  out may be NULL when
+ * act_elu == 0.  hub_scratch floats: n_hub_seg * H. */
+GATK_API int gatk_attn_bwd_dst(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp,
+                      const float* wh, int64_t ldw, const float* f, const float* g, const float* lse,
+                      const uint8_t* keep_att, float inv_keep, float alpha,
+                      const float* gout, int64_t ldgo, const float* out, int64_t ldo, int act_elu,
+                      const float* hagg, int64_t ldh,
+                      float* dhp, int64_t lddhp, float* df, float* edge_alpha, float* edge_dz,
+                      int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr,
+                      int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream);
+
+/* ------------------------------------------------------------------ K4: backward, source pass (CSR-transpose, scatter-free)
+ * dWh_j = sum_i alpha~_ij dhp_i + df_j a_src + dg_j a_dst,  dg_j = sum_i dz_ij, then the
+ * post-projection dropout mask (keep_wh) if any.  df may be NULL (sharded mode: the
+ * a-terms are added by the owner).  hub_* describe the TRANSPOSED graph's long rows;
+ * hub_scratch floats: n_hub_seg * (H*Dp + H). */
+GATK_API int gatk_attn_bwd_src(int64_t n_src, const int64_t* tptr, const int32_t* trow, const int32_t* perm,
+                      int H, int Dp, const float* dhp, int64_t lddhp,
+                      const float* edge_alpha, const float* edge_dz,
+                      const float* df, const float* a_src, const float* a_dst,
+                      const uint8_t* keep_wh, float inv_keep,
+                      float* dwh, int64_t lddwh, float* dg,
+                      int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr,
+                      int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream);
+
+/* da_src[h,:] = sum_i df[i,h] Wh[i,h,:],  da_dst[h,:] = sum_j dg[j,h] Wh[j,h,:]  (autograd of
+ * layers.py:60-61 / :144).  ws floats: gatk_da_workspace_floats(H, Dp). Deterministic. */
+GATK_API size_t gatk_da_workspace_floats(int H, int Dp);
+GATK_API int gatk_da_reduce(int64_t n, int H, int Dp, const float* wh, int64_t ldw, const float* df,
+                   const float* dg, float* da_src, float* da_dst, float* ws, void* stream);
+
+/* ------------------------------------------------------------------ K6: head combine (models.py:32-34)
+ * mode 0: strip the Dp padding -> out [n, H*D] (torch.cat);  mode 1: mean over heads ->
+ * out [n, D] (torch.mean(torch.stack)).  The backward scatters gout back to [n, H*Dp]. */
+GATK_API int gatk_head_combine(int64_t n, int H, int D, int Dp, const float* in, int64_t ldi, int mode,
+                      float* out, void* stream);
+GATK_API int gatk_head_combine_bwd(int64_t n, int H, int D, int Dp, const float* gout, int mode,
+                          float* gin, int64_t ldi, void* stream);
+
+/* ------------------------------------------------------------------ SpecialSpmm (layers.py:70-95)
+ * out[n_rows, k] = COO(row, col, val) @ b ; grad_val[e] = gout[row_e] . b[col_e] ;
+ * grad_b = COO^T @ gout.  Indices int64 [E] each, any order.  out / grad_b must be
+ * zero-filled by the caller (scatter with float atomics). */
+GATK_API int gatk_spmm_coo_fwd(const int64_t* row, const int64_t* col, const float* val, int64_t e, int64_t k,
+                      const float* b, float* out, void* stream);
+GATK_API int gatk_spmm_coo_bwd(const int64_t* row, const int64_t* col, const float* val, int64_t e, int64_t k,
+                      const float* b, const float* gout, float* grad_val, float* grad_b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GATK_H */

@@ -237,15 +237,16 @@ def gat_forward(params, x, adj, alpha, kind="sparse", p=0.0, masks=None, faithfu
 
 
 # --------------------------------------------------------------------------- synthetic graphs
-def power_law_edges(n: int, avg_deg: float, seed: int, exponent: float = 0.8):
-    """Synthetic power-law graph in the reference's adjacency convention: Zipf-ranked
-    endpoint sampling, symmetrised, de-duplicated, one self-loop per node, sorted
-    row-major (what ``utils.load_data`` + ``adj.nonzero()`` would yield,
-    utils.py:49-55, layers.py:129).  Returns rowptr int64, col int32 (numpy-free)."""
+def power_law_edges(n: int, avg_deg: float, seed: int, exponent: float = 0.5):
+    """Synthetic power-law graph in the reference's adjacency convention: one endpoint drawn
+    Zipf(exponent) over node rank by inverse CDF, the other uniform; symmetrised,
+    de-duplicated, one self-loop per node, sorted row-major (what ``utils.load_data`` +
+    ``adj.nonzero()`` would yield, utils.py:49-55, layers.py:129).  Same recipe as
+    pygat_b200.synth.power_law_csr.  Returns rowptr int64, col int32."""
     g = torch.Generator().manual_seed(seed)
     m = int(n * max(avg_deg - 1.0, 0.0) / 2.0)
-    w = torch.arange(1, n + 1, dtype=torch.float64).pow(-exponent)
-    src = torch.multinomial(w, m, replacement=True, generator=g)
+    u = torch.rand(m, generator=g, dtype=torch.float64)
+    src = (u.pow(1.0 / (1.0 - exponent)) * n).long().clamp_(max=n - 1)
     dst = torch.randint(0, n, (m,), generator=g)
     r = torch.cat([src, dst, torch.arange(n)])
     c = torch.cat([dst, src, torch.arange(n)])

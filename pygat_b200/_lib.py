@@ -1,0 +1,88 @@
+"""ctypes binding of libgatk.so (the C ABI declared in include/gatk.h).
+
+There is no CPU fallback: importing works anywhere (so the symbol table can be checked
+without a GPU), but every compute entry point needs CUDA tensors and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgatk.so")
+
+P = c_void_p  # every device pointer / stream crosses the ABI as void*
+
+# name -> (restype, argtypes); mirrors include/gatk.h one to one
+PROTOTYPES = {
+    "gatk_version": (c_int, []),
+    "gatk_last_error": (c_char_p, []),
+    "gatk_sm_count": (c_int, []),
+    "gatk_scan_workspace_bytes": (c_size_t, [c_int64]),
+    "gatk_csr_from_dense_rowptr": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P, c_size_t, P]),
+    "gatk_csr_from_dense_fill": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P, P]),
+    "gatk_csr_from_coo": (c_int, [P, P, c_int64, c_int64, P, P, P, c_size_t, P]),
+    "gatk_transpose_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "gatk_csr_transpose": (c_int, [c_int64, c_int64, c_int64, P, P, P, P, P, P, c_size_t, P]),
+    "gatk_dropout_keep_mask": (c_int, [P, c_int64, c_float, c_uint64, c_uint64, P]),
+    "gatk_mask_scale": (c_int, [P, c_int64, P, c_float, P, c_int64, c_int64, c_int64, P]),
+    "gatk_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int64, c_int64]),
+    "gatk_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int,
+                          P, c_size_t, P]),
+    "gatk_logits_fwd": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_float, P, P, P, P, P]),
+    "gatk_attn_fwd": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, P, P, c_float, c_float,
+                              P, c_int64, c_int, P, P, c_int64, P,
+                              c_int, P, P, c_int, c_int, P, P, P]),
+    "gatk_attn_bwd_dst": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, P, P, P, c_float, c_float,
+                                  P, c_int64, P, c_int64, c_int, P, c_int64,
+                                  P, c_int64, P, P, P,
+                                  c_int, P, P, c_int, c_int, P, P, P]),
+    "gatk_attn_bwd_src": (c_int, [c_int64, P, P, P, c_int, c_int, P, c_int64, P, P, P, P, P, P, c_float,
+                                  P, c_int64, P,
+                                  c_int, P, P, c_int, c_int, P, P, P]),
+    "gatk_da_workspace_floats": (c_size_t, [c_int, c_int]),
+    "gatk_da_reduce": (c_int, [c_int64, c_int, c_int, P, c_int64, P, P, P, P, P, P]),
+    "gatk_head_combine": (c_int, [c_int64, c_int, c_int, c_int, P, c_int64, c_int, P, P]),
+    "gatk_head_combine_bwd": (c_int, [c_int64, c_int, c_int, c_int, P, c_int, P, c_int64, P]),
+    "gatk_spmm_coo_fwd": (c_int, [P, P, P, c_int64, c_int64, P, P, P]),
+    "gatk_spmm_coo_bwd": (c_int, [P, P, P, c_int64, c_int64, P, P, P, P, P]),
+}
+
+_lib = None
+
+
+class GatkError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load libgatk.so (building it first if the toolkit is present and it is stale/missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) or os.environ.get("GATK_REBUILD"):
+        from . import _build
+        _build.build(force=bool(os.environ.get("GATK_REBUILD")))
+    if not os.path.exists(LIB_PATH):
+        raise GatkError(f"{LIB_PATH} is missing: the CUDA extension is required (there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point; non-zero -> GatkError(gatk_last_error())."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise GatkError(f"{name} failed ({rc}): {lib.gatk_last_error().decode(errors='replace')}")
+
+
+def query(name: str, *args):
+    """Invoke a size/value query (no error code)."""
+    return getattr(load(), name)(*args)

@@ -1,0 +1,176 @@
+// fp32 SIMT GEMM (FFMA, 128x128x8 tiles, 8x8 register blocking, register-prefetch double
+// buffering) with deterministic split-K.  It is the exact-fp32 projection path for operands
+// the TMA/tcgen05 kernel cannot take (row strides that are not multiples of 16 bytes, e.g.
+// Cora's 1433 or PPI's 50 input features) and the yardstick that kernel is tested against.
+// Replaces torch.mm at layers.py:35,48,134,166 and its autograd.
+#include "common.cuh"
+
+namespace gatk {
+
+constexpr int BM = 128, BN = 128, BK = 8, PAD = 4;
+
+// Element (m,k) of op(A) / (k,n) of op(B) with zero fill outside the matrix.
+template <bool T>
+__device__ __forceinline__ float load_a(const float* A, int64_t lda, int64_t m, int64_t k, int64_t M, int64_t K1) {
+  if (m >= M || k >= K1) return 0.f;
+  return T ? __ldg(A + k * lda + m) : __ldg(A + m * lda + k);
+}
+template <bool T>
+__device__ __forceinline__ float load_b(const float* B, int64_t ldb, int64_t k, int64_t n, int64_t N, int64_t K1) {
+  if (n >= N || k >= K1) return 0.f;
+  return T ? __ldg(B + n * ldb + k) : __ldg(B + k * ldb + n);
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A,
+                                                    int64_t lda, const float* __restrict__ B, int64_t ldb,
+                                                    float* __restrict__ C, int64_t ldc, int accumulate, int64_t kchunk,
+                                                    float* __restrict__ part, int64_t ncol_tiles) {
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int64_t tile = blockIdx.x;
+  const int64_t m0 = (tile / ncol_tiles) * BM, n0 = (tile % ncol_tiles) * BN;
+  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < K ? k0 + kchunk : K;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  // global->register staging indices: 4 elements of each operand tile per thread
+  int am[4], ak[4], bk[4], bn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + i * 256;
+    if (TA) { am[i] = idx % BM; ak[i] = idx / BM; } else { am[i] = idx / BK; ak[i] = idx % BK; }
+    if (TB) { bn[i] = idx / BK; bk[i] = idx % BK; } else { bn[i] = idx % BN; bk[i] = idx / BN; }
+  }
+  float ra[4], rb[4];
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  auto fetch = [&](int64_t kt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ra[i] = load_a<TA>(A, lda, m0 + am[i], kt + ak[i], M, k1);
+      rb[i] = load_b<TB>(B, ldb, kt + bk[i], n0 + bn[i], N, k1);
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[buf][ak[i]][am[i]] = ra[i];
+      Bs[buf][bk[i]][bn[i]] = rb[i];
+    }
+  };
+
+  int buf = 0;
+  if (k0 < k1) {
+    fetch(k0);
+    stash(0);
+  }
+  __syncthreads();
+  for (int64_t kt = k0; kt < k1; kt += BK) {
+    const bool more = kt + BK < k1;
+    if (more) fetch(kt + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  float* out = part ? part + (int64_t)blockIdx.z * M * N : C;
+  const int64_t ldo = part ? N : ldc;
+  const bool add = part ? false : (accumulate != 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= N) continue;
+      float* p = out + m * ldo + n;
+      *p = add ? *p + acc[i][j] : acc[i][j];
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(int64_t M, int64_t N, int splits, const float* __restrict__ part,
+                                     float* __restrict__ C, int64_t ldc, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * M * N + i];
+  float* p = C + (i / N) * ldc + (i % N);
+  *p = accumulate ? *p + s : s;
+}
+
+static int choose_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int64_t target = 2LL * sm_count();
+  if (tiles >= target || K <= 512) return 1;
+  int64_t s = target / tiles;
+  const int64_t maxs = (K + 255) / 256;
+  if (s > maxs) s = maxs;
+  if (s > 512) s = 512;
+  return s < 1 ? 1 : (int)s;
+}
+
+}  // namespace gatk
+
+using namespace gatk;
+
+extern "C" size_t gatk_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K) {
+  (void)transA; (void)transB;
+  const int s = choose_splits(M, N, K);
+  return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+}
+
+extern "C" int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                         const float* B, int64_t ldb, float* C, int64_t ldc, int accumulate, void* ws, size_t ws_bytes,
+                         void* stream) {
+  GATK_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative GEMM size");
+  if (M == 0 || N == 0) return 0;
+  GATK_REQUIRE(A && B && C, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int splits = choose_splits(M, N, K);
+  if (splits > 1 && (ws == nullptr || ws_bytes < (size_t)splits * M * N * sizeof(float))) splits = 1;
+  int64_t kchunk = (K + splits - 1) / splits;
+  kchunk = (kchunk + BK - 1) / BK * BK;
+  if (kchunk < BK) kchunk = BK;
+  splits = K > 0 ? (int)((K + kchunk - 1) / kchunk) : 1;
+  const int64_t ncol = (N + BN - 1) / BN, nrow = (M + BM - 1) / BM;
+  GATK_REQUIRE(nrow * ncol < (1LL << 31), "GEMM grid too large");
+  dim3 grid((unsigned)(nrow * ncol), 1, (unsigned)splits);
+  float* part = splits > 1 ? static_cast<float*>(ws) : nullptr;
+  if (transA && transB)
+    sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kchunk, part, ncol);
+  else if (transA)
+    sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kchunk, part, ncol);
+  else if (transB)
+    sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kchunk, part, ncol);
+  else
+    sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kchunk, part, ncol);
+  GATK_CHECK_LAUNCH();
+  if (splits > 1) {
+    splitk_reduce_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(M, N, splits, part, C, ldc, accumulate);
+    GATK_CHECK_LAUNCH();
+  }
+  return 0;
+}

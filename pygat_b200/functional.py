@@ -1,0 +1,280 @@
+"""Host side of the fused GAT layer: one autograd.Function per LAYER (all heads batched)
+driving the C-ABI kernels of libgatk.so.
+
+What it replaces (reference /root/reference): the per-head Python loop of models.py:29-35
+around SpGraphAttentionLayer.forward (layers.py:125-173) / GraphAttentionLayer.forward
+(layers.py:32-53) and autograd through SpecialSpmmFunction (layers.py:70-90).
+
+Layout: heads are packed side by side, each padded from D to Dp = 4*2^k columns, so the
+projected features are one [N, H*Dp] matrix (== torch.cat over heads, models.py:32, when
+D == Dp).  The skip projection (layers.py:48,166) rides in the same GEMM as extra columns.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .graph import Graph, _ptr, _require_cuda, _stream
+
+
+def padded_width(d: int) -> int:
+    """Per-head width the kernels use: 4 * 2^k >= d (float4 slots, power-of-two slots per head)."""
+    l = 1
+    while 4 * l < d:
+        l *= 2
+    return 4 * l
+
+
+@dataclass
+class LayerMasks:
+    """Explicit keep masks (uint8, 1 = keep) for the three dropout sites of a layer
+    (layers.py:34/132 input, :37/136 projected features, :43/153 attention).
+    keep_in [H, N, F]; keep_wh [N, H*Dp]; keep_att [E, H].  None = site not dropped."""
+    keep_in: Optional[torch.Tensor] = None
+    keep_wh: Optional[torch.Tensor] = None
+    keep_att: Optional[torch.Tensor] = None
+
+
+def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=0, a_off=0, b_off=0, c_off=0):
+    """C[M,N] (+)= op(A) op(B) on raw pointers; *_off are element offsets into the tensors."""
+    ws_bytes = _lib.query("gatk_gemm_workspace_bytes", ta, tb, M, N, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=C.device) if ws_bytes else None
+    _lib.call("gatk_gemm", ta, tb, M, N, K, A.data_ptr() + 4 * a_off, lda, B.data_ptr() + 4 * b_off, ldb,
+              C.data_ptr() + 4 * c_off, ldc, accumulate, _ptr(ws), ws_bytes, _stream())
+
+
+def random_masks(n: int, f_in: int, H: int, Dp: int, nnz: int, p: float, device) -> LayerMasks:
+    """Draw the three masks with the in-library Philox generator.  The 64-bit seed comes from
+    torch's CPU generator, so torch.manual_seed (train.py:91-99) makes runs reproducible."""
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    sizes = (H * n * f_in, n * H * Dp, nnz * H)
+    bufs, off = [], 0
+    for sz in sizes:
+        t = torch.empty(sz, dtype=torch.uint8, device=device)
+        _lib.call("gatk_dropout_keep_mask", t.data_ptr(), sz, float(p), seed, off, _stream())
+        off += (sz + 3) // 4
+        bufs.append(t)
+    return LayerMasks(bufs[0].view(H, n, f_in), bufs[1].view(n, H * Dp), bufs[2].view(nnz, H))
+
+
+class GatLayerFunction(torch.autograd.Function):
+    """out[N, H*Dp] = act( softmax_j(LeakyReLU(f_i + g_j)) @ Wh  (+ x_drop @ S) ), all heads."""
+
+    @staticmethod
+    def forward(ctx, x, w_ext, a_src, a_dst, graph: Graph, H: int, Dp: int, has_skip: bool, alpha: float,
+                act_elu: bool, p: float, masks: Optional[LayerMasks]):
+        _require_cuda(x, "input features")
+        dev = x.device
+        n, f_in = x.shape
+        if graph.n_dst != n or graph.n_src != n:
+            raise RuntimeError(f"adjacency is {graph.n_dst}x{graph.n_src} but the input has {n} rows")
+        HD = H * Dp
+        M_out = HD * (2 if has_skip else 1)
+        assert w_ext.shape == (f_in, M_out) and a_src.shape == (H, Dp) and a_dst.shape == (H, Dp)
+        x = x.contiguous()
+        w_ext = w_ext.contiguous()
+        a_src = a_src.contiguous()
+        a_dst = a_dst.contiguous()
+        masks = masks if (masks is not None and p > 0.0) else LayerMasks()
+        inv_keep = 1.0 / (1.0 - p) if p > 0.0 else 1.0
+        st = _stream()
+
+        # ---- K1: projection (+ skip columns) ---------------------------------------------
+        z = torch.empty(n, M_out, dtype=torch.float32, device=dev)
+        if masks.keep_in is None:
+            _gemm(0, 0, n, M_out, f_in, x, f_in, w_ext, M_out, z, M_out)
+        else:
+            xh = torch.empty_like(x)
+            for h in range(H):  # every head drops the input with its own mask (layers.py:34,132)
+                _lib.call("gatk_mask_scale", x.data_ptr(), f_in, masks.keep_in[h].data_ptr(), inv_keep,
+                          xh.data_ptr(), f_in, n, f_in, st)
+                for base in ((0, HD) if has_skip else (0,)):
+                    off = base + h * Dp
+                    _gemm(0, 0, n, Dp, f_in, xh, f_in, w_ext, M_out, z, M_out, b_off=off, c_off=off)
+        wh_ptr = z.data_ptr()
+        skip_ptr = z.data_ptr() + 4 * HD if has_skip else None
+
+        # ---- logits (and the post-projection dropout, in place) --------------------------
+        f = torch.empty(n, H, dtype=torch.float32, device=dev)
+        g = torch.empty(n, H, dtype=torch.float32, device=dev)
+        _lib.call("gatk_logits_fwd", n, H, Dp, wh_ptr, M_out, _ptr(masks.keep_wh), inv_keep,
+                  a_src.data_ptr(), a_dst.data_ptr(), f.data_ptr(), g.data_ptr(), st)
+
+        # ---- K2: fused attention -----------------------------------------------------------
+        need_grad = any(ctx.needs_input_grad[:4])
+        out = torch.empty(n, HD, dtype=torch.float32, device=dev)
+        separate_hagg = need_grad and (has_skip or act_elu)
+        hagg = torch.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
+        lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        hubs = graph.hubs
+        scratch = torch.empty(hubs.n_seg * (HD + 2 * H), dtype=torch.float32, device=dev) if hubs.n_seg else None
+        _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_ptr, M_out,
+                  f.data_ptr(), g.data_ptr(), _ptr(masks.keep_att), inv_keep, float(alpha),
+                  skip_ptr, M_out, int(act_elu), _ptr(hagg), out.data_ptr(), HD, _ptr(lse),
+                  *hubs.args(scratch), graph.counter.data_ptr(), st)
+
+        if need_grad:
+            ctx.graph, ctx.masks = graph, masks
+            ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu), float(p), inv_keep)
+            ctx.save_for_backward(x, w_ext, a_src, a_dst, z, f, g, lse, out, hagg if separate_hagg else out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w_ext, a_src, a_dst, z, f, g, lse, out, hagg = ctx.saved_tensors
+        graph, masks = ctx.graph, ctx.masks
+        H, Dp, has_skip, alpha, act_elu, p, inv_keep = ctx.cfg
+        dev = x.device
+        n, f_in = x.shape
+        HD = H * Dp
+        M_out = HD * (2 if has_skip else 1)
+        st = _stream()
+        gout = gout.contiguous()
+        tptr, trow, perm, thubs = graph.transpose()
+
+        # dZ = [dWh | dSkip]; with a skip projection dL/dh' IS dSkip, so K3 writes it in place.
+        dz_rows = torch.empty(n, M_out, dtype=torch.float32, device=dev)
+        if has_skip:
+            dhp_ptr, lddhp, dhp_keepalive = dz_rows.data_ptr() + 4 * HD, M_out, None
+        else:
+            dhp_keepalive = torch.empty(n, HD, dtype=torch.float32, device=dev)
+            dhp_ptr, lddhp = dhp_keepalive.data_ptr(), HD
+        df = torch.empty(n, H, dtype=torch.float32, device=dev)
+        dg = torch.empty(n, H, dtype=torch.float32, device=dev)
+        edge_alpha = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+
+        # ---- K3: destination pass ----------------------------------------------------------
+        hubs = graph.hubs
+        scratch = torch.empty(hubs.n_seg * H, dtype=torch.float32, device=dev) if hubs.n_seg else None
+        _lib.call("gatk_attn_bwd_dst", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, z.data_ptr(), M_out,
+                  f.data_ptr(), g.data_ptr(), lse.data_ptr(), _ptr(masks.keep_att), inv_keep, alpha,
+                  gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD, int(act_elu),
+                  hagg.data_ptr(), HD, dhp_ptr, lddhp, df.data_ptr(), edge_alpha.data_ptr(), edge_dz.data_ptr(),
+                  *hubs.args(scratch), graph.counter.data_ptr(), st)
+
+        # ---- K4: source pass over the transposed pattern -----------------------------------
+        scratch_t = torch.empty(thubs.n_seg * (HD + H), dtype=torch.float32, device=dev) if thubs.n_seg else None
+        _lib.call("gatk_attn_bwd_src", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, dhp_ptr, lddhp,
+                  edge_alpha.data_ptr(), edge_dz.data_ptr(), df.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(),
+                  _ptr(masks.keep_wh), inv_keep, dz_rows.data_ptr(), M_out, dg.data_ptr(),
+                  *thubs.args(scratch_t), graph.counter.data_ptr(), st)
+        del edge_alpha, edge_dz
+
+        # ---- da ------------------------------------------------------------------------------
+        da_src = torch.empty(H, Dp, dtype=torch.float32, device=dev)
+        da_dst = torch.empty(H, Dp, dtype=torch.float32, device=dev)
+        ws = torch.empty(_lib.query("gatk_da_workspace_floats", H, Dp), dtype=torch.float32, device=dev)
+        _lib.call("gatk_da_reduce", n, H, Dp, z.data_ptr(), M_out, df.data_ptr(), dg.data_ptr(),
+                  da_src.data_ptr(), da_dst.data_ptr(), ws.data_ptr(), st)
+
+        # ---- K5: projection backward -------------------------------------------------------
+        need_dx = ctx.needs_input_grad[0]
+        dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
+        dx = torch.empty(n, f_in, dtype=torch.float32, device=dev) if need_dx else None
+        if masks.keep_in is None:
+            _gemm(1, 0, f_in, M_out, n, x, f_in, dz_rows, M_out, dw_ext, M_out)
+            if need_dx:
+                _gemm(0, 1, n, f_in, M_out, dz_rows, M_out, w_ext, M_out, dx, f_in)
+        else:
+            xh = torch.empty_like(x)
+            dxh = torch.empty_like(x) if need_dx else None
+            if need_dx:
+                dx.zero_()
+            for h in range(H):
+                _lib.call("gatk_mask_scale", x.data_ptr(), f_in, masks.keep_in[h].data_ptr(), inv_keep,
+                          xh.data_ptr(), f_in, n, f_in, st)
+                for k, base in enumerate((0, HD) if has_skip else (0,)):
+                    off = base + h * Dp
+                    _gemm(1, 0, f_in, Dp, n, xh, f_in, dz_rows, M_out, dw_ext, M_out, b_off=off, c_off=off)
+                    if need_dx:
+                        _gemm(0, 1, n, f_in, Dp, dz_rows, M_out, w_ext, M_out, dxh, f_in, accumulate=int(k > 0),
+                              a_off=off, b_off=off)
+                if need_dx:
+                    _lib.call("gatk_mask_scale", dxh.data_ptr(), f_in, masks.keep_in[h].data_ptr(), inv_keep,
+                              dxh.data_ptr(), f_in, n, f_in, st)
+                    dx.add_(dxh)
+        del dhp_keepalive
+        return dx, dw_ext, da_src, da_dst, None, None, None, None, None, None, None, None
+
+
+class HeadCombineFunction(torch.autograd.Function):
+    """[N, H*Dp] -> torch.cat of the unpadded heads (mode 0, models.py:32) or their mean
+    (mode 1, models.py:34)."""
+
+    @staticmethod
+    def forward(ctx, rows, H: int, D: int, Dp: int, mode: int):
+        rows = rows.contiguous()
+        n = rows.shape[0]
+        out = torch.empty(n, H * D if mode == 0 else D, dtype=torch.float32, device=rows.device)
+        _lib.call("gatk_head_combine", n, H, D, Dp, rows.data_ptr(), H * Dp, mode, out.data_ptr(), _stream())
+        ctx.cfg = (n, H, D, Dp, mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        n, H, D, Dp, mode = ctx.cfg
+        gout = gout.contiguous()
+        gin = torch.empty(n, H * Dp, dtype=torch.float32, device=gout.device)
+        _lib.call("gatk_head_combine_bwd", n, H, D, Dp, gout.data_ptr(), mode, gin.data_ptr(), H * Dp, _stream())
+        return gin, None, None, None, None
+
+
+def _pad_cols(t: torch.Tensor, Dp: int) -> torch.Tensor:
+    d = t.shape[-1]
+    return t if d == Dp else torch.nn.functional.pad(t, (0, Dp - d))
+
+
+def pack_heads(Ws: Sequence[torch.Tensor], a_srcs: Sequence[torch.Tensor], a_dsts: Sequence[torch.Tensor],
+               skips: Optional[Sequence[torch.Tensor]]):
+    """Per-head parameters (the reference's nn.Parameters, models.py:27) -> packed operands.
+    Plain torch ops on parameter-sized tensors, so autograd splits the packed gradients back."""
+    D = Ws[0].shape[1]
+    Dp = padded_width(D)
+    cols = [_pad_cols(w, Dp) for w in Ws]
+    if skips is not None:
+        cols += [_pad_cols(s, Dp) for s in skips]
+    w_ext = torch.cat(cols, dim=1) if len(cols) > 1 else cols[0]
+    a_src = torch.stack([_pad_cols(a.reshape(-1), Dp) for a in a_srcs])
+    a_dst = torch.stack([_pad_cols(a.reshape(-1), Dp) for a in a_dsts])
+    return w_ext, a_src, a_dst, D, Dp
+
+
+def gat_layer(x: torch.Tensor, graph: Graph, Ws, a_srcs, a_dsts, skips, alpha: float, concat: bool,
+              p: float = 0.0, training: bool = False, masks: Optional[LayerMasks] = None,
+              combine: str = "cat") -> torch.Tensor:
+    """All heads of one GAT layer.  concat=True applies ELU inside each head (layers.py:50-53);
+    combine="cat" -> [N, H*D] (models.py:32), "mean" -> [N, D] (models.py:34),
+    "none" -> the padded [N, H*Dp] rows."""
+    H = len(Ws)
+    if x.dtype != torch.float32:
+        x = x.float()
+    w_ext, a_src, a_dst, D, Dp = pack_heads(Ws, a_srcs, a_dsts, skips)
+    p_eff = float(p) if training else 0.0
+    if p_eff > 0.0 and masks is None:
+        masks = random_masks(x.shape[0], x.shape[1], H, Dp, graph.nnz, p_eff, x.device)
+    rows = GatLayerFunction.apply(x, w_ext, a_src, a_dst, graph, H, Dp, skips is not None, float(alpha),
+                                  bool(concat), p_eff, masks)
+    if combine == "none":
+        return rows
+    if combine == "mean":
+        return HeadCombineFunction.apply(rows, H, D, Dp, 1)
+    if D == Dp:
+        return rows
+    return HeadCombineFunction.apply(rows, H, D, Dp, 0)
+
+
+def pack_masks(keep_in: Optional[List[torch.Tensor]], keep_wh: Optional[List[torch.Tensor]],
+               keep_att: Optional[List[torch.Tensor]], Dp: int) -> LayerMasks:
+    """Per-head boolean masks (as a test draws them for the oracle) -> the packed uint8 layout."""
+    m = LayerMasks()
+    if keep_in is not None:
+        m.keep_in = torch.stack([k.to(torch.uint8) for k in keep_in]).contiguous()
+    if keep_wh is not None:
+        m.keep_wh = torch.cat([_pad_cols(k.to(torch.uint8), Dp) for k in keep_wh], dim=1).contiguous()
+    if keep_att is not None:
+        m.keep_att = torch.stack([k.to(torch.uint8) for k in keep_att], dim=1).contiguous()
+    return m

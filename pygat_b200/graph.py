@@ -1,0 +1,168 @@
+"""Graph handle: the CSR form of the adjacency pattern the reference recomputes per head with
+``adj.nonzero()`` (layers.py:129) or masks with ``adj > 0`` (layers.py:41), built once by the
+K0 kernels and cached per adjacency tensor."""
+from __future__ import annotations
+
+import os
+import weakref
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+RULE_NONZERO = 0   # SpGraphAttentionLayer: every entry != 0 (layers.py:129)
+RULE_POSITIVE = 1  # GraphAttentionLayer:   entries > 0   (layers.py:41)
+
+DEFAULT_SEG_LEN = int(os.environ.get("GATK_SEG_LEN", "1024"))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"pygat_b200: {what} must be a CUDA tensor (the engine has no CPU path); got {t.device}")
+
+
+class HubPartition:
+    """Rows longer than seg_len, cut into segments (see gatk_attn_fwd in include/gatk.h)."""
+
+    def __init__(self, ptr: torch.Tensor, seg_len: int):
+        deg = ptr[1:] - ptr[:-1]
+        rows = torch.nonzero(deg > seg_len).flatten()
+        self.seg_len = int(seg_len)
+        self.n_hub = int(rows.numel())
+        if self.n_hub:
+            nseg = (deg[rows] + seg_len - 1) // seg_len
+            seg_ptr = torch.zeros(self.n_hub + 1, dtype=torch.int64, device=ptr.device)
+            seg_ptr[1:] = torch.cumsum(nseg, 0)
+            self.rows = rows.to(torch.int32)
+            self.seg_ptr = seg_ptr.to(torch.int32)
+            self.n_seg = int(seg_ptr[-1].item())
+        else:
+            self.rows = self.seg_ptr = None
+            self.n_seg = 0
+
+    def args(self, scratch: Optional[torch.Tensor]):
+        return (self.seg_len, _ptr(self.rows), _ptr(self.seg_ptr), self.n_hub, self.n_seg, _ptr(scratch))
+
+
+class Graph:
+    """CSR pattern (rows = destinations) + lazily built transpose for the backward pass.
+
+    n_dst rows, n_src columns (equal unless the handle is a destination-row shard).
+    """
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, n_src: Optional[int] = None,
+                 seg_len: Optional[int] = None):
+        _require_cuda(rowptr, "rowptr")
+        _require_cuda(col, "col")
+        assert rowptr.dtype == torch.int64 and col.dtype == torch.int32
+        self.rowptr = rowptr.contiguous()
+        self.col = col.contiguous()
+        self.n_dst = rowptr.numel() - 1
+        self.n_src = int(n_src) if n_src is not None else self.n_dst
+        self.nnz = int(col.numel())
+        self.device = rowptr.device
+        self.seg_len = int(seg_len or DEFAULT_SEG_LEN)
+        self.hubs = HubPartition(self.rowptr, self.seg_len)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._t: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, HubPartition]] = None
+
+    # ------------------------------------------------------------------ constructors
+    @staticmethod
+    def from_dense(adj: torch.Tensor, rule: int = RULE_NONZERO, seg_len: Optional[int] = None) -> "Graph":
+        _require_cuda(adj, "adj")
+        if adj.dim() != 2 or adj.shape[0] != adj.shape[1]:
+            raise RuntimeError(f"adj must be square, got {tuple(adj.shape)}")
+        if adj.dtype != torch.float32:
+            adj = adj.float()
+        n = adj.shape[0]
+        rowptr = torch.empty(n + 1, dtype=torch.int64, device=adj.device)
+        ws_bytes = _lib.query("gatk_scan_workspace_bytes", n)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=adj.device)
+        rs, cs = adj.stride()
+        _lib.call("gatk_csr_from_dense_rowptr", adj.data_ptr(), n, rs, cs, rule, rowptr.data_ptr(),
+                  ws.data_ptr(), ws_bytes, _stream())
+        e = int(rowptr[-1].item())  # the one host sync of the graph build (the reference syncs per head)
+        col = torch.empty(e, dtype=torch.int32, device=adj.device)
+        _lib.call("gatk_csr_from_dense_fill", adj.data_ptr(), n, rs, cs, rule, rowptr.data_ptr(),
+                  col.data_ptr(), _stream())
+        return Graph(rowptr, col, seg_len=seg_len)
+
+    @staticmethod
+    def from_coo(edge: torch.Tensor, n: int, seg_len: Optional[int] = None) -> "Graph":
+        """edge: (2, E) int64, row-major sorted (what adj.nonzero().t() yields)."""
+        _require_cuda(edge, "edge")
+        edge = edge.contiguous()
+        e = edge.shape[1]
+        rowptr = torch.empty(n + 1, dtype=torch.int64, device=edge.device)
+        col = torch.empty(e, dtype=torch.int32, device=edge.device)
+        ws_bytes = _lib.query("gatk_scan_workspace_bytes", n)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=edge.device)
+        _lib.call("gatk_csr_from_coo", edge[0].data_ptr(), edge[1].data_ptr(), e, n, rowptr.data_ptr(),
+                  col.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+        return Graph(rowptr, col, seg_len=seg_len)
+
+    @staticmethod
+    def from_csr(rowptr: torch.Tensor, col: torch.Tensor, n_src: Optional[int] = None,
+                 seg_len: Optional[int] = None) -> "Graph":
+        return Graph(rowptr.to(torch.int64), col.to(torch.int32), n_src=n_src, seg_len=seg_len)
+
+    # ------------------------------------------------------------------ transpose (backward only)
+    def transpose(self):
+        if self._t is None:
+            tptr = torch.empty(self.n_src + 1, dtype=torch.int64, device=self.device)
+            trow = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            perm = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            ws_bytes = _lib.query("gatk_transpose_workspace_bytes", self.n_dst, self.n_src, self.nnz)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=self.device)
+            _lib.call("gatk_csr_transpose", self.n_dst, self.n_src, self.nnz, self.rowptr.data_ptr(),
+                      _ptr(self.col), tptr.data_ptr(), _ptr(trow), _ptr(perm), ws.data_ptr(), ws_bytes, _stream())
+            del ws
+            self._t = (tptr, trow, perm, HubPartition(tptr, self.seg_len))
+        return self._t
+
+    def edge_index(self) -> torch.Tensor:
+        """(2, E) int64 in adj.nonzero().t() order (layers.py:129)."""
+        deg = self.rowptr[1:] - self.rowptr[:-1]
+        row = torch.repeat_interleave(torch.arange(self.n_dst, device=self.device), deg)
+        return torch.stack([row, self.col.long()])
+
+
+# ---------------------------------------------------------------------- per-adjacency cache
+# Keyed on the identity of the tensor OBJECT (weakly referenced, so a recycled data_ptr of a
+# freed adjacency can never alias) plus its version counter, strides and the pattern rule.
+_cache: "dict[tuple, tuple]" = {}
+
+
+def graph_of(adj, rule: int = RULE_NONZERO) -> Graph:
+    if isinstance(adj, Graph):
+        return adj
+    if not torch.is_tensor(adj):
+        raise RuntimeError(f"adj must be a dense tensor, a sparse tensor or a pygat_b200.Graph, got {type(adj)}")
+    key = (id(adj), rule)
+    hit = _cache.get(key)
+    sig = (adj._version, adj.data_ptr() if not adj.is_sparse else 0, tuple(adj.shape), adj.layout)
+    if hit is not None and hit[0]() is adj and hit[1] == sig:
+        return hit[2]
+    if adj.layout == torch.strided:
+        g = Graph.from_dense(adj, rule)
+    else:
+        coo = adj.coalesce() if adj.layout == torch.sparse_coo else adj.to_sparse_coo().coalesce()
+        idx, val = coo.indices(), coo.values()
+        sel = val != 0 if rule == RULE_NONZERO else val > 0
+        g = Graph.from_coo(idx[:, sel], adj.shape[0])
+    ref = weakref.ref(adj, lambda _r, k=key: _cache.pop(k, None))
+    _cache[key] = (ref, sig, g)
+    return g
+
+
+def clear_cache():
+    _cache.clear()

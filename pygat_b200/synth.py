@@ -1,0 +1,42 @@
+"""Synthetic inputs of the benchmark shapes: power-law graphs in the
+reference's adjacency convention (symmetric, one self-loop per node, row-major sorted;
+utils.py:49-55), built directly as CSR on whatever device is asked for -- the dense N x N
+matrix the reference's loaders produce never exists at these sizes."""
+from __future__ import annotations
+
+import torch
+
+
+def power_law_csr(n: int, avg_deg: float, seed: int, exponent: float = 0.5, device="cpu"):
+    """rowptr int64 [n+1], col int32 [E]; E ~ n*avg_deg before de-duplication.
+
+    One endpoint of every sampled edge is Zipf(exponent) over node rank (inverse CDF: rank =
+    n * u^(1/(1-exponent))), the other uniform.  exponent 0.5 at the ogbn-products shape gives a
+    max degree of ~2e4, like the real graph's 17.5k."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    m = int(n * max(avg_deg - 1.0, 0.0) / 2.0)
+    u = torch.rand(m, generator=g, dtype=torch.float64, device=dev)
+    src = (u.pow(1.0 / (1.0 - exponent)) * n).long().clamp_(max=n - 1)
+    del u
+    dst = torch.randint(0, n, (m,), generator=g, device=dev)
+    loops = torch.arange(n, device=dev)
+    key = torch.cat([src * n + dst, dst * n + src, loops * n + loops])
+    del src, dst
+    key = torch.unique(key)  # sorted => row-major (row, col) order, duplicates dropped
+    row = key // n
+    col = (key - row * n).to(torch.int32)
+    del key
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    rowptr[1:] = torch.cumsum(torch.bincount(row, minlength=n), 0)
+    return rowptr, col
+
+
+def shard_rows_by_nnz(rowptr: torch.Tensor, world: int):
+    """Contiguous destination-row ranges with ~equal stored entries (power-law graphs are not
+    balanced by row count).  Returns world+1 row boundaries (python ints)."""
+    n = rowptr.numel() - 1
+    total = int(rowptr[-1].item())
+    targets = torch.arange(1, world, device=rowptr.device, dtype=torch.int64) * total // world
+    cuts = torch.searchsorted(rowptr, targets).clamp_(max=n).tolist()
+    return [0] + [int(c) for c in cuts] + [n]

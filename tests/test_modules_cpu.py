@@ -1,0 +1,85 @@
+"""Host-side mirror of the reference interface: names, shapes, init order, error behaviour."""
+import pytest
+import torch
+
+import layers
+import models
+from pygat_b200.functional import pack_heads, padded_width
+from pygat_b200.layers import can_fuse
+from tests.golden_io import load
+
+# seeds used by tests/golden/make_golden.py
+GAT_SEEDS = {"gat_sp_pubmed_like": 31, "gat_de_cora_like": 32, "gat_de_ppi_like": 33, "gat_sp_ppi_like": 34,
+             "gat_sp_cora_topology": 72}
+HEAD_SEEDS = {"sp_head_basic": 11, "sp_head_skip_last": 12, "de_head_basic": 21, "de_head_skip_last": 22}
+
+
+@pytest.mark.parametrize("name", sorted(GAT_SEEDS))
+def test_gat_same_seed_same_parameters_as_reference(name):
+    d = load(name)
+    cls = layers.SpGraphAttentionLayer if "_sp_" in name else layers.GraphAttentionLayer
+    torch.manual_seed(GAT_SEEDS[name])
+    nheads = [int(v) for v in d["nheads"]]
+    model = models.GAT(nfeat=[int(v) for v in d["nfeat"]], nheads=nheads, nlayers=len(nheads), dropout=d["p"],
+                       alpha=d["alpha"], layer_type=cls, skip_connection=bool(d["skip"]))
+    ref = {k[len("param."):]: v for k, v in d.items() if k.startswith("param.")}
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(ref.keys())  # models.py:27 naming and order
+    for k, v in ref.items():
+        assert sd[k].shape == v.shape
+        assert torch.equal(sd[k], v), k
+    model.load_state_dict(ref)  # reference checkpoints load
+
+
+@pytest.mark.parametrize("name", sorted(HEAD_SEEDS))
+def test_head_same_seed_same_parameters_as_reference(name):
+    d = load(name)
+    cls = layers.SpGraphAttentionLayer if name.startswith("sp_") else layers.GraphAttentionLayer
+    torch.manual_seed(HEAD_SEEDS[name])
+    f_in, dd = d["W"].shape
+    head = cls(f_in, dd, dropout=d["p"], alpha=d["alpha"], concat=bool(d["concat"]), skip_connection="skip" in d)
+    assert torch.equal(head.W.data, d["W"]) and torch.equal(head.a.data, d["a"])
+    if "skip" in d:
+        assert torch.equal(head.skip_projection.data, d["skip"])
+    assert repr(head) == f"{cls.__name__} ({f_in} -> {dd})"
+    assert isinstance(head.leakyrelu, torch.nn.LeakyReLU)
+
+
+def test_all_four_layer_names_importable():
+    for n in ("GraphAttentionLayer", "GraphAttentionLayerV2", "SpGraphAttentionLayer", "SpGraphAttentionLayerV2",
+              "SpecialSpmm", "SpecialSpmmFunction"):
+        assert hasattr(layers, n)
+    v2 = layers.SpGraphAttentionLayerV2(6, 4, 0.0, 0.2)
+    assert v2.W.shape == (12, 4) and v2.a.shape == (1, 4)
+    assert layers.GraphAttentionLayerV2(6, 4, 0.0, 0.2).a.shape == (4, 1)
+
+
+def test_cpu_tensors_are_refused_loudly():
+    head = layers.SpGraphAttentionLayer(5, 4, 0.0, 0.2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        head(torch.randn(6, 5), torch.eye(6))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layers.SpecialSpmm()(torch.zeros(2, 1, dtype=torch.long), torch.ones(1), torch.Size([3, 3]), torch.ones(3, 2))
+
+
+def test_can_fuse_rules():
+    a = [layers.SpGraphAttentionLayer(5, 4, 0.1, 0.2) for _ in range(3)]
+    assert can_fuse(a)
+    a[1].eval()
+    assert not can_fuse(a)
+    assert not can_fuse([layers.SpGraphAttentionLayer(5, 4, 0.1, 0.2), layers.GraphAttentionLayer(5, 4, 0.1, 0.2)])
+    assert not can_fuse([layers.SpGraphAttentionLayerV2(5, 4, 0.1, 0.2)])
+
+
+def test_padded_width_and_packing():
+    assert [padded_width(d) for d in (1, 3, 4, 7, 8, 64, 100, 121, 256)] == [4, 4, 4, 8, 8, 64, 128, 128, 256]
+    heads = [layers.GraphAttentionLayer(6, 7, 0.0, 0.2, skip_connection=True) for _ in range(3)]
+    vec = [h.attention_vectors() for h in heads]
+    w_ext, a_src, a_dst, D, Dp = pack_heads([h.W for h in heads], [v[0] for v in vec], [v[1] for v in vec],
+                                            [h.skip_projection for h in heads])
+    assert (D, Dp) == (7, 8) and w_ext.shape == (6, 48) and a_src.shape == (3, 8)
+    assert torch.equal(w_ext[:, 8:15], heads[1].W) and torch.all(w_ext[:, 15] == 0)
+    assert torch.equal(w_ext[:, 24:31], heads[0].skip_projection)
+    assert torch.equal(a_src[2, :7], heads[2].a[:7, 0]) and torch.equal(a_dst[2, :7], heads[2].a[7:, 0])
+    w_ext.sum().backward()  # gradients flow back to the per-head parameters
+    assert heads[0].W.grad is not None and heads[2].skip_projection.grad is not None
