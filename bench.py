@@ -1,0 +1,337 @@
+"""Benchmark of the GAT-layer hot path (BASELINE.json metric: GAT layer fwd+bwd head-edges/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload products|pubmed]
+
+A step is one forward + backward of one hidden GAT layer (all heads, ELU, no dropout) over the
+whole synthetic graph.  Default workload: the ogbn-products shape BASELINE.json's target is
+quoted on (2.45 M nodes, ~61.9 M stored entries incl. self-loops, 100 features, 8 heads x 64).
+Rank 0 prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the
+reference's sparse CPU path (the oracle port of layers.py:125-173 + its autograd, all host
+threads) on a bounded power-law sample of the same shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: nodes, average stored entries per row, in-features, heads, per-head width, zipf exponent
+    "products": dict(n=2_449_029, avg_deg=25.26, f_in=100, H=8, D=64, exponent=0.5),
+    "pubmed": dict(n=19_717, avg_deg=5.5, f_in=500, H=8, D=8, exponent=0.5),
+    "papers_shard": dict(n=13_882_495, avg_deg=14.55, f_in=128, H=4, D=32, exponent=0.5),
+}
+CPU_SAMPLE_NODES = 16_384  # reference backward is O(N^2) memory (layers.py:85): 1 GiB per product here
+
+
+def algorithmic_bytes(n, e, H, D, f_in, need_dx=False):
+    """no-reuse gather model, fp32, 4-byte col ids, 8-byte rowptr."""
+    k2 = e * H * (4 * D + 4) + 4 * e + n * H * (4 * D + 12) + 8 * n
+    k3 = e * H * (4 * D + 4 + 4) + 4 * e + n * H * (8 * D + 16)
+    k4 = e * H * (4 * D + 4 + 12) + 8 * e + n * H * (4 * D + 4)
+    k1 = 4 * n * f_in + 4 * f_in * H * D + 4 * n * H * (D + 2)
+    k5 = 4 * n * f_in + 4 * n * H * D + 4 * f_in * H * D + ((4 * n * H * D + 4 * n * f_in) if need_dx else 0)
+    return {"gatk_attn_fwd": k2, "gatk_attn_bwd_dst": k3, "gatk_attn_bwd_src": k4, "projection_fwd": k1,
+            "projection_bwd": k5, "layer": k2 + k3 + k4 + k1 + k5}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.split(",") for r in open(self.tmp.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.tmp.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({nm for r in rows for nm, v in zip(names, r[5:9]) if "Active" in v and "Not" not in v})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ------------------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_rate(cfg, steps: int, warmup: int, nodes: int = CPU_SAMPLE_NODES):
+    """head-edges/s of the reference's sparse CPU path on a bounded sample (oracle port, faithful
+    dense N x N backward of layers.py:85 included), all host threads."""
+    import torch
+    from oracle import gat_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    H, D, f_in = cfg["H"], cfg["D"], cfg["f_in"]
+    rowptr, col = O.power_law_edges(nodes, cfg["avg_deg"], seed=72, exponent=cfg["exponent"])
+    adj = O.PatternAdj(rowptr, col)
+    e = int(col.numel())
+    torch.manual_seed(72)
+    heads = [O.init_head(f_in, D, "sparse", False) for _ in range(H)]
+    x = torch.randn(nodes, f_in)
+    gout = torch.randn(nodes, H * D)
+
+    def step():
+        xs = x.clone().requires_grad_(True)
+        ps = [{k: v.clone().requires_grad_(True) for k, v in hp.items()} for hp in heads]
+        edge = adj.nonzero().t()  # layers.py:129 (the duck-typed adj makes this free)
+        outs = [O.sparse_head(xs, hp["W"], hp["a"], edge, 0.2, True, None, 0.0, faithful=True) for hp in ps]
+        torch.cat(outs, dim=1).backward(gout)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": e * H / dt, "unit": "head-edges/s", "cores": cores, "kind": "port",
+            "sample": f"power-law N={nodes} E={e} F={f_in} H={H} D={D}, fwd+bwd incl. the reference's dense "
+                      f"N x N backward, {steps} step(s) of {dt:.2f} s", "ms_per_step": dt * 1e3, "edges": e}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = WORKLOADS[args.workload]
+    steps = max(1, min(args.steps, 3))
+    r = cpu_reference_rate(cfg, steps=steps, warmup=max(1, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": "gat_layer_fwd_bwd_head_edges_per_s", "value": r["value"],
+            "unit": "head-edges/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}-shape power-law sample", "nodes": CPU_SAMPLE_NODES,
+                       "edges": r["edges"], "f_in": cfg["f_in"], "heads": cfg["H"], "head_dim": cfg["D"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "head-edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from pygat_b200 import _lib
+    from pygat_b200.functional import gat_layer
+    from pygat_b200.graph import Graph
+    from pygat_b200.synth import power_law_csr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = WORKLOADS[args.workload]
+    n, H, D, f_in = cfg["n"], cfg["H"], cfg["D"], cfg["f_in"]
+
+    if world > 1:
+        from pygat_b200.sharded import ShardedLayerBench
+        runner = ShardedLayerBench(cfg, rank, world, dev)
+    else:
+        runner = SingleGpuLayerBench(cfg, dev)
+    e_total = runner.e_total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        runner.step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    _lib.timer = _lib.KernelTimer()
+    calls0 = _lib.call_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        runner.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    kern = _lib.timer.summary()
+    _lib.timer = None
+    launches = runner.launches_per_step * args.steps
+    calls = _lib.call_count - calls0
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- end-to-end through the public API with host buffers (pinned H2D of the step's input
+    # features, D2H of the step's results: parameter gradients + a checksum of the output)
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_ms, h2d, d2h = runner.e2e(e2e_steps)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    ab = algorithmic_bytes(n, e_total, H, D, f_in)
+    per_kernel = {}
+    for name in ("gatk_attn_fwd", "gatk_attn_bwd_dst", "gatk_attn_bwd_src"):
+        if name in kern:
+            gbs = ab[name] / world / (kern[name]["ms_avg"] * 1e-3) / 1e9
+            per_kernel[name] = {"ms": round(kern[name]["ms_avg"], 4), "algorithmic_GB": round(ab[name] / world / 1e9, 3),
+                                "achieved_GBs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    other = {k: round(v["ms_total"] / args.steps, 4) for k, v in kern.items() if k not in per_kernel}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"]) if per_kernel else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if dom and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["achieved_GBs"], "peak": peak,
+                    "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "layer_frac": round(ab["layer"] / world / (ms * 1e-3) / 1e9 / peak, 4),
+                    "layer_algorithmic_GB": round(ab["layer"] / 1e9, 2)}
+
+    cpu = cpu_reference_rate(cfg, steps=1, warmup=1)
+    line = {
+        "metric": "gat_layer_fwd_bwd_head_edges_per_s", "value": e_total * H / (ms * 1e-3), "unit": "head-edges/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}-shape power-law graph, one hidden GAT layer fwd+bwd",
+                   "nodes": n, "edges": e_total, "f_in": f_in, "heads": H, "head_dim": D, "dropout": 0.0,
+                   "parallelism": f"dst-row shards x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (Wh alone is %.1f GB)" % (n * H * D * 4 / 1e9)},
+        "e2e": {"value": e_total * H / (e2e_ms * 1e-3), "unit": "head-edges/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "gpu_launches": launches, "abi_calls": calls, "clocks": clk, "roofline": roofline,
+        "kernels": per_kernel, "other_ms_per_step": other,
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class SingleGpuLayerBench:
+    """Whole graph on one GPU; the layer is driven through the public functional API."""
+
+    def __init__(self, cfg, dev):
+        import torch
+
+        from pygat_b200.graph import Graph
+        from pygat_b200.synth import init_layer_params, power_law_csr
+        self.torch = torch
+        n, H, D, f_in = cfg["n"], cfg["H"], cfg["D"], cfg["f_in"]
+        rowptr, col = power_law_csr(n, cfg["avg_deg"], seed=72, exponent=cfg["exponent"], device=dev)
+        self.graph = Graph.from_csr(rowptr, col)
+        self.graph.transpose()  # cached per adjacency, like the CSR itself; not part of a step
+        self.e_total = self.graph.nnz
+        g = torch.Generator(device=dev).manual_seed(72)
+        self.x = torch.randn(n, f_in, generator=g, device=dev)
+        self.gout = torch.randn(n, H * D, generator=g, device=dev)
+        self.Ws, self.a_src, self.a_dst = init_layer_params(f_in, H, D, dev, seed=72)
+        self.params = self.Ws + self.a_src + self.a_dst
+        self.cfg = cfg
+        hubs = 2 if self.graph.hubs.n_seg else 0
+        thubs = 2 if self.graph.transpose()[3].n_seg else 0
+        # gemm fwd 1, logits 1, attn fwd 1(+2), bwd dst 1(+2), bwd src 1(+2), da 2, gemm dW 2 (split-K)
+        self.launches_per_step = 1 + 1 + (1 + hubs) + (1 + hubs) + (1 + thubs) + 2 + 2
+        self.x_host = None
+
+    def _layer(self, x):
+        from pygat_b200.functional import gat_layer
+        return gat_layer(x, self.graph, self.Ws, self.a_src, self.a_dst, None, 0.2, concat=True)
+
+    def step(self):
+        for p in self.params:
+            p.grad = None
+        y = self._layer(self.x)
+        y.backward(self.gout)
+        return y
+
+    def e2e(self, steps):
+        torch = self.torch
+        if self.x_host is None:
+            self.x_host = self.x.cpu().pin_memory()
+        n_par = sum(p.numel() for p in self.params)
+        host_out = torch.empty(n_par + 1, dtype=torch.float32).pin_memory()
+
+        def one():
+            x = self.x_host.to(self.x.device, non_blocking=True)
+            for p in self.params:
+                p.grad = None
+            y = self._layer(x)
+            y.backward(self.gout)
+            flat = torch.cat([p.grad.reshape(-1) for p in self.params] + [y[:: max(1, y.shape[0] // 1024)].sum().reshape(1)])
+            host_out.copy_(flat, non_blocking=True)
+
+        one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, self.x_host.numel() * 4, host_out.numel() * 4
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

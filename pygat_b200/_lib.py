@@ -75,10 +75,42 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+class KernelTimer:
+    """Optional per-entry-point CUDA-event timing (bench.py's roofline numbers).  Events are
+    recorded on the stream the call launches on; nothing synchronises until summary()."""
+
+    def __init__(self):
+        self.records = []  # (name, start_event, end_event)
+        self.calls = 0
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.records:
+            tot, cnt = out.get(name, (0.0, 0))
+            out[name] = (tot + e0.elapsed_time(e1), cnt + 1)
+        return {k: {"ms_total": v[0], "calls": v[1], "ms_avg": v[0] / v[1]} for k, v in out.items()}
+
+
+timer: "KernelTimer | None" = None  # set by bench.py around its timed region
+call_count = 0                      # entry-point invocations (every one launches >= 1 kernel)
+
+
 def call(name: str, *args):
     """Invoke an int-returning entry point; non-zero -> GatkError(gatk_last_error())."""
+    global call_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    call_count += 1
+    if timer is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        timer.records.append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise GatkError(f"{name} failed ({rc}): {lib.gatk_last_error().decode(errors='replace')}")
 

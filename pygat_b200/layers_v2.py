@@ -60,7 +60,7 @@ class GraphAttentionLayerV2(_V2Base):
 
 class SpGraphAttentionLayerV2(_V2Base):
     """Sparse GATv2 (layers.py:255-313): score_ij = a . LeakyReLU(Whi_i + Whj_j), softmax over the
-    stored entries of row i, aggregation of Whi_i (as the reference does)."""
+    stored entries of row i, aggregation of the first projection Whi_j (as the reference does)."""
 
     def __init__(self, in_features, out_features, dropout, alpha, concat=True, skip_connection=False):
         super().__init__()

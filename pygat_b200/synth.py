@@ -40,3 +40,18 @@ def shard_rows_by_nnz(rowptr: torch.Tensor, world: int):
     targets = torch.arange(1, world, device=rowptr.device, dtype=torch.int64) * total // world
     cuts = torch.searchsorted(rowptr, targets).clamp_(max=n).tolist()
     return [0] + [int(c) for c in cuts] + [n]
+
+
+def init_layer_params(f_in: int, H: int, D: int, device, seed: int = 72):
+    """Per-head parameters of one sparse-class layer (W xavier-normal gain 1.414, a (1,2D)
+    xavier-normal; layers.py:111-115) as leaf tensors on `device`, split into (Ws, a_src, a_dst)."""
+    import math
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    Ws, a_src, a_dst = [], [], []
+    for _ in range(H):
+        w = torch.randn(f_in, D, generator=g) * (1.414 * math.sqrt(2.0 / (f_in + D)))
+        a = torch.randn(2 * D, generator=g) * (1.414 * math.sqrt(2.0 / (1 + 2 * D)))
+        Ws.append(w.to(device).requires_grad_(True))
+        a_src.append(a[:D].clone().to(device).requires_grad_(True))
+        a_dst.append(a[D:].clone().to(device).requires_grad_(True))
+    return Ws, a_src, a_dst

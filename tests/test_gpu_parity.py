@@ -1,0 +1,313 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden vectors.
+
+Tolerance: fp32, max-abs-diff / max-abs-ref <= 1e-5 per output and per
+gradient tensor; CSR arrays bit-exact against adj.nonzero().
+"""
+import pytest
+import torch
+
+import layers
+import models
+from oracle import gat_oracle as O
+from pygat_b200 import _lib
+from pygat_b200.functional import gat_layer, pack_masks, padded_width
+from pygat_b200.graph import RULE_NONZERO, RULE_POSITIVE, Graph, graph_of
+from pygat_b200.layers import fused_heads
+from pygat_b200.synth import power_law_csr
+from tests.golden_io import GAT_CASES, HEAD_CASES, dense_adj, gat_params, head_masks, load, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda"
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------ K0
+@pytest.mark.parametrize("name", ["sp_head_basic", "sp_head_neg_asym", "sp_head_hub"])
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("rule", [RULE_NONZERO, RULE_POSITIVE])
+def test_csr_matches_nonzero_bit_exact(name, order, rule):
+    adj = dense_adj(load(name))
+    n = adj.shape[0]
+    dev_adj = adj.to(DEV)
+    if order == "F":  # what utils.load_data hands the layers (utils.py:55)
+        dev_adj = dev_adj.t().contiguous().t()
+        assert dev_adj.stride() == (1, n)
+    g = Graph.from_dense(dev_adj, rule)
+    edge = O.edge_list(adj, "nonzero" if rule == RULE_NONZERO else "positive")
+    rowptr, col = O.csr_from_edges(edge, n)
+    assert torch.equal(g.rowptr.cpu(), rowptr) and torch.equal(g.col.cpu(), col)
+    assert torch.equal(g.edge_index().cpu(), edge)
+    tptr, trow, perm, _ = g.transpose()
+    o_tptr, o_trow, o_perm = O.csr_transpose(rowptr, col, n)
+    assert torch.equal(tptr.cpu(), o_tptr) and torch.equal(trow.cpu(), o_trow)
+    assert torch.equal(perm.cpu().long(), o_perm)
+
+
+def test_csr_from_coo_and_sparse_tensor_inputs():
+    adj = dense_adj(load("sp_head_neg_asym"))
+    n = adj.shape[0]
+    edge = O.edge_list(adj)
+    rowptr, col = O.csr_from_edges(edge, n)
+    g = Graph.from_coo(edge.to(DEV), n)
+    assert torch.equal(g.rowptr.cpu(), rowptr) and torch.equal(g.col.cpu(), col)
+    g2 = graph_of(adj.to(DEV).to_sparse(), RULE_NONZERO)
+    assert torch.equal(g2.rowptr.cpu(), rowptr) and torch.equal(g2.col.cpu(), col)
+
+
+def test_graph_cache_is_keyed_on_tensor_identity_and_version():
+    adj = dense_adj(load("sp_head_basic")).to(DEV)
+    g1 = graph_of(adj)
+    assert graph_of(adj) is g1
+    assert graph_of(adj, RULE_POSITIVE) is not g1
+    adj[0, 5] = 0.0 if adj[0, 5] != 0 else 1.0  # in-place edit bumps _version
+    g3 = graph_of(adj)
+    assert g3 is not g1 and g3.nnz != g1.nnz
+    empty = torch.zeros(7, 7, device=DEV)
+    assert graph_of(empty).nnz == 0
+
+
+# ------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(257, 130, 77), (1000, 24, 1433), (50, 512, 20000), (3, 5, 1), (4096, 512, 100)])
+def test_gemm_matches_fp64(ta, tb, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    ref = (A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double())
+    dA, dB = A.to(DEV), B.to(DEV)
+    C = torch.full((M, N + 3), 7.0, device=DEV)  # ldc > N: the pad columns must stay untouched
+    ws_bytes = _lib.query("gatk_gemm_workspace_bytes", ta, tb, M, N, K)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=DEV)
+    _lib.call("gatk_gemm", ta, tb, M, N, K, dA.data_ptr(), dA.shape[1], dB.data_ptr(), dB.shape[1],
+              C.data_ptr(), N + 3, 0, ws.data_ptr(), ws_bytes, _stream())
+    assert rel_err(C[:, :N], ref) < 2e-6
+    assert torch.all(C[:, N:] == 7.0)
+    _lib.call("gatk_gemm", ta, tb, M, N, K, dA.data_ptr(), dA.shape[1], dB.data_ptr(), dB.shape[1],
+              C.data_ptr(), N + 3, 1, ws.data_ptr(), ws_bytes, _stream())
+    assert rel_err(C[:, :N], 2 * ref) < 2e-6
+
+
+# ------------------------------------------------------------------------------ heads
+def _run_head(d, kind, adj_arg, masks=None):
+    cls = layers.SpGraphAttentionLayer if kind == "sparse" else layers.GraphAttentionLayer
+    f_in, dd = d["W"].shape
+    head = cls(f_in, dd, dropout=d["p"], alpha=d["alpha"], concat=bool(d["concat"]), skip_connection="skip" in d)
+    with torch.no_grad():
+        head.W.copy_(d["W"])
+        head.a.copy_(d["a"])
+        if "skip" in d:
+            head.skip_projection.copy_(d["skip"])
+    head = head.to(DEV)
+    head.train(bool(d["train"]))
+    x = d["x"].to(DEV).requires_grad_(True)
+    y = fused_heads([head], x, adj_arg, masks=masks) if masks is not None else head(x, adj_arg)
+    y.backward(d["gout"].to(DEV))
+    return head, x, y
+
+
+def _check_head(d, head, x, y):
+    assert y.shape == d["y"].shape
+    assert rel_err(y, d["y"]) < TOL
+    assert rel_err(x.grad, d["dx"]) < TOL
+    assert rel_err(head.W.grad, d["dW"]) < TOL
+    assert rel_err(head.a.grad, d["da"]) < TOL
+    if "skip" in d:
+        assert rel_err(head.skip_projection.grad, d["dskip"]) < TOL
+
+
+@pytest.mark.parametrize("name", [n for n in HEAD_CASES if "train" not in n])
+def test_head_matches_reference_golden(name):
+    d = load(name)
+    kind = "sparse" if name.startswith("sp_") else "dense"
+    head, x, y = _run_head(d, kind, dense_adj(d).to(DEV))
+    _check_head(d, head, x, y)
+
+
+@pytest.mark.parametrize("name", ["sp_head_train_p06", "de_head_train_p06"])
+def test_head_train_mode_with_the_reference_masks(name):
+    """Dropout p=0.6 in training mode, the three masks the reference drew handed to the engine."""
+    d = load(name)
+    kind = "sparse" if name.startswith("sp_") else "dense"
+    adj = dense_adj(d)
+    mk = head_masks(d, kind)
+    edge = O.edge_list(adj, "nonzero" if kind == "sparse" else "positive")
+    att = mk["keep_att"] if kind == "sparse" else mk["keep_att"][edge[0], edge[1]]
+    Dp = padded_width(d["W"].shape[1])
+    masks = pack_masks([mk["keep_in"].to(DEV)], [mk["keep_wh"].to(DEV)], [att.to(DEV)], Dp)
+    head, x, y = _run_head(d, kind, adj.to(DEV), masks=masks)
+    _check_head(d, head, x, y)
+
+
+@pytest.mark.parametrize("seg_len", [16, 64, 100000])
+def test_hub_rows_split_into_segments(seg_len):
+    """Row 0 has 700 stored entries: segment + merge path (fwd, bwd dst, bwd src) vs golden."""
+    d = load("sp_head_hub")
+    g = Graph.from_dense(dense_adj(d).to(DEV), RULE_NONZERO, seg_len=seg_len)
+    assert (g.hubs.n_hub > 0) == (seg_len < 700)
+    head, x, y = _run_head(d, "sparse", g)
+    _check_head(d, head, x, y)
+
+
+def test_dense_and_sparse_classes_agree():
+    d = load("sp_head_basic")
+    adj = dense_adj(d).to(DEV)
+    h_sp, x1, y1 = _run_head(d, "sparse", adj)
+    d2 = dict(d)
+    d2["a"] = d["a"].reshape(-1, 1)
+    h_de, x2, y2 = _run_head(d2, "dense", adj)
+    assert rel_err(y2, y1) < 1e-6 and rel_err(x2.grad, x1.grad) < 1e-6
+    assert rel_err(h_de.a.grad.reshape(-1), h_sp.a.grad.reshape(-1)) < 1e-6
+
+
+# ------------------------------------------------------------------------------ whole model
+@pytest.mark.parametrize("name", GAT_CASES)
+def test_gat_matches_reference_golden(name):
+    d = load(name)
+    cls = layers.SpGraphAttentionLayer if "_sp_" in name else layers.GraphAttentionLayer
+    nheads = [int(v) for v in d["nheads"]]
+    model = models.GAT(nfeat=[int(v) for v in d["nfeat"]], nheads=nheads, nlayers=len(nheads), dropout=d["p"],
+                       alpha=d["alpha"], layer_type=cls, skip_connection=bool(d["skip"]))
+    model.load_state_dict({k[len("param."):]: v for k, v in d.items() if k.startswith("param.")})
+    model = model.to(DEV)
+    model.train(bool(d["train"]))
+    x = d["x"].to(DEV).requires_grad_(True)
+    y = model(x, dense_adj(d).to(DEV))
+    y.backward(d["gout"].to(DEV))
+    assert rel_err(y, d["y"]) < TOL
+    assert rel_err(x.grad, d["dx"]) < TOL
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad, d["grad." + k]) < TOL, k
+
+
+def test_unfused_per_head_calls_equal_the_batched_layer():
+    d = load("gat_sp_pubmed_like")
+    params = gat_params(d)
+    adj = dense_adj(d).to(DEV)
+    x = d["x"].to(DEV)
+    heads = []
+    for hp in params[0]:
+        h = layers.SpGraphAttentionLayer(*hp["W"].shape, dropout=0.0, alpha=d["alpha"])
+        with torch.no_grad():
+            h.W.copy_(hp["W"])
+            h.a.copy_(hp["a"])
+        heads.append(h.to(DEV).eval())
+    batched = fused_heads(heads, x, adj)
+    looped = torch.cat([h(x, adj) for h in heads], dim=1)
+    assert rel_err(batched, looped) < 1e-6
+
+
+def test_training_mode_random_dropout_is_seeded_and_unbiased():
+    d = load("sp_head_basic")
+    adj = dense_adj(d).to(DEV)
+    head = layers.SpGraphAttentionLayer(24, 8, dropout=0.5, alpha=0.2).to(DEV).train()
+    x = d["x"].to(DEV)
+    torch.manual_seed(5)
+    y1 = head(x, adj)
+    torch.manual_seed(5)
+    y2 = head(x, adj)
+    y3 = head(x, adj)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    keep = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    _lib.call("gatk_dropout_keep_mask", keep.data_ptr(), keep.numel(), 0.6, 1234, 0, _stream())
+    assert abs(keep.float().mean().item() - 0.4) < 5e-3
+
+
+# ------------------------------------------------------------------------------ SpecialSpmm
+def test_special_spmm_matches_oracle():
+    d = load("sp_head_neg_asym")
+    adj = dense_adj(d)
+    n = adj.shape[0]
+    edge = O.edge_list(adj)
+    g = torch.Generator().manual_seed(3)
+    vals = torch.randn(edge.shape[1], generator=g)
+    b = torch.randn(n, 5, generator=g)
+    gout = torch.randn(n, 5, generator=g)
+    v0, b0 = vals.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    O.coo_matmul(edge, v0, torch.Size([n, n]), b0).backward(gout)
+    ref_out = O.coo_matmul(edge, vals, torch.Size([n, n]), b)
+    v1, b1 = vals.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    out = layers.SpecialSpmm()(edge.to(DEV), v1, torch.Size([n, n]), b1)
+    out.backward(gout.to(DEV))
+    assert rel_err(out, ref_out) < TOL and rel_err(v1.grad, v0.grad) < TOL and rel_err(b1.grad, b0.grad) < TOL
+
+
+# ------------------------------------------------------------------------------ benchmark shapes
+def _layer_inputs(n, f_in, H, D, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, f_in, generator=g)
+    Ws = [torch.randn(f_in, D, generator=g) * O.xavier_std(f_in, D) for _ in range(H)]
+    As = [torch.randn(1, 2 * D, generator=g) * O.xavier_std(1, 2 * D) for _ in range(H)]
+    gout = torch.randn(n, H * D, generator=g)
+    return x, Ws, As, gout
+
+
+@pytest.mark.parametrize("H,D,f_in", [(8, 64, 100), (4, 32, 128), (4, 256, 50), (6, 121, 64)])
+def test_power_law_layer_matches_oracle(H, D, f_in):
+    """The benchmark shapes' head geometry (products 8x64, papers 4x32, PPI 4x256 / 6x121) on a
+    power-law graph the oracle finishes in seconds."""
+    n = 6000
+    rowptr, col = power_law_csr(n, 20.0, seed=72, exponent=0.7)
+    assert (rowptr[1:] - rowptr[:-1]).max().item() > 300
+    x, Ws, As, gout = _layer_inputs(n, f_in, H, D, 1)
+    adj = O.PatternAdj(rowptr, col)
+    xo = x.clone().requires_grad_(True)
+    Wo = [w.clone().requires_grad_(True) for w in Ws]
+    Ao = [a.clone().requires_grad_(True) for a in As]
+    edge = adj.nonzero().t()
+    yo = torch.cat([O.sparse_head(xo, w, a, edge, 0.2, True, None, 0.0, faithful=False) for w, a in zip(Wo, Ao)], 1)
+    yo.backward(gout)
+
+    graph = Graph.from_csr(rowptr.to(DEV), col.to(DEV), seg_len=128)
+    assert graph.hubs.n_hub > 0
+    xd = x.to(DEV).requires_grad_(True)
+    Wd = [w.to(DEV).requires_grad_(True) for w in Ws]
+    Ad = [a.to(DEV).requires_grad_(True) for a in As]
+    y = gat_layer(xd, graph, Wd, [a[0, :D] for a in Ad], [a[0, D:] for a in Ad], None, 0.2, True)
+    y.backward(gout.to(DEV))
+    assert rel_err(y, yo) < TOL
+    assert rel_err(xd.grad, xo.grad) < TOL
+    for k in range(H):
+        assert rel_err(Wd[k].grad, Wo[k].grad) < TOL, k
+        assert rel_err(Ad[k].grad, Ao[k].grad) < TOL, k
+
+
+def test_products_shape_invariants_at_full_size():
+    """ogbn-products shape (N=2.45M, ~62M stored entries, 8 heads x 64): properties that need no
+    oracle.  (1) attention rows sum to one, so constant source features come back unchanged;
+    (2) with a == 0 attention is uniform, so the aggregation equals the neighbourhood mean and
+    sum_j dWh_j == sum_i dh'_i."""
+    n, H, D = 2_449_029, 8, 64
+    rowptr, col = power_law_csr(n, 25.26, seed=72, device=DEV)
+    graph = Graph.from_csr(rowptr, col)
+    assert 0.97 * 61_859_140 < graph.nnz < 1.03 * 61_859_140
+    deg = (rowptr[1:] - rowptr[:-1])
+    assert deg.min().item() >= 1 and deg.max().item() > graph.seg_len
+    f_in = 8
+    x = torch.ones(n, f_in, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    Ws = [torch.randn(f_in, D, generator=g, device=DEV) * 0.1 for _ in range(H)]
+    a_s = [torch.randn(D, generator=g, device=DEV) for _ in range(H)]
+    a_d = [torch.randn(D, generator=g, device=DEV) for _ in range(H)]
+    y = gat_layer(x, graph, Ws, a_s, a_d, None, 0.2, concat=False)
+    expect = torch.cat([x[:1] @ w for w in Ws], dim=1)
+    assert (y - expect).abs().max().item() < 1e-5 * expect.abs().max().item() + 1e-6
+    del y
+    # uniform attention: out_i = mean over neighbours
+    xr = torch.randn(n, f_in, generator=g, device=DEV).requires_grad_(True)
+    zero = [torch.zeros(D, device=DEV) for _ in range(H)]
+    y = gat_layer(xr, graph, Ws, zero, zero, None, 0.2, concat=False)
+    wh0 = (xr.detach() @ Ws[0])
+    rows = torch.tensor([0, 1, n // 2, n - 1], device=DEV)
+    for r in rows.tolist():
+        nb = col[rowptr[r]:rowptr[r + 1]].long()
+        assert torch.allclose(y[r, :D], wh0[nb].mean(0), rtol=1e-4, atol=1e-5)
+    gout = torch.randn(n, H * D, generator=g, device=DEV)
+    y.backward(gout)
+    # dx = dWh @ W^T with dWh_j = sum_i (1/deg_i) dh'_i  =>  column sums are preserved
+    lhs = xr.grad.sum(0)
+    rhs = torch.cat(Ws, dim=1) @ gout.sum(0)
+    assert rel_err(lhs, rhs) < 1e-3
