@@ -95,10 +95,13 @@ GATK_API int gatk_logits_fwd(int64_t n, int H, int Dp, float* wh, int64_t ldw, c
  * Rows are local [0, n_dst); col indexes wh / g (global sources).  Rows longer than
  * seg_len are listed in hub_rows and processed as segments (hub_seg_ptr: int32
  * [n_hub+1], exclusive scan of per-hub segment counts) with partial softmax states in
- * hub_scratch (floats: n_hub_seg * (H*Dp + 2*H)) merged by a second kernel.
+ * hub_scratch (gatk_hub_scratch_floats) merged by a second kernel.
  * keep_att: [E, H] or NULL.  hagg (pre-skip, pre-ELU aggregation) and lse
  * (m + log l per row/head) are saved for backward; either may be NULL.
- * counter: one int32 of scratch (dynamic row scheduler). */
+ * counter: one int32 of scratch (dynamic row scheduler).
+ * gatk_hub_scratch_floats(which, ...): floats of hub_scratch for which = 0 (attn_fwd),
+ * 1 (attn_bwd_dst), 2 (attn_bwd_src). */
+GATK_API size_t gatk_hub_scratch_floats(int which, int H, int Dp, int n_hub_seg);
 GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp,
                   const float* wh, int64_t ldw, const float* f, const float* g,
                   const uint8_t* keep_att, float inv_keep, float alpha,
@@ -112,7 +115,7 @@ GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* 
  * dz_ij = alpha_ij * (keep/(1-p) * (dhp_i . Wh_j) - c_i) * LeakyReLU'(f_i+g_j); writes
  * edge_alpha (post-dropout attention), edge_dz, df_i = sum_j dz_ij.  O(E*D): replaces the
  * dense N x N SpecialSpmmFunction.backward (layers.py:81-90).  out may be NULL when
- * act_elu == 0.  hub_scratch floats: n_hub_seg * H. */
+ * act_elu == 0. */
 GATK_API int gatk_attn_bwd_dst(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp,
                       const float* wh, int64_t ldw, const float* f, const float* g, const float* lse,
                       const uint8_t* keep_att, float inv_keep, float alpha,
@@ -126,7 +129,7 @@ GATK_API int gatk_attn_bwd_dst(int64_t n_dst, const int64_t* rowptr, const int32
  * dWh_j = sum_i alpha~_ij dhp_i + df_j a_src + dg_j a_dst,  dg_j = sum_i dz_ij, then the
  * post-projection dropout mask (keep_wh) if any.  df may be NULL (sharded mode: the
  * a-terms are added by the owner).  hub_* describe the TRANSPOSED graph's long rows;
- * hub_scratch floats: n_hub_seg * (H*Dp + H). */
+ */
 GATK_API int gatk_attn_bwd_src(int64_t n_src, const int64_t* tptr, const int32_t* trow, const int32_t* perm,
                       int H, int Dp, const float* dhp, int64_t lddhp,
                       const float* edge_alpha, const float* edge_dz,

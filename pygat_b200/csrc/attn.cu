@@ -38,6 +38,10 @@ __device__ __forceinline__ int warp_grab(int32_t* counter, int lane) {
   return __shfl_sync(FULL, r, 0);
 }
 
+// Per-segment scratch strides (floats), padded so the float4 slots stay 16-byte aligned.
+__host__ __device__ __forceinline__ int64_t fwd_scratch_stride(int H, int V) { return V * 4 + ((2 * H + 3) & ~3); }
+__host__ __device__ __forceinline__ int64_t src_scratch_stride(int H, int V) { return V * 4 + ((H + 3) & ~3); }
+
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 
 // Hub lookup: segment id -> (hub index, row, [beg,end)).
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) attn_fwd_kernel(const FwdArgs 
     int64_t beg, end;
     hub_locate(seg, a.hub_rows, a.hub_seg_ptr, a.n_hub, a.rowptr, a.seg_len, row, beg, end);
     fwd_segment<NV>(a, row, beg, end, lane, geo, acc, m_reg, l_reg, col_s, p_s, scale_s);
-    float* sc = a.scratch + (int64_t)seg * (a.V * 4 + 2 * a.H);
+    float* sc = a.scratch + (int64_t)seg * fwd_scratch_stride(a.H, a.V);
 #pragma unroll
     for (int v = 0; v < NV; ++v)
       if (geo.act[v]) stg4(sc + (lane + 32 * v) * 4, acc[v]);
@@ -232,7 +236,7 @@ __global__ void attn_fwd_hub_merge_kernel(const FwdArgs a) {
   const int hub = blockIdx.x;
   const int row = a.hub_rows[hub];
   const int s0 = a.hub_seg_ptr[hub], s1 = a.hub_seg_ptr[hub + 1];
-  const int64_t stride = a.V * 4 + 2 * a.H;
+  const int64_t stride = fwd_scratch_stride(a.H, a.V);
   for (int slot = threadIdx.x; slot < a.V; slot += blockDim.x) {
     const int h = slot / a.lph;
     float M = -INFINITY;
@@ -562,7 +566,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) attn_bwd_src_kernel(const BwdS
     int64_t beg, end;
     hub_locate(seg, a.hub_rows, a.hub_seg_ptr, a.n_hub, a.tptr, a.seg_len, j, beg, end);
     bwd_src_segment<NV>(a, beg, end, lane, geo, acc, dg_reg, row_s, p_s);
-    float* sc = a.scratch + (int64_t)seg * (a.V * 4 + a.H);
+    float* sc = a.scratch + (int64_t)seg * src_scratch_stride(a.H, a.V);
 #pragma unroll
     for (int v = 0; v < NV; ++v)
       if (geo.act[v]) stg4(sc + (lane + 32 * v) * 4, acc[v]);
@@ -593,7 +597,7 @@ __global__ void attn_bwd_src_hub_merge_kernel(const BwdSrcArgs a) {
   const int hub = blockIdx.x;
   const int j = a.hub_rows[hub];
   const int s0 = a.hub_seg_ptr[hub], s1 = a.hub_seg_ptr[hub + 1];
-  const int64_t stride = a.V * 4 + a.H;
+  const int64_t stride = src_scratch_stride(a.H, a.V);
   for (int slot = threadIdx.x; slot < a.V; slot += blockDim.x) {
     const int h = slot / a.lph;
     float dgv = 0.f;
@@ -718,6 +722,14 @@ static int check_hub(int seg_len, int n_hub, int n_hub_seg, const void* rows, co
 }  // namespace gatk
 
 using namespace gatk;
+
+extern "C" size_t gatk_hub_scratch_floats(int which, int H, int Dp, int n_hub_seg) {
+  const int V = H * (Dp / 4);
+  if (n_hub_seg <= 0) return 0;
+  if (which == 0) return (size_t)n_hub_seg * fwd_scratch_stride(H, V);
+  if (which == 1) return (size_t)n_hub_seg * H;
+  return (size_t)n_hub_seg * src_scratch_stride(H, V);
+}
 
 extern "C" int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp,
                              const float* wh, int64_t ldw, const float* f, const float* g,

@@ -46,6 +46,12 @@ def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=0, a_off=0, b_off=
               C.data_ptr() + 4 * c_off, ldc, accumulate, _ptr(ws), ws_bytes, _stream())
 
 
+def _hub_scratch(which: int, H: int, Dp: int, n_seg: int, dev):
+    if not n_seg:
+        return None
+    return torch.empty(_lib.query("gatk_hub_scratch_floats", which, H, Dp, n_seg), dtype=torch.float32, device=dev)
+
+
 def random_masks(n: int, f_in: int, H: int, Dp: int, nnz: int, p: float, device) -> LayerMasks:
     """Draw the three masks with the in-library Philox generator.  The 64-bit seed comes from
     torch's CPU generator, so torch.manual_seed (train.py:91-99) makes runs reproducible."""
@@ -110,7 +116,7 @@ class GatLayerFunction(torch.autograd.Function):
         hagg = torch.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
         lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
         hubs = graph.hubs
-        scratch = torch.empty(hubs.n_seg * (HD + 2 * H), dtype=torch.float32, device=dev) if hubs.n_seg else None
+        scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_ptr, M_out,
                   f.data_ptr(), g.data_ptr(), _ptr(masks.keep_att), inv_keep, float(alpha),
                   skip_ptr, M_out, int(act_elu), _ptr(hagg), out.data_ptr(), HD, _ptr(lse),
@@ -149,7 +155,7 @@ class GatLayerFunction(torch.autograd.Function):
 
         # ---- K3: destination pass ----------------------------------------------------------
         hubs = graph.hubs
-        scratch = torch.empty(hubs.n_seg * H, dtype=torch.float32, device=dev) if hubs.n_seg else None
+        scratch = _hub_scratch(1, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_dst", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, z.data_ptr(), M_out,
                   f.data_ptr(), g.data_ptr(), lse.data_ptr(), _ptr(masks.keep_att), inv_keep, alpha,
                   gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD, int(act_elu),
@@ -157,7 +163,7 @@ class GatLayerFunction(torch.autograd.Function):
                   *hubs.args(scratch), graph.counter.data_ptr(), st)
 
         # ---- K4: source pass over the transposed pattern -----------------------------------
-        scratch_t = torch.empty(thubs.n_seg * (HD + H), dtype=torch.float32, device=dev) if thubs.n_seg else None
+        scratch_t = _hub_scratch(2, H, Dp, thubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_src", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, dhp_ptr, lddhp,
                   edge_alpha.data_ptr(), edge_dz.data_ptr(), df.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(),
                   _ptr(masks.keep_wh), inv_keep, dz_rows.data_ptr(), M_out, dg.data_ptr(),
