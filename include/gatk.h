@@ -75,6 +75,10 @@ GATK_API int gatk_mask_scale(const float* x, int64_t ldx, const uint8_t* keep, f
  * autograd (dW = h^T dWh, dh = dWh W^T).  transA: A stored [K,M]; transB: B stored [N,K].
  * ws: split-K scratch (gatk_gemm_workspace_bytes). */
 GATK_API size_t gatk_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K);
+/* 1 when gatk_gemm would take the tcgen05/TMA 3xTF32 kernel for 16-byte aligned A and C (large
+ * NN products whose row pitches are multiples of 16 bytes), 0 when it takes the fp32 SIMT kernel. */
+GATK_API int gatk_gemm_uses_tensor_cores(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda,
+                                         int64_t ldc, int accumulate);
 GATK_API int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
               const float* B, int64_t ldb, float* C, int64_t ldc, int accumulate,
               void* ws, size_t ws_bytes, void* stream);

@@ -28,6 +28,7 @@ PROTOTYPES = {
     "gatk_dropout_keep_mask": (c_int, [P, c_int64, c_float, c_uint64, c_uint64, P]),
     "gatk_mask_scale": (c_int, [P, c_int64, P, c_float, P, c_int64, c_int64, c_int64, P]),
     "gatk_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int64, c_int64]),
+    "gatk_gemm_uses_tensor_cores": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int]),
     "gatk_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int,
                           P, c_size_t, P]),
     "gatk_logits_fwd": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_float, P, P, P, P, P]),

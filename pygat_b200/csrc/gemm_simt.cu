@@ -3,6 +3,9 @@
 // the TMA/tcgen05 kernel cannot take (row strides that are not multiples of 16 bytes, e.g.
 // Cora's 1433 or PPI's 50 input features) and the yardstick that kernel is tested against.
 // Replaces torch.mm at layers.py:35,48,134,166 and its autograd.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace gatk {
@@ -132,14 +135,36 @@ static int choose_splits(int64_t M, int64_t N, int64_t K) {
   return s < 1 ? 1 : (int)s;
 }
 
+// tensor-core path (gemm_tc.cu)
+bool gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                      const float* C, int64_t ldc, int accumulate);
+size_t gemm_tc_workspace_bytes(int64_t N, int64_t K);
+int gemm_tc_launch(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                   int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t st);
+
+static bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GATK_GEMM");
+    v = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace gatk
 
 using namespace gatk;
 
 extern "C" size_t gatk_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K) {
-  (void)transA; (void)transB;
   const int s = choose_splits(M, N, K);
-  return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+  size_t simt = s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+  size_t tcb = (!transA && !transB && tc_enabled()) ? gemm_tc_workspace_bytes(N, K) : 0;
+  return simt > tcb ? simt : tcb;
+}
+
+extern "C" int gatk_gemm_uses_tensor_cores(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda,
+                                           int64_t ldc, int accumulate) {
+  return tc_enabled() && gemm_tc_eligible(transA, transB, M, N, K, nullptr, lda, nullptr, ldc, accumulate) ? 1 : 0;
 }
 
 extern "C" int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
@@ -149,6 +174,9 @@ extern "C" int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K
   if (M == 0 || N == 0) return 0;
   GATK_REQUIRE(A && B && C, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
+  if (tc_enabled() && ws && ws_bytes >= gemm_tc_workspace_bytes(N, K) &&
+      gemm_tc_eligible(transA, transB, M, N, K, A, lda, C, ldc, accumulate))
+    return gemm_tc_launch(M, N, K, A, lda, B, ldb, C, ldc, ws, ws_bytes, st);
   int splits = choose_splits(M, N, K);
   if (splits > 1 && (ws == nullptr || ws_bytes < (size_t)splits * M * N * sizeof(float))) splits = 1;
   int64_t kchunk = (K + splits - 1) / splits;

@@ -1,0 +1,391 @@
+// K1: projection GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32-accurate.
+//
+//   C[M,N] = A[M,K] * B[K,N]     A, C row-major fp32 (rows = nodes), B = packed per-head weights.
+//
+// torch.mm(h, W) (layers.py:35,134) is the one dense contraction on the path.  fp32 parity
+// (rel 1e-5) through kind::tf32 needs an error-compensated split:  x = hi + lo with hi the
+// tf32 truncation, and  A*B ~= Ahi*Bhi + Alo*Bhi + Ahi*Blo  (fp32 accumulation in TMEM; the
+// dropped lo*lo term is 2^-22 relative).  B (small) is split and transposed to K-major once
+// by a prep kernel; A (large, streamed once) is split on the fly in shared memory by a
+// dedicated warpgroup between the TMA load and the MMA issue.
+//
+// Warp roles (384 threads, 1 CTA / SM, persistent over 128x128 output tiles):
+//   warp 0      TMA producer: A tile (fp32), Bhi, Blo tiles -> 3-stage smem ring (128B swizzle)
+//   warp 1      MMA issuer (one elected lane): 12 x tcgen05.mma.kind::tf32 per 32-wide k-block
+//   warp 2      TMEM allocator (2 x 128 accumulator columns, double buffered)
+//   warps 4-7   splitter: A tile -> (Ahi in place, Alo) in smem, generic->async proxy fence
+//   warps 8-11  epilogue: tcgen05.ld -> swizzled smem staging -> TMA store (clips M/N tails)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace gatk {
+
+namespace tc {
+
+constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32;  // BLOCK_K fp32 = one 128-byte swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 4;          // 16 KiB, same for A and B tiles
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;                // Ahi, Alo, Bhi, Blo
+constexpr int CSTAGE_BYTES = BLOCK_M * 32 * 4;             // one 128 x 32 fp32 store chunk
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 384;
+constexpr int TMEM_COLS = 2 * BLOCK_N;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;                  // a protocol bug traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows 128 B apart, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused with swizzle), canonical 1
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Ring {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c,
+                   int m_tiles, int n_tiles, int k_blocks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* cstage = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cstage + 2 * CSTAGE_BYTES);
+  // barrier slots: full[S], split[S], empty[S], tmem_full[2], tmem_empty[2]; then the TMEM base address
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto split_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(split_bar(s), 4);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      Ring r;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(r.stage), r.phase ^ 1);
+          const uint32_t st = smem_base + r.stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(r.stage), 3 * TILE_BYTES);
+          tma_load_2d(st, &map_a, full_bar(r.stage), kb * BLOCK_K, m0);
+          tma_load_2d(st + 2 * TILE_BYTES, &map_bhi, full_bar(r.stage), kb * BLOCK_K, n0);
+          tma_load_2d(st + 3 * TILE_BYTES, &map_blo, full_bar(r.stage), kb * BLOCK_K, n0);
+          r.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    Ring r;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(r.stage), r.phase);
+        mbar_wait(split_bar(r.stage), r.phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_base + r.stage * STAGE_BYTES;
+          const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TILE_BYTES);
+          const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle row
+            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, (kb | k) != 0);
+            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, 1);
+            umma_tf32(tmem_d, a_hi + adv, b_hi + adv, 1);
+          }
+          umma_commit(empty_bar(r.stage));
+          if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        r.advance();
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ splitter: A -> (hi, lo)
+    Ring r;
+    const int t = threadIdx.x - 128;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(r.stage), r.phase);
+        float4* hi = reinterpret_cast<float4*>(smem + r.stage * STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + r.stage * STAGE_BYTES + TILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+          const int idx = t + i * 128;
+          float4 v = hi[idx];
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          hi[idx] = h;
+          lo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(r.stage));
+        r.advance();
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 8;            // == warp % 4: the TMEM lane quarter this warp may read
+    const int row = ew * 32 + lane;     // row inside the tile
+    const bool issuer = threadIdx.x == 256;
+    int it = 0, chunk_id = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c, ++chunk_id) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N + c * 32, v);
+        uint8_t* buf = cstage + (chunk_id & 1) * CSTAGE_BYTES;
+        if (issuer) tma_store_wait_read<1>();  // the store that last read this buffer has drained
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          *reinterpret_cast<uint4*>(buf + row * 128 + ((j ^ (row & 7)) << 4)) = q;
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          tma_store_2d(&map_c, smem_u32(buf), n0 + c * 32, m0);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// B[K,N] row-major -> K-major hi / lo copies Bt[Npad, Kpad], zero padded.
+__global__ void split_transpose_b_kernel(const float* __restrict__ B, int64_t ldb, int K, int N, int Kpad, int Npad,
+                                         float* __restrict__ bhi, float* __restrict__ blo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)Npad * Kpad) return;
+  const int n = (int)(i / Kpad), k = (int)(i % Kpad);
+  float v = (n < N && k < K) ? B[(int64_t)k * ldb + n] : 0.f;
+  float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  bhi[i] = h;
+  blo[i] = v - h;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D fp32 row-major tensor [rows, cols] with row pitch ld floats; box = 32 columns x 128 rows, 128B swizzle.
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  GATK_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GATK_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)rc,
+               (long long)rows, (long long)cols, (long long)ld);
+  return 0;
+}
+
+}  // namespace tc
+
+bool gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                      const float* C, int64_t ldc, int accumulate) {
+  if (transA || transB || accumulate) return false;
+  if (M < 1024 || N < 8 || K < 1) return false;  // small problems: launch-bound either way, keep exact-fp32 SIMT
+  if (M >= (1LL << 31) - 256 || N > 65536 || K > 65536) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(C) & 15)) return false;
+  if ((lda & 3) || (ldc & 3)) return false;
+  return true;
+}
+
+size_t gemm_tc_workspace_bytes(int64_t N, int64_t K) {
+  const int64_t Kpad = (K + tc::BLOCK_K - 1) / tc::BLOCK_K * tc::BLOCK_K;
+  const int64_t Npad = (N + tc::BLOCK_N - 1) / tc::BLOCK_N * tc::BLOCK_N;
+  return (size_t)(2 * Npad * Kpad * sizeof(float) + 256);
+}
+
+int gemm_tc_launch(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                   int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace tc;
+  const int Kpad = (int)((K + BLOCK_K - 1) / BLOCK_K * BLOCK_K);
+  const int Npad = (int)((N + BLOCK_N - 1) / BLOCK_N * BLOCK_N);
+  GATK_REQUIRE(ws && ws_bytes >= gemm_tc_workspace_bytes(N, K), "tensor-core GEMM workspace too small");
+  float* bhi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  float* blo = bhi + (size_t)Npad * Kpad;
+  const int64_t total = (int64_t)Npad * Kpad;
+  split_transpose_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, ldb, (int)K, (int)N, Kpad, Npad, bhi, blo);
+  GATK_CHECK_LAUNCH();
+
+  CUtensorMap map_a, map_bhi, map_blo, map_c;
+  if (int rc = make_map(&map_a, A, M, K, lda)) return rc;
+  if (int rc = make_map(&map_bhi, bhi, Npad, Kpad, Kpad)) return rc;
+  if (int rc = make_map(&map_blo, blo, Npad, Kpad, Kpad)) return rc;
+  if (int rc = make_map(&map_c, C, M, N, ldc)) return rc;
+
+  static bool configured = false;
+  if (!configured) {
+    GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = Npad / BLOCK_N, k_blocks = Kpad / BLOCK_K;
+  const int64_t tiles = (int64_t)m_tiles * n_tiles;
+  GATK_REQUIRE(tiles < (1LL << 31), "too many tiles");
+  int grid = sm_count();
+  if (tiles < grid) grid = (int)tiles;
+  gemm_tf32x3_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_bhi, map_blo, map_c, m_tiles, n_tiles, k_blocks);
+  GATK_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace gatk

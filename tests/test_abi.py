@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_queries_work_without_gpu():
-    assert _lib.query("gatk_gemm_workspace_bytes", 0, 0, 1000, 512, 100) == 0
+    assert _lib.query("gatk_gemm_workspace_bytes", 1, 0, 100, 512, 1000) >= 0
     assert _lib.query("gatk_da_workspace_floats", 8, 64) > 0
     assert _lib.query("gatk_scan_workspace_bytes", 1000) >= 0  # CUB sizes its scratch per device: 0 without one
     assert _lib.query("gatk_transpose_workspace_bytes", 1000, 1000, 5000) >= 3 * 5000 * 4

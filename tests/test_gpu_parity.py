@@ -91,6 +91,29 @@ def test_gemm_matches_fp64(ta, tb, M, N, K):
     assert rel_err(C[:, :N], 2 * ref) < 2e-6
 
 
+@pytest.mark.parametrize("M,N,K,pad", [(4096, 512, 100, 0), (5000, 136, 76, 4), (2449, 1024, 1024, 0),
+                                       (100_000, 512, 128, 0), (1500, 64, 500, 0), (1025, 8, 4, 0)])
+def test_tensor_core_gemm_is_fp32_accurate(M, N, K, pad):
+    """tcgen05 kind::tf32 with the hi/lo split (3 MMAs per product) against an fp64 product."""
+    assert _lib.query("gatk_gemm_uses_tensor_cores", 0, 0, M, N, K, K, N + pad, 0) == 1
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(K, N, generator=g)
+    ref = A.double() @ B.double()
+    dA, dB = A.to(DEV), B.to(DEV)
+    C = torch.full((M, N + pad), 7.0, device=DEV)
+    ws_bytes = _lib.query("gatk_gemm_workspace_bytes", 0, 0, M, N, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    _lib.call("gatk_gemm", 0, 0, M, N, K, dA.data_ptr(), K, dB.data_ptr(), N, C.data_ptr(), N + pad, 0,
+              ws.data_ptr(), ws_bytes, _stream())
+    torch.cuda.synchronize()
+    assert rel_err(C[:, :N], ref) < 3e-6
+    assert torch.all(C[:, N:] == 7.0)
+    # plain tf32 would be ~1e-3: make sure the compensation terms are really there
+    scale = ref.abs().max().item()
+    assert (C[:, :N].double().cpu() - ref).abs().max().item() < 1e-5 * scale
+
+
 # ------------------------------------------------------------------------------ heads
 def _run_head(d, kind, adj_arg, masks=None):
     cls = layers.SpGraphAttentionLayer if kind == "sparse" else layers.GraphAttentionLayer
