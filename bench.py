@@ -34,14 +34,25 @@ CPU_SAMPLE_NODES = 16_384  # reference backward is O(N^2) memory (layers.py:85):
 
 
 def algorithmic_bytes(n, e, H, D, f_in, need_dx=False):
-    """no-reuse gather model, fp32, 4-byte col ids, 8-byte rowptr."""
+    """Bytes each kernel's algorithm must move (no-reuse gather model: every stored entry moves its
+    neighbour row once per pass; fp32, 4-byte col ids, 8-byte rowptr).
+
+    `layer_survey` is SURVEY.md section 8(d)'s model of the layer (three row gathers per edge: K2,
+    a destination-pass K3 and a source-pass K4); `layer` is the sum over the kernels this engine
+    actually runs, whose backward gathers each row once instead of twice."""
     k2 = e * H * (4 * D + 4) + 4 * e + n * H * (4 * D + 12) + 8 * n
-    k3 = e * H * (4 * D + 4 + 4) + 4 * e + n * H * (8 * D + 16)
-    k4 = e * H * (4 * D + 4 + 12) + 8 * e + n * H * (4 * D + 4)
+    k3_survey = e * H * (4 * D + 4 + 4) + 4 * e + n * H * (8 * D + 16)
+    k4_survey = e * H * (4 * D + 4 + 12) + 8 * e + n * H * (4 * D + 4)
     k1 = 4 * n * f_in + 4 * f_in * H * D + 4 * n * H * (D + 2)
     k5 = 4 * n * f_in + 4 * n * H * D + 4 * f_in * H * D + ((4 * n * H * D + 4 * n * f_in) if need_dx else 0)
-    return {"gatk_attn_fwd": k2, "gatk_attn_bwd_dst": k3, "gatk_attn_bwd_src": k4, "projection_fwd": k1,
-            "projection_bwd": k5, "layer": k2 + k3 + k4 + k1 + k5}
+    prep = n * H * (16 * D + 4)                      # gout, out, hagg read; dhp write; c write
+    fused = e * H * (4 * D + 12 + 4) + 8 * e + n * H * (8 * D + 8)   # dhp_i gather, f/lse/c, dz write, trow+perm
+    finish = 4 * e * H + n * H * (8 * D + 4) + 8 * n  # dz read, dWh read-modify-write, df write
+    da = n * H * (4 * D + 8)
+    return {"gatk_attn_fwd": k2, "gatk_attn_bwd_prep": prep, "gatk_attn_bwd_fused": fused,
+            "gatk_attn_bwd_finish": finish, "gatk_da_reduce": da, "projection_fwd": k1, "projection_bwd": k5,
+            "layer_survey": k2 + k3_survey + k4_survey + k1 + k5,
+            "layer": k2 + prep + fused + finish + da + k1 + k5}
 
 
 def measured_peak():
@@ -217,7 +228,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     ab = algorithmic_bytes(n, e_total, H, D, f_in)
     per_kernel = {}
-    for name in ("gatk_attn_fwd", "gatk_attn_bwd_dst", "gatk_attn_bwd_src"):
+    for name in ("gatk_attn_fwd", "gatk_attn_bwd_fused", "gatk_attn_bwd_prep", "gatk_attn_bwd_finish"):
         if name in kern:
             gbs = ab[name] / world / (kern[name]["ms_avg"] * 1e-3) / 1e9
             per_kernel[name] = {"ms": round(kern[name]["ms_avg"], 4), "algorithmic_GB": round(ab[name] / world / 1e9, 3),
@@ -233,7 +244,9 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["achieved_GBs"], "peak": peak,
                     "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                     "layer_frac": round(ab["layer"] / world / (ms * 1e-3) / 1e9 / peak, 4),
-                    "layer_algorithmic_GB": round(ab["layer"] / 1e9, 2)}
+                    "layer_algorithmic_GB": round(ab["layer"] / 1e9, 2),
+                    "layer_frac_survey_model": round(ab["layer_survey"] / world / (ms * 1e-3) / 1e9 / peak, 4),
+                    "layer_survey_model_GB": round(ab["layer_survey"] / 1e9, 2)}
 
     cpu = cpu_reference_rate(cfg, steps=1, warmup=1)
     line = {
@@ -277,8 +290,9 @@ class SingleGpuLayerBench:
         self.cfg = cfg
         hubs = 2 if self.graph.hubs.n_seg else 0
         thubs = 2 if self.graph.transpose()[3].n_seg else 0
-        # gemm fwd 1, logits 1, attn fwd 1(+2), bwd dst 1(+2), bwd src 1(+2), da 2, gemm dW 2 (split-K)
-        self.launches_per_step = 1 + 1 + (1 + hubs) + (1 + hubs) + (1 + thubs) + 2 + 2
+        # gemm fwd 2 (B split + tcgen05), logits 1, attn fwd 1(+2), prep 1, fused 1(+2), finish 1(+2),
+        # da 2, gemm dW 2 (split-K)
+        self.launches_per_step = 2 + 1 + (1 + hubs) + 1 + (1 + thubs) + (1 + hubs) + 2 + 2
         self.x_host = None
 
     def _layer(self, x):

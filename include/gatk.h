@@ -104,7 +104,7 @@ GATK_API int gatk_logits_fwd(int64_t n, int H, int Dp, float* wh, int64_t ldw, c
  * (m + log l per row/head) are saved for backward; either may be NULL.
  * counter: one int32 of scratch (dynamic row scheduler).
  * gatk_hub_scratch_floats(which, ...): floats of hub_scratch for which = 0 (attn_fwd),
- * 1 (attn_bwd_dst), 2 (attn_bwd_src). */
+ * 1 (attn_bwd_fused), 2 (attn_bwd_finish). */
 GATK_API size_t gatk_hub_scratch_floats(int which, int H, int Dp, int n_hub_seg);
 GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp,
                   const float* wh, int64_t ldw, const float* f, const float* g,
@@ -114,34 +114,35 @@ GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* 
                   int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr,
                   int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream);
 
-/* ------------------------------------------------------------------ K3: backward, destination-row pass
- * From gout = dL/d(out): dhp = dL/dh' (ELU' applied), c_i = dhp_i . hagg_i, and per edge
- * dz_ij = alpha_ij * (keep/(1-p) * (dhp_i . Wh_j) - c_i) * LeakyReLU'(f_i+g_j); writes
- * edge_alpha (post-dropout attention), edge_dz, df_i = sum_j dz_ij.  O(E*D): replaces the
- * dense N x N SpecialSpmmFunction.backward (layers.py:81-90).  out may be NULL when
- * act_elu == 0. */
-GATK_API int gatk_attn_bwd_dst(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp,
-                      const float* wh, int64_t ldw, const float* f, const float* g, const float* lse,
-                      const uint8_t* keep_att, float inv_keep, float alpha,
-                      const float* gout, int64_t ldgo, const float* out, int64_t ldo, int act_elu,
-                      const float* hagg, int64_t ldh,
-                      float* dhp, int64_t lddhp, float* df, float* edge_alpha, float* edge_dz,
-                      int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr,
-                      int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream);
-
-/* ------------------------------------------------------------------ K4: backward, source pass (CSR-transpose, scatter-free)
- * dWh_j = sum_i alpha~_ij dhp_i + df_j a_src + dg_j a_dst,  dg_j = sum_i dz_ij, then the
- * post-projection dropout mask (keep_wh) if any.  df may be NULL (sharded mode: the
- * a-terms are added by the owner).  hub_* describe the TRANSPOSED graph's long rows;
- */
-GATK_API int gatk_attn_bwd_src(int64_t n_src, const int64_t* tptr, const int32_t* trow, const int32_t* perm,
-                      int H, int Dp, const float* dhp, int64_t lddhp,
-                      const float* edge_alpha, const float* edge_dz,
-                      const float* df, const float* a_src, const float* a_dst,
-                      const uint8_t* keep_wh, float inv_keep,
-                      float* dwh, int64_t lddwh, float* dg,
-                      int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr,
-                      int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream);
+/* ------------------------------------------------------------------ K3/K4: backward of the fused attention
+ * Autograd of layers.py:141-160, with the reference's dense N x N SpecialSpmmFunction.backward
+ * (layers.py:81-90) replaced by O(E*D) CSR work that gathers each feature row ONCE:
+ *
+ *  prep    per destination row: dhp = dL/dh' = gout * ELU'(out) (out may be NULL if !act_elu),
+ *          c[i,h] = dhp_i . hagg_i  (the softmax-backward row term).
+ *  fused   per SOURCE row j over the transposed pattern (scatter-free): gathers dhp_i once and
+ *          uses it for both  dz_ij = alpha_ij (keep/(1-p) dhp_i.Wh_j - c_i) LeakyReLU'(f_i+g_j)
+ *          and  dwh_j = sum_i alpha~_ij dhp_i + dg_j a_dst,  dg_j = sum_i dz_ij.  dz is written
+ *          in CSR edge order (edge_dz [E,H]); keep_att is in CSR edge order as well.
+ *          hub_* describe the TRANSPOSED pattern's long rows (scratch: which = 1).
+ *  finish  per destination row: df_i = sum_j dz_ij (segmented sum over CSR rows), then
+ *          dwh_i += df_i a_src and the post-projection dropout mask keep_wh (layers.py:37,136).
+ *          hub_* describe the CSR pattern's long rows (scratch: which = 2). */
+GATK_API int gatk_attn_bwd_prep(int64_t n, int H, int Dp, const float* gout, int64_t ldgo, const float* out,
+                                int64_t ldo, int act_elu, const float* hagg, int64_t ldh, float* dhp,
+                                int64_t lddhp, float* c, void* stream);
+GATK_API int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int32_t* trow, const int32_t* perm,
+                                 int H, int Dp, const float* wh, int64_t ldw, const float* g, const float* f,
+                                 const float* lse, const float* c, const uint8_t* keep_att, float inv_keep,
+                                 float alpha, const float* dhp, int64_t lddhp, const float* a_dst, float* dwh,
+                                 int64_t lddwh, float* dg, float* edge_dz, int seg_len, const int32_t* hub_rows,
+                                 const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
+                                 int32_t* counter, void* stream);
+GATK_API int gatk_attn_bwd_finish(int64_t n, const int64_t* rowptr, int H, int Dp, const float* edge_dz,
+                                  const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
+                                  int64_t lddwh, float* df, int seg_len, const int32_t* hub_rows,
+                                  const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
+                                  void* stream);
 
 /* da_src[h,:] = sum_i df[i,h] Wh[i,h,:],  da_dst[h,:] = sum_j dg[j,h] Wh[j,h,:]  (autograd of
  * layers.py:60-61 / :144).  ws floats: gatk_da_workspace_floats(H, Dp). Deterministic. */

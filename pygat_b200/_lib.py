@@ -36,13 +36,12 @@ PROTOTYPES = {
     "gatk_attn_fwd": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, P, P, c_float, c_float,
                               P, c_int64, c_int, P, P, c_int64, P,
                               c_int, P, P, c_int, c_int, P, P, P]),
-    "gatk_attn_bwd_dst": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, P, P, P, c_float, c_float,
-                                  P, c_int64, P, c_int64, c_int, P, c_int64,
-                                  P, c_int64, P, P, P,
-                                  c_int, P, P, c_int, c_int, P, P, P]),
-    "gatk_attn_bwd_src": (c_int, [c_int64, P, P, P, c_int, c_int, P, c_int64, P, P, P, P, P, P, c_float,
-                                  P, c_int64, P,
-                                  c_int, P, P, c_int, c_int, P, P, P]),
+    "gatk_attn_bwd_prep": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_int64, c_int, P, c_int64, P, c_int64, P, P]),
+    "gatk_attn_bwd_fused": (c_int, [c_int64, P, P, P, c_int, c_int, P, c_int64, P, P, P, P, P, c_float, c_float,
+                                    P, c_int64, P, P, c_int64, P, P,
+                                    c_int, P, P, c_int, c_int, P, P, P]),
+    "gatk_attn_bwd_finish": (c_int, [c_int64, P, c_int, c_int, P, P, P, c_float, P, c_int64, P,
+                                     c_int, P, P, c_int, c_int, P, P]),
     "gatk_da_workspace_floats": (c_size_t, [c_int, c_int]),
     "gatk_da_reduce": (c_int, [c_int64, c_int, c_int, P, c_int64, P, P, P, P, P, P]),
     "gatk_head_combine": (c_int, [c_int64, c_int, c_int, c_int, P, c_int64, c_int, P, P]),

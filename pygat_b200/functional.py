@@ -150,25 +150,27 @@ class GatLayerFunction(torch.autograd.Function):
             dhp_ptr, lddhp = dhp_keepalive.data_ptr(), HD
         df = torch.empty(n, H, dtype=torch.float32, device=dev)
         dg = torch.empty(n, H, dtype=torch.float32, device=dev)
-        edge_alpha = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        c = torch.empty(n, H, dtype=torch.float32, device=dev)
         edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
 
-        # ---- K3: destination pass ----------------------------------------------------------
-        hubs = graph.hubs
-        scratch = _hub_scratch(1, H, Dp, hubs.n_seg, dev)
-        _lib.call("gatk_attn_bwd_dst", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, z.data_ptr(), M_out,
-                  f.data_ptr(), g.data_ptr(), lse.data_ptr(), _ptr(masks.keep_att), inv_keep, alpha,
-                  gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD, int(act_elu),
-                  hagg.data_ptr(), HD, dhp_ptr, lddhp, df.data_ptr(), edge_alpha.data_ptr(), edge_dz.data_ptr(),
-                  *hubs.args(scratch), graph.counter.data_ptr(), st)
+        # ---- K3 prep: dh' = gout * ELU'(out), c_i = dh'_i . hagg_i ----------------------------
+        _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
+                  int(act_elu), hagg.data_ptr(), HD, dhp_ptr, lddhp, c.data_ptr(), st)
 
-        # ---- K4: source pass over the transposed pattern -----------------------------------
-        scratch_t = _hub_scratch(2, H, Dp, thubs.n_seg, dev)
-        _lib.call("gatk_attn_bwd_src", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, dhp_ptr, lddhp,
-                  edge_alpha.data_ptr(), edge_dz.data_ptr(), df.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(),
-                  _ptr(masks.keep_wh), inv_keep, dz_rows.data_ptr(), M_out, dg.data_ptr(),
+        # ---- K4 fused source pass over the transposed pattern (one gather of dh' per edge) ------
+        scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
+        _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, z.data_ptr(), M_out,
+                  g.data_ptr(), f.data_ptr(), lse.data_ptr(), c.data_ptr(), _ptr(masks.keep_att), inv_keep, alpha,
+                  dhp_ptr, lddhp, a_dst.data_ptr(), dz_rows.data_ptr(), M_out, dg.data_ptr(), edge_dz.data_ptr(),
                   *thubs.args(scratch_t), graph.counter.data_ptr(), st)
-        del edge_alpha, edge_dz
+
+        # ---- finish: df = segmented sum of dz, dWh += df a_src, Wh-dropout mask ------------------
+        hubs = graph.hubs
+        scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
+        _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), a_src.data_ptr(),
+                  _ptr(masks.keep_wh), inv_keep, dz_rows.data_ptr(), M_out, df.data_ptr(),
+                  *hubs.args(scratch), st)
+        del edge_dz
 
         # ---- da ------------------------------------------------------------------------------
         da_src = torch.empty(H, Dp, dtype=torch.float32, device=dev)
