@@ -110,7 +110,7 @@ template <int NV>
 __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, int64_t beg, int64_t end, int lane,
                                                   const LaneGeom<NV>& geo, float4 (&acc)[NV], float& dg_reg,
                                                   const FusedSmem& sm) {
-  constexpr int U = NV >= 4 ? 1 : 4 / NV;
+  constexpr int U = NV >= 8 ? 1 : 8 / NV;  // 8 x LDG.128 in flight per lane, like the forward
   const int H = a.H, HP = a.HP;
   float4 wj[NV];
 #pragma unroll

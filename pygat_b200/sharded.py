@@ -1,0 +1,298 @@
+"""Multi-GPU execution of the GAT layer; one process per GPU, NCCL through
+torch.distributed.  The reference has no distributed code -- everything here is new design.
+
+* One big graph (products / papers shapes): 1-D DESTINATION-ROW sharding, contiguous row ranges
+  balanced by stored entries.  Rank r owns rows [b_r, b_{r+1}): its slice of the input features, its
+  CSR rows (column ids stay global) and its outputs.  Softmax and aggregation of a destination row
+  need only that row's edges plus Wh_j / g_j of its sources, so the one exchange per layer and
+  direction is: forward an ALL-GATHER of the projected rows [Wh | g], backward a REDUCE-SCATTER of
+  the partial dWh / dg rows; the parameter gradients (dW, da) are all-reduced.
+* Independent graphs (PPI): graph-level data parallelism, `allreduce_gradients` with node-count
+  weights so the result equals the reference's merged-batch mean loss (train_ppi.py:114-119).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .functional import (HeadCombineFunction, LayerMasks, _gemm, _hub_scratch, pack_heads)
+from .graph import Graph, _ptr, _stream
+from .synth import shard_rows_by_nnz
+
+
+class ShardPlan:
+    """Row boundaries of every rank (python ints), identical on all ranks."""
+
+    def __init__(self, bounds: Sequence[int], rank: int, group=None):
+        self.bounds = [int(b) for b in bounds]
+        self.world = len(self.bounds) - 1
+        self.rank = rank
+        self.group = group
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.n_local = self.hi - self.lo
+        self.n_total = self.bounds[-1]
+
+    @staticmethod
+    def by_nnz(rowptr: torch.Tensor, rank: int, world: int, group=None) -> "ShardPlan":
+        return ShardPlan(shard_rows_by_nnz(rowptr, world), rank, group)
+
+    def rows(self, full: torch.Tensor, r: Optional[int] = None) -> torch.Tensor:
+        r = self.rank if r is None else r
+        return full[self.bounds[r]:self.bounds[r + 1]]
+
+    def local_graph(self, rowptr: torch.Tensor, col: torch.Tensor, seg_len: Optional[int] = None) -> Graph:
+        """This rank's destination rows of the global CSR (global column ids kept)."""
+        e0, e1 = int(rowptr[self.lo].item()), int(rowptr[self.hi].item())
+        return Graph((rowptr[self.lo:self.hi + 1] - e0).contiguous(), col[e0:e1].contiguous(),
+                     n_src=self.n_total, seg_len=seg_len)
+
+
+def _uneven_ok(group) -> bool:
+    return dist.get_backend(group) == "nccl"
+
+
+def gather_rows(full: torch.Tensor, plan: ShardPlan):
+    """In-place all-gather of row shards: on entry rank r has filled full[b_r:b_{r+1}]."""
+    if plan.world == 1:
+        return
+    if _uneven_ok(plan.group):
+        dist.all_gather([plan.rows(full, r) for r in range(plan.world)], plan.rows(full), group=plan.group)
+    else:  # gloo (CPU tests): all_gather needs equal sizes there
+        for r in range(plan.world):
+            dist.broadcast(plan.rows(full, r), src=dist.get_global_rank(plan.group, r) if plan.group else r,
+                           group=plan.group)
+
+
+def reduce_rows(partial: torch.Tensor, plan: ShardPlan) -> torch.Tensor:
+    """Reduce-scatter of row shards: returns the sum over ranks of partial[b_r:b_{r+1}] on rank r."""
+    if plan.world == 1:
+        return plan.rows(partial)
+    if _uneven_ok(plan.group):
+        out = torch.empty_like(plan.rows(partial))
+        dist.reduce_scatter(out, [plan.rows(partial, r) for r in range(plan.world)], group=plan.group)
+        return out
+    for r in range(plan.world):
+        dist.reduce(plan.rows(partial, r), dst=dist.get_global_rank(plan.group, r) if plan.group else r,
+                    group=plan.group)
+    return plan.rows(partial)
+
+
+def allreduce_(tensors: Sequence[torch.Tensor], plan_or_group=None):
+    """Sum small tensors over ranks with one flat all-reduce."""
+    group = plan_or_group.group if isinstance(plan_or_group, ShardPlan) else plan_or_group
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+
+
+class ShardedGatLayerFunction(torch.autograd.Function):
+    """GatLayerFunction for a destination-row shard (no dropout: the sharded shapes train with p = 0)."""
+
+    @staticmethod
+    def forward(ctx, x, w_ext, a_src, a_dst, graph: Graph, plan: ShardPlan, H: int, Dp: int, has_skip: bool,
+                alpha: float, act_elu: bool):
+        dev = x.device
+        n, f_in = x.shape
+        assert n == plan.n_local == graph.n_dst and graph.n_src == plan.n_total
+        HD = H * Dp
+        x, w_ext, a_src, a_dst = x.contiguous(), w_ext.contiguous(), a_src.contiguous(), a_dst.contiguous()
+        M_out = w_ext.shape[1]
+        st = _stream()
+        # projection of the local rows straight into this rank's slice of the gathered buffers
+        wh_full = torch.empty(plan.n_total, HD, dtype=torch.float32, device=dev)
+        g_full = torch.empty(plan.n_total, H, dtype=torch.float32, device=dev)
+        wh_loc, g_loc = plan.rows(wh_full), plan.rows(g_full)
+        _gemm(0, 0, n, HD, f_in, x, f_in, w_ext, M_out, wh_loc, HD)
+        skipv = None
+        if has_skip:
+            skipv = torch.empty(n, HD, dtype=torch.float32, device=dev)
+            _gemm(0, 0, n, HD, f_in, x, f_in, w_ext, M_out, skipv, HD, b_off=HD)
+        f = torch.empty(n, H, dtype=torch.float32, device=dev)
+        _lib.call("gatk_logits_fwd", n, H, Dp, wh_loc.data_ptr(), HD, None, 1.0, a_src.data_ptr(), a_dst.data_ptr(),
+                  f.data_ptr(), g_loc.data_ptr(), st)
+        gather_rows(wh_full, plan)
+        gather_rows(g_full, plan)
+
+        need_grad = any(ctx.needs_input_grad[:4])
+        out = torch.empty(n, HD, dtype=torch.float32, device=dev)
+        separate_hagg = need_grad and (has_skip or act_elu)
+        hagg = torch.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
+        lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        hubs = graph.hubs
+        scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
+        _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_full.data_ptr(), HD,
+                  f.data_ptr(), g_full.data_ptr(), None, 1.0, float(alpha), _ptr(skipv), HD, int(act_elu),
+                  _ptr(hagg), out.data_ptr(), HD, _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), st)
+        if need_grad:
+            ctx.graph, ctx.plan = graph, plan
+            ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu))
+            ctx.save_for_backward(x, w_ext, a_src, a_dst, wh_full, g_full, f, lse, out,
+                                  hagg if separate_hagg else out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w_ext, a_src, a_dst, wh_full, g_full, f, lse, out, hagg = ctx.saved_tensors
+        graph, plan = ctx.graph, ctx.plan
+        H, Dp, has_skip, alpha, act_elu = ctx.cfg
+        dev = x.device
+        n, f_in = x.shape
+        HD = H * Dp
+        M_out = w_ext.shape[1]
+        N = plan.n_total
+        st = _stream()
+        gout = gout.contiguous()
+        tptr, trow, perm, thubs = graph.transpose()
+
+        dz_rows = torch.empty(n, M_out, dtype=torch.float32, device=dev)   # [dWh | dSkip] of the local rows
+        if has_skip:
+            dhp_keep, dhp_ptr, lddhp = None, dz_rows.data_ptr() + 4 * HD, M_out
+        else:
+            dhp_keep = torch.empty(n, HD, dtype=torch.float32, device=dev)
+            dhp_ptr, lddhp = dhp_keep.data_ptr(), HD
+        c = torch.empty(n, H, dtype=torch.float32, device=dev)
+        _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
+                  int(act_elu), hagg.data_ptr(), HD, dhp_ptr, lddhp, c.data_ptr(), st)
+
+        # partial dWh / dg for EVERY source from this rank's destination rows
+        dwh_part = torch.empty(N, HD, dtype=torch.float32, device=dev)
+        dg_part = torch.empty(N, H, dtype=torch.float32, device=dev)
+        edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
+        _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, wh_full.data_ptr(), HD,
+                  g_full.data_ptr(), f.data_ptr(), lse.data_ptr(), c.data_ptr(), None, 1.0, alpha, dhp_ptr, lddhp,
+                  a_dst.data_ptr(), dwh_part.data_ptr(), HD, dg_part.data_ptr(), edge_dz.data_ptr(),
+                  *thubs.args(scratch_t), graph.counter.data_ptr(), st)
+        dwh_loc = reduce_rows(dwh_part, plan)
+        dg_loc = reduce_rows(dg_part, plan)
+        # local rows: df, dst-side term; written into the dZ buffer the projection backward reads
+        dz_wh = dz_rows[:, :HD]
+        dz_wh.copy_(dwh_loc)
+        del dwh_part
+        df = torch.empty(n, H, dtype=torch.float32, device=dev)
+        hubs = graph.hubs
+        scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
+        _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), a_src.data_ptr(),
+                  None, 1.0, dz_rows.data_ptr(), M_out, df.data_ptr(), *hubs.args(scratch), st)
+        del edge_dz
+
+        da_src = torch.empty(H, Dp, dtype=torch.float32, device=dev)
+        da_dst = torch.empty(H, Dp, dtype=torch.float32, device=dev)
+        ws = torch.empty(_lib.query("gatk_da_workspace_floats", H, Dp), dtype=torch.float32, device=dev)
+        dg_c = dg_loc.contiguous()
+        _lib.call("gatk_da_reduce", n, H, Dp, plan.rows(wh_full).data_ptr(), HD, df.data_ptr(), dg_c.data_ptr(),
+                  da_src.data_ptr(), da_dst.data_ptr(), ws.data_ptr(), st)
+        dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
+        _gemm(1, 0, f_in, M_out, n, x, f_in, dz_rows, M_out, dw_ext, M_out)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(n, f_in, dtype=torch.float32, device=dev)
+            _gemm(0, 1, n, f_in, M_out, dz_rows, M_out, w_ext, M_out, dx, f_in)
+        if plan.world > 1:
+            allreduce_([dw_ext, da_src, da_dst], plan)
+        del dhp_keep
+        return dx, dw_ext, da_src, da_dst, None, None, None, None, None, None, None
+
+
+def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, a_srcs, a_dsts, skips, alpha: float,
+                      concat: bool, combine: str = "cat") -> torch.Tensor:
+    """All heads of one GAT layer on this rank's destination rows (see functional.gat_layer)."""
+    H = len(Ws)
+    w_ext, a_src, a_dst, D, Dp = pack_heads(Ws, a_srcs, a_dsts, skips)
+    rows = ShardedGatLayerFunction.apply(x_local.float(), w_ext, a_src, a_dst, graph, plan, H, Dp, skips is not None,
+                                         float(alpha), bool(concat))
+    if combine == "none" or (combine == "cat" and D == Dp):
+        return rows
+    return HeadCombineFunction.apply(rows, H, D, Dp, 1 if combine == "mean" else 0)
+
+
+# ---------------------------------------------------------------------- graph-level data parallelism (PPI)
+def allreduce_gradients(params, n_local_nodes: int, group=None):
+    """Make per-rank mean-loss gradients equal the gradient of the mean over ALL ranks' nodes: the
+    reference's BCEWithLogitsLoss(reduction='mean') over a merged batch (train_ppi.py:114-119,
+    load_data_ppi.py:84-86) weights every node equally, so each rank's gradient is scaled by
+    n_local / n_total before the sum."""
+    params = [p for p in params if p.grad is not None]
+    if not params:
+        return
+    dev = params[0].grad.device
+    cnt = torch.tensor([float(n_local_nodes)], device=dev)
+    dist.all_reduce(cnt, group=group)
+    w = float(n_local_nodes) / float(cnt.item())
+    flat = torch.cat([p.grad.reshape(-1) for p in params]) * w
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for p in params:
+        p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+        off += p.numel()
+
+
+# ---------------------------------------------------------------------- bench harness (bench.py --gpus N)
+class ShardedLayerBench:
+    """The bench.py workload on `world` GPUs: the whole synthetic graph is generated identically on
+    every rank (same seed) and each rank keeps its destination-row shard."""
+
+    def __init__(self, cfg, rank: int, world: int, dev):
+        from .synth import init_layer_params, power_law_csr
+        n, H, D, f_in = cfg["n"], cfg["H"], cfg["D"], cfg["f_in"]
+        rowptr, col = power_law_csr(n, cfg["avg_deg"], seed=72, exponent=cfg["exponent"], device=dev)
+        self.e_total = int(col.numel())
+        self.plan = ShardPlan.by_nnz(rowptr, rank, world)
+        self.graph = self.plan.local_graph(rowptr, col)
+        del rowptr, col
+        self.graph.transpose()
+        g = torch.Generator(device=dev).manual_seed(72)
+        x = torch.randn(n, f_in, generator=g, device=dev)
+        gout = torch.randn(n, H * D, generator=g, device=dev)
+        self.x = self.plan.rows(x).clone()
+        self.gout = self.plan.rows(gout).clone()
+        del x, gout
+        torch.cuda.empty_cache()
+        self.Ws, self.a_src, self.a_dst = init_layer_params(f_in, H, D, dev, seed=72)
+        self.params = self.Ws + self.a_src + self.a_dst
+        hubs = 2 if self.graph.hubs.n_seg else 0
+        thubs = 2 if self.graph.transpose()[3].n_seg else 0
+        self.launches_per_step = 2 + 1 + (1 + hubs) + 1 + (1 + thubs) + (1 + hubs) + 2 + 2
+        self.x_host = None
+
+    def _layer(self, x):
+        return sharded_gat_layer(x, self.graph, self.plan, self.Ws, self.a_src, self.a_dst, None, 0.2, concat=True)
+
+    def step(self):
+        for p in self.params:
+            p.grad = None
+        y = self._layer(self.x)
+        y.backward(self.gout)
+        return y
+
+    def e2e(self, steps: int):
+        if self.x_host is None:
+            self.x_host = self.x.cpu().pin_memory()
+        n_par = sum(p.numel() for p in self.params)
+        host_out = torch.empty(n_par + 1, dtype=torch.float32).pin_memory()
+
+        def one():
+            x = self.x_host.to(self.x.device, non_blocking=True)
+            for p in self.params:
+                p.grad = None
+            y = self._layer(x)
+            y.backward(self.gout)
+            flat = torch.cat([p.grad.reshape(-1) for p in self.params] + [y[:: max(1, y.shape[0] // 1024)].sum().reshape(1)])
+            host_out.copy_(flat, non_blocking=True)
+
+        one()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, self.x_host.numel() * 4, host_out.numel() * 4

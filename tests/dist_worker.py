@@ -1,0 +1,116 @@
+"""Worker for the multi-process tests (launched by torchrun / mp.spawn from tests/test_sharded_*.py).
+
+mode "gloo":  host-side sharding logic on CPU tensors (row gather / reduce helpers, plan, weighted
+              gradient all-reduce), world_size 2, backend gloo.
+mode "nccl":  the sharded GAT layer on 2+ GPUs against the single-GPU layer (same inputs on every rank).
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def run_gloo(rank, world):
+    from pygat_b200.sharded import ShardPlan, allreduce_, allreduce_gradients, gather_rows, reduce_rows
+    from pygat_b200.synth import power_law_csr, shard_rows_by_nnz
+    rowptr, col = power_law_csr(500, 8.0, seed=1)
+    bounds = shard_rows_by_nnz(rowptr, world)
+    assert bounds[0] == 0 and bounds[-1] == 500 and all(b1 >= b0 for b0, b1 in zip(bounds, bounds[1:]))
+    nnz = [int(rowptr[b1] - rowptr[b0]) for b0, b1 in zip(bounds, bounds[1:])]
+    assert max(nnz) - min(nnz) <= int((rowptr[1:] - rowptr[:-1]).max())  # balanced up to one row
+    plan = ShardPlan(bounds, rank)
+    # gather: every rank fills its slice, afterwards all ranks hold the same full matrix
+    ref = torch.arange(500 * 3, dtype=torch.float32).view(500, 3)
+    full = torch.full((500, 3), -1.0)
+    plan.rows(full).copy_(plan.rows(ref))
+    gather_rows(full, plan)
+    assert torch.equal(full, ref)
+    # reduce: rank r ends up with the sum over ranks of its row range
+    part = ref * (rank + 1)
+    got = reduce_rows(part.clone(), plan)
+    assert torch.equal(got, plan.rows(ref) * sum(r + 1 for r in range(world)))
+    a, b = torch.ones(3) * (rank + 1), torch.ones(2, 2) * rank
+    allreduce_([a, b], plan)
+    assert torch.equal(a, torch.ones(3) * sum(r + 1 for r in range(world)))
+    assert torch.equal(b, torch.ones(2, 2) * sum(range(world)))
+    # node-count weighted gradient all-reduce == gradient of the mean loss over the merged batch
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4, 3)
+    sizes = [5, 11][:world] if world == 2 else [3 + r for r in range(world)]
+    xs = [torch.randn(s, 4, generator=torch.Generator().manual_seed(10 + r)) for r, s in enumerate(sizes)]
+    ys = [torch.rand(s, 3, generator=torch.Generator().manual_seed(20 + r)).round() for r, s in enumerate(sizes)]
+    loss_fn = torch.nn.BCEWithLogitsLoss(reduction="mean")
+    loss_fn(lin(torch.cat(xs)), torch.cat(ys)).backward()
+    merged = [p.grad.clone() for p in lin.parameters()]
+    lin.zero_grad()
+    loss_fn(lin(xs[rank]), ys[rank]).backward()
+    allreduce_gradients(lin.parameters(), sizes[rank])
+    for p, m in zip(lin.parameters(), merged):
+        assert torch.allclose(p.grad, m, atol=1e-6), (p.grad, m)
+    # local graph slices reassemble the global CSR
+    g_rows = [int(rowptr[b1] - rowptr[b0]) for b0, b1 in zip(bounds, bounds[1:])]
+    assert sum(g_rows) == col.numel()
+
+
+def run_nccl(rank, world):
+    from pygat_b200.functional import gat_layer
+    from pygat_b200.graph import Graph
+    from pygat_b200.sharded import ShardPlan, sharded_gat_layer
+    from pygat_b200.synth import init_layer_params, power_law_csr
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
+    torch.cuda.set_device(dev)
+    for (n, H, D, f_in, skip, concat) in [(5000, 8, 64, 100, False, True), (3000, 4, 32, 36, True, False)]:
+        rowptr, col = power_law_csr(n, 14.0, seed=5, exponent=0.7, device=dev)
+        gen = torch.Generator(device=dev).manual_seed(3)
+        x = torch.randn(n, f_in, generator=gen, device=dev)
+        gout = torch.randn(n, H * D, generator=gen, device=dev)
+        Ws, a_s, a_d = init_layer_params(f_in, H, D, dev, seed=9)
+        Ss = [w.detach().clone().flip(0).requires_grad_(True) for w in Ws] if skip else None
+        # single GPU reference on every rank
+        xr = x.clone().requires_grad_(True)
+        y_ref = gat_layer(xr, Graph.from_csr(rowptr, col, seg_len=256), Ws, a_s, a_d, Ss, 0.2, concat)
+        y_ref.backward(gout)
+        ref = {"dx": xr.grad.clone(), "dW": [w.grad.clone() for w in Ws], "da": [a.grad.clone() for a in a_s + a_d],
+               "dS": [s.grad.clone() for s in Ss] if skip else []}
+        for p in Ws + a_s + a_d + (Ss or []):
+            p.grad = None
+        plan = ShardPlan.by_nnz(rowptr, rank, world)
+        graph = plan.local_graph(rowptr, col, seg_len=256)
+        xl = plan.rows(x).clone().requires_grad_(True)
+        y = sharded_gat_layer(xl, graph, plan, Ws, a_s, a_d, Ss, 0.2, concat)
+        y.backward(plan.rows(gout))
+
+        def rel(a, b):
+            return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+        assert rel(y, plan.rows(y_ref)) < 1e-5, rel(y, plan.rows(y_ref))
+        assert rel(xl.grad, plan.rows(ref["dx"])) < 1e-5
+        for got, want in zip([w.grad for w in Ws], ref["dW"]):
+            assert rel(got, want) < 1e-5, rel(got, want)
+        for got, want in zip([a.grad for a in a_s + a_d], ref["da"]):
+            assert rel(got, want) < 1e-5, rel(got, want)
+        if skip:
+            for got, want in zip([s.grad for s in Ss], ref["dS"]):
+                assert rel(got, want) < 1e-5
+    torch.cuda.synchronize()
+
+
+def main():
+    mode = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo" if mode == "gloo" else "nccl")
+    try:
+        (run_gloo if mode == "gloo" else run_nccl)(rank, world)
+        dist.barrier()
+        if rank == 0:
+            print(f"DIST_OK mode={mode} world={world}")
+    finally:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
