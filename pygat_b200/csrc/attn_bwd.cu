@@ -86,31 +86,92 @@ struct BwdFusedArgs {
   int n_hub, n_hub_seg;
   float* scratch;
   int32_t* counter;
+  int ring;  // slots of the per-warp row ring
 };
 
+constexpr int FUSED_WARPS = 8;
+
+// ---- bulk-async row gather ---------------------------------------------------------------------
+// The kernel is bound by bytes in flight (Little's law: ~1.5-2 us loaded DRAM latency x 6.5 TB/s is
+// ~70 KB per SM).  Register-staged LDG.128 gathers top out at 64 KB per SM; instead every gathered
+// dh'_i row (H*Dp*4 bytes, contiguous) is fetched by ONE cp.async.bulk (the TMA unit's 1-D copy)
+// into a per-warp ring of shared-memory slots, completion signalled on an mbarrier per slot.  Lane 0
+// issues, the whole warp consumes with conflict-free LDS.128.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 28)) __trap();  // a protocol bug traps instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void bulk_row_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 struct FusedSmem {
+  uint8_t* ring;   // R slots of row_bytes
+  uint32_t bars;   // R mbarriers (shared-space address)
   int* row_s;
   int* perm_s;
   float* at_s;  // post-dropout attention (aggregation weight)
   float* A_s;   // alpha * slope * keep/(1-p)
   float* B_s;   // alpha * slope * c_i
   float* dz_s;
-  __device__ __forceinline__ static int floats_per_warp(int HP) { return 64 + 4 * 32 * HP; }
-  __device__ __forceinline__ void carve(float* base, int HP) {
-    row_s = reinterpret_cast<int*>(base);
+  int R;
+  uint32_t row_bytes;
+  uint32_t issued, consumed;  // rows issued / consumed by this warp since kernel start (warp-uniform)
+  __host__ __device__ static size_t bytes_per_warp(int R, int V, int HP) {
+    size_t b = (size_t)R * V * 16 + (size_t)R * 8 + 256 + (size_t)4 * 32 * HP * 4;
+    return (b + 127) & ~(size_t)127;
+  }
+  __device__ __forceinline__ void carve(uint8_t* base, int R_, int V, int HP, int lane) {
+    R = R_;
+    row_bytes = (uint32_t)V * 16u;
+    ring = base;
+    uint8_t* p = base + (size_t)R * row_bytes;
+    bars = smem_addr(p);
+    p += (size_t)R * 8;
+    row_s = reinterpret_cast<int*>(p);
     perm_s = row_s + 32;
-    at_s = base + 64;
+    at_s = reinterpret_cast<float*>(p + 256);
     A_s = at_s + 32 * HP;
     B_s = A_s + 32 * HP;
     dz_s = B_s + 32 * HP;
+    issued = consumed = 0;
+    if (lane == 0) {
+      for (int k = 0; k < R; ++k) mbar_init(bars + 8u * k, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  // lane 0 only
+  __device__ __forceinline__ void issue(const float* src) {
+    const uint32_t slot = issued % (uint32_t)R;
+    mbar_expect_tx(bars + 8u * slot, row_bytes);
+    bulk_row_copy(smem_addr(ring + (size_t)slot * row_bytes), src, row_bytes, bars + 8u * slot);
   }
 };
 
 template <int NV>
 __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, int64_t beg, int64_t end, int lane,
                                                   const LaneGeom<NV>& geo, float4 (&acc)[NV], float& dg_reg,
-                                                  const FusedSmem& sm) {
-  constexpr int U = NV >= 8 ? 1 : 8 / NV;  // 8 x LDG.128 in flight per lane, like the forward
+                                                  FusedSmem& sm) {
   const int H = a.H, HP = a.HP;
   float4 wj[NV];
 #pragma unroll
@@ -129,6 +190,13 @@ __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, 
     const int pe = valid ? __ldg(a.perm + e) : 0;
     sm.row_s[lane] = i;
     sm.perm_s[lane] = pe;
+    __syncwarp();
+    // prime the ring with the first rows of this chunk; the weight computation below overlaps them
+    int queued = 0;
+    for (; queued < cnt && queued < sm.R; ++queued) {
+      if (lane == 0) sm.issue(a.dhp + (int64_t)sm.row_s[queued] * a.lddhp);
+      ++sm.issued;
+    }
     const float* fi = a.f + (int64_t)i * H;
     const float* li = a.lse + (int64_t)i * H;
     const float* ci = a.c + (int64_t)i * H;
@@ -151,48 +219,26 @@ __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, 
       sm.B_s[lane * HP + h] = B;
     }
     __syncwarp();
-    const float* dl = a.dhp + lane * 4;
-    int t = 0;
-    for (; t + U <= cnt; t += U) {
-      float4 w[U][NV];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float* di = dl + (int64_t)sm.row_s[t + u] * a.lddhp;
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-          if (geo.act[v]) w[u][v] = ldg4(di + v * 128);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float pr[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          pr[v] = 0.f;
-          if (geo.act[v]) {
-            fma4(acc[v], sm.at_s[(t + u) * HP + geo.hv[v]], w[u][v]);
-            pr[v] = dot4(w[u][v], wj[v]);
-          }
-        }
-        head_reduce<NV>(pr, a.lph);
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-          if (geo.leader[v]) {
-            const int k = (t + u) * HP + geo.hv[v];
-            sm.dz_s[k] = fmaf(sm.A_s[k], pr[v], -sm.B_s[k]);
-          }
-      }
-    }
-    for (; t < cnt; ++t) {
-      const float* di = dl + (int64_t)sm.row_s[t] * a.lddhp;
+    for (int t = 0; t < cnt; ++t) {
+      const uint32_t slot = sm.consumed % (uint32_t)sm.R;
+      mbar_wait(sm.bars + 8u * slot, (sm.consumed / (uint32_t)sm.R) & 1u);
+      const float4* rowp = reinterpret_cast<const float4*>(sm.ring + (size_t)slot * sm.row_bytes) + lane;
       float pr[NV];
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         pr[v] = 0.f;
         if (geo.act[v]) {
-          const float4 w = ldg4(di + v * 128);
+          const float4 w = rowp[32 * v];
           fma4(acc[v], sm.at_s[t * HP + geo.hv[v]], w);
           pr[v] = dot4(w, wj[v]);
         }
+      }
+      __syncwarp();  // every lane has read the slot: it can be refilled
+      ++sm.consumed;
+      if (queued < cnt) {
+        if (lane == 0) sm.issue(a.dhp + (int64_t)sm.row_s[queued] * a.lddhp);
+        ++sm.issued;
+        ++queued;
       }
       head_reduce<NV>(pr, a.lph);
 #pragma unroll
@@ -222,18 +268,18 @@ __device__ __forceinline__ void bwd_fused_store_slot(const BwdFusedArgs& a, int 
 }
 
 template <int NV, bool HUB>
-__global__ void __launch_bounds__(BWD_WARPS * 32) attn_bwd_fused_kernel(const BwdFusedArgs a) {
-  extern __shared__ float smem[];
+__global__ void __launch_bounds__(FUSED_WARPS * 32) attn_bwd_fused_kernel(const BwdFusedArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_fused[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   FusedSmem sm;
-  sm.carve(smem + warp * FusedSmem::floats_per_warp(a.HP), a.HP);
+  sm.carve(smem_fused + warp * FusedSmem::bytes_per_warp(a.ring, a.V, a.HP), a.ring, a.V, a.HP, lane);
   LaneGeom<NV> geo;
   geo.init(lane, a.lph, a.V);
   float4 acc[NV];
   float dg_reg;
 
   if (HUB) {
-    const int seg = blockIdx.x * BWD_WARPS + warp;
+    const int seg = blockIdx.x * FUSED_WARPS + warp;
     if (seg >= a.n_hub_seg) return;
     int j;
     int64_t beg, end;
@@ -382,23 +428,33 @@ __global__ void attn_bwd_finish_hub_merge_kernel(const FinishArgs a) {
 // =====================================================================================
 // host side
 // =====================================================================================
+// Ring depth: as many row slots per warp as fit when two 8-warp CTAs share an SM (>= 2, <= 8).
+static int fused_ring_slots(int V, int HP) {
+  const size_t budget = 110 * 1024 / FUSED_WARPS;
+  int r = 8;
+  while (r > 2 && FusedSmem::bytes_per_warp(r, V, HP) > budget) --r;
+  return r;
+}
+
 template <int NV>
-static int launch_fused(const BwdFusedArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)BWD_WARPS * (64 + 4 * 32 * a.HP) * sizeof(float);
+static int launch_fused(BwdFusedArgs a, cudaStream_t st) {
+  a.ring = fused_ring_slots(a.V, a.HP);
+  const size_t smem = (size_t)FUSED_WARPS * FusedSmem::bytes_per_warp(a.ring, a.V, a.HP);
+  GATK_REQUIRE(smem <= 227 * 1024, "row too wide for the gather ring (%zu bytes of shared memory)", smem);
   if (a.n_hub_seg > 0) {
     if (smem > 48 * 1024)
       GATK_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_fused_kernel<NV, true><<<(a.n_hub_seg + BWD_WARPS - 1) / BWD_WARPS, BWD_WARPS * 32, smem, st>>>(a);
+    attn_bwd_fused_kernel<NV, true><<<(a.n_hub_seg + FUSED_WARPS - 1) / FUSED_WARPS, FUSED_WARPS * 32, smem, st>>>(a);
     GATK_CHECK_LAUNCH();
     attn_bwd_fused_hub_merge_kernel<<<a.n_hub, 128, 0, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   if (a.n_src > 0) {
     int grid = 0;
-    if (int rc = persistent_grid(attn_bwd_fused_kernel<NV, false>, BWD_WARPS * 32, smem, &grid)) return rc;
-    const int64_t need = (a.n_src + (int64_t)BWD_WARPS * GRAB - 1) / ((int64_t)BWD_WARPS * GRAB);
+    if (int rc = persistent_grid(attn_bwd_fused_kernel<NV, false>, FUSED_WARPS * 32, smem, &grid)) return rc;
+    const int64_t need = (a.n_src + (int64_t)FUSED_WARPS * GRAB - 1) / ((int64_t)FUSED_WARPS * GRAB);
     if (need < grid) grid = (int)need;
-    attn_bwd_fused_kernel<NV, false><<<grid, BWD_WARPS * 32, smem, st>>>(a);
+    attn_bwd_fused_kernel<NV, false><<<grid, FUSED_WARPS * 32, smem, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   return 0;
