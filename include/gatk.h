@@ -118,26 +118,29 @@ GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* 
  * Autograd of layers.py:141-160, with the reference's dense N x N SpecialSpmmFunction.backward
  * (layers.py:81-90) replaced by O(E*D) CSR work that gathers each feature row ONCE:
  *
- *  prep    per destination row: dhp = dL/dh' = gout * ELU'(out) (out may be NULL if !act_elu),
- *          c[i,h] = dhp_i . hagg_i  (the softmax-backward row term).
- *  fused   per SOURCE row j over the transposed pattern (scatter-free): gathers dhp_i once and
- *          uses it for both  dz_ij = alpha_ij (keep/(1-p) dhp_i.Wh_j - c_i) LeakyReLU'(f_i+g_j)
- *          and  dwh_j = sum_i alpha~_ij dhp_i + dg_j a_dst,  dg_j = sum_i dz_ij.  dz is written
- *          in CSR edge order (edge_dz [E,H]); keep_att is in CSR edge order as well.
+ *  prep    per destination row i, one contiguous RECORD of ldrec = gatk_attn_bwd_record_ld(H, Dp)
+ *          floats:  [ dhp_i = dL/dh'_i = gout_i * ELU'(out_i)  |  (f_i, lse_i, c_i, 0) per head ]
+ *          with c[i,h] = dhp_i . hagg_i (the softmax-backward row term); out may be NULL if
+ *          !act_elu; dhp2 (optional) receives a second copy of dhp (it is also dL/d(skip)).
+ *  fused   per SOURCE row j over the transposed pattern (scatter-free): gathers record i once
+ *          per edge and uses it for both  dz_ij = alpha_ij (keep/(1-p) dhp_i.Wh_j - c_i)
+ *          LeakyReLU'(f_i+g_j)  and  dwh_j = sum_i alpha~_ij dhp_i + dg_j a_dst,  dg_j = sum_i
+ *          dz_ij.  dz is written in CSR edge order (edge_dz [E,H]); keep_att is in CSR edge order.
  *          hub_* describe the TRANSPOSED pattern's long rows (scratch: which = 1).
  *  finish  per destination row: df_i = sum_j dz_ij (segmented sum over CSR rows), then
  *          dwh_i += df_i a_src and the post-projection dropout mask keep_wh (layers.py:37,136).
  *          hub_* describe the CSR pattern's long rows (scratch: which = 2). */
+GATK_API int64_t gatk_attn_bwd_record_ld(int H, int Dp);
 GATK_API int gatk_attn_bwd_prep(int64_t n, int H, int Dp, const float* gout, int64_t ldgo, const float* out,
-                                int64_t ldo, int act_elu, const float* hagg, int64_t ldh, float* dhp,
-                                int64_t lddhp, float* c, void* stream);
+                                int64_t ldo, int act_elu, const float* hagg, int64_t ldh, const float* f,
+                                const float* lse, float* rec, int64_t ldrec, float* dhp2, int64_t lddhp2,
+                                void* stream);
 GATK_API int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int32_t* trow, const int32_t* perm,
-                                 int H, int Dp, const float* wh, int64_t ldw, const float* g, const float* f,
-                                 const float* lse, const float* c, const uint8_t* keep_att, float inv_keep,
-                                 float alpha, const float* dhp, int64_t lddhp, const float* a_dst, float* dwh,
-                                 int64_t lddwh, float* dg, float* edge_dz, int seg_len, const int32_t* hub_rows,
-                                 const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
-                                 int32_t* counter, void* stream);
+                                 int H, int Dp, const float* wh, int64_t ldw, const float* g, const float* rec,
+                                 int64_t ldrec, const uint8_t* keep_att, float inv_keep, float alpha,
+                                 const float* a_dst, float* dwh, int64_t lddwh, float* dg, float* edge_dz,
+                                 int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
+                                 int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream);
 GATK_API int gatk_attn_bwd_finish(int64_t n, const int64_t* rowptr, int H, int Dp, const float* edge_dz,
                                   const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
                                   int64_t lddwh, float* df, int seg_len, const int32_t* hub_rows,

@@ -36,9 +36,11 @@ PROTOTYPES = {
     "gatk_attn_fwd": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, P, P, c_float, c_float,
                               P, c_int64, c_int, P, P, c_int64, P,
                               c_int, P, P, c_int, c_int, P, P, P]),
-    "gatk_attn_bwd_prep": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_int64, c_int, P, c_int64, P, c_int64, P, P]),
-    "gatk_attn_bwd_fused": (c_int, [c_int64, P, P, P, c_int, c_int, P, c_int64, P, P, P, P, P, c_float, c_float,
-                                    P, c_int64, P, P, c_int64, P, P,
+    "gatk_attn_bwd_record_ld": (c_int64, [c_int, c_int]),
+    "gatk_attn_bwd_prep": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_int64, c_int, P, c_int64, P, P,
+                                   P, c_int64, P, c_int64, P]),
+    "gatk_attn_bwd_fused": (c_int, [c_int64, P, P, P, c_int, c_int, P, c_int64, P, P, c_int64, P, c_float, c_float,
+                                    P, P, c_int64, P, P,
                                     c_int, P, P, c_int, c_int, P, P, P]),
     "gatk_attn_bwd_finish": (c_int, [c_int64, P, c_int, c_int, P, P, P, c_float, P, c_int64, P,
                                      c_int, P, P, c_int, c_int, P, P]),

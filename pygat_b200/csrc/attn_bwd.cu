@@ -4,10 +4,12 @@
 // dh'_i along the source rows).  Walking the TRANSPOSED pattern, a warp that owns source row j
 // keeps Wh_j in registers and gathers dh'_i for every destination i it feeds; the same gathered
 // row serves both the dot product (-> dz_ij, the logit gradient) and the aggregation (-> dWh_j).
-// Everything per-destination the softmax backward needs (f_i, lse_i, c_i = dh'_i . h_i) is a
-// per-node scalar per head, gathered as 32-byte sectors.
 //
-//   prep   (rows)    dh' = gout * ELU'(out);  c_i = dh'_i . hagg_i
+// Measured on B200: a random 32-byte access costs about as much DRAM time as ~340 streamed bytes,
+// so everything the softmax backward needs from destination i (f_i, lse_i, c_i = dh'_i . h_i, per
+// head) is packed BEHIND the dh'_i row in one contiguous record; an edge touches DRAM once.
+//
+//   prep   (rows)    rec_i = [ dh'_i = gout * ELU'(out) | (f_i, lse_i, c_i, 0) per head ]
 //   fused  (sources) dz_ij -> edge_dz[CSR edge id]; dWh_j = sum_i alpha~_ij dh'_i + dg_j a_dst;
 //                    dg_j = sum_i dz_ij
 //   finish (rows)    df_i = sum_j dz_ij (CSR segmented sum); dWh_i += df_i a_src; Wh-dropout mask
@@ -24,8 +26,9 @@ namespace gatk {
 template <int NV>
 __global__ void attn_bwd_prep_kernel(int64_t n, int H, int lph, int V, const float* __restrict__ gout, int64_t ldgo,
                                      const float* __restrict__ out, int64_t ldo, int act_elu,
-                                     const float* __restrict__ hagg, int64_t ldh, float* __restrict__ dhp,
-                                     int64_t lddhp, float* __restrict__ c) {
+                                     const float* __restrict__ hagg, int64_t ldh, const float* __restrict__ f,
+                                     const float* __restrict__ lse, float* __restrict__ rec, int64_t ldrec,
+                                     float* __restrict__ dhp2, int64_t lddhp2) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -44,7 +47,8 @@ __global__ void attn_bwd_prep_kernel(int64_t n, int H, int lph, int V, const flo
         go.z *= o.z > 0.f ? 1.f : o.z + 1.f;
         go.w *= o.w > 0.f ? 1.f : o.w + 1.f;
       }
-      stg4(dhp + row * lddhp + off, go);
+      stg4(rec + row * ldrec + off, go);
+      if (dhp2) stg4(dhp2 + row * lddhp2 + off, go);
       part[v] = dot4(go, ldg4_stream(hagg + row * ldh + off));
     }
   }
@@ -52,7 +56,10 @@ __global__ void attn_bwd_prep_kernel(int64_t n, int H, int lph, int V, const flo
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int slot = lane + 32 * v;
-    if (slot < V && slot % lph == 0) c[row * H + slot / lph] = part[v];
+    if (slot < V && slot % lph == 0) {
+      const int h = slot / lph;
+      stg4(rec + row * ldrec + V * 4 + h * 4, make_float4(__ldg(f + row * H + h), __ldg(lse + row * H + h), part[v], 0.f));
+    }
   }
 }
 
@@ -64,17 +71,14 @@ struct BwdFusedArgs {
   const int64_t* tptr;
   const int32_t* trow;
   const int32_t* perm;
-  int H, Dp, lph, V, HP;
+  int H, Dp, lph, V;
   const float* wh;
   int64_t ldw;
   const float* g;
-  const float* f;
-  const float* lse;
-  const float* c;
+  const float* rec;  // [n_dst, ldrec]: dh'_i row followed by (f, lse, c, 0) per head
+  int64_t ldrec;
   const uint8_t* keep;
   float inv_keep, alpha;
-  const float* dhp;
-  int64_t lddhp;
   const float* a_dst;
   float* dwh;
   int64_t lddwh;
@@ -86,179 +90,86 @@ struct BwdFusedArgs {
   int n_hub, n_hub_seg;
   float* scratch;
   int32_t* counter;
-  int ring;  // slots of the per-warp row ring
 };
 
-constexpr int FUSED_WARPS = 8;
+constexpr int FUSED_WARPS = 4;
 
-// ---- bulk-async row gather ---------------------------------------------------------------------
-// The kernel is bound by bytes in flight (Little's law: ~1.5-2 us loaded DRAM latency x 6.5 TB/s is
-// ~70 KB per SM).  Register-staged LDG.128 gathers top out at 64 KB per SM; instead every gathered
-// dh'_i row (H*Dp*4 bytes, contiguous) is fetched by ONE cp.async.bulk (the TMA unit's 1-D copy)
-// into a per-warp ring of shared-memory slots, completion signalled on an mbarrier per slot.  Lane 0
-// issues, the whole warp consumes with conflict-free LDS.128.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1u << 28)) __trap();  // a protocol bug traps instead of hanging the GPU
-  }
-}
-__device__ __forceinline__ void bulk_row_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-struct FusedSmem {
-  uint8_t* ring;   // R slots of row_bytes
-  uint32_t bars;   // R mbarriers (shared-space address)
-  int* row_s;
-  int* perm_s;
-  float* at_s;  // post-dropout attention (aggregation weight)
-  float* A_s;   // alpha * slope * keep/(1-p)
-  float* B_s;   // alpha * slope * c_i
-  float* dz_s;
-  int R;
-  uint32_t row_bytes;
-  uint32_t issued, consumed;  // rows issued / consumed by this warp since kernel start (warp-uniform)
-  __host__ __device__ static size_t bytes_per_warp(int R, int V, int HP) {
-    size_t b = (size_t)R * V * 16 + (size_t)R * 8 + 256 + (size_t)4 * 32 * HP * 4;
-    return (b + 127) & ~(size_t)127;
-  }
-  __device__ __forceinline__ void carve(uint8_t* base, int R_, int V, int HP, int lane) {
-    R = R_;
-    row_bytes = (uint32_t)V * 16u;
-    ring = base;
-    uint8_t* p = base + (size_t)R * row_bytes;
-    bars = smem_addr(p);
-    p += (size_t)R * 8;
-    row_s = reinterpret_cast<int*>(p);
-    perm_s = row_s + 32;
-    at_s = reinterpret_cast<float*>(p + 256);
-    A_s = at_s + 32 * HP;
-    B_s = A_s + 32 * HP;
-    dz_s = B_s + 32 * HP;
-    issued = consumed = 0;
-    if (lane == 0) {
-      for (int k = 0; k < R; ++k) mbar_init(bars + 8u * k, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+// One gathered record: its dh' slots feed the aggregation and the dot product, its tail the softmax.
+template <int NV>
+__device__ __forceinline__ void fused_edge(const BwdFusedArgs& a, const LaneGeom<NV>& geo, const float4 (&w)[NV],
+                                           const float4 (&tl)[NV], const float4 (&wj)[NV], const float (&gj)[NV],
+                                           int pe, float4 (&acc)[NV], float (&dgacc)[NV]) {
+  float pr[NV], coef[NV], kvv[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    pr[v] = coef[v] = kvv[v] = 0.f;
+    if (geo.act[v]) {
+      const float z = tl[v].x + gj[v];
+      const float s = z > 0.f ? z : a.alpha * z;
+      const float al = expf(s - tl[v].y);
+      const float kv = a.keep ? (a.keep[(int64_t)pe * a.H + geo.hv[v]] ? a.inv_keep : 0.f) : 1.f;
+      fma4(acc[v], al * kv, w[v]);
+      pr[v] = dot4(w[v], wj[v]);
+      coef[v] = al * (z > 0.f ? 1.f : a.alpha);
+      kvv[v] = kv;
     }
-    __syncwarp();
   }
-  // lane 0 only
-  __device__ __forceinline__ void issue(const float* src) {
-    const uint32_t slot = issued % (uint32_t)R;
-    mbar_expect_tx(bars + 8u * slot, row_bytes);
-    bulk_row_copy(smem_addr(ring + (size_t)slot * row_bytes), src, row_bytes, bars + 8u * slot);
+  head_reduce<NV>(pr, a.lph);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float dz = coef[v] * fmaf(kvv[v], pr[v], -tl[v].z);
+    dgacc[v] += dz;
+    if (geo.leader[v]) a.edge_dz[(int64_t)pe * a.H + geo.hv[v]] = dz;
   }
-};
+}
 
 template <int NV>
 __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, int64_t beg, int64_t end, int lane,
-                                                  const LaneGeom<NV>& geo, float4 (&acc)[NV], float& dg_reg,
-                                                  FusedSmem& sm) {
-  const int H = a.H, HP = a.HP;
+                                                  const LaneGeom<NV>& geo, float4 (&acc)[NV], float (&dgacc)[NV]) {
+  constexpr int U = NV >= 4 ? 1 : 4 / NV;
   float4 wj[NV];
+  float gj[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dgacc[v] = 0.f;
     wj[v] = geo.act[v] ? ldg4(a.wh + (int64_t)j * a.ldw + (lane + 32 * v) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gj[v] = geo.act[v] ? __ldg(a.g + (int64_t)j * a.H + geo.hv[v]) : 0.f;
   }
-  const float g_reg = lane < H ? __ldg(a.g + (int64_t)j * H + lane) : 0.f;
-  dg_reg = 0.f;
-
+  const int tail0 = a.V * 4;
   for (int64_t base = beg; base < end; base += 32) {
     const int cnt = (end - base) < 32 ? (int)(end - base) : 32;
     const bool valid = lane < cnt;
-    const int64_t e = base + lane;
-    const int i = valid ? __ldg(a.trow + e) : 0;
-    const int pe = valid ? __ldg(a.perm + e) : 0;
-    sm.row_s[lane] = i;
-    sm.perm_s[lane] = pe;
-    __syncwarp();
-    // prime the ring with the first rows of this chunk; the weight computation below overlaps them
-    int queued = 0;
-    for (; queued < cnt && queued < sm.R; ++queued) {
-      if (lane == 0) sm.issue(a.dhp + (int64_t)sm.row_s[queued] * a.lddhp);
-      ++sm.issued;
-    }
-    const float* fi = a.f + (int64_t)i * H;
-    const float* li = a.lse + (int64_t)i * H;
-    const float* ci = a.c + (int64_t)i * H;
-    const uint8_t* kp = a.keep ? a.keep + (int64_t)pe * H : nullptr;
-    for (int h = 0; h < H; ++h) {
-      const float gj = __shfl_sync(FULL, g_reg, h);
-      float at = 0.f, A = 0.f, B = 0.f;
-      if (valid) {
-        const float z = __ldg(fi + h) + gj;
-        const float s = z > 0.f ? z : a.alpha * z;
-        const float al = expf(s - __ldg(li + h));
-        const float slope = z > 0.f ? 1.f : a.alpha;
-        const float kv = kp ? (kp[h] ? a.inv_keep : 0.f) : 1.f;
-        at = al * kv;
-        A = al * slope * kv;
-        B = al * slope * __ldg(ci + h);
-      }
-      sm.at_s[lane * HP + h] = at;
-      sm.A_s[lane * HP + h] = A;
-      sm.B_s[lane * HP + h] = B;
-    }
-    __syncwarp();
-    for (int t = 0; t < cnt; ++t) {
-      const uint32_t slot = sm.consumed % (uint32_t)sm.R;
-      mbar_wait(sm.bars + 8u * slot, (sm.consumed / (uint32_t)sm.R) & 1u);
-      const float4* rowp = reinterpret_cast<const float4*>(sm.ring + (size_t)slot * sm.row_bytes) + lane;
-      float pr[NV];
+    const int i_reg = valid ? __ldg(a.trow + base + lane) : 0;
+    const int pe_reg = valid ? __ldg(a.perm + base + lane) : 0;
+    int t = 0;
+    for (; t + U <= cnt; t += U) {
+      float4 w[U][NV], tl[U][NV];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        pr[v] = 0.f;
-        if (geo.act[v]) {
-          const float4 w = rowp[32 * v];
-          fma4(acc[v], sm.at_s[t * HP + geo.hv[v]], w);
-          pr[v] = dot4(w, wj[v]);
-        }
+      for (int u = 0; u < U; ++u) {
+        const float* rp = a.rec + (int64_t)__shfl_sync(FULL, i_reg, t + u) * a.ldrec;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          if (geo.act[v]) {
+            w[u][v] = ldg4(rp + (lane + 32 * v) * 4);
+            tl[u][v] = ldg4(rp + tail0 + geo.hv[v] * 4);
+          }
       }
-      __syncwarp();  // every lane has read the slot: it can be refilled
-      ++sm.consumed;
-      if (queued < cnt) {
-        if (lane == 0) sm.issue(a.dhp + (int64_t)sm.row_s[queued] * a.lddhp);
-        ++sm.issued;
-        ++queued;
-      }
-      head_reduce<NV>(pr, a.lph);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        fused_edge<NV>(a, geo, w[u], tl[u], wj, gj, __shfl_sync(FULL, pe_reg, t + u), acc, dgacc);
+    }
+    for (; t < cnt; ++t) {
+      float4 w[NV], tl[NV];
+      const float* rp = a.rec + (int64_t)__shfl_sync(FULL, i_reg, t) * a.ldrec;
 #pragma unroll
       for (int v = 0; v < NV; ++v)
-        if (geo.leader[v]) {
-          const int k = t * HP + geo.hv[v];
-          sm.dz_s[k] = fmaf(sm.A_s[k], pr[v], -sm.B_s[k]);
+        if (geo.act[v]) {
+          w[v] = ldg4(rp + (lane + 32 * v) * 4);
+          tl[v] = ldg4(rp + tail0 + geo.hv[v] * 4);
         }
+      fused_edge<NV>(a, geo, w, tl, wj, gj, __shfl_sync(FULL, pe_reg, t), acc, dgacc);
     }
-    __syncwarp();
-    // dz back to CSR edge order (each edge's H values are one contiguous sector), dg accumulation
-    for (int idx = lane; idx < cnt * H; idx += 32) {
-      const int tt = idx / H, h = idx - tt * H;
-      a.edge_dz[(int64_t)sm.perm_s[tt] * H + h] = sm.dz_s[tt * HP + h];
-    }
-    for (int h = 0; h < H; ++h) {
-      const float s = warp_sum(valid ? sm.dz_s[lane * HP + h] : 0.f);
-      if (lane == h) dg_reg += s;
-    }
-    __syncwarp();
   }
 }
 
@@ -268,15 +179,12 @@ __device__ __forceinline__ void bwd_fused_store_slot(const BwdFusedArgs& a, int 
 }
 
 template <int NV, bool HUB>
-__global__ void __launch_bounds__(FUSED_WARPS * 32) attn_bwd_fused_kernel(const BwdFusedArgs a) {
-  extern __shared__ __align__(128) uint8_t smem_fused[];
+__global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 4 : 1) attn_bwd_fused_kernel(const BwdFusedArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  FusedSmem sm;
-  sm.carve(smem_fused + warp * FusedSmem::bytes_per_warp(a.ring, a.V, a.HP), a.ring, a.V, a.HP, lane);
   LaneGeom<NV> geo;
   geo.init(lane, a.lph, a.V);
   float4 acc[NV];
-  float dg_reg;
+  float dgacc[NV];
 
   if (HUB) {
     const int seg = blockIdx.x * FUSED_WARPS + warp;
@@ -284,12 +192,13 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32) attn_bwd_fused_kernel(const 
     int j;
     int64_t beg, end;
     hub_locate(seg, a.hub_rows, a.hub_seg_ptr, a.n_hub, a.tptr, a.seg_len, j, beg, end);
-    bwd_fused_segment<NV>(a, j, beg, end, lane, geo, acc, dg_reg, sm);
+    bwd_fused_segment<NV>(a, j, beg, end, lane, geo, acc, dgacc);
     float* sc = a.scratch + (int64_t)seg * src_scratch_stride(a.H, a.V);
 #pragma unroll
-    for (int v = 0; v < NV; ++v)
+    for (int v = 0; v < NV; ++v) {
       if (geo.act[v]) stg4(sc + (lane + 32 * v) * 4, acc[v]);
-    if (lane < a.H) sc[a.V * 4 + lane] = dg_reg;
+      if (geo.leader[v]) sc[a.V * 4 + geo.hv[v]] = dgacc[v];
+    }
     return;
   }
 
@@ -300,13 +209,12 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32) attn_bwd_fused_kernel(const 
     for (int j = cur; j < rend; ++j) {
       const int64_t beg = a.tptr[j], end = a.tptr[j + 1];
       if (end - beg > a.seg_len) continue;
-      bwd_fused_segment<NV>(a, j, beg, end, lane, geo, acc, dg_reg, sm);
+      bwd_fused_segment<NV>(a, j, beg, end, lane, geo, acc, dgacc);
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        const float dgv = __shfl_sync(FULL, dg_reg, geo.hv[v]);
-        if (geo.act[v]) bwd_fused_store_slot(a, j, lane + 32 * v, acc[v], dgv);
+        if (geo.act[v]) bwd_fused_store_slot(a, j, lane + 32 * v, acc[v], dgacc[v]);
+        if (geo.leader[v]) a.dg[(int64_t)j * a.H + geo.hv[v]] = dgacc[v];
       }
-      if (lane < a.H) a.dg[(int64_t)j * a.H + lane] = dg_reg;
     }
     cur = nxt;
   }
@@ -428,33 +336,20 @@ __global__ void attn_bwd_finish_hub_merge_kernel(const FinishArgs a) {
 // =====================================================================================
 // host side
 // =====================================================================================
-// Ring depth: as many row slots per warp as fit when two 8-warp CTAs share an SM (>= 2, <= 8).
-static int fused_ring_slots(int V, int HP) {
-  const size_t budget = 110 * 1024 / FUSED_WARPS;
-  int r = 8;
-  while (r > 2 && FusedSmem::bytes_per_warp(r, V, HP) > budget) --r;
-  return r;
-}
-
 template <int NV>
-static int launch_fused(BwdFusedArgs a, cudaStream_t st) {
-  a.ring = fused_ring_slots(a.V, a.HP);
-  const size_t smem = (size_t)FUSED_WARPS * FusedSmem::bytes_per_warp(a.ring, a.V, a.HP);
-  GATK_REQUIRE(smem <= 227 * 1024, "row too wide for the gather ring (%zu bytes of shared memory)", smem);
+static int launch_fused(const BwdFusedArgs& a, cudaStream_t st) {
   if (a.n_hub_seg > 0) {
-    if (smem > 48 * 1024)
-      GATK_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_fused_kernel<NV, true><<<(a.n_hub_seg + FUSED_WARPS - 1) / FUSED_WARPS, FUSED_WARPS * 32, smem, st>>>(a);
+    attn_bwd_fused_kernel<NV, true><<<(a.n_hub_seg + FUSED_WARPS - 1) / FUSED_WARPS, FUSED_WARPS * 32, 0, st>>>(a);
     GATK_CHECK_LAUNCH();
     attn_bwd_fused_hub_merge_kernel<<<a.n_hub, 128, 0, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   if (a.n_src > 0) {
     int grid = 0;
-    if (int rc = persistent_grid(attn_bwd_fused_kernel<NV, false>, FUSED_WARPS * 32, smem, &grid)) return rc;
+    if (int rc = persistent_grid(attn_bwd_fused_kernel<NV, false>, FUSED_WARPS * 32, 0, &grid)) return rc;
     const int64_t need = (a.n_src + (int64_t)FUSED_WARPS * GRAB - 1) / ((int64_t)FUSED_WARPS * GRAB);
     if (need < grid) grid = (int)need;
-    attn_bwd_fused_kernel<NV, false><<<grid, FUSED_WARPS * 32, smem, st>>>(a);
+    attn_bwd_fused_kernel<NV, false><<<grid, FUSED_WARPS * 32, 0, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   return 0;
@@ -487,44 +382,47 @@ extern "C" size_t gatk_hub_scratch_floats(int which, int H, int Dp, int n_hub_se
   return (size_t)n_hub_seg * H;
 }
 
+extern "C" int64_t gatk_attn_bwd_record_ld(int H, int Dp) { return (int64_t)H * Dp + 4 * H; }
+
 extern "C" int gatk_attn_bwd_prep(int64_t n, int H, int Dp, const float* gout, int64_t ldgo, const float* out,
-                                  int64_t ldo, int act_elu, const float* hagg, int64_t ldh, float* dhp, int64_t lddhp,
-                                  float* c, void* stream) {
+                                  int64_t ldo, int act_elu, const float* hagg, int64_t ldh, const float* f,
+                                  const float* lse, float* rec, int64_t ldrec, float* dhp2, int64_t lddhp2,
+                                  void* stream) {
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
-  GATK_REQUIRE(gout && hagg && dhp && c, "null pointer argument");
+  GATK_REQUIRE(gout && hagg && f && lse && rec, "null pointer argument");
   GATK_REQUIRE(!act_elu || out, "out is required when act_elu is set");
-  GATK_REQUIRE(ldgo % 4 == 0 && ldh % 4 == 0 && lddhp % 4 == 0 && (!act_elu || ldo % 4 == 0),
-               "leading dims must be multiples of 4 floats");
+  GATK_REQUIRE(ldgo % 4 == 0 && ldh % 4 == 0 && ldrec % 4 == 0 && ldrec >= (int64_t)H * Dp + 4 * H &&
+                   (!act_elu || ldo % 4 == 0) && (!dhp2 || lddhp2 % 4 == 0),
+               "leading dims must be multiples of 4 floats (record: >= H*Dp + 4*H)");
   if (n == 0) return 0;
   const int lph = Dp / 4, V = H * lph;
   const unsigned grid = (unsigned)((n + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
   NV_DISPATCH(nv, (attn_bwd_prep_kernel<NV><<<grid, 256, 0, st>>>(n, H, lph, V, gout, ldgo, out, ldo, act_elu, hagg,
-                                                                  ldh, dhp, lddhp, c)));
+                                                                  ldh, f, lse, rec, ldrec, dhp2, lddhp2)));
   GATK_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int32_t* trow, const int32_t* perm, int H,
-                                   int Dp, const float* wh, int64_t ldw, const float* g, const float* f,
-                                   const float* lse, const float* c, const uint8_t* keep_att, float inv_keep,
-                                   float alpha, const float* dhp, int64_t lddhp, const float* a_dst, float* dwh,
-                                   int64_t lddwh, float* dg, float* edge_dz, int seg_len, const int32_t* hub_rows,
-                                   const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
-                                   int32_t* counter, void* stream) {
+                                   int Dp, const float* wh, int64_t ldw, const float* g, const float* rec,
+                                   int64_t ldrec, const uint8_t* keep_att, float inv_keep, float alpha,
+                                   const float* a_dst, float* dwh, int64_t lddwh, float* dg, float* edge_dz,
+                                   int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
+                                   int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream) {
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
   if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
   GATK_REQUIRE(n_src < (1LL << 31), "n_src too large for one shard");
-  GATK_REQUIRE(ldw % 4 == 0 && lddhp % 4 == 0 && lddwh % 4 == 0, "leading dims must be multiples of 4 floats");
-  GATK_REQUIRE(tptr && wh && g && f && lse && c && dhp && a_dst && dwh && dg && counter, "null pointer argument");
+  GATK_REQUIRE(ldw % 4 == 0 && ldrec % 4 == 0 && lddwh % 4 == 0, "leading dims must be multiples of 4 floats");
+  GATK_REQUIRE(tptr && wh && g && rec && a_dst && dwh && dg && edge_dz && counter, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
   BwdFusedArgs a;
   a.n_src = n_src; a.tptr = tptr; a.trow = trow; a.perm = perm; a.H = H; a.Dp = Dp; a.lph = Dp / 4;
-  a.V = H * (Dp / 4); a.HP = H | 1;
-  a.wh = wh; a.ldw = ldw; a.g = g; a.f = f; a.lse = lse; a.c = c; a.keep = keep_att; a.inv_keep = inv_keep;
-  a.alpha = alpha; a.dhp = dhp; a.lddhp = lddhp; a.a_dst = a_dst; a.dwh = dwh; a.lddwh = lddwh; a.dg = dg;
+  a.V = H * (Dp / 4);
+  a.wh = wh; a.ldw = ldw; a.g = g; a.rec = rec; a.ldrec = ldrec; a.keep = keep_att; a.inv_keep = inv_keep;
+  a.alpha = alpha; a.a_dst = a_dst; a.dwh = dwh; a.lddwh = lddwh; a.dg = dg;
   a.edge_dz = edge_dz; a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub;
   a.n_hub_seg = n_hub_seg; a.scratch = hub_scratch; a.counter = counter;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));

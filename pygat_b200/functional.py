@@ -141,28 +141,26 @@ class GatLayerFunction(torch.autograd.Function):
         gout = gout.contiguous()
         tptr, trow, perm, thubs = graph.transpose()
 
-        # dZ = [dWh | dSkip]; with a skip projection dL/dh' IS dSkip, so K3 writes it in place.
+        # dZ = [dWh | dSkip]; with a skip projection dL/dh' IS dSkip, so prep writes it there as well.
         dz_rows = torch.empty(n, M_out, dtype=torch.float32, device=dev)
-        if has_skip:
-            dhp_ptr, lddhp, dhp_keepalive = dz_rows.data_ptr() + 4 * HD, M_out, None
-        else:
-            dhp_keepalive = torch.empty(n, HD, dtype=torch.float32, device=dev)
-            dhp_ptr, lddhp = dhp_keepalive.data_ptr(), HD
+        ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
+        rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
         df = torch.empty(n, H, dtype=torch.float32, device=dev)
         dg = torch.empty(n, H, dtype=torch.float32, device=dev)
-        c = torch.empty(n, H, dtype=torch.float32, device=dev)
         edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
 
-        # ---- K3 prep: dh' = gout * ELU'(out), c_i = dh'_i . hagg_i ----------------------------
+        # ---- K3 prep: per-destination records [dh' | f, lse, c] -------------------------------------
         _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
-                  int(act_elu), hagg.data_ptr(), HD, dhp_ptr, lddhp, c.data_ptr(), st)
+                  int(act_elu), hagg.data_ptr(), HD, f.data_ptr(), lse.data_ptr(), rec.data_ptr(), ldrec,
+                  dz_rows.data_ptr() + 4 * HD if has_skip else None, M_out, st)
 
-        # ---- K4 fused source pass over the transposed pattern (one gather of dh' per edge) ------
+        # ---- K4 fused source pass over the transposed pattern (one gather of the record per edge) -----
         scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, z.data_ptr(), M_out,
-                  g.data_ptr(), f.data_ptr(), lse.data_ptr(), c.data_ptr(), _ptr(masks.keep_att), inv_keep, alpha,
-                  dhp_ptr, lddhp, a_dst.data_ptr(), dz_rows.data_ptr(), M_out, dg.data_ptr(), edge_dz.data_ptr(),
+                  g.data_ptr(), rec.data_ptr(), ldrec, _ptr(masks.keep_att), inv_keep, alpha,
+                  a_dst.data_ptr(), dz_rows.data_ptr(), M_out, dg.data_ptr(), edge_dz.data_ptr(),
                   *thubs.args(scratch_t), graph.counter.data_ptr(), st)
+        del rec
 
         # ---- finish: df = segmented sum of dz, dWh += df a_src, Wh-dropout mask ------------------
         hubs = graph.hubs
@@ -205,7 +203,6 @@ class GatLayerFunction(torch.autograd.Function):
                     _lib.call("gatk_mask_scale", dxh.data_ptr(), f_in, masks.keep_in[h].data_ptr(), inv_keep,
                               dxh.data_ptr(), f_in, n, f_in, st)
                     dx.add_(dxh)
-        del dhp_keepalive
         return dx, dw_ext, da_src, da_dst, None, None, None, None, None, None, None, None
 
 

@@ -151,14 +151,11 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         tptr, trow, perm, thubs = graph.transpose()
 
         dz_rows = torch.empty(n, M_out, dtype=torch.float32, device=dev)   # [dWh | dSkip] of the local rows
-        if has_skip:
-            dhp_keep, dhp_ptr, lddhp = None, dz_rows.data_ptr() + 4 * HD, M_out
-        else:
-            dhp_keep = torch.empty(n, HD, dtype=torch.float32, device=dev)
-            dhp_ptr, lddhp = dhp_keep.data_ptr(), HD
-        c = torch.empty(n, H, dtype=torch.float32, device=dev)
+        ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
+        rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
         _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
-                  int(act_elu), hagg.data_ptr(), HD, dhp_ptr, lddhp, c.data_ptr(), st)
+                  int(act_elu), hagg.data_ptr(), HD, f.data_ptr(), lse.data_ptr(), rec.data_ptr(), ldrec,
+                  dz_rows.data_ptr() + 4 * HD if has_skip else None, M_out, st)
 
         # partial dWh / dg for EVERY source from this rank's destination rows
         dwh_part = torch.empty(N, HD, dtype=torch.float32, device=dev)
@@ -166,9 +163,10 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
         scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, wh_full.data_ptr(), HD,
-                  g_full.data_ptr(), f.data_ptr(), lse.data_ptr(), c.data_ptr(), None, 1.0, alpha, dhp_ptr, lddhp,
+                  g_full.data_ptr(), rec.data_ptr(), ldrec, None, 1.0, alpha,
                   a_dst.data_ptr(), dwh_part.data_ptr(), HD, dg_part.data_ptr(), edge_dz.data_ptr(),
                   *thubs.args(scratch_t), graph.counter.data_ptr(), st)
+        del rec
         dwh_loc = reduce_rows(dwh_part, plan)
         dg_loc = reduce_rows(dg_part, plan)
         # local rows: df, dst-side term; written into the dZ buffer the projection backward reads
@@ -196,7 +194,6 @@ class ShardedGatLayerFunction(torch.autograd.Function):
             _gemm(0, 1, n, f_in, M_out, dz_rows, M_out, w_ext, M_out, dx, f_in)
         if plan.world > 1:
             allreduce_([dw_ext, da_src, da_dst], plan)
-        del dhp_keep
         return dx, dw_ext, da_src, da_dst, None, None, None, None, None, None, None
 
 
