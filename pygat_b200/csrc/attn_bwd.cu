@@ -94,82 +94,169 @@ struct BwdFusedArgs {
 
 constexpr int FUSED_WARPS = 4;
 
-// One gathered record: its dh' slots feed the aggregation and the dot product, its tail the softmax.
-template <int NV>
-__device__ __forceinline__ void fused_edge(const BwdFusedArgs& a, const LaneGeom<NV>& geo, const float4 (&w)[NV],
-                                           const float4 (&tl)[NV], const float4 (&wj)[NV], const float (&gj)[NV],
-                                           int pe, float4 (&acc)[NV], float (&dgacc)[NV]) {
-  float pr[NV], coef[NV], kvv[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    pr[v] = coef[v] = kvv[v] = 0.f;
-    if (geo.act[v]) {
-      const float z = tl[v].x + gj[v];
-      const float s = z > 0.f ? z : a.alpha * z;
-      const float al = expf(s - tl[v].y);
-      const float kv = a.keep ? (a.keep[(int64_t)pe * a.H + geo.hv[v]] ? a.inv_keep : 0.f) : 1.f;
-      fma4(acc[v], al * kv, w[v]);
-      pr[v] = dot4(w[v], wj[v]);
-      coef[v] = al * (z > 0.f ? 1.f : a.alpha);
-      kvv[v] = kv;
-    }
+// Per-edge softmax terms are staged in shared memory in the order the consuming lanes want them:
+// position (g, v) = g*NV + v holds the value for the head of slot  g*lph + 32*v, where g = lane / lph
+// is the lane group (one group when a head is at least a warp wide).  A lane then reads the NV values
+// of its own slots with one vector LDS.
+struct FusedLayout {
+  int G, WS;        // lane groups per 32 slots, floats per edge in the staging arrays
+  int my_base;      // g * NV for this lane
+  bool writer;      // first lane of its group: stores the group's dz values
+  template <int NV>
+  __device__ __forceinline__ void init(int lane, int lph) {
+    G = lph < 32 ? 32 / lph : 1;
+    WS = G * NV + 4;  // +4: keeps 16-byte alignment and spreads the per-edge rows over banks
+    const int g = lph < 32 ? lane / lph : 0;
+    my_base = g * NV;
+    writer = lph < 32 ? (lane % lph == 0) : (lane == 0);
   }
-  head_reduce<NV>(pr, a.lph);
+  __host__ __device__ static int floats_per_edge(int lph, int NV) { return (lph < 32 ? 32 / lph : 1) * NV + 4; }
+};
+
+template <int NV>
+__device__ __forceinline__ void lds_vec(const float* p, float (&o)[NV]) {
+  if constexpr (NV % 4 == 0) {
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    const float dz = coef[v] * fmaf(kvv[v], pr[v], -tl[v].z);
-    dgacc[v] += dz;
-    if (geo.leader[v]) a.edge_dz[(int64_t)pe * a.H + geo.hv[v]] = dz;
+    for (int k = 0; k < NV / 4; ++k) {
+      const float4 t = reinterpret_cast<const float4*>(p)[k];
+      o[4 * k] = t.x; o[4 * k + 1] = t.y; o[4 * k + 2] = t.z; o[4 * k + 3] = t.w;
+    }
+  } else if constexpr (NV == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    o[0] = t.x; o[1] = t.y;
+  } else {
+    o[0] = p[0];
+  }
+}
+template <int NV>
+__device__ __forceinline__ void sts_vec(float* p, const float (&o)[NV]) {
+  if constexpr (NV % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k)
+      reinterpret_cast<float4*>(p)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+  } else if constexpr (NV == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1]);
+  } else {
+    p[0] = o[0];
   }
 }
 
-template <int NV>
+// One gathered dh' row: aggregation with the staged attention weights, dot product with the
+// resident Wh_j, head reduction, dz = A * (dh'.Wh_j) - B for this lane's NV slots.
+template <int NV, bool FULLROW>
+__device__ __forceinline__ void fused_edge(const LaneGeom<NV>& geo, int lph, const float4 (&w)[NV],
+                                           const float4 (&wj)[NV], const float* at_p, const float* A_p,
+                                           const float* B_p, float* dz_p, bool writer, float4 (&acc)[NV],
+                                           float (&dgacc)[NV]) {
+  float at[NV], pr[NV], A[NV], B[NV];
+  lds_vec<NV>(at_p, at);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    if (FULLROW || geo.act[v]) {
+      fma4(acc[v], at[v], w[v]);
+      pr[v] = dot4(w[v], wj[v]);
+    } else {
+      pr[v] = 0.f;
+    }
+  }
+  head_reduce<NV>(pr, lph);
+  lds_vec<NV>(A_p, A);
+  lds_vec<NV>(B_p, B);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    pr[v] = fmaf(A[v], pr[v], -B[v]);
+    dgacc[v] += pr[v];
+  }
+  if (writer) sts_vec<NV>(dz_p, pr);
+}
+
+template <int NV, bool FULLROW>
 __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, int64_t beg, int64_t end, int lane,
-                                                  const LaneGeom<NV>& geo, float4 (&acc)[NV], float (&dgacc)[NV]) {
-  constexpr int U = NV >= 4 ? 1 : 4 / NV;
+                                                  const LaneGeom<NV>& geo, const FusedLayout& lay, float4 (&acc)[NV],
+                                                  float (&dgacc)[NV], int* row_s, int* perm_s, float* at_s, float* A_s,
+                                                  float* B_s, float* dz_s) {
+  constexpr int U = NV >= 8 ? 1 : (NV == 4 ? 2 : 4);
+  const int H = a.H, WS = lay.WS, lph = a.lph;
   float4 wj[NV];
-  float gj[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     dgacc[v] = 0.f;
-    wj[v] = geo.act[v] ? ldg4(a.wh + (int64_t)j * a.ldw + (lane + 32 * v) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    gj[v] = geo.act[v] ? __ldg(a.g + (int64_t)j * a.H + geo.hv[v]) : 0.f;
+    wj[v] = (FULLROW || geo.act[v]) ? ldg4(a.wh + (int64_t)j * a.ldw + (lane + 32 * v) * 4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  const float g_reg = lane < H ? __ldg(a.g + (int64_t)j * H + lane) : 0.f;
   const int tail0 = a.V * 4;
+  const int q = lph >= 32 ? lph >> 5 : 1;
+
   for (int64_t base = beg; base < end; base += 32) {
     const int cnt = (end - base) < 32 ? (int)(end - base) : 32;
     const bool valid = lane < cnt;
-    const int i_reg = valid ? __ldg(a.trow + base + lane) : 0;
-    const int pe_reg = valid ? __ldg(a.perm + base + lane) : 0;
+    const int i = valid ? __ldg(a.trow + base + lane) : 0;
+    const int pe = valid ? __ldg(a.perm + base + lane) : 0;
+    row_s[lane] = i;
+    perm_s[lane] = pe;
+    // ---- lanes = edges: softmax terms of every head, stored at the positions the slot lanes read
+    const float* tl = a.rec + (int64_t)i * a.ldrec + tail0;
+    const uint8_t* kp = a.keep ? a.keep + (int64_t)pe * H : nullptr;
+    for (int h = 0; h < H; ++h) {
+      const float gj = __shfl_sync(FULL, g_reg, h);
+      float at = 0.f, A = 0.f, B = 0.f;
+      if (valid) {
+        const float4 t4 = ldg4(tl + 4 * h);  // (f_i, lse_i, c_i, 0)
+        const float z = t4.x + gj;
+        const float s = z > 0.f ? z : a.alpha * z;
+        const float al = expf(s - t4.y);
+        const float slope = z > 0.f ? 1.f : a.alpha;
+        const float kv = kp ? (kp[h] ? a.inv_keep : 0.f) : 1.f;
+        at = al * kv;
+        A = al * slope * kv;
+        B = al * slope * t4.z;
+      }
+      const int pos = lph < 32 ? (h % lay.G) * NV + h / lay.G : h * q;
+      for (int k = 0; k < q; ++k) {
+        at_s[lane * WS + pos + k] = at;
+        A_s[lane * WS + pos + k] = A;
+        B_s[lane * WS + pos + k] = B;
+      }
+    }
+    __syncwarp();
+    // ---- lanes = slots: gather each destination's dh' row once
+    const float* dl = a.rec + lane * 4;
+    const int lo = lay.my_base;
     int t = 0;
     for (; t + U <= cnt; t += U) {
-      float4 w[U][NV], tl[U][NV];
+      float4 w[U][NV];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const float* rp = a.rec + (int64_t)__shfl_sync(FULL, i_reg, t + u) * a.ldrec;
+        const float* di = dl + (int64_t)row_s[t + u] * a.ldrec;
 #pragma unroll
         for (int v = 0; v < NV; ++v)
-          if (geo.act[v]) {
-            w[u][v] = ldg4(rp + (lane + 32 * v) * 4);
-            tl[u][v] = ldg4(rp + tail0 + geo.hv[v] * 4);
-          }
+          if (FULLROW || geo.act[v]) w[u][v] = ldg4(di + v * 128);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        fused_edge<NV>(a, geo, w[u], tl[u], wj, gj, __shfl_sync(FULL, pe_reg, t + u), acc, dgacc);
+      for (int u = 0; u < U; ++u) {
+        const int o = (t + u) * WS + lo;
+        fused_edge<NV, FULLROW>(geo, lph, w[u], wj, at_s + o, A_s + o, B_s + o, dz_s + o, lay.writer, acc, dgacc);
+      }
     }
     for (; t < cnt; ++t) {
-      float4 w[NV], tl[NV];
-      const float* rp = a.rec + (int64_t)__shfl_sync(FULL, i_reg, t) * a.ldrec;
+      float4 w[NV];
+      const float* di = dl + (int64_t)row_s[t] * a.ldrec;
 #pragma unroll
       for (int v = 0; v < NV; ++v)
-        if (geo.act[v]) {
-          w[v] = ldg4(rp + (lane + 32 * v) * 4);
-          tl[v] = ldg4(rp + tail0 + geo.hv[v] * 4);
-        }
-      fused_edge<NV>(a, geo, w, tl, wj, gj, __shfl_sync(FULL, pe_reg, t), acc, dgacc);
+        if (FULLROW || geo.act[v]) w[v] = ldg4(di + v * 128);
+      const int o = t * WS + lo;
+      fused_edge<NV, FULLROW>(geo, lph, w, wj, at_s + o, A_s + o, B_s + o, dz_s + o, lay.writer, acc, dgacc);
     }
+    __syncwarp();
+    // ---- dz back to CSR edge order: each edge's H values are one contiguous sector
+    for (int idx = lane; idx < cnt * H; idx += 32) {
+      const int tt = idx / H, h = idx - tt * H;
+      const int pos = lph < 32 ? (h % lay.G) * NV + h / lay.G : h * q;
+      a.edge_dz[(int64_t)perm_s[tt] * H + h] = dz_s[tt * WS + pos];
+    }
+    __syncwarp();
   }
 }
 
@@ -178,11 +265,21 @@ __device__ __forceinline__ void bwd_fused_store_slot(const BwdFusedArgs& a, int 
   stg4(a.dwh + (int64_t)j * a.lddwh + slot * 4, r);
 }
 
-template <int NV, bool HUB>
+template <int NV, bool HUB, bool FULLROW>
 __global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 4 : 1) attn_bwd_fused_kernel(const BwdFusedArgs a) {
+  extern __shared__ __align__(16) float smem_fused[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   LaneGeom<NV> geo;
   geo.init(lane, a.lph, a.V);
+  FusedLayout lay = {};
+  lay.init<NV>(lane, a.lph);
+  float* base_s = smem_fused + warp * (64 + 4 * 32 * lay.WS);
+  int* row_s = reinterpret_cast<int*>(base_s);
+  int* perm_s = row_s + 32;
+  float* at_s = base_s + 64;
+  float* A_s = at_s + 32 * lay.WS;
+  float* B_s = A_s + 32 * lay.WS;
+  float* dz_s = B_s + 32 * lay.WS;
   float4 acc[NV];
   float dgacc[NV];
 
@@ -192,7 +289,7 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 4 : 1) attn_bwd_fu
     int j;
     int64_t beg, end;
     hub_locate(seg, a.hub_rows, a.hub_seg_ptr, a.n_hub, a.tptr, a.seg_len, j, beg, end);
-    bwd_fused_segment<NV>(a, j, beg, end, lane, geo, acc, dgacc);
+    bwd_fused_segment<NV, FULLROW>(a, j, beg, end, lane, geo, lay, acc, dgacc, row_s, perm_s, at_s, A_s, B_s, dz_s);
     float* sc = a.scratch + (int64_t)seg * src_scratch_stride(a.H, a.V);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -209,7 +306,7 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 4 : 1) attn_bwd_fu
     for (int j = cur; j < rend; ++j) {
       const int64_t beg = a.tptr[j], end = a.tptr[j + 1];
       if (end - beg > a.seg_len) continue;
-      bwd_fused_segment<NV>(a, j, beg, end, lane, geo, acc, dgacc);
+      bwd_fused_segment<NV, FULLROW>(a, j, beg, end, lane, geo, lay, acc, dgacc, row_s, perm_s, at_s, A_s, B_s, dz_s);
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         if (geo.act[v]) bwd_fused_store_slot(a, j, lane + 32 * v, acc[v], dgacc[v]);
@@ -336,23 +433,33 @@ __global__ void attn_bwd_finish_hub_merge_kernel(const FinishArgs a) {
 // =====================================================================================
 // host side
 // =====================================================================================
-template <int NV>
-static int launch_fused(const BwdFusedArgs& a, cudaStream_t st) {
+template <int NV, bool FULLROW>
+static int launch_fused_t(const BwdFusedArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)FUSED_WARPS * (64 + 4 * 32 * FusedLayout::floats_per_edge(a.lph, NV)) * sizeof(float);
   if (a.n_hub_seg > 0) {
-    attn_bwd_fused_kernel<NV, true><<<(a.n_hub_seg + FUSED_WARPS - 1) / FUSED_WARPS, FUSED_WARPS * 32, 0, st>>>(a);
+    if (smem > 48 * 1024)
+      GATK_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<NV, true, FULLROW>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_bwd_fused_kernel<NV, true, FULLROW>
+        <<<(a.n_hub_seg + FUSED_WARPS - 1) / FUSED_WARPS, FUSED_WARPS * 32, smem, st>>>(a);
     GATK_CHECK_LAUNCH();
     attn_bwd_fused_hub_merge_kernel<<<a.n_hub, 128, 0, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   if (a.n_src > 0) {
     int grid = 0;
-    if (int rc = persistent_grid(attn_bwd_fused_kernel<NV, false>, FUSED_WARPS * 32, 0, &grid)) return rc;
+    if (int rc = persistent_grid(attn_bwd_fused_kernel<NV, false, FULLROW>, FUSED_WARPS * 32, smem, &grid)) return rc;
     const int64_t need = (a.n_src + (int64_t)FUSED_WARPS * GRAB - 1) / ((int64_t)FUSED_WARPS * GRAB);
     if (need < grid) grid = (int)need;
-    attn_bwd_fused_kernel<NV, false><<<grid, FUSED_WARPS * 32, 0, st>>>(a);
+    attn_bwd_fused_kernel<NV, false, FULLROW><<<grid, FUSED_WARPS * 32, smem, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   return 0;
+}
+
+template <int NV>
+static int launch_fused(const BwdFusedArgs& a, cudaStream_t st) {
+  return a.V == 32 * NV ? launch_fused_t<NV, true>(a, st) : launch_fused_t<NV, false>(a, st);
 }
 
 template <int NV>
