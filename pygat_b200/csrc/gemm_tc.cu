@@ -347,6 +347,260 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
 
 }  // namespace tc
 
+// =====================================================================================================
+// K5: dW[Mo,No] = A^T B with A = x [K, Mo] and B = dZ [K, No], both row-major, K = number of nodes.
+//
+// Both operands are "MN-major" for the tensor core (the reduction index is the slow one in memory), so
+// tiles are loaded as 32-float x 32-row TMA boxes (128-byte swizzled rows) and described to
+// tcgen05.mma with MN-major descriptors: an 8-row (K) x 32-float (MN) swizzle atom of 1 KiB, atoms
+// along K 1 KiB apart inside a box (stride byte offset), the four 32-float blocks of a 128-wide tile
+// 4 KiB apart (leading byte offset).  Both operands are large, so both are split hi/lo on the fly.
+// The reduction is split over CTAs (deterministic partial tiles + a reduce kernel), and because the
+// tensor core truncates when it accumulates, every PROMOTE k-blocks the TMEM accumulators are drained
+// into fp32 registers of the epilogue warps (round-to-nearest adds) -- the MMA warp meanwhile
+// continues into the other TMEM buffer.
+//
+// Warp roles (512 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 splitter (A and B tiles), warps 8-15 epilogue (lane quarter = warp % 4, column half =
+// (warp - 8) / 4).
+// =====================================================================================================
+namespace tn {
+
+using namespace tc;
+
+constexpr int TN_THREADS = 512;
+constexpr int PROMOTE = 16;               // k-blocks (of 32 rows) between accumulator drains
+constexpr int BOX_BYTES = 32 * 32 * 4;    // one TMA box: 32 floats x 32 rows
+constexpr int TN_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(BOX_BYTES >> 4) << 16;   // leading byte offset: next 32-float block along M/N
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: next 8 rows along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16), M = 128, N = 128
+constexpr uint32_t IDESC_MN = IDESC | (1u << 15) | (1u << 16);
+
+__device__ __forceinline__ void umma_tf32_mn(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(IDESC_MN), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(TN_THREADS, 1)
+gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      float* __restrict__ part, int Mo, int No, int m_tiles, int n_tiles, int splits,
+                      int kb_total, int kb_per_split) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto split_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = m_tiles * n_tiles;
+  const int items = tiles * splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(split_bar(s), 4);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  // item -> (split, m tile, n tile); consecutive CTAs share the k range (A tiles hit in L2)
+  auto decode = [&](int item, int& m0, int& n0, int& kb0, int& kb1, int& sp) {
+    sp = item / tiles;
+    const int t = item - sp * tiles;
+    m0 = (t / n_tiles) * BLOCK_M;
+    n0 = (t % n_tiles) * BLOCK_N;
+    kb0 = sp * kb_per_split;
+    kb1 = kb0 + kb_per_split < kb_total ? kb0 + kb_per_split : kb_total;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring r;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int m0, n0, kb0, kb1, sp;
+        decode(item, m0, n0, kb0, kb1, sp);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(r.stage), r.phase ^ 1);
+          const uint32_t st = smem_base + r.stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(r.stage), 2 * TILE_BYTES);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            tma_load_2d(st + b * BOX_BYTES, &map_a, full_bar(r.stage), m0 + b * 32, kb * BLOCK_K);
+            tma_load_2d(st + 2 * TILE_BYTES + b * BOX_BYTES, &map_b, full_bar(r.stage), n0 + b * 32, kb * BLOCK_K);
+          }
+          r.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    Ring r;
+    int drain = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int m0, n0, kb0, kb1, sp;
+      decode(item, m0, n0, kb0, kb1, sp);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int rel = kb - kb0;
+        const int acc = drain & 1;
+        if (rel % PROMOTE == 0) {
+          mbar_wait(tempty_bar(acc), ((drain >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t tmem_d = tmem_base + acc * 2 * BLOCK_N;
+        const uint32_t tmem_c = tmem_d + BLOCK_N;
+        mbar_wait(full_bar(r.stage), r.phase);
+        mbar_wait(split_bar(r.stage), r.phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_base + r.stage * STAGE_BYTES;
+          const uint64_t a_hi = umma_desc_mn(st), a_lo = umma_desc_mn(st + TILE_BYTES);
+          const uint64_t b_hi = umma_desc_mn(st + 2 * TILE_BYTES), b_lo = umma_desc_mn(st + 3 * TILE_BYTES);
+          const uint32_t fresh = (rel % PROMOTE) == 0 ? 0u : 1u;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 1024 >> 4);  // next 8 rows along K
+            umma_tf32_mn(tmem_c, a_lo + adv, b_hi + adv, fresh | (uint32_t)(k != 0));
+            umma_tf32_mn(tmem_c, a_hi + adv, b_lo + adv, 1);
+            umma_tf32_mn(tmem_d, a_hi + adv, b_hi + adv, fresh | (uint32_t)(k != 0));
+          }
+          umma_commit(empty_bar(r.stage));
+          if ((rel + 1) % PROMOTE == 0 || kb == kb1 - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if ((rel + 1) % PROMOTE == 0 || kb == kb1 - 1) ++drain;
+        r.advance();
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    Ring r;
+    const int t = threadIdx.x - 128;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int m0, n0, kb0, kb1, sp;
+      decode(item, m0, n0, kb0, kb1, sp);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(r.stage), r.phase);
+        uint8_t* st = smem + r.stage * STAGE_BYTES;
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {  // A then B
+          float4* hi = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES + TILE_BYTES);
+#pragma unroll
+          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+            const int idx = t + i * 128;
+            float4 v = hi[idx];
+            float4 h;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            hi[idx] = h;
+            lo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(r.stage));
+        r.advance();
+      }
+    }
+  } else if (warp >= 8) {
+    const int quarter = warp & 3;             // TMEM lanes [32*quarter, +32)
+    const int half = (warp - 8) >> 2;         // columns [64*half, +64) of the tile
+    const int row = quarter * 32 + lane;
+    int drain = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int m0, n0, kb0, kb1, sp;
+      decode(item, m0, n0, kb0, kb1, sp);
+      float racc[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) racc[j] = 0.f;
+      const int n_drains = (kb1 - kb0 + PROMOTE - 1) / PROMOTE;
+      for (int d = 0; d < n_drains; ++d, ++drain) {
+        const int acc = drain & 1;
+        mbar_wait(tfull_bar(acc), (drain >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 2 * BLOCK_N + half * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32], w[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld32(taddr + BLOCK_N + c * 32, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      // partial tile of this k range -> workspace [split][Mo][No]
+      const int gm = m0 + row;
+      if (gm < Mo) {
+        float* dst = part + ((int64_t)sp * Mo + gm) * No + n0 + half * 64;
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+          if (n0 + half * 64 + j < No) dst[j] = racc[j];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// 2-D fp32 row-major tensor [rows, cols]; box = 32 columns x 32 rows, 128B swizzle.
+static int make_map_box32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  GATK_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GATK_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)rc,
+               (long long)rows, (long long)cols, (long long)ld);
+  return 0;
+}
+
+}  // namespace tn
+
+
 bool gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
                       const float* C, int64_t ldc, int accumulate) {
   if (transA || transB || accumulate) return false;
@@ -394,6 +648,61 @@ int gemm_tc_launch(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
   if (tiles < grid) grid = (int)tiles;
   gemm_tf32x3_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_bhi, map_blo, map_c, m_tiles, n_tiles, k_blocks);
   GATK_CHECK_LAUNCH();
+  return 0;
+}
+
+
+// ---- TN (dW) path ---------------------------------------------------------------------------------
+static void tn_plan(int64_t Mo, int64_t No, int64_t K, int* m_tiles, int* n_tiles, int* splits, int* kb_total,
+                    int* kb_per_split) {
+  *m_tiles = (int)((Mo + tc::BLOCK_M - 1) / tc::BLOCK_M);
+  *n_tiles = (int)((No + tc::BLOCK_N - 1) / tc::BLOCK_N);
+  *kb_total = (int)((K + tc::BLOCK_K - 1) / tc::BLOCK_K);
+  const int tiles = *m_tiles * *n_tiles;
+  int s = sm_count() / tiles;
+  if (s < 1) s = 1;
+  const int max_s = (*kb_total + tn::PROMOTE - 1) / tn::PROMOTE;  // at least one drain interval per split
+  if (s > max_s) s = max_s;
+  *kb_per_split = (*kb_total + s - 1) / s;
+  *splits = (*kb_total + *kb_per_split - 1) / *kb_per_split;
+}
+
+bool gemm_tn_tc_eligible(int transA, int transB, int64_t Mo, int64_t No, int64_t K, const float* A, int64_t lda,
+                         const float* B, int64_t ldb, int accumulate) {
+  (void)accumulate;
+  if (!transA || transB) return false;
+  if (K < 16384 || Mo < 8 || No < 8 || Mo > 4096 || No > 8192) return false;
+  if (K >= (1LL << 31) - 64) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
+  if ((lda & 3) || (ldb & 3)) return false;
+  return true;
+}
+
+size_t gemm_tn_tc_workspace_bytes(int64_t Mo, int64_t No, int64_t K) {
+  int mt, nt, sp, kbt, kbs;
+  tn_plan(Mo, No, K, &mt, &nt, &sp, &kbt, &kbs);
+  return (size_t)sp * Mo * No * sizeof(float);
+}
+
+int gemm_tn_tc_launch(int64_t Mo, int64_t No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                      float* part, int* splits_out, cudaStream_t st) {
+  using namespace tn;
+  int mt, nt, sp, kbt, kbs;
+  tn_plan(Mo, No, K, &mt, &nt, &sp, &kbt, &kbs);
+  CUtensorMap map_a, map_b;
+  if (int rc = make_map_box32(&map_a, A, K, Mo, lda)) return rc;
+  if (int rc = make_map_box32(&map_b, B, K, No, ldb)) return rc;
+  static bool configured = false;
+  if (!configured) {
+    GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+    configured = true;
+  }
+  const int items = mt * nt * sp;
+  int grid = sm_count();
+  if (items < grid) grid = items;
+  gemm_tn_tf32x3_kernel<<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(map_a, map_b, part, (int)Mo, (int)No, mt, nt, sp, kbt, kbs);
+  GATK_CHECK_LAUNCH();
+  *splits_out = sp;
   return 0;
 }
 

@@ -114,6 +114,31 @@ def test_tensor_core_gemm_is_fp32_accurate(M, N, K, pad):
     assert (C[:, :N].double().cpu() - ref).abs().max().item() < 1e-5 * scale
 
 
+@pytest.mark.parametrize("M,N,K,padb", [(100, 512, 200_000, 0), (128, 640, 65_536, 0), (256, 136, 30_001, 4),
+                                        (20, 24, 50_000, 0), (500, 64, 19_717, 0)])
+def test_tensor_core_weight_gradient_gemm(M, N, K, padb):
+    """dW = x^T dZ (reduction over the nodes) on tcgen05: MN-major operands, both split hi/lo on the fly,
+    periodic promotion of the TMEM accumulators, deterministic split-K -- against an fp64 product."""
+    assert _lib.query("gatk_gemm_uses_tensor_cores", 1, 0, M, N, K, M, N + padb, 0) == 1
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(K, M, generator=g)
+    B = torch.randn(K, N + padb, generator=g)
+    ref = A.double().t() @ B[:, :N].double()
+    dA, dB = A.to(DEV), B.to(DEV)
+    C = torch.full((M, N + 1), 7.0, device=DEV)
+    ws_bytes = _lib.query("gatk_gemm_workspace_bytes", 1, 0, M, N, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    outs = []
+    for _ in range(2):
+        _lib.call("gatk_gemm", 1, 0, M, N, K, dA.data_ptr(), M, dB.data_ptr(), N + padb, C.data_ptr(), N + 1, 0,
+                  ws.data_ptr(), ws_bytes, _stream())
+        torch.cuda.synchronize()
+        outs.append(C.clone())
+    assert rel_err(C[:, :N], ref) < 3e-6
+    assert torch.all(C[:, N:] == 7.0)
+    assert torch.equal(outs[0], outs[1])  # split-K partials are reduced in a fixed order
+
+
 # ------------------------------------------------------------------------------ heads
 def _run_head(d, kind, adj_arg, masks=None):
     cls = layers.SpGraphAttentionLayer if kind == "sparse" else layers.GraphAttentionLayer
