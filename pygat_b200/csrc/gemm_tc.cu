@@ -351,10 +351,11 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
 // K5: dW[Mo,No] = A^T B with A = x [K, Mo] and B = dZ [K, No], both row-major, K = number of nodes.
 //
 // Both operands are "MN-major" for the tensor core (the reduction index is the slow one in memory), so
-// tiles are loaded as 32-float x 32-row TMA boxes (128-byte swizzled rows) and described to
-// tcgen05.mma with MN-major descriptors: an 8-row (K) x 32-float (MN) swizzle atom of 1 KiB, atoms
-// along K 1 KiB apart inside a box (stride byte offset), the four 32-float blocks of a 128-wide tile
-// 4 KiB apart (leading byte offset).  Both operands are large, so both are split hi/lo on the fly.
+// tiles are loaded as 32-float x 32-row TMA boxes and described to tcgen05.mma with MN-major
+// descriptors.  32-bit MN-major operands have exactly one legal layout: 128-byte rows swizzled in
+// 32-byte units (TMA SWIZZLE_128B_ATOM_32B / UMMA SWIZZLE_128B_BASE32B), i.e. a 4-row (K) x 32-float
+// (MN) atom of 512 B; atoms along K are 512 B apart inside a box (stride byte offset), the four
+// 32-float blocks of a 128-wide tile 4 KiB apart (leading byte offset).  Both operands are large, so both are split hi/lo on the fly.
 // The reduction is split over CTAs (deterministic partial tiles + a reduce kernel), and because the
 // tensor core truncates when it accumulates, every PROMOTE k-blocks the TMEM accumulators are drained
 // into fp32 registers of the epilogue warps (round-to-nearest adds) -- the MMA warp meanwhile
@@ -377,9 +378,9 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)(BOX_BYTES >> 4) << 16;   // leading byte offset: next 32-float block along M/N
-  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: next 8 rows along K
+  d |= (uint64_t)(512 >> 4) << 32;         // stride byte offset: next 4-row swizzle atom along K
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  d |= (uint64_t)1 << 61;                  // SWIZZLE_128B_BASE32B: the only MN-major layout for 32-bit operands
   return d;
 }
 // kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16), M = 128, N = 128
@@ -591,8 +592,8 @@ static int make_map_box32(CUtensorMap* map, const void* base, int64_t rows, int6
   cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GATK_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)rc,
                (long long)rows, (long long)cols, (long long)ld);
   return 0;
