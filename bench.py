@@ -249,6 +249,18 @@ def run_ours(args):
                     "layer_survey_model_GB": round(ab["layer_survey"] / 1e9, 2)}
 
     cpu = cpu_reference_rate(cfg, steps=1, warmup=1)
+    epochs = None
+    if not args.no_epochs:
+        epochs = {}
+        try:
+            from pygat_b200 import epoch_bench
+            ms_e, info = epoch_bench.pubmed_epoch_ms(dev)
+            epochs["pubmed_GAT_sparse_train_plus_eval"] = {"ms_per_epoch": round(ms_e, 3), **info}
+            if world == 1:
+                ms_e, info = epoch_bench.ppi_epoch_ms(dev)
+                epochs["ppi_GAT_dense_class_train"] = {"ms_per_epoch": round(ms_e, 3), **info}
+        except Exception as exc:  # the headline metric must still be printed
+            epochs["error"] = repr(exc)[:300]
     line = {
         "metric": "gat_layer_fwd_bwd_head_edges_per_s", "value": e_total * H / (ms * 1e-3), "unit": "head-edges/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
@@ -262,6 +274,7 @@ def run_ours(args):
         "gpu_launches": launches, "abi_calls": calls, "clocks": clk, "roofline": roofline,
         "kernels": per_kernel, "other_ms_per_step": other,
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "epoch_times": epochs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -340,6 +353,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-epochs", action="store_true", help="skip the Pubmed / PPI epoch-time add-on measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1,0 +1,120 @@
+"""Epoch-time workloads of BASELINE.json's configs 2 and 3, driven exactly as the reference's
+training loops drive the model (train.py:154-179, train_ppi.py:112-132) but on synthetic data of
+the same shapes (the reference's feature blobs are missing and nothing of it travels to the GPU
+box).  Used by bench.py; returns milliseconds per epoch."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+# node counts of the 20 PPI training graphs (data/ppi/train_graph_id.npy of the reference)
+PPI_TRAIN_GRAPH_NODES = [1767, 1377, 2263, 2339, 1578, 1021, 1823, 2488, 591, 3312, 2401, 1878, 1819, 3480, 2794,
+                         2326, 2650, 2815, 3163, 3021]
+
+
+def _dense_from_csr(rowptr, col, n, device, column_major=False):
+    row = torch.repeat_interleave(torch.arange(n, device=device), rowptr[1:] - rowptr[:-1])
+    adj = torch.zeros(n, n, device=device)
+    adj[row, col.long()] = 1.0
+    if column_major:  # what utils.load_data hands the model (utils.py:55, normalize_adj returns CSC)
+        adj = adj.t().contiguous().t()
+    return adj
+
+
+def pubmed_epoch_ms(device, epochs: int = 20, warmup: int = 3, seed: int = 72):
+    """`python train.py --dataset pubmed --model GAT_sparse` shape: N=19717, ~108k stored entries,
+    500 features, 8x8 hidden heads, 8x3 output heads averaged, dropout 0.6, Adam lr 0.01 wd 0.001;
+    one epoch = train step + eval forward (train.py:154-170)."""
+    import layers
+    import models
+    from .synth import power_law_csr
+    n, f_in, classes = 19717, 500, 3
+    torch.manual_seed(seed)
+    rowptr, col = power_law_csr(n, 5.5, seed=seed, device=device)
+    adj = _dense_from_csr(rowptr, col, n, device, column_major=True)
+    x = torch.rand(n, f_in, device=device)
+    x = x / x.sum(1, keepdim=True)
+    labels = torch.randint(0, classes, (n,), device=device)
+    idx_train = torch.arange(60, device=device)
+    idx_val = torch.arange(200, 700, device=device)
+    model = models.GAT(nfeat=[f_in, 8, classes], nheads=[8, 8], nlayers=2, dropout=0.6, alpha=0.2,
+                       layer_type=layers.SpGraphAttentionLayer, skip_connection=False).to(device)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0.001)
+
+    def epoch():
+        model.train()
+        opt.zero_grad()
+        out = F.log_softmax(F.elu(model(x, adj)), dim=1)
+        loss = F.nll_loss(out[idx_train], labels[idx_train])
+        loss.backward()
+        opt.step()
+        model.eval()
+        with torch.no_grad():
+            out = F.log_softmax(F.elu(model(x, adj)), dim=1)
+            lv = F.nll_loss(out[idx_val], labels[idx_val])
+        return loss.item() + lv.item()  # the reference prints both every epoch (host sync)
+
+    for _ in range(warmup):
+        epoch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(epochs):
+        epoch()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / epochs, {"nodes": n, "stored_entries": int(col.numel()), "epochs": epochs}
+
+
+def ppi_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup: int = 1, seed: int = 72):
+    """`python train_ppi.py` shape: 20 training graphs, batches of 2 merged by block_diag
+    (load_data_ppi.py:84-86), 3 layers 50 -> 4x256 -> 4x256 -> 6x121 (mean), skip connections, dense
+    class (the script's default), BCEWithLogits, Adam lr 0.005.  With world > 1 the batches of an epoch
+    are dealt round-robin to the ranks (graph-level data parallelism) and gradients are all-reduced
+    with node-count weights."""
+    import layers
+    import models
+    from .sharded import allreduce_gradients
+    from .synth import power_law_csr
+    torch.manual_seed(seed)
+    graphs = []
+    for k, n in enumerate(PPI_TRAIN_GRAPH_NODES):
+        rowptr, col = power_law_csr(n, 29.0, seed=seed + k, exponent=0.3, device=device)
+        adj = _dense_from_csr(rowptr, col, n, device)
+        g = torch.Generator(device=device).manual_seed(seed + 100 + k)
+        feats = torch.randn(n, 50, generator=g, device=device)
+        labels = (torch.rand(n, 121, generator=g, device=device) < 0.3).float()
+        graphs.append((feats, labels, adj))
+    batches = [(torch.cat([graphs[i][0], graphs[i + 1][0]]), torch.cat([graphs[i][1], graphs[i + 1][1]]),
+                torch.block_diag(graphs[i][2], graphs[i + 1][2])) for i in range(0, len(graphs), 2)]
+    model = models.GAT(nfeat=[50, 256, 256, 121], nheads=[4, 4, 6], nlayers=3, dropout=0.0, alpha=0.2,
+                       layer_type=layers.GraphAttentionLayer, skip_connection=True).to(device)
+    opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0)
+    loss_fn = torch.nn.BCEWithLogitsLoss(reduction="mean")
+    mine = batches[rank::world]
+
+    def epoch():
+        model.train()
+        tot = 0.0
+        for feats, labels, adj in mine:
+            out = model(feats, adj)
+            loss = loss_fn(out, labels)
+            opt.zero_grad()
+            loss.backward()
+            if world > 1:
+                allreduce_gradients(model.parameters(), feats.shape[0])
+            opt.step()
+            tot += loss.item()  # the reference prints the loss of every batch (host sync)
+        return tot
+
+    for _ in range(warmup):
+        epoch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(epochs):
+        epoch()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / epochs, {"graphs": len(graphs), "batches_per_rank": len(mine), "epochs": epochs,
+                                          "nodes": sum(PPI_TRAIN_GRAPH_NODES)}
