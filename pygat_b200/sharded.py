@@ -92,7 +92,16 @@ def allreduce_(tensors: Sequence[torch.Tensor], plan_or_group=None):
 
 
 class ShardedGatLayerFunction(torch.autograd.Function):
-    """GatLayerFunction for a destination-row shard (no dropout: the sharded shapes train with p = 0)."""
+    """GatLayerFunction for a destination-row shard (no dropout: the sharded shapes train with p = 0).
+
+    What crosses NVLink per layer:
+      forward   all-gather of the INPUT rows x [N, F] (F << H*D) and of g [N, H]; every rank then
+                projects all N rows itself -- re-computing Wh costs one GEMM pass, all-gathering it
+                would move H*D/F times more bytes than gathering x;
+      backward  reduce-scatter of dg [N, H] and all-reduce of dW / da.  When the layer input needs no
+                gradient (first layer), dW = x_full^T dWh_partial is formed from the PARTIAL dWh rows on
+                every rank and only the F x H*D result is all-reduced; otherwise the partial dWh rows
+                are reduce-scattered to their owners (dx needs the complete rows)."""
 
     @staticmethod
     def forward(ctx, x, w_ext, a_src, a_dst, graph: Graph, plan: ShardPlan, H: int, Dp: int, has_skip: bool,
@@ -101,22 +110,26 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         n, f_in = x.shape
         assert n == plan.n_local == graph.n_dst and graph.n_src == plan.n_total
         HD = H * Dp
+        N = plan.n_total
         x, w_ext, a_src, a_dst = x.contiguous(), w_ext.contiguous(), a_src.contiguous(), a_dst.contiguous()
         M_out = w_ext.shape[1]
         st = _stream()
-        # projection of the local rows straight into this rank's slice of the gathered buffers
-        wh_full = torch.empty(plan.n_total, HD, dtype=torch.float32, device=dev)
-        g_full = torch.empty(plan.n_total, H, dtype=torch.float32, device=dev)
-        wh_loc, g_loc = plan.rows(wh_full), plan.rows(g_full)
-        _gemm(0, 0, n, HD, f_in, x, f_in, w_ext, M_out, wh_loc, HD)
+        if plan.world > 1:
+            x_full = torch.empty(N, f_in, dtype=torch.float32, device=dev)
+            plan.rows(x_full).copy_(x)
+            gather_rows(x_full, plan)
+        else:
+            x_full = x
+        wh_full = torch.empty(N, HD, dtype=torch.float32, device=dev)
+        _gemm(0, 0, N, HD, f_in, x_full, f_in, w_ext, M_out, wh_full, HD)
         skipv = None
         if has_skip:
             skipv = torch.empty(n, HD, dtype=torch.float32, device=dev)
             _gemm(0, 0, n, HD, f_in, x, f_in, w_ext, M_out, skipv, HD, b_off=HD)
         f = torch.empty(n, H, dtype=torch.float32, device=dev)
-        _lib.call("gatk_logits_fwd", n, H, Dp, wh_loc.data_ptr(), HD, None, 1.0, a_src.data_ptr(), a_dst.data_ptr(),
-                  f.data_ptr(), g_loc.data_ptr(), st)
-        gather_rows(wh_full, plan)
+        g_full = torch.empty(N, H, dtype=torch.float32, device=dev)
+        _lib.call("gatk_logits_fwd", n, H, Dp, plan.rows(wh_full).data_ptr(), HD, None, 1.0, a_src.data_ptr(),
+                  a_dst.data_ptr(), f.data_ptr(), plan.rows(g_full).data_ptr(), st)
         gather_rows(g_full, plan)
 
         need_grad = any(ctx.needs_input_grad[:4])
@@ -132,13 +145,13 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         if need_grad:
             ctx.graph, ctx.plan = graph, plan
             ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu))
-            ctx.save_for_backward(x, w_ext, a_src, a_dst, wh_full, g_full, f, lse, out,
+            ctx.save_for_backward(x, x_full, w_ext, a_src, a_dst, wh_full, g_full, f, lse, out,
                                   hagg if separate_hagg else out)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, w_ext, a_src, a_dst, wh_full, g_full, f, lse, out, hagg = ctx.saved_tensors
+        x, x_full, w_ext, a_src, a_dst, wh_full, g_full, f, lse, out, hagg = ctx.saved_tensors
         graph, plan = ctx.graph, ctx.plan
         H, Dp, has_skip, alpha, act_elu = ctx.cfg
         dev = x.device
@@ -148,14 +161,15 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         N = plan.n_total
         st = _stream()
         gout = gout.contiguous()
+        need_dx = ctx.needs_input_grad[0]
         tptr, trow, perm, thubs = graph.transpose()
 
-        dz_rows = torch.empty(n, M_out, dtype=torch.float32, device=dev)   # [dWh | dSkip] of the local rows
         ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
         rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
+        dskip = torch.empty(n, HD, dtype=torch.float32, device=dev) if has_skip else None
         _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
                   int(act_elu), hagg.data_ptr(), HD, f.data_ptr(), lse.data_ptr(), rec.data_ptr(), ldrec,
-                  dz_rows.data_ptr() + 4 * HD if has_skip else None, M_out, st)
+                  _ptr(dskip), HD, st)
 
         # partial dWh / dg for EVERY source from this rank's destination rows
         dwh_part = torch.empty(N, HD, dtype=torch.float32, device=dev)
@@ -167,31 +181,37 @@ class ShardedGatLayerFunction(torch.autograd.Function):
                   a_dst.data_ptr(), dwh_part.data_ptr(), HD, dg_part.data_ptr(), edge_dz.data_ptr(),
                   *thubs.args(scratch_t), graph.counter.data_ptr(), st)
         del rec
-        dwh_loc = reduce_rows(dwh_part, plan)
-        dg_loc = reduce_rows(dg_part, plan)
-        # local rows: df, dst-side term; written into the dZ buffer the projection backward reads
-        dz_wh = dz_rows[:, :HD]
-        dz_wh.copy_(dwh_loc)
-        del dwh_part
+        dg_loc = reduce_rows(dg_part, plan).contiguous()
+        # owned rows: df = segmented sum of dz, dWh_i += df_i a_src (added once, on the owner's partial rows)
         df = torch.empty(n, H, dtype=torch.float32, device=dev)
         hubs = graph.hubs
         scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
+        dwh_own = plan.rows(dwh_part)
         _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), a_src.data_ptr(),
-                  None, 1.0, dz_rows.data_ptr(), M_out, df.data_ptr(), *hubs.args(scratch), st)
+                  None, 1.0, dwh_own.data_ptr(), HD, df.data_ptr(), *hubs.args(scratch), st)
         del edge_dz
 
         da_src = torch.empty(H, Dp, dtype=torch.float32, device=dev)
         da_dst = torch.empty(H, Dp, dtype=torch.float32, device=dev)
         ws = torch.empty(_lib.query("gatk_da_workspace_floats", H, Dp), dtype=torch.float32, device=dev)
-        dg_c = dg_loc.contiguous()
-        _lib.call("gatk_da_reduce", n, H, Dp, plan.rows(wh_full).data_ptr(), HD, df.data_ptr(), dg_c.data_ptr(),
+        _lib.call("gatk_da_reduce", n, H, Dp, plan.rows(wh_full).data_ptr(), HD, df.data_ptr(), dg_loc.data_ptr(),
                   da_src.data_ptr(), da_dst.data_ptr(), ws.data_ptr(), st)
+
         dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
-        _gemm(1, 0, f_in, M_out, n, x, f_in, dz_rows, M_out, dw_ext, M_out)
         dx = None
-        if ctx.needs_input_grad[0]:
+        if not need_dx:
+            # dW = sum over ranks of x_full^T dWh_partial: no row exchange, only the F x H*D all-reduce below
+            _gemm(1, 0, f_in, HD, N, x_full, f_in, dwh_part, HD, dw_ext, M_out)
+            if has_skip:
+                _gemm(1, 0, f_in, HD, n, x, f_in, dskip, HD, dw_ext, M_out, c_off=HD)
+        else:
+            dwh_loc = reduce_rows(dwh_part, plan)
+            _gemm(1, 0, f_in, HD, n, x, f_in, dwh_loc, HD, dw_ext, M_out)
             dx = torch.empty(n, f_in, dtype=torch.float32, device=dev)
-            _gemm(0, 1, n, f_in, M_out, dz_rows, M_out, w_ext, M_out, dx, f_in)
+            _gemm(0, 1, n, f_in, HD, dwh_loc, HD, w_ext, M_out, dx, f_in)
+            if has_skip:
+                _gemm(1, 0, f_in, HD, n, x, f_in, dskip, HD, dw_ext, M_out, c_off=HD)
+                _gemm(0, 1, n, f_in, HD, dskip, HD, w_ext, M_out, dx, f_in, accumulate=1, b_off=HD)
         if plan.world > 1:
             allreduce_([dw_ext, da_src, da_dst], plan)
         return dx, dw_ext, da_src, da_dst, None, None, None, None, None, None, None
