@@ -94,53 +94,6 @@ struct BwdFusedArgs {
 
 constexpr int FUSED_WARPS = 4;
 
-// Per-edge softmax terms are staged in shared memory in the order the consuming lanes want them:
-// position (g, v) = g*NV + v holds the value for the head of slot  g*lph + 32*v, where g = lane / lph
-// is the lane group (one group when a head is at least a warp wide).  A lane then reads the NV values
-// of its own slots with one vector LDS.
-struct FusedLayout {
-  int G, WS;        // lane groups per 32 slots, floats per edge in the staging arrays
-  int my_base;      // g * NV for this lane
-  bool writer;      // first lane of its group: stores the group's dz values
-  template <int NV>
-  __device__ __forceinline__ void init(int lane, int lph) {
-    G = lph < 32 ? 32 / lph : 1;
-    WS = G * NV + 4;  // +4: keeps 16-byte alignment and spreads the per-edge rows over banks
-    const int g = lph < 32 ? lane / lph : 0;
-    my_base = g * NV;
-    writer = lph < 32 ? (lane % lph == 0) : (lane == 0);
-  }
-  __host__ __device__ static int floats_per_edge(int lph, int NV) { return (lph < 32 ? 32 / lph : 1) * NV + 4; }
-};
-
-template <int NV>
-__device__ __forceinline__ void lds_vec(const float* p, float (&o)[NV]) {
-  if constexpr (NV % 4 == 0) {
-#pragma unroll
-    for (int k = 0; k < NV / 4; ++k) {
-      const float4 t = reinterpret_cast<const float4*>(p)[k];
-      o[4 * k] = t.x; o[4 * k + 1] = t.y; o[4 * k + 2] = t.z; o[4 * k + 3] = t.w;
-    }
-  } else if constexpr (NV == 2) {
-    const float2 t = *reinterpret_cast<const float2*>(p);
-    o[0] = t.x; o[1] = t.y;
-  } else {
-    o[0] = p[0];
-  }
-}
-template <int NV>
-__device__ __forceinline__ void sts_vec(float* p, const float (&o)[NV]) {
-  if constexpr (NV % 4 == 0) {
-#pragma unroll
-    for (int k = 0; k < NV / 4; ++k)
-      reinterpret_cast<float4*>(p)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-  } else if constexpr (NV == 2) {
-    *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1]);
-  } else {
-    p[0] = o[0];
-  }
-}
-
 // One gathered dh' row: aggregation with the staged attention weights, dot product with the
 // resident Wh_j, head reduction, dz = A * (dh'.Wh_j) - B for this lane's NV slots.
 template <int NV, bool FULLROW>
@@ -172,7 +125,7 @@ __device__ __forceinline__ void fused_edge(const LaneGeom<NV>& geo, int lph, con
 
 template <int NV, bool FULLROW>
 __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, int64_t beg, int64_t end, int lane,
-                                                  const LaneGeom<NV>& geo, const FusedLayout& lay, float4 (&acc)[NV],
+                                                  const LaneGeom<NV>& geo, const SlotLayout& lay, float4 (&acc)[NV],
                                                   float (&dgacc)[NV], int* row_s, int* perm_s, float* at_s, float* A_s,
                                                   float* B_s, float* dz_s) {
   constexpr int U = NV >= 8 ? 1 : (NV == 4 ? 2 : 4);
@@ -271,7 +224,7 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 4 : 1) attn_bwd_fu
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   LaneGeom<NV> geo;
   geo.init(lane, a.lph, a.V);
-  FusedLayout lay = {};
+  SlotLayout lay = {};
   lay.init<NV>(lane, a.lph);
   float* base_s = smem_fused + warp * (64 + 4 * 32 * lay.WS);
   int* row_s = reinterpret_cast<int*>(base_s);
@@ -435,7 +388,7 @@ __global__ void attn_bwd_finish_hub_merge_kernel(const FinishArgs a) {
 // =====================================================================================
 template <int NV, bool FULLROW>
 static int launch_fused_t(const BwdFusedArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)FUSED_WARPS * (64 + 4 * 32 * FusedLayout::floats_per_edge(a.lph, NV)) * sizeof(float);
+  const size_t smem = (size_t)FUSED_WARPS * (64 + 4 * 32 * SlotLayout::floats_per_edge(a.lph, NV)) * sizeof(float);
   if (a.n_hub_seg > 0) {
     if (smem > 48 * 1024)
       GATK_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<NV, true, FULLROW>,

@@ -52,6 +52,53 @@ __device__ __forceinline__ void hub_locate(int seg, const int32_t* hub_rows, con
 }
 
 
+// Per-edge softmax terms are staged in shared memory in the order the consuming lanes want them:
+// position (g, v) = g*NV + v holds the value for the head of slot  g*lph + 32*v, where g = lane / lph
+// is the lane group (one group when a head is at least a warp wide).  A lane then reads the NV values
+// of its own slots with one vector LDS.
+struct SlotLayout {
+  int G, WS;        // lane groups per 32 slots, floats per edge in the staging arrays
+  int my_base;      // g * NV for this lane
+  bool writer;      // first lane of its group: stores the group's dz values
+  template <int NV>
+  __device__ __forceinline__ void init(int lane, int lph) {
+    G = lph < 32 ? 32 / lph : 1;
+    WS = G * NV + 4;  // +4: keeps 16-byte alignment and spreads the per-edge rows over banks
+    const int g = lph < 32 ? lane / lph : 0;
+    my_base = g * NV;
+    writer = lph < 32 ? (lane % lph == 0) : (lane == 0);
+  }
+  __host__ __device__ static int floats_per_edge(int lph, int NV) { return (lph < 32 ? 32 / lph : 1) * NV + 4; }
+};
+
+template <int NV>
+__device__ __forceinline__ void lds_vec(const float* p, float (&o)[NV]) {
+  if constexpr (NV % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k) {
+      const float4 t = reinterpret_cast<const float4*>(p)[k];
+      o[4 * k] = t.x; o[4 * k + 1] = t.y; o[4 * k + 2] = t.z; o[4 * k + 3] = t.w;
+    }
+  } else if constexpr (NV == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    o[0] = t.x; o[1] = t.y;
+  } else {
+    o[0] = p[0];
+  }
+}
+template <int NV>
+__device__ __forceinline__ void sts_vec(float* p, const float (&o)[NV]) {
+  if constexpr (NV % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < NV / 4; ++k)
+      reinterpret_cast<float4*>(p)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+  } else if constexpr (NV == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1]);
+  } else {
+    p[0] = o[0];
+  }
+}
+
 template <typename K>
 static int persistent_grid(K kernel, int threads, size_t smem, int* grid) {
   if (smem > 48 * 1024) GATK_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

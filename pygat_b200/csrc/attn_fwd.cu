@@ -43,12 +43,13 @@ struct FwdArgs {
 
 // Online-softmax aggregation of edges [beg,end) of destination `row` into (acc, m, l).
 // m_reg / l_reg: lane h holds the running max / sum of head h.
-template <int NV>
+template <int NV, bool FULLROW>
 __device__ __forceinline__ void fwd_segment(const FwdArgs& a, int row, int64_t beg, int64_t end, int lane,
-                                            const LaneGeom<NV>& geo, float4 (&acc)[NV], float& m_reg, float& l_reg,
-                                            int* col_s, float* p_s, float* scale_s) {
+                                            const LaneGeom<NV>& geo, const SlotLayout& lay, float4 (&acc)[NV],
+                                            float& m_reg, float& l_reg, int* col_s, float* p_s, float* scale_s) {
   constexpr int U = NV >= 8 ? 1 : 8 / NV;
-  const int H = a.H, HP = a.HP;
+  const int H = a.H, WS = lay.WS, lph = a.lph;
+  const int q = lph >= 32 ? lph >> 5 : 1;
   float f_reg = lane < H ? __ldg(a.f + (int64_t)row * H + lane) : 0.f;
   m_reg = -INFINITY;
   l_reg = 0.f;
@@ -73,21 +74,25 @@ __device__ __forceinline__ void fwd_segment(const FwdArgs& a, int row, int64_t b
       float m_new = fmaxf(m_old, cmax);
       float pe = valid ? expf(s - m_new) : 0.f;
       float csum = warp_sum(pe);
+      const int pos = lph < 32 ? (h % lay.G) * NV + h / lay.G : h * q;
       if (lane == h) {
         float sc = (m_old == -INFINITY) ? 0.f : expf(m_old - m_new);
         l_reg = l_reg * sc + csum;
         m_reg = m_new;
-        scale_s[h] = sc;
+        for (int k = 0; k < q; ++k) scale_s[pos + k] = sc;
       }
       if (kp) pe = (valid && kp[h]) ? pe * a.inv_keep : 0.f;
-      p_s[lane * HP + h] = pe;
+      for (int k = 0; k < q; ++k) p_s[lane * WS + pos + k] = pe;
     }
     __syncwarp();
     if (base != beg) {
+      float sc[NV];
+      lds_vec<NV>(scale_s + lay.my_base, sc);
 #pragma unroll
-      for (int v = 0; v < NV; ++v) scale4(acc[v], scale_s[geo.hv[v]]);
+      for (int v = 0; v < NV; ++v) scale4(acc[v], sc[v]);
     }
     const float* whl = a.wh + lane * 4;
+    const float* pl = p_s + lay.my_base;
     int t = 0;
     for (; t + U <= cnt; t += U) {
       float4 w[U][NV];
@@ -96,20 +101,24 @@ __device__ __forceinline__ void fwd_segment(const FwdArgs& a, int row, int64_t b
         const float* wj = whl + (int64_t)col_s[t + u] * a.ldw;
 #pragma unroll
         for (int v = 0; v < NV; ++v)
-          if (geo.act[v]) w[u][v] = ldg4(wj + v * 128);
+          if (FULLROW || geo.act[v]) w[u][v] = ldg4(wj + v * 128);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
+        float pv[NV];
+        lds_vec<NV>(pl + (t + u) * WS, pv);
 #pragma unroll
         for (int v = 0; v < NV; ++v)
-          if (geo.act[v]) fma4(acc[v], p_s[(t + u) * HP + geo.hv[v]], w[u][v]);
+          if (FULLROW || geo.act[v]) fma4(acc[v], pv[v], w[u][v]);
       }
     }
     for (; t < cnt; ++t) {
       const float* wj = whl + (int64_t)col_s[t] * a.ldw;
+      float pv[NV];
+      lds_vec<NV>(pl + t * WS, pv);
 #pragma unroll
       for (int v = 0; v < NV; ++v)
-        if (geo.act[v]) fma4(acc[v], p_s[t * HP + geo.hv[v]], ldg4(wj + v * 128));
+        if (FULLROW || geo.act[v]) fma4(acc[v], pv[v], ldg4(wj + v * 128));
     }
     __syncwarp();
   }
@@ -133,17 +142,19 @@ __device__ __forceinline__ void fwd_store_slot(const FwdArgs& a, int row, int sl
   stg4(a.out + (int64_t)row * a.ldo + slot * 4, r);
 }
 
-template <int NV, bool HUB>
+template <int NV, bool HUB, bool FULLROW>
 __global__ void __launch_bounds__(FWD_WARPS * 32) attn_fwd_kernel(const FwdArgs a) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per_warp = 32 + 32 * a.HP + 32;
+  LaneGeom<NV> geo;
+  geo.init(lane, a.lph, a.V);
+  SlotLayout lay = {};
+  lay.init<NV>(lane, a.lph);
+  const int per_warp = 32 + 32 * lay.WS + lay.WS;
   float* base_s = smem + warp * per_warp;
   int* col_s = reinterpret_cast<int*>(base_s);
   float* p_s = base_s + 32;
-  float* scale_s = p_s + 32 * a.HP;
-  LaneGeom<NV> geo;
-  geo.init(lane, a.lph, a.V);
+  float* scale_s = p_s + 32 * lay.WS;
   float4 acc[NV];
   float m_reg, l_reg;
 
@@ -153,7 +164,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) attn_fwd_kernel(const FwdArgs 
     int row;
     int64_t beg, end;
     hub_locate(seg, a.hub_rows, a.hub_seg_ptr, a.n_hub, a.rowptr, a.seg_len, row, beg, end);
-    fwd_segment<NV>(a, row, beg, end, lane, geo, acc, m_reg, l_reg, col_s, p_s, scale_s);
+    fwd_segment<NV, FULLROW>(a, row, beg, end, lane, geo, lay, acc, m_reg, l_reg, col_s, p_s, scale_s);
     float* sc = a.scratch + (int64_t)seg * fwd_scratch_stride(a.H, a.V);
 #pragma unroll
     for (int v = 0; v < NV; ++v)
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) attn_fwd_kernel(const FwdArgs 
     for (int row = cur; row < rend; ++row) {
       int64_t beg = a.rowptr[row], end = a.rowptr[row + 1];
       if (end - beg > a.seg_len) continue;  // hub: handled by the segment kernels
-      fwd_segment<NV>(a, row, beg, end, lane, geo, acc, m_reg, l_reg, col_s, p_s, scale_s);
+      fwd_segment<NV, FULLROW>(a, row, beg, end, lane, geo, lay, acc, m_reg, l_reg, col_s, p_s, scale_s);
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         float l = __shfl_sync(FULL, l_reg, geo.hv[v]);
@@ -207,26 +218,32 @@ __global__ void attn_fwd_hub_merge_kernel(const FwdArgs a) {
   }
 }
 
-template <int NV>
-static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)FWD_WARPS * (32 + 32 * a.HP + 32) * sizeof(float);
+template <int NV, bool FULLROW>
+static int launch_fwd_t(const FwdArgs& a, cudaStream_t st) {
+  const int ws = SlotLayout::floats_per_edge(a.lph, NV);
+  const size_t smem = (size_t)FWD_WARPS * (32 + 32 * ws + ws) * sizeof(float);
   if (a.n_hub_seg > 0) {
     if (smem > 48 * 1024)
-      GATK_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_kernel<NV, true><<<(a.n_hub_seg + FWD_WARPS - 1) / FWD_WARPS, FWD_WARPS * 32, smem, st>>>(a);
+      GATK_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NV, true, FULLROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_fwd_kernel<NV, true, FULLROW><<<(a.n_hub_seg + FWD_WARPS - 1) / FWD_WARPS, FWD_WARPS * 32, smem, st>>>(a);
     GATK_CHECK_LAUNCH();
     attn_fwd_hub_merge_kernel<<<a.n_hub, 128, 0, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   if (a.n_dst > 0) {
     int grid = 0;
-    if (int rc = persistent_grid(attn_fwd_kernel<NV, false>, FWD_WARPS * 32, smem, &grid)) return rc;
+    if (int rc = persistent_grid(attn_fwd_kernel<NV, false, FULLROW>, FWD_WARPS * 32, smem, &grid)) return rc;
     int64_t need = (a.n_dst + (int64_t)FWD_WARPS * GRAB - 1) / ((int64_t)FWD_WARPS * GRAB);
     if (need < grid) grid = (int)need;
-    attn_fwd_kernel<NV, false><<<grid, FWD_WARPS * 32, smem, st>>>(a);
+    attn_fwd_kernel<NV, false, FULLROW><<<grid, FWD_WARPS * 32, smem, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   return 0;
+}
+
+template <int NV>
+static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
+  return a.V == 32 * NV ? launch_fwd_t<NV, true>(a, st) : launch_fwd_t<NV, false>(a, st);
 }
 
 }  // namespace gatk
