@@ -148,6 +148,10 @@ size_t gemm_tn_tc_workspace_bytes(int64_t Mo, int64_t No, int64_t K);
 int gemm_tn_tc_launch(int64_t Mo, int64_t No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
                       float* part, int* splits_out, cudaStream_t st);
 
+bool gemm_long_tc_eligible(int transA, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda);
+int gemm_long_tc_launch(int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                        int64_t ldb, float* C, int64_t ldc, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
+
 static bool tc_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -164,8 +168,8 @@ using namespace gatk;
 extern "C" size_t gatk_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K) {
   const int s = choose_splits(M, N, K);
   size_t simt = s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
-  size_t tcb = (!transA && !transB && tc_enabled()) ? gemm_tc_workspace_bytes(N, K) : 0;
-  if (transA && !transB && tc_enabled() && K >= 16384) {
+  size_t tcb = (!transA && tc_enabled()) ? gemm_tc_workspace_bytes(N, K) : 0;
+  if (transA && !transB && tc_enabled() && K >= 2048) {
     const size_t t = gemm_tn_tc_workspace_bytes(M, N, K);
     if (t > tcb) tcb = t;
   }
@@ -177,7 +181,8 @@ extern "C" int gatk_gemm_uses_tensor_cores(int transA, int transB, int64_t M, in
   if (!tc_enabled()) return 0;
   if (transA && !transB)  // here lda is A's pitch and "ldc" carries B's pitch (both operands are TMA-loaded)
     return gemm_tn_tc_eligible(transA, transB, M, N, K, nullptr, lda, nullptr, ldc, accumulate) ? 1 : 0;
-  return gemm_tc_eligible(transA, transB, M, N, K, nullptr, lda, nullptr, ldc, accumulate) ? 1 : 0;
+  if (gemm_tc_eligible(transA, transB, M, N, K, nullptr, lda, nullptr, ldc, accumulate)) return 1;
+  return gemm_long_tc_eligible(transA, M, N, K, nullptr, lda) ? 1 : 0;
 }
 
 extern "C" int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
@@ -190,6 +195,8 @@ extern "C" int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K
   if (tc_enabled() && ws && ws_bytes >= gemm_tc_workspace_bytes(N, K) &&
       gemm_tc_eligible(transA, transB, M, N, K, A, lda, C, ldc, accumulate))
     return gemm_tc_launch(M, N, K, A, lda, B, ldb, C, ldc, ws, ws_bytes, st);
+  if (tc_enabled() && ws && ws_bytes >= gemm_tc_workspace_bytes(N, K) && gemm_long_tc_eligible(transA, M, N, K, A, lda))
+    return gemm_long_tc_launch(transB, M, N, K, A, lda, B, ldb, C, ldc, accumulate, ws, ws_bytes, st);
   if (tc_enabled() && gemm_tn_tc_eligible(transA, transB, M, N, K, A, lda, B, ldb, accumulate) && ws &&
       ws_bytes >= gemm_tn_tc_workspace_bytes(M, N, K)) {
     int sp = 1;

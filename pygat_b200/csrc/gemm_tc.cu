@@ -303,11 +303,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
 // B[K,N] row-major -> K-major hi / lo copies Bt[Npad, Kpad], zero padded.
 __global__ void split_transpose_b_kernel(const float* __restrict__ B, int64_t ldb, int K, int N, int Kpad, int Npad,
-                                         float* __restrict__ bhi, float* __restrict__ blo) {
+                                         int b_is_nk, float* __restrict__ bhi, float* __restrict__ blo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)Npad * Kpad) return;
   const int n = (int)(i / Kpad), k = (int)(i % Kpad);
-  float v = (n < N && k < K) ? B[(int64_t)k * ldb + n] : 0.f;
+  float v = (n < N && k < K) ? (b_is_nk ? B[(int64_t)n * ldb + k] : B[(int64_t)k * ldb + n]) : 0.f;
   float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
   bhi[i] = h;
   blo[i] = v - h;
@@ -395,10 +395,16 @@ __device__ __forceinline__ void umma_tf32_mn(uint32_t tmem_d, uint64_t adesc, ui
       : "memory");
 }
 
+// KMAJOR = false: the TN product above (both operands MN-major, both split on the fly, split-K partials).
+// KMAJOR = true : C[Mo,No] (+)= A[Mo,K] * W with A row-major (K-major) split on the fly and the weights
+//                 pre-split / pre-transposed to K-major (map_b = hi, map_b2 = lo): the long-K version of the
+//                 projection kernel (any K, drains every PROMOTE k-blocks), writing C directly.
+template <bool KMAJOR>
 __global__ void __launch_bounds__(TN_THREADS, 1)
-gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      float* __restrict__ part, int Mo, int No, int m_tiles, int n_tiles, int splits,
-                      int kb_total, int kb_per_split) {
+gemm_promoted_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                            const __grid_constant__ CUtensorMap map_b2, float* __restrict__ part, int64_t ld_out,
+                            int accumulate, int Mo, int No, int m_tiles, int n_tiles, int splits, int kb_total,
+                            int kb_per_split) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -455,11 +461,18 @@ gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(r.stage), r.phase ^ 1);
           const uint32_t st = smem_base + r.stage * STAGE_BYTES;
-          mbar_expect_tx(full_bar(r.stage), 2 * TILE_BYTES);
+          if constexpr (KMAJOR) {
+            mbar_expect_tx(full_bar(r.stage), 3 * TILE_BYTES);
+            tma_load_2d(st, &map_a, full_bar(r.stage), kb * BLOCK_K, m0);
+            tma_load_2d(st + 2 * TILE_BYTES, &map_b, full_bar(r.stage), kb * BLOCK_K, n0);
+            tma_load_2d(st + 3 * TILE_BYTES, &map_b2, full_bar(r.stage), kb * BLOCK_K, n0);
+          } else {
+            mbar_expect_tx(full_bar(r.stage), 2 * TILE_BYTES);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            tma_load_2d(st + b * BOX_BYTES, &map_a, full_bar(r.stage), m0 + b * 32, kb * BLOCK_K);
-            tma_load_2d(st + 2 * TILE_BYTES + b * BOX_BYTES, &map_b, full_bar(r.stage), n0 + b * 32, kb * BLOCK_K);
+            for (int b = 0; b < 4; ++b) {
+              tma_load_2d(st + b * BOX_BYTES, &map_a, full_bar(r.stage), m0 + b * 32, kb * BLOCK_K);
+              tma_load_2d(st + 2 * TILE_BYTES + b * BOX_BYTES, &map_b, full_bar(r.stage), n0 + b * 32, kb * BLOCK_K);
+            }
           }
           r.advance();
         }
@@ -485,15 +498,27 @@ gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         tc_fence_after();
         if (lane == 0) {
           const uint32_t st = smem_base + r.stage * STAGE_BYTES;
-          const uint64_t a_hi = umma_desc_mn(st), a_lo = umma_desc_mn(st + TILE_BYTES);
-          const uint64_t b_hi = umma_desc_mn(st + 2 * TILE_BYTES), b_lo = umma_desc_mn(st + 3 * TILE_BYTES);
           const uint32_t fresh = (rel % PROMOTE) == 0 ? 0u : 1u;
+          if constexpr (KMAJOR) {
+            const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TILE_BYTES);
+            const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 3 * TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 1024 >> 4);  // next 8 rows along K
-            umma_tf32_mn(tmem_c, a_lo + adv, b_hi + adv, fresh | (uint32_t)(k != 0));
-            umma_tf32_mn(tmem_c, a_hi + adv, b_lo + adv, 1);
-            umma_tf32_mn(tmem_d, a_hi + adv, b_hi + adv, fresh | (uint32_t)(k != 0));
+            for (int k = 0; k < BLOCK_K / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle row
+              umma_tf32(tmem_c, a_lo + adv, b_hi + adv, fresh | (uint32_t)(k != 0));
+              umma_tf32(tmem_c, a_hi + adv, b_lo + adv, 1);
+              umma_tf32(tmem_d, a_hi + adv, b_hi + adv, fresh | (uint32_t)(k != 0));
+            }
+          } else {
+            const uint64_t a_hi = umma_desc_mn(st), a_lo = umma_desc_mn(st + TILE_BYTES);
+            const uint64_t b_hi = umma_desc_mn(st + 2 * TILE_BYTES), b_lo = umma_desc_mn(st + 3 * TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * 1024 >> 4);  // next 8 rows along K
+              umma_tf32_mn(tmem_c, a_lo + adv, b_hi + adv, fresh | (uint32_t)(k != 0));
+              umma_tf32_mn(tmem_c, a_hi + adv, b_lo + adv, 1);
+              umma_tf32_mn(tmem_d, a_hi + adv, b_hi + adv, fresh | (uint32_t)(k != 0));
+            }
           }
           umma_commit(empty_bar(r.stage));
           if ((rel + 1) % PROMOTE == 0 || kb == kb1 - 1) umma_commit(tfull_bar(acc));
@@ -513,7 +538,7 @@ gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         mbar_wait(full_bar(r.stage), r.phase);
         uint8_t* st = smem + r.stage * STAGE_BYTES;
 #pragma unroll
-        for (int op = 0; op < 2; ++op) {  // A then B
+        for (int op = 0; op < (KMAJOR ? 1 : 2); ++op) {  // A, then B unless the weights came pre-split
           float4* hi = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES);
           float4* lo = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES + TILE_BYTES);
 #pragma unroll
@@ -564,13 +589,19 @@ gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-      // partial tile of this k range -> workspace [split][Mo][No]
       const int gm = m0 + row;
       if (gm < Mo) {
-        float* dst = part + ((int64_t)sp * Mo + gm) * No + n0 + half * 64;
+        if constexpr (KMAJOR) {  // final values straight into C (row pitch ld_out), optional accumulate
+          float* dst = part + (int64_t)gm * ld_out + n0 + half * 64;
 #pragma unroll
-        for (int j = 0; j < 64; ++j)
-          if (n0 + half * 64 + j < No) dst[j] = racc[j];
+          for (int j = 0; j < 64; ++j)
+            if (n0 + half * 64 + j < No) dst[j] = accumulate ? dst[j] + racc[j] : racc[j];
+        } else {                 // partial tile of this k range -> workspace [split][Mo][No]
+          float* dst = part + ((int64_t)sp * Mo + gm) * No + n0 + half * 64;
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (n0 + half * 64 + j < No) dst[j] = racc[j];
+        }
       }
     }
   }
@@ -628,7 +659,7 @@ int gemm_tc_launch(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
   float* bhi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   float* blo = bhi + (size_t)Npad * Kpad;
   const int64_t total = (int64_t)Npad * Kpad;
-  split_transpose_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, ldb, (int)K, (int)N, Kpad, Npad, bhi, blo);
+  split_transpose_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, ldb, (int)K, (int)N, Kpad, Npad, 0, bhi, blo);
   GATK_CHECK_LAUNCH();
 
   CUtensorMap map_a, map_bhi, map_blo, map_c;
@@ -672,7 +703,7 @@ bool gemm_tn_tc_eligible(int transA, int transB, int64_t Mo, int64_t No, int64_t
                          const float* B, int64_t ldb, int accumulate) {
   (void)accumulate;
   if (!transA || transB) return false;
-  if (K < 16384 || Mo < 8 || No < 8 || Mo > 4096 || No > 8192) return false;
+  if (K < 2048 || Mo < 8 || No < 8 || Mo > 4096 || No > 8192) return false;
   if (K >= (1LL << 31) - 64) return false;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
   if ((lda & 3) || (ldb & 3)) return false;
@@ -695,15 +726,57 @@ int gemm_tn_tc_launch(int64_t Mo, int64_t No, int64_t K, const float* A, int64_t
   if (int rc = make_map_box32(&map_b, B, K, No, ldb)) return rc;
   static bool configured = false;
   if (!configured) {
-    GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+    GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_promoted_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
     configured = true;
   }
   const int items = mt * nt * sp;
   int grid = sm_count();
   if (items < grid) grid = items;
-  gemm_tn_tf32x3_kernel<<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(map_a, map_b, part, (int)Mo, (int)No, mt, nt, sp, kbt, kbs);
+  gemm_promoted_tf32x3_kernel<false><<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(map_a, map_b, map_b, part, 0, 0, (int)Mo, (int)No,
+                                                                             mt, nt, sp, kbt, kbs);
   GATK_CHECK_LAUNCH();
   *splits_out = sp;
+  return 0;
+}
+
+// ---- long-K / NT projection path: C[M,N] (+)= A[M,K] * op(B), any K, C written with plain stores ---------
+bool gemm_long_tc_eligible(int transA, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda) {
+  if (transA) return false;
+  if (M < 1024 || N < 8 || K < 1 || K > 65536 || N > 65536 || M >= (1LL << 31) - 256) return false;
+  if (reinterpret_cast<uintptr_t>(A) & 15) return false;
+  return (lda & 3) == 0;
+}
+
+int gemm_long_tc_launch(int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                        int64_t ldb, float* C, int64_t ldc, int accumulate, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
+  using namespace tn;
+  const int Kpad = (int)((K + BLOCK_K - 1) / BLOCK_K * BLOCK_K);
+  const int Npad = (int)((N + BLOCK_N - 1) / BLOCK_N * BLOCK_N);
+  GATK_REQUIRE(ws && ws_bytes >= gemm_tc_workspace_bytes(N, K), "tensor-core GEMM workspace too small");
+  float* bhi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  float* blo = bhi + (size_t)Npad * Kpad;
+  const int64_t total = (int64_t)Npad * Kpad;
+  split_transpose_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, ldb, (int)K, (int)N, Kpad, Npad,
+                                                                             transB ? 1 : 0, bhi, blo);
+  GATK_CHECK_LAUNCH();
+  CUtensorMap map_a, map_bhi, map_blo;
+  if (int rc = make_map(&map_a, A, M, K, lda)) return rc;
+  if (int rc = make_map(&map_bhi, bhi, Npad, Kpad, Kpad)) return rc;
+  if (int rc = make_map(&map_blo, blo, Npad, Kpad, Kpad)) return rc;
+  static bool configured = false;
+  if (!configured) {
+    GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_promoted_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+    configured = true;
+  }
+  const int mt = (int)((M + BLOCK_M - 1) / BLOCK_M), nt = Npad / BLOCK_N, kbt = Kpad / BLOCK_K;
+  const int64_t items = (int64_t)mt * nt;
+  GATK_REQUIRE(items < (1LL << 31), "too many tiles");
+  int grid = sm_count();
+  if (items < grid) grid = (int)items;
+  gemm_promoted_tf32x3_kernel<true><<<grid, TN_THREADS, TN_SMEM_BYTES, st>>>(map_a, map_bhi, map_blo, C, ldc, accumulate, (int)M,
+                                                                            (int)N, mt, nt, 1, kbt, kbt);
+  GATK_CHECK_LAUNCH();
   return 0;
 }
 

@@ -114,7 +114,29 @@ def test_tensor_core_gemm_is_fp32_accurate(M, N, K, pad):
     assert (C[:, :N].double().cpu() - ref).abs().max().item() < 1e-5 * scale
 
 
-@pytest.mark.parametrize("M,N,K,padb", [(100, 512, 200_000, 0), (128, 640, 65_536, 0), (256, 136, 30_001, 4),
+@pytest.mark.parametrize("tb,M,N,K,ldc_pad,acc", [(0, 4500, 2048, 1024, 0, 0), (1, 4500, 1024, 2048, 0, 0),
+                                                  (1, 3000, 100, 1536, 3, 1), (0, 2449, 1024, 1024, 1, 1)])
+def test_tensor_core_long_k_projection(tb, M, N, K, ldc_pad, acc):
+    """PPI-sized products (K up to 2048, dx = dZ W^T with the weights already K-major): the promoted
+    tcgen05 kernel drains its TMEM accumulators every 16 k-blocks, so accuracy does not degrade with K."""
+    assert _lib.query("gatk_gemm_uses_tensor_cores", 0, tb, M, N, K, K, N + ldc_pad, acc) == 1
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    ref = A.double() @ (B.double().t() if tb else B.double())
+    dA, dB = A.to(DEV), B.to(DEV)
+    C = torch.full((M, N + ldc_pad), 7.0, device=DEV)
+    ws_bytes = _lib.query("gatk_gemm_workspace_bytes", 0, tb, M, N, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    _lib.call("gatk_gemm", 0, tb, M, N, K, dA.data_ptr(), K, dB.data_ptr(), dB.shape[1], C.data_ptr(), N + ldc_pad,
+              acc, ws.data_ptr(), ws_bytes, _stream())
+    torch.cuda.synchronize()
+    want = ref + 7.0 if acc else ref
+    assert rel_err(C[:, :N], want) < 3e-6
+    assert torch.all(C[:, N:] == 7.0)
+
+
+@pytest.mark.parametrize("M,N,K,padb", [(1024, 2048, 4500, 0), (100, 512, 200_000, 0), (128, 640, 65_536, 0), (256, 136, 30_001, 4),
                                         (20, 24, 50_000, 0), (500, 64, 19_717, 0)])
 def test_tensor_core_weight_gradient_gemm(M, N, K, padb):
     """dW = x^T dZ (reduction over the nodes) on tcgen05: MN-major operands, both split hi/lo on the fly,
