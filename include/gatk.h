@@ -61,8 +61,6 @@ GATK_API size_t gatk_transpose_workspace_bytes(int64_t n_rows, int64_t n_cols, i
 GATK_API int gatk_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t e, const int64_t* rowptr,
                        const int32_t* col, int64_t* tptr, int32_t* trow, int32_t* perm,
                        void* ws, size_t ws_bytes, void* stream);
-/* iperm[perm[k]] = k: CSR edge id -> its position in the transposed order. */
-GATK_API int gatk_invert_permutation(const int32_t* perm, int64_t e, int32_t* iperm, void* stream);
 
 /* ------------------------------------------------------------------ dropout (F.dropout, layers.py:34,37,43 / :132,136,153)
  * keep[i] = 1 with probability 1-p (Philox4x32-10 keyed by seed, counter = offset + i/4). */
@@ -127,11 +125,9 @@ GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* 
  *  fused   per SOURCE row j over the transposed pattern (scatter-free): gathers record i once
  *          per edge and uses it for both  dz_ij = alpha_ij (keep/(1-p) dhp_i.Wh_j - c_i)
  *          LeakyReLU'(f_i+g_j)  and  dwh_j = sum_i alpha~_ij dhp_i + dg_j a_dst,  dg_j = sum_i
- *          dz_ij.  dz is written in TRANSPOSED edge order (edge_dz [E,H], a streaming write); keep_att
- *          is in CSR edge order (looked up through perm).
+ *          dz_ij.  dz is written in CSR edge order (edge_dz [E,H]); keep_att is in CSR edge order.
  *          hub_* describe the TRANSPOSED pattern's long rows (scratch: which = 1).
- *  finish  per destination row: df_i = sum_j dz_ij (segmented sum over CSR rows, dz gathered through
- *          iperm = inverse of perm: CSR edge id -> transposed position), then
+ *  finish  per destination row: df_i = sum_j dz_ij (segmented sum over CSR rows), then
  *          dwh_i += df_i a_src and the post-projection dropout mask keep_wh (layers.py:37,136).
  *          hub_* describe the CSR pattern's long rows (scratch: which = 2). */
 GATK_API int64_t gatk_attn_bwd_record_ld(int H, int Dp);
@@ -146,7 +142,7 @@ GATK_API int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int32
                                  int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                                  int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream);
 GATK_API int gatk_attn_bwd_finish(int64_t n, const int64_t* rowptr, int H, int Dp, const float* edge_dz,
-                                  const int32_t* iperm, const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
+                                  const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
                                   int64_t lddwh, float* df, int seg_len, const int32_t* hub_rows,
                                   const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
                                   void* stream);

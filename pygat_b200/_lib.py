@@ -25,7 +25,6 @@ PROTOTYPES = {
     "gatk_csr_from_coo": (c_int, [P, P, c_int64, c_int64, P, P, P, c_size_t, P]),
     "gatk_transpose_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "gatk_csr_transpose": (c_int, [c_int64, c_int64, c_int64, P, P, P, P, P, P, c_size_t, P]),
-    "gatk_invert_permutation": (c_int, [P, c_int64, P, P]),
     "gatk_dropout_keep_mask": (c_int, [P, c_int64, c_float, c_uint64, c_uint64, P]),
     "gatk_mask_scale": (c_int, [P, c_int64, P, c_float, P, c_int64, c_int64, c_int64, P]),
     "gatk_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int64, c_int64]),
@@ -43,7 +42,7 @@ PROTOTYPES = {
     "gatk_attn_bwd_fused": (c_int, [c_int64, P, P, P, c_int, c_int, P, c_int64, P, P, c_int64, P, c_float, c_float,
                                     P, P, c_int64, P, P,
                                     c_int, P, P, c_int, c_int, P, P, P]),
-    "gatk_attn_bwd_finish": (c_int, [c_int64, P, c_int, c_int, P, P, P, P, c_float, P, c_int64, P,
+    "gatk_attn_bwd_finish": (c_int, [c_int64, P, c_int, c_int, P, P, P, c_float, P, c_int64, P,
                                      c_int, P, P, c_int, c_int, P, P]),
     "gatk_da_workspace_floats": (c_size_t, [c_int, c_int]),
     "gatk_da_reduce": (c_int, [c_int64, c_int, c_int, P, c_int64, P, P, P, P, P, P]),

@@ -128,7 +128,7 @@ __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, 
                                                   const LaneGeom<NV>& geo, const SlotLayout& lay, float4 (&acc)[NV],
                                                   float (&dgacc)[NV], int* row_s, int* perm_s, float* at_s, float* A_s,
                                                   float* B_s, float* dz_s) {
-  constexpr int U = NV >= 8 ? 1 : (NV == 4 ? 2 : 4);  // gathered rows in flight per warp (deeper did not help)
+  constexpr int U = NV >= 8 ? 1 : (NV == 4 ? 4 : 8 / NV);  // gathered rows in flight per warp
   const int H = a.H, WS = lay.WS, lph = a.lph;
   float4 wj[NV];
 #pragma unroll
@@ -203,12 +203,11 @@ __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, 
       fused_edge<NV, FULLROW>(geo, lph, w, wj, at_s + o, A_s + o, B_s + o, dz_s + o, lay.writer, acc, dgacc);
     }
     __syncwarp();
-    // ---- dz in TRANSPOSED edge order (coalesced streaming write; the finish pass gathers it through
-    // the inverse permutation -- scattered 32-byte writes cost far more DRAM time than scattered reads)
+    // ---- dz back to CSR edge order: each edge's H values are one contiguous sector
     for (int idx = lane; idx < cnt * H; idx += 32) {
       const int tt = idx / H, h = idx - tt * H;
       const int pos = lph < 32 ? (h % lay.G) * NV + h / lay.G : h * q;
-      a.edge_dz[(base + tt) * H + h] = dz_s[tt * WS + pos];
+      a.edge_dz[(int64_t)perm_s[tt] * H + h] = dz_s[tt * WS + pos];
     }
     __syncwarp();
   }
@@ -220,7 +219,7 @@ __device__ __forceinline__ void bwd_fused_store_slot(const BwdFusedArgs& a, int 
 }
 
 template <int NV, bool HUB, bool FULLROW>
-__global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 4 : 1) attn_bwd_fused_kernel(const BwdFusedArgs a) {
+__global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 3 : 1) attn_bwd_fused_kernel(const BwdFusedArgs a) {
   extern __shared__ __align__(16) float smem_fused[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   LaneGeom<NV> geo;
@@ -299,7 +298,6 @@ struct FinishArgs {
   const int64_t* rowptr;
   int H, lph, V;
   const float* edge_dz;
-  const int32_t* iperm;  // CSR edge id -> position in the transposed order (where fused wrote dz)
   const float* a_src;
   const uint8_t* keep_wh;
   float inv_keep;
@@ -314,17 +312,18 @@ struct FinishArgs {
 };
 
 // sum over edges [beg,end) of dz[e][h]; lane h ends up holding head h's sum
-__device__ __forceinline__ float segsum_heads(const float* __restrict__ dz, const int32_t* __restrict__ iperm, int H,
-                                              int64_t beg, int64_t end, int lane) {
+__device__ __forceinline__ float segsum_heads(const float* __restrict__ dz, int H, int64_t beg, int64_t end, int lane) {
   float mine = 0.f;
-  for (int64_t base = beg; base < end; base += 64) {
-    const int64_t e0 = base + lane, e1 = base + 32 + lane;
-    const float* p0 = e0 < end ? dz + (int64_t)__ldg(iperm + e0) * H : nullptr;
-    const float* p1 = e1 < end ? dz + (int64_t)__ldg(iperm + e1) * H : nullptr;
-    for (int h = 0; h < H; ++h) {
-      const float s = warp_sum((p0 ? __ldg(p0 + h) : 0.f) + (p1 ? __ldg(p1 + h) : 0.f));
-      if (lane == h) mine += s;
+  for (int h = 0; h < H; ++h) {
+    float s0 = 0.f, s1 = 0.f;
+    int64_t e = beg + lane;
+    for (; e + 32 < end; e += 64) {
+      s0 += __ldg(dz + e * H + h);
+      s1 += __ldg(dz + (e + 32) * H + h);
     }
+    if (e < end) s0 += __ldg(dz + e * H + h);
+    const float s = warp_sum(s0 + s1);
+    if (lane == h) mine = s;
   }
   return mine;
 }
@@ -359,7 +358,7 @@ __global__ void attn_bwd_finish_kernel(const FinishArgs a) {
   if (row >= a.n) return;
   const int64_t beg = a.rowptr[row], end = a.rowptr[row + 1];
   if (end - beg > a.seg_len) return;  // hub rows: segment kernels below
-  finish_row<NV>(a, row, segsum_heads(a.edge_dz, a.iperm, a.H, beg, end, lane), lane);
+  finish_row<NV>(a, row, segsum_heads(a.edge_dz, a.H, beg, end, lane), lane);
 }
 
 __global__ void attn_bwd_finish_hub_seg_kernel(const FinishArgs a) {
@@ -369,7 +368,7 @@ __global__ void attn_bwd_finish_hub_seg_kernel(const FinishArgs a) {
   int row;
   int64_t beg, end;
   hub_locate(seg, a.hub_rows, a.hub_seg_ptr, a.n_hub, a.rowptr, a.seg_len, row, beg, end);
-  const float s = segsum_heads(a.edge_dz, a.iperm, a.H, beg, end, lane);
+  const float s = segsum_heads(a.edge_dz, a.H, beg, end, lane);
   if (lane < a.H) a.scratch[(int64_t)seg * a.H + lane] = s;
 }
 
@@ -492,17 +491,16 @@ extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int
 }
 
 extern "C" int gatk_attn_bwd_finish(int64_t n, const int64_t* rowptr, int H, int Dp, const float* edge_dz,
-                                    const int32_t* iperm, const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
+                                    const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
                                     int64_t lddwh, float* df, int seg_len, const int32_t* hub_rows,
                                     const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
                                     void* stream) {
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
   if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
-  GATK_REQUIRE(rowptr && a_src && dwh && df && iperm && lddwh % 4 == 0, "bad arguments");
+  GATK_REQUIRE(rowptr && a_src && dwh && df && lddwh % 4 == 0, "bad arguments");
   FinishArgs a;
-  a.n = n; a.rowptr = rowptr; a.H = H; a.lph = Dp / 4; a.V = H * (Dp / 4); a.edge_dz = edge_dz; a.iperm = iperm;
-  a.a_src = a_src;
+  a.n = n; a.rowptr = rowptr; a.H = H; a.lph = Dp / 4; a.V = H * (Dp / 4); a.edge_dz = edge_dz; a.a_src = a_src;
   a.keep_wh = keep_wh; a.inv_keep = inv_keep; a.dwh = dwh; a.lddwh = lddwh; a.df = df; a.seg_len = seg_len;
   a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub; a.n_hub_seg = n_hub_seg; a.scratch = hub_scratch;
   cudaStream_t st = (cudaStream_t)stream;

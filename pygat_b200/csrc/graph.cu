@@ -116,11 +116,6 @@ __global__ void gather_rows_kernel(const int32_t* __restrict__ erow, const int32
   if (i < e) trow[i] = erow[perm[i]];
 }
 
-__global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t e, int32_t* __restrict__ iperm) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < e) iperm[perm[i]] = (int32_t)i;
-}
-
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static size_t scan_temp_bytes(int64_t n) {
@@ -236,14 +231,6 @@ extern "C" int gatk_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t e, con
   GATK_REQUIRE(tmp_bytes >= sort_bytes, "sort workspace too small");
   GATK_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, sort_bytes, col, skeys, (const int32_t*)eid, perm, e, 0, bits, st));
   gather_rows_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(erow, perm, e, trow);
-  GATK_CHECK_LAUNCH();
-  return 0;
-}
-
-extern "C" int gatk_invert_permutation(const int32_t* perm, int64_t e, int32_t* iperm, void* stream) {
-  if (e == 0) return 0;
-  GATK_REQUIRE(perm && iperm && e > 0, "bad arguments");
-  invert_perm_kernel<<<(unsigned)((e + 255) / 256), 256, 0, (cudaStream_t)stream>>>(perm, e, iperm);
   GATK_CHECK_LAUNCH();
   return 0;
 }

@@ -139,7 +139,7 @@ class GatLayerFunction(torch.autograd.Function):
         M_out = HD * (2 if has_skip else 1)
         st = _stream()
         gout = gout.contiguous()
-        tptr, trow, perm, thubs, iperm = graph.transpose()
+        tptr, trow, perm, thubs = graph.transpose()
 
         # dZ = [dWh | dSkip]; with a skip projection dL/dh' IS dSkip, so prep writes it there as well.
         dz_rows = torch.empty(n, M_out, dtype=torch.float32, device=dev)
@@ -165,8 +165,7 @@ class GatLayerFunction(torch.autograd.Function):
         # ---- finish: df = segmented sum of dz, dWh += df a_src, Wh-dropout mask ------------------
         hubs = graph.hubs
         scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
-        _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), _ptr(iperm),
-                  a_src.data_ptr(),
+        _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), a_src.data_ptr(),
                   _ptr(masks.keep_wh), inv_keep, dz_rows.data_ptr(), M_out, df.data_ptr(),
                   *hubs.args(scratch), st)
         del edge_dz

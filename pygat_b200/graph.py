@@ -73,7 +73,7 @@ class Graph:
         self.seg_len = int(seg_len or DEFAULT_SEG_LEN)
         self.hubs = HubPartition(self.rowptr, self.seg_len)
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._t = None  # (tptr, trow, perm, hubs of the transpose, iperm)
+        self._t: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, HubPartition]] = None
 
     # ------------------------------------------------------------------ constructors
     @staticmethod
@@ -126,9 +126,7 @@ class Graph:
             _lib.call("gatk_csr_transpose", self.n_dst, self.n_src, self.nnz, self.rowptr.data_ptr(),
                       _ptr(self.col), tptr.data_ptr(), _ptr(trow), _ptr(perm), ws.data_ptr(), ws_bytes, _stream())
             del ws
-            iperm = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
-            _lib.call("gatk_invert_permutation", _ptr(perm), self.nnz, _ptr(iperm), _stream())
-            self._t = (tptr, trow, perm, HubPartition(tptr, self.seg_len), iperm)
+            self._t = (tptr, trow, perm, HubPartition(tptr, self.seg_len))
         return self._t
 
     def edge_index(self) -> torch.Tensor:

@@ -162,7 +162,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         st = _stream()
         gout = gout.contiguous()
         need_dx = ctx.needs_input_grad[0]
-        tptr, trow, perm, thubs, iperm = graph.transpose()
+        tptr, trow, perm, thubs = graph.transpose()
 
         ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
         rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
@@ -187,8 +187,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         hubs = graph.hubs
         scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
         dwh_own = plan.rows(dwh_part)
-        _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), _ptr(iperm),
-                  a_src.data_ptr(),
+        _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), a_src.data_ptr(),
                   None, 1.0, dwh_own.data_ptr(), HD, df.data_ptr(), *hubs.args(scratch), st)
         del edge_dz
 

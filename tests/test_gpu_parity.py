@@ -41,11 +41,10 @@ def test_csr_matches_nonzero_bit_exact(name, order, rule):
     rowptr, col = O.csr_from_edges(edge, n)
     assert torch.equal(g.rowptr.cpu(), rowptr) and torch.equal(g.col.cpu(), col)
     assert torch.equal(g.edge_index().cpu(), edge)
-    tptr, trow, perm, _, iperm = g.transpose()
+    tptr, trow, perm, _ = g.transpose()
     o_tptr, o_trow, o_perm = O.csr_transpose(rowptr, col, n)
     assert torch.equal(tptr.cpu(), o_tptr) and torch.equal(trow.cpu(), o_trow)
     assert torch.equal(perm.cpu().long(), o_perm)
-    assert torch.equal(iperm.cpu().long()[o_perm], torch.arange(o_perm.numel()))
 
 
 def test_csr_from_coo_and_sparse_tensor_inputs():
