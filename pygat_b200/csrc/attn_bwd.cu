@@ -128,7 +128,7 @@ __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, 
                                                   const LaneGeom<NV>& geo, const SlotLayout& lay, float4 (&acc)[NV],
                                                   float (&dgacc)[NV], int* row_s, int* perm_s, float* at_s, float* A_s,
                                                   float* B_s, float* dz_s) {
-  constexpr int U = NV >= 8 ? 1 : (NV == 4 ? 4 : 8 / NV);  // gathered rows in flight per warp
+  constexpr int U = NV >= 8 ? 1 : (NV == 4 ? 2 : 4);  // gathered rows in flight per warp (deeper did not help)
   const int H = a.H, WS = lay.WS, lph = a.lph;
   float4 wj[NV];
 #pragma unroll
@@ -219,7 +219,7 @@ __device__ __forceinline__ void bwd_fused_store_slot(const BwdFusedArgs& a, int 
 }
 
 template <int NV, bool HUB, bool FULLROW>
-__global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 3 : 1) attn_bwd_fused_kernel(const BwdFusedArgs a) {
+__global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 4 : 1) attn_bwd_fused_kernel(const BwdFusedArgs a) {
   extern __shared__ __align__(16) float smem_fused[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   LaneGeom<NV> geo;
