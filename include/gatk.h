@@ -102,7 +102,9 @@ GATK_API int gatk_logits_fwd(int64_t n, int H, int Dp, float* wh, int64_t ldw, c
  * hub_scratch (gatk_hub_scratch_floats) merged by a second kernel.
  * keep_att: [E, H] or NULL.  hagg (pre-skip, pre-ELU aggregation) and lse
  * (m + log l per row/head) are saved for backward; either may be NULL.
- * counter: one int32 of scratch (dynamic row scheduler).
+ * counter: one int32 of scratch (dynamic scheduler).  item_ptr (int32 [n_items+1], optional): edge-balanced
+ * work items, item k = rows [item_ptr[k], item_ptr[k+1]); a warp claims one item per atomic, so skewed
+ * degree distributions do not leave a few warps with all the long rows.  NULL: 8 rows per claim.
  * gatk_hub_scratch_floats(which, ...): floats of hub_scratch for which = 0 (attn_fwd),
  * 1 (attn_bwd_fused), 2 (attn_bwd_finish). */
 GATK_API size_t gatk_hub_scratch_floats(int which, int H, int Dp, int n_hub_seg);
@@ -112,7 +114,8 @@ GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* 
                   const float* skipv, int64_t lds, int act_elu,
                   float* hagg, float* out, int64_t ldo, float* lse,
                   int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr,
-                  int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream);
+                  int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter,
+                  const int32_t* item_ptr, int n_items, void* stream);
 
 /* ------------------------------------------------------------------ K3/K4: backward of the fused attention
  * Autograd of layers.py:141-160, with the reference's dense N x N SpecialSpmmFunction.backward
@@ -140,7 +143,8 @@ GATK_API int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int32
                                  int64_t ldrec, const uint8_t* keep_att, float inv_keep, float alpha,
                                  const float* a_dst, float* dwh, int64_t lddwh, float* dg, float* edge_dz,
                                  int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
-                                 int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream);
+                                 int n_hub_seg, float* hub_scratch, int32_t* counter,
+                                 const int32_t* item_ptr, int n_items, void* stream);
 GATK_API int gatk_attn_bwd_finish(int64_t n, const int64_t* rowptr, int H, int Dp, const float* edge_dz,
                                   const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
                                   int64_t lddwh, float* df, int seg_len, const int32_t* hub_rows,

@@ -90,6 +90,8 @@ struct BwdFusedArgs {
   int n_hub, n_hub_seg;
   float* scratch;
   int32_t* counter;
+  const int32_t* item_ptr;  // edge-balanced work items over the transposed rows (NULL: 8 rows per grab)
+  int n_items;
 };
 
 constexpr int FUSED_WARPS = 4;
@@ -252,11 +254,20 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 4 : 1) attn_bwd_fu
     return;
   }
 
-  int cur = warp_grab(a.counter, lane);
-  while (cur < a.n_src) {
-    const int nxt = warp_grab(a.counter, lane);
-    const int rend = cur + GRAB < a.n_src ? cur + GRAB : (int)a.n_src;
-    for (int j = cur; j < rend; ++j) {
+  const int n_work = a.item_ptr ? a.n_items : (int)a.n_src;
+  const int step = a.item_ptr ? 1 : GRAB;
+  int cur = warp_grab(a.counter, lane, step);
+  while (cur < n_work) {
+    const int nxt = warp_grab(a.counter, lane, step);
+    int rbeg, rend;
+    if (a.item_ptr) {
+      rbeg = a.item_ptr[cur];
+      rend = a.item_ptr[cur + 1];
+    } else {
+      rbeg = cur;
+      rend = cur + GRAB < a.n_src ? cur + GRAB : (int)a.n_src;
+    }
+    for (int j = rbeg; j < rend; ++j) {
       const int64_t beg = a.tptr[j], end = a.tptr[j + 1];
       if (end - beg > a.seg_len) continue;
       bwd_fused_segment<NV, FULLROW>(a, j, beg, end, lane, geo, lay, acc, dgacc, row_s, perm_s, at_s, A_s, B_s, dz_s);
@@ -402,7 +413,8 @@ static int launch_fused_t(const BwdFusedArgs& a, cudaStream_t st) {
   if (a.n_src > 0) {
     int grid = 0;
     if (int rc = persistent_grid(attn_bwd_fused_kernel<NV, false, FULLROW>, FUSED_WARPS * 32, smem, &grid)) return rc;
-    const int64_t need = (a.n_src + (int64_t)FUSED_WARPS * GRAB - 1) / ((int64_t)FUSED_WARPS * GRAB);
+    const int64_t need = a.item_ptr ? (a.n_items + FUSED_WARPS - 1) / FUSED_WARPS
+                                    : (a.n_src + (int64_t)FUSED_WARPS * GRAB - 1) / ((int64_t)FUSED_WARPS * GRAB);
     if (need < grid) grid = (int)need;
     attn_bwd_fused_kernel<NV, false, FULLROW><<<grid, FUSED_WARPS * 32, smem, st>>>(a);
     GATK_CHECK_LAUNCH();
@@ -470,7 +482,8 @@ extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int
                                    int64_t ldrec, const uint8_t* keep_att, float inv_keep, float alpha,
                                    const float* a_dst, float* dwh, int64_t lddwh, float* dg, float* edge_dz,
                                    int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
-                                   int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream) {
+                                   int n_hub_seg, float* hub_scratch, int32_t* counter, const int32_t* item_ptr,
+                                   int n_items, void* stream) {
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
   if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
@@ -484,7 +497,7 @@ extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int
   a.wh = wh; a.ldw = ldw; a.g = g; a.rec = rec; a.ldrec = ldrec; a.keep = keep_att; a.inv_keep = inv_keep;
   a.alpha = alpha; a.a_dst = a_dst; a.dwh = dwh; a.lddwh = lddwh; a.dg = dg;
   a.edge_dz = edge_dz; a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub;
-  a.n_hub_seg = n_hub_seg; a.scratch = hub_scratch; a.counter = counter;
+  a.n_hub_seg = n_hub_seg; a.scratch = hub_scratch; a.counter = counter; a.item_ptr = item_ptr; a.n_items = n_items;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
   NV_DISPATCH(nv, return launch_fused<NV>(a, st));
   return 0;

@@ -26,9 +26,9 @@ struct LaneGeom {
   }
 };
 
-__device__ __forceinline__ int warp_grab(int32_t* counter, int lane) {
+__device__ __forceinline__ int warp_grab(int32_t* counter, int lane, int step) {
   int r = 0;
-  if (lane == 0) r = atomicAdd(counter, GRAB);
+  if (lane == 0) r = atomicAdd(counter, step);
   return __shfl_sync(FULL, r, 0);
 }
 

@@ -39,6 +39,8 @@ struct FwdArgs {
   int n_hub, n_hub_seg;
   float* scratch;
   int32_t* counter;
+  const int32_t* item_ptr;  // edge-balanced work items: rows [item_ptr[k], item_ptr[k+1]) (NULL: 8 rows per grab)
+  int n_items;
 };
 
 // Online-softmax aggregation of edges [beg,end) of destination `row` into (acc, m, l).
@@ -176,11 +178,20 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) attn_fwd_kernel(const FwdArgs 
     return;
   }
 
-  int cur = warp_grab(a.counter, lane);
-  while (cur < a.n_dst) {
-    int nxt = warp_grab(a.counter, lane);
-    int rend = cur + GRAB < a.n_dst ? cur + GRAB : (int)a.n_dst;
-    for (int row = cur; row < rend; ++row) {
+  const int n_work = a.item_ptr ? a.n_items : (int)a.n_dst;
+  const int step = a.item_ptr ? 1 : GRAB;
+  int cur = warp_grab(a.counter, lane, step);
+  while (cur < n_work) {
+    int nxt = warp_grab(a.counter, lane, step);
+    int rbeg, rend;
+    if (a.item_ptr) {
+      rbeg = a.item_ptr[cur];
+      rend = a.item_ptr[cur + 1];
+    } else {
+      rbeg = cur;
+      rend = cur + GRAB < a.n_dst ? cur + GRAB : (int)a.n_dst;
+    }
+    for (int row = rbeg; row < rend; ++row) {
       int64_t beg = a.rowptr[row], end = a.rowptr[row + 1];
       if (end - beg > a.seg_len) continue;  // hub: handled by the segment kernels
       fwd_segment<NV, FULLROW>(a, row, beg, end, lane, geo, lay, acc, m_reg, l_reg, col_s, p_s, scale_s);
@@ -233,7 +244,8 @@ static int launch_fwd_t(const FwdArgs& a, cudaStream_t st) {
   if (a.n_dst > 0) {
     int grid = 0;
     if (int rc = persistent_grid(attn_fwd_kernel<NV, false, FULLROW>, FWD_WARPS * 32, smem, &grid)) return rc;
-    int64_t need = (a.n_dst + (int64_t)FWD_WARPS * GRAB - 1) / ((int64_t)FWD_WARPS * GRAB);
+    int64_t need = a.item_ptr ? (a.n_items + FWD_WARPS - 1) / FWD_WARPS
+                              : (a.n_dst + (int64_t)FWD_WARPS * GRAB - 1) / ((int64_t)FWD_WARPS * GRAB);
     if (need < grid) grid = (int)need;
     attn_fwd_kernel<NV, false, FULLROW><<<grid, FWD_WARPS * 32, smem, st>>>(a);
     GATK_CHECK_LAUNCH();
@@ -256,7 +268,8 @@ extern "C" int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t
                              const float* skipv, int64_t lds, int act_elu,
                              float* hagg, float* out, int64_t ldo, float* lse,
                              int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr,
-                             int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter, void* stream) {
+                             int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter,
+                             const int32_t* item_ptr, int n_items, void* stream) {
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
   if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
@@ -270,7 +283,7 @@ extern "C" int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t
   a.wh = wh; a.ldw = ldw; a.f = f; a.g = g; a.keep = keep_att; a.inv_keep = inv_keep; a.alpha = alpha;
   a.skipv = skipv; a.lds = lds; a.act_elu = act_elu; a.hagg = hagg; a.out = out; a.ldo = ldo; a.lse = lse;
   a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub; a.n_hub_seg = n_hub_seg;
-  a.scratch = hub_scratch; a.counter = counter;
+  a.scratch = hub_scratch; a.counter = counter; a.item_ptr = item_ptr; a.n_items = n_items;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
   NV_DISPATCH(nv, return launch_fwd<NV>(a, st));
   return 0;

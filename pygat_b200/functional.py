@@ -120,7 +120,7 @@ class GatLayerFunction(torch.autograd.Function):
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_ptr, M_out,
                   f.data_ptr(), g.data_ptr(), _ptr(masks.keep_att), inv_keep, float(alpha),
                   skip_ptr, M_out, int(act_elu), _ptr(hagg), out.data_ptr(), HD, _ptr(lse),
-                  *hubs.args(scratch), graph.counter.data_ptr(), st)
+                  *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
 
         if need_grad:
             ctx.graph, ctx.masks = graph, masks
@@ -159,7 +159,7 @@ class GatLayerFunction(torch.autograd.Function):
         _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, z.data_ptr(), M_out,
                   g.data_ptr(), rec.data_ptr(), ldrec, _ptr(masks.keep_att), inv_keep, alpha,
                   a_dst.data_ptr(), dz_rows.data_ptr(), M_out, dg.data_ptr(), edge_dz.data_ptr(),
-                  *thubs.args(scratch_t), graph.counter.data_ptr(), st)
+                  *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), st)
         del rec
 
         # ---- finish: df = segmented sum of dz, dWh += df a_src, Wh-dropout mask ------------------

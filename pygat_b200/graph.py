@@ -14,7 +14,8 @@ from . import _lib
 RULE_NONZERO = 0   # SpGraphAttentionLayer: every entry != 0 (layers.py:129)
 RULE_POSITIVE = 1  # GraphAttentionLayer:   entries > 0   (layers.py:41)
 
-DEFAULT_SEG_LEN = int(os.environ.get("GATK_SEG_LEN", "1024"))
+DEFAULT_SEG_LEN = int(os.environ.get("GATK_SEG_LEN", "512"))   # rows longer than this are split into segments
+ITEM_EDGES = int(os.environ.get("GATK_ITEM_EDGES", "256"))   # target stored entries per scheduler work item
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -48,9 +49,24 @@ class HubPartition:
         else:
             self.rows = self.seg_ptr = None
             self.n_seg = 0
+        # edge-balanced work items for the dynamic scheduler of the gather kernels: consecutive rows are
+        # grouped until they hold ~ITEM_EDGES stored entries (hub rows are skipped by those kernels)
+        n, e = ptr.numel() - 1, int(ptr[-1].item()) if ptr.numel() > 1 else 0
+        if n > 0 and e > 0:
+            cuts = torch.searchsorted(ptr[:-1].contiguous(), torch.arange(0, e, ITEM_EDGES, device=ptr.device))
+            bounds = torch.unique_consecutive(torch.cat([cuts, torch.tensor([n], device=ptr.device)]))
+            if int(bounds[0].item()) != 0:
+                bounds = torch.cat([torch.zeros(1, dtype=bounds.dtype, device=ptr.device), bounds])
+            self.items = bounds.to(torch.int32).contiguous()
+            self.n_items = int(self.items.numel()) - 1
+        else:
+            self.items, self.n_items = None, 0
 
     def args(self, scratch: Optional[torch.Tensor]):
         return (self.seg_len, _ptr(self.rows), _ptr(self.seg_ptr), self.n_hub, self.n_seg, _ptr(scratch))
+
+    def item_args(self):
+        return (_ptr(self.items), self.n_items)
 
 
 class Graph:

@@ -141,7 +141,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_full.data_ptr(), HD,
                   f.data_ptr(), g_full.data_ptr(), None, 1.0, float(alpha), _ptr(skipv), HD, int(act_elu),
-                  _ptr(hagg), out.data_ptr(), HD, _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), st)
+                  _ptr(hagg), out.data_ptr(), HD, _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         if need_grad:
             ctx.graph, ctx.plan = graph, plan
             ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu))
@@ -179,7 +179,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, wh_full.data_ptr(), HD,
                   g_full.data_ptr(), rec.data_ptr(), ldrec, None, 1.0, alpha,
                   a_dst.data_ptr(), dwh_part.data_ptr(), HD, dg_part.data_ptr(), edge_dz.data_ptr(),
-                  *thubs.args(scratch_t), graph.counter.data_ptr(), st)
+                  *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), st)
         del rec
         dg_loc = reduce_rows(dg_part, plan).contiguous()
         # owned rows: df = segmented sum of dz, dWh_i += df_i a_src (added once, on the owner's partial rows)
