@@ -48,13 +48,12 @@ def algorithmic_bytes(n, e, H, D, f_in, need_dx=False):
     k1 = 4 * n * f_in + 4 * f_in * H * D + 4 * n * H * (D + 2)
     k5 = 4 * n * f_in + 4 * n * H * D + 4 * f_in * H * D + ((4 * n * H * D + 4 * n * f_in) if need_dx else 0)
     prep = n * H * (16 * D + 4)                      # gout, out, hagg read; dhp write; c write
-    fused = e * H * (4 * D + 12 + 4) + 8 * e + n * H * (8 * D + 8)   # dhp_i gather, f/lse/c, dz write, trow+perm
-    finish = 4 * e * H + n * H * (8 * D + 4) + 8 * n  # dz read, dWh read-modify-write, df write
-    da = n * H * (4 * D + 8)
+    fused = e * H * (4 * D + 16 + 4) + 8 * e + n * H * (8 * D + 8)   # record gather (dh' + f,lse,c,pad), dz write, trow+perm
+    finish = 4 * e * H + 4 * n * H + 8 * n            # dz read, df write (folded form: no dWh update, no da pass)
     return {"gatk_attn_fwd": k2, "gatk_attn_bwd_prep": prep, "gatk_attn_bwd_fused": fused,
-            "gatk_attn_bwd_finish": finish, "gatk_da_reduce": da, "projection_fwd": k1, "projection_bwd": k5,
+            "gatk_attn_bwd_finish": finish, "projection_fwd": k1, "projection_bwd": k5,
             "layer_survey": k2 + k3_survey + k4_survey + k1 + k5,
-            "layer": k2 + prep + fused + finish + da + k1 + k5}
+            "layer": k2 + prep + fused + finish + k1 + k5}
 
 
 def measured_peak():
@@ -306,9 +305,9 @@ class SingleGpuLayerBench:
         self.cfg = cfg
         hubs = 2 if self.graph.hubs.n_seg else 0
         thubs = 2 if self.graph.transpose()[3].n_seg else 0
-        # gemm fwd 2 (B split + tcgen05), logits 1, attn fwd 1(+2), prep 1, fused 1(+2), finish 1(+2),
-        # da 2, gemm dW 2 (split-K)
-        self.launches_per_step = 2 + 1 + (1 + hubs) + 1 + (1 + thubs) + (1 + hubs) + 2 + 2
+        # gemm fwd 2 (weight split + tcgen05), attn fwd 1(+2), prep 1, fused 1(+2), finish 1(+2),
+        # gemm dW 2 (tcgen05 split-K + reduce)
+        self.launches_per_step = 2 + (1 + hubs) + 1 + (1 + thubs) + (1 + hubs) + 2
         self.x_host = None
 
     def _layer(self, x):

@@ -109,7 +109,7 @@ GATK_API int gatk_logits_fwd(int64_t n, int H, int Dp, float* wh, int64_t ldw, c
  * 1 (attn_bwd_fused), 2 (attn_bwd_finish). */
 GATK_API size_t gatk_hub_scratch_floats(int which, int H, int Dp, int n_hub_seg);
 GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp,
-                  const float* wh, int64_t ldw, const float* f, const float* g,
+                  const float* wh, int64_t ldw, const float* f, const float* g, int64_t ldfg,
                   const uint8_t* keep_att, float inv_keep, float alpha,
                   const float* skipv, int64_t lds, int act_elu,
                   float* hagg, float* out, int64_t ldo, float* lse,
@@ -132,22 +132,28 @@ GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* 
  *          hub_* describe the TRANSPOSED pattern's long rows (scratch: which = 1).
  *  finish  per destination row: df_i = sum_j dz_ij (segmented sum over CSR rows), then
  *          dwh_i += df_i a_src and the post-projection dropout mask keep_wh (layers.py:37,136).
- *          hub_* describe the CSR pattern's long rows (scratch: which = 2). */
+ *          hub_* describe the CSR pattern's long rows (scratch: which = 2).
+ * f, g, df, dg are [rows, H] with explicit row pitches (ldf*, ldg, lddf, lddg): they may be column blocks of
+ * the projection output / its gradient.  a_dst == NULL (fused) and a_src == NULL (finish) select the FOLDED
+ * form used when no dropout sits between projection and logits: f = x (W a_src), g = x (W a_dst) come out of
+ * the projection GEMM as extra columns, df / dg go back into its backward as extra columns, and the
+ * dg a_dst / df a_src terms and the da reduction become parameter-sized algebra on the host side. */
 GATK_API int64_t gatk_attn_bwd_record_ld(int H, int Dp);
 GATK_API int gatk_attn_bwd_prep(int64_t n, int H, int Dp, const float* gout, int64_t ldgo, const float* out,
                                 int64_t ldo, int act_elu, const float* hagg, int64_t ldh, const float* f,
-                                const float* lse, float* rec, int64_t ldrec, float* dhp2, int64_t lddhp2,
+                                int64_t ldf, const float* lse, float* rec, int64_t ldrec, float* dhp2, int64_t lddhp2,
                                 void* stream);
 GATK_API int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int32_t* trow, const int32_t* perm,
-                                 int H, int Dp, const float* wh, int64_t ldw, const float* g, const float* rec,
-                                 int64_t ldrec, const uint8_t* keep_att, float inv_keep, float alpha,
-                                 const float* a_dst, float* dwh, int64_t lddwh, float* dg, float* edge_dz,
+                                 int H, int Dp, const float* wh, int64_t ldw, const float* g, int64_t ldg,
+                                 const float* rec, int64_t ldrec, const uint8_t* keep_att, float inv_keep,
+                                 float alpha, const float* a_dst, float* dwh, int64_t lddwh, float* dg,
+                                 int64_t lddg, float* edge_dz,
                                  int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                                  int n_hub_seg, float* hub_scratch, int32_t* counter,
                                  const int32_t* item_ptr, int n_items, void* stream);
 GATK_API int gatk_attn_bwd_finish(int64_t n, const int64_t* rowptr, int H, int Dp, const float* edge_dz,
                                   const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
-                                  int64_t lddwh, float* df, int seg_len, const int32_t* hub_rows,
+                                  int64_t lddwh, float* df, int64_t lddf, int seg_len, const int32_t* hub_rows,
                                   const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
                                   void* stream);
 

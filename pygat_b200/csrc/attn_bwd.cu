@@ -27,7 +27,7 @@ template <int NV>
 __global__ void attn_bwd_prep_kernel(int64_t n, int H, int lph, int V, const float* __restrict__ gout, int64_t ldgo,
                                      const float* __restrict__ out, int64_t ldo, int act_elu,
                                      const float* __restrict__ hagg, int64_t ldh, const float* __restrict__ f,
-                                     const float* __restrict__ lse, float* __restrict__ rec, int64_t ldrec,
+                                     int64_t ldf, const float* __restrict__ lse, float* __restrict__ rec, int64_t ldrec,
                                      float* __restrict__ dhp2, int64_t lddhp2) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -58,7 +58,7 @@ __global__ void attn_bwd_prep_kernel(int64_t n, int H, int lph, int V, const flo
     const int slot = lane + 32 * v;
     if (slot < V && slot % lph == 0) {
       const int h = slot / lph;
-      stg4(rec + row * ldrec + V * 4 + h * 4, make_float4(__ldg(f + row * H + h), __ldg(lse + row * H + h), part[v], 0.f));
+      stg4(rec + row * ldrec + V * 4 + h * 4, make_float4(__ldg(f + row * ldf + h), __ldg(lse + row * H + h), part[v], 0.f));
     }
   }
 }
@@ -75,6 +75,7 @@ struct BwdFusedArgs {
   const float* wh;
   int64_t ldw;
   const float* g;
+  int64_t ldg;       // row pitch of g (floats)
   const float* rec;  // [n_dst, ldrec]: dh'_i row followed by (f, lse, c, 0) per head
   int64_t ldrec;
   const uint8_t* keep;
@@ -83,6 +84,7 @@ struct BwdFusedArgs {
   float* dwh;
   int64_t lddwh;
   float* dg;
+  int64_t lddg;      // row pitch of dg (floats)
   float* edge_dz;
   int seg_len;
   const int32_t* hub_rows;
@@ -140,7 +142,7 @@ __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, 
     wj[v] = (FULLROW || geo.act[v]) ? ldg4(a.wh + (int64_t)j * a.ldw + (lane + 32 * v) * 4)
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const float g_reg = lane < H ? __ldg(a.g + (int64_t)j * H + lane) : 0.f;
+  const float g_reg = lane < H ? __ldg(a.g + (int64_t)j * a.ldg + lane) : 0.f;
   const int tail0 = a.V * 4;
   const int q = lph >= 32 ? lph >> 5 : 1;
 
@@ -216,7 +218,7 @@ __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, 
 }
 
 __device__ __forceinline__ void bwd_fused_store_slot(const BwdFusedArgs& a, int j, int slot, float4 r, float dgv) {
-  fma4(r, dgv, ldg4(a.a_dst + slot * 4));
+  if (a.a_dst) fma4(r, dgv, ldg4(a.a_dst + slot * 4));  // NULL: the dg term is folded into the projection backward
   stg4(a.dwh + (int64_t)j * a.lddwh + slot * 4, r);
 }
 
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, NV <= 4 ? 4 : 1) attn_bwd_fu
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         if (geo.act[v]) bwd_fused_store_slot(a, j, lane + 32 * v, acc[v], dgacc[v]);
-        if (geo.leader[v]) a.dg[(int64_t)j * a.H + geo.hv[v]] = dgacc[v];
+        if (geo.leader[v]) a.dg[(int64_t)j * a.lddg + geo.hv[v]] = dgacc[v];
       }
     }
     cur = nxt;
@@ -297,7 +299,7 @@ __global__ void attn_bwd_fused_hub_merge_kernel(const BwdFusedArgs a) {
       A.x += t.x; A.y += t.y; A.z += t.z; A.w += t.w;
     }
     bwd_fused_store_slot(a, j, slot, A, dgv);
-    if (slot % a.lph == 0) a.dg[(int64_t)j * a.H + h] = dgv;
+    if (slot % a.lph == 0) a.dg[(int64_t)j * a.lddg + h] = dgv;
   }
 }
 
@@ -315,6 +317,7 @@ struct FinishArgs {
   float* dwh;
   int64_t lddwh;
   float* df;
+  int64_t lddf;  // row pitch of df (floats)
   int seg_len;
   const int32_t* hub_rows;
   const int32_t* hub_seg_ptr;
@@ -341,7 +344,8 @@ __device__ __forceinline__ float segsum_heads(const float* __restrict__ dz, int 
 
 template <int NV>
 __device__ __forceinline__ void finish_row(const FinishArgs& a, int64_t row, float df_reg, int lane) {
-  if (lane < a.H) a.df[row * a.H + lane] = df_reg;
+  if (lane < a.H) a.df[row * a.lddf + lane] = df_reg;
+  if (!a.a_src) return;  // the df term is folded into the projection backward: no row update here
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int slot = lane + 32 * v;
@@ -458,7 +462,7 @@ extern "C" int64_t gatk_attn_bwd_record_ld(int H, int Dp) { return (int64_t)H * 
 
 extern "C" int gatk_attn_bwd_prep(int64_t n, int H, int Dp, const float* gout, int64_t ldgo, const float* out,
                                   int64_t ldo, int act_elu, const float* hagg, int64_t ldh, const float* f,
-                                  const float* lse, float* rec, int64_t ldrec, float* dhp2, int64_t lddhp2,
+                                  int64_t ldf, const float* lse, float* rec, int64_t ldrec, float* dhp2, int64_t lddhp2,
                                   void* stream) {
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
@@ -472,15 +476,16 @@ extern "C" int gatk_attn_bwd_prep(int64_t n, int H, int Dp, const float* gout, i
   const unsigned grid = (unsigned)((n + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
   NV_DISPATCH(nv, (attn_bwd_prep_kernel<NV><<<grid, 256, 0, st>>>(n, H, lph, V, gout, ldgo, out, ldo, act_elu, hagg,
-                                                                  ldh, f, lse, rec, ldrec, dhp2, lddhp2)));
+                                                                  ldh, f, ldf, lse, rec, ldrec, dhp2, lddhp2)));
   GATK_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int32_t* trow, const int32_t* perm, int H,
-                                   int Dp, const float* wh, int64_t ldw, const float* g, const float* rec,
+                                   int Dp, const float* wh, int64_t ldw, const float* g, int64_t ldg, const float* rec,
                                    int64_t ldrec, const uint8_t* keep_att, float inv_keep, float alpha,
-                                   const float* a_dst, float* dwh, int64_t lddwh, float* dg, float* edge_dz,
+                                   const float* a_dst, float* dwh, int64_t lddwh, float* dg, int64_t lddg,
+                                   float* edge_dz,
                                    int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                                    int n_hub_seg, float* hub_scratch, int32_t* counter, const int32_t* item_ptr,
                                    int n_items, void* stream) {
@@ -489,13 +494,14 @@ extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int
   if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
   GATK_REQUIRE(n_src < (1LL << 31), "n_src too large for one shard");
   GATK_REQUIRE(ldw % 4 == 0 && ldrec % 4 == 0 && lddwh % 4 == 0, "leading dims must be multiples of 4 floats");
-  GATK_REQUIRE(tptr && wh && g && rec && a_dst && dwh && dg && edge_dz && counter, "null pointer argument");
+  GATK_REQUIRE(tptr && wh && g && rec && dwh && dg && edge_dz && counter, "null pointer argument");
+  GATK_REQUIRE(ldg >= H && lddg >= H, "ldg / lddg must be >= H");
   cudaStream_t st = (cudaStream_t)stream;
   BwdFusedArgs a;
   a.n_src = n_src; a.tptr = tptr; a.trow = trow; a.perm = perm; a.H = H; a.Dp = Dp; a.lph = Dp / 4;
   a.V = H * (Dp / 4);
-  a.wh = wh; a.ldw = ldw; a.g = g; a.rec = rec; a.ldrec = ldrec; a.keep = keep_att; a.inv_keep = inv_keep;
-  a.alpha = alpha; a.a_dst = a_dst; a.dwh = dwh; a.lddwh = lddwh; a.dg = dg;
+  a.wh = wh; a.ldw = ldw; a.g = g; a.ldg = ldg; a.rec = rec; a.ldrec = ldrec; a.keep = keep_att; a.inv_keep = inv_keep;
+  a.alpha = alpha; a.a_dst = a_dst; a.dwh = dwh; a.lddwh = lddwh; a.dg = dg; a.lddg = lddg;
   a.edge_dz = edge_dz; a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub;
   a.n_hub_seg = n_hub_seg; a.scratch = hub_scratch; a.counter = counter; a.item_ptr = item_ptr; a.n_items = n_items;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
@@ -505,16 +511,16 @@ extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int
 
 extern "C" int gatk_attn_bwd_finish(int64_t n, const int64_t* rowptr, int H, int Dp, const float* edge_dz,
                                     const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
-                                    int64_t lddwh, float* df, int seg_len, const int32_t* hub_rows,
+                                    int64_t lddwh, float* df, int64_t lddf, int seg_len, const int32_t* hub_rows,
                                     const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
                                     void* stream) {
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
   if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
-  GATK_REQUIRE(rowptr && a_src && dwh && df && lddwh % 4 == 0, "bad arguments");
+  GATK_REQUIRE(rowptr && df && lddf >= H && (!a_src || (dwh && lddwh % 4 == 0)) && (a_src || !keep_wh), "bad arguments");
   FinishArgs a;
   a.n = n; a.rowptr = rowptr; a.H = H; a.lph = Dp / 4; a.V = H * (Dp / 4); a.edge_dz = edge_dz; a.a_src = a_src;
-  a.keep_wh = keep_wh; a.inv_keep = inv_keep; a.dwh = dwh; a.lddwh = lddwh; a.df = df; a.seg_len = seg_len;
+  a.keep_wh = keep_wh; a.inv_keep = inv_keep; a.dwh = dwh; a.lddwh = lddwh; a.df = df; a.lddf = lddf; a.seg_len = seg_len;
   a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub; a.n_hub_seg = n_hub_seg; a.scratch = hub_scratch;
   cudaStream_t st = (cudaStream_t)stream;
   NV_DISPATCH(nv, return launch_finish<NV>(a, st));

@@ -20,6 +20,13 @@ from . import _lib
 from .graph import Graph, _ptr, _require_cuda, _stream
 
 
+import os
+
+# The folded form needs no logits pass, no da reduction and no dWh read-modify-write; GATK_FOLD=0 keeps
+# the explicit kernels even without dropout (used by the tests to compare the two forms).
+FOLD_LOGITS = os.environ.get("GATK_FOLD", "1") != "0"
+
+
 def padded_width(d: int) -> int:
     """Per-head width the kernels use: 4 * 2^k >= d (float4 slots, power-of-two slots per head)."""
     l = 1
@@ -118,7 +125,7 @@ class GatLayerFunction(torch.autograd.Function):
         hubs = graph.hubs
         scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_ptr, M_out,
-                  f.data_ptr(), g.data_ptr(), _ptr(masks.keep_att), inv_keep, float(alpha),
+                  f.data_ptr(), g.data_ptr(), H, _ptr(masks.keep_att), inv_keep, float(alpha),
                   skip_ptr, M_out, int(act_elu), _ptr(hagg), out.data_ptr(), HD, _ptr(lse),
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
 
@@ -151,14 +158,14 @@ class GatLayerFunction(torch.autograd.Function):
 
         # ---- K3 prep: per-destination records [dh' | f, lse, c] -------------------------------------
         _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
-                  int(act_elu), hagg.data_ptr(), HD, f.data_ptr(), lse.data_ptr(), rec.data_ptr(), ldrec,
+                  int(act_elu), hagg.data_ptr(), HD, f.data_ptr(), H, lse.data_ptr(), rec.data_ptr(), ldrec,
                   dz_rows.data_ptr() + 4 * HD if has_skip else None, M_out, st)
 
         # ---- K4 fused source pass over the transposed pattern (one gather of the record per edge) -----
         scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, z.data_ptr(), M_out,
-                  g.data_ptr(), rec.data_ptr(), ldrec, _ptr(masks.keep_att), inv_keep, alpha,
-                  a_dst.data_ptr(), dz_rows.data_ptr(), M_out, dg.data_ptr(), edge_dz.data_ptr(),
+                  g.data_ptr(), H, rec.data_ptr(), ldrec, _ptr(masks.keep_att), inv_keep, alpha,
+                  a_dst.data_ptr(), dz_rows.data_ptr(), M_out, dg.data_ptr(), H, edge_dz.data_ptr(),
                   *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), st)
         del rec
 
@@ -166,7 +173,7 @@ class GatLayerFunction(torch.autograd.Function):
         hubs = graph.hubs
         scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), a_src.data_ptr(),
-                  _ptr(masks.keep_wh), inv_keep, dz_rows.data_ptr(), M_out, df.data_ptr(),
+                  _ptr(masks.keep_wh), inv_keep, dz_rows.data_ptr(), M_out, df.data_ptr(), H,
                   *hubs.args(scratch), st)
         del edge_dz
 
@@ -204,6 +211,101 @@ class GatLayerFunction(torch.autograd.Function):
                               dxh.data_ptr(), f_in, n, f_in, st)
                     dx.add_(dxh)
         return dx, dw_ext, da_src, da_dst, None, None, None, None, None, None, None, None
+
+
+class GatLayerFoldedFunction(torch.autograd.Function):
+    """The layer when no dropout sits between projection and logits (eval, or p == 0 as in train_ppi.py:49
+    and the benchmark shapes).  The attention-logit halves are linear in the input,
+    f = (x W) a_src = x (W a_src), so they ride in the projection GEMM as 2H extra output columns and
+    their gradients df, dg ride in its backward as 2H extra columns of dZ:
+
+        Z  = x [W | S | W a_src | W a_dst]          (one GEMM;  w_full is built from the per-head parameters
+        dW_full = x^T [dWh | dSkip | df | dg]        by parameter-sized torch ops, so autograd routes
+        dx = dZ w_full^T                              dW_full back into dW, da_src, da_dst)
+
+    which removes the logits pass, the da reduction over the nodes and the read-modify-write of dWh for
+    the df a_src / dg a_dst terms.  Same math as GatLayerFunction up to fp32 re-association."""
+
+    @staticmethod
+    def forward(ctx, x, w_full, graph: Graph, H: int, Dp: int, has_skip: bool, alpha: float, act_elu: bool):
+        _require_cuda(x, "input features")
+        dev = x.device
+        n, f_in = x.shape
+        if graph.n_dst != n or graph.n_src != n:
+            raise RuntimeError(f"adjacency is {graph.n_dst}x{graph.n_src} but the input has {n} rows")
+        HD = H * Dp
+        M_out = HD * (2 if has_skip else 1)
+        Mz = w_full.shape[1]
+        assert Mz >= M_out + 2 * H and Mz % 4 == 0
+        x = x.contiguous()
+        w_full = w_full.contiguous()
+        st = _stream()
+        z = torch.empty(n, Mz, dtype=torch.float32, device=dev)
+        _gemm(0, 0, n, Mz, f_in, x, f_in, w_full, Mz, z, Mz)
+        f_ptr = z.data_ptr() + 4 * M_out
+        g_ptr = f_ptr + 4 * H
+        need_grad = any(ctx.needs_input_grad[:2])
+        out = torch.empty(n, HD, dtype=torch.float32, device=dev)
+        separate_hagg = need_grad and (has_skip or act_elu)
+        hagg = torch.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
+        lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        hubs = graph.hubs
+        scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
+        _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, z.data_ptr(), Mz,
+                  f_ptr, g_ptr, Mz, None, 1.0, float(alpha),
+                  z.data_ptr() + 4 * HD if has_skip else None, Mz, int(act_elu), _ptr(hagg), out.data_ptr(), HD,
+                  _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+        if need_grad:
+            ctx.graph = graph
+            ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu))
+            ctx.save_for_backward(x, w_full, z, lse, out, hagg if separate_hagg else out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w_full, z, lse, out, hagg = ctx.saved_tensors
+        graph = ctx.graph
+        H, Dp, has_skip, alpha, act_elu = ctx.cfg
+        dev = x.device
+        n, f_in = x.shape
+        HD = H * Dp
+        M_out = HD * (2 if has_skip else 1)
+        Mz = w_full.shape[1]
+        st = _stream()
+        gout = gout.contiguous()
+        tptr, trow, perm, thubs = graph.transpose()[:4]
+        f_ptr = z.data_ptr() + 4 * M_out
+        g_ptr = f_ptr + 4 * H
+
+        dz_rows = torch.empty(n, Mz, dtype=torch.float32, device=dev)   # [dWh | dSkip | df | dg | pad]
+        if Mz > M_out + 2 * H:
+            dz_rows[:, M_out + 2 * H:].zero_()
+        df_ptr = dz_rows.data_ptr() + 4 * M_out
+        dg_ptr = df_ptr + 4 * H
+        ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
+        rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
+        edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
+                  int(act_elu), hagg.data_ptr(), HD, f_ptr, Mz, lse.data_ptr(), rec.data_ptr(), ldrec,
+                  dz_rows.data_ptr() + 4 * HD if has_skip else None, Mz, st)
+        scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
+        _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, z.data_ptr(), Mz,
+                  g_ptr, Mz, rec.data_ptr(), ldrec, None, 1.0, alpha,
+                  None, dz_rows.data_ptr(), Mz, dg_ptr, Mz, edge_dz.data_ptr(),
+                  *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), st)
+        del rec
+        hubs = graph.hubs
+        scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
+        _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), None,
+                  None, 1.0, None, 0, df_ptr, Mz, *hubs.args(scratch), st)
+        del edge_dz
+        dw_full = torch.empty(f_in, Mz, dtype=torch.float32, device=dev)
+        _gemm(1, 0, f_in, Mz, n, x, f_in, dz_rows, Mz, dw_full, Mz)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(n, f_in, dtype=torch.float32, device=dev)
+            _gemm(0, 1, n, f_in, Mz, dz_rows, Mz, w_full, Mz, dx, f_in)
+        return dx, dw_full, None, None, None, None, None, None
 
 
 class HeadCombineFunction(torch.autograd.Function):
@@ -261,8 +363,18 @@ def gat_layer(x: torch.Tensor, graph: Graph, Ws, a_srcs, a_dsts, skips, alpha: f
     p_eff = float(p) if training else 0.0
     if p_eff > 0.0 and masks is None:
         masks = random_masks(x.shape[0], x.shape[1], H, Dp, graph.nnz, p_eff, x.device)
-    rows = GatLayerFunction.apply(x, w_ext, a_src, a_dst, graph, H, Dp, skips is not None, float(alpha),
-                                  bool(concat), p_eff, masks)
+    if p_eff == 0.0 and FOLD_LOGITS:
+        # f = x (W a_src), g = x (W a_dst): 2H extra columns of the projection (see GatLayerFoldedFunction)
+        w3 = w_ext[:, : H * Dp].reshape(x.shape[1], H, Dp)
+        cols = [w_ext, (w3 * a_src).sum(-1), (w3 * a_dst).sum(-1)]
+        pad = (-2 * H) % 4
+        if pad:
+            cols.append(w_ext.new_zeros(x.shape[1], pad))
+        rows = GatLayerFoldedFunction.apply(x, torch.cat(cols, dim=1), graph, H, Dp, skips is not None,
+                                            float(alpha), bool(concat))
+    else:
+        rows = GatLayerFunction.apply(x, w_ext, a_src, a_dst, graph, H, Dp, skips is not None, float(alpha),
+                                      bool(concat), p_eff, masks)
     if combine == "none":
         return rows
     if combine == "mean":

@@ -140,7 +140,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         hubs = graph.hubs
         scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_full.data_ptr(), HD,
-                  f.data_ptr(), g_full.data_ptr(), None, 1.0, float(alpha), _ptr(skipv), HD, int(act_elu),
+                  f.data_ptr(), g_full.data_ptr(), H, None, 1.0, float(alpha), _ptr(skipv), HD, int(act_elu),
                   _ptr(hagg), out.data_ptr(), HD, _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         if need_grad:
             ctx.graph, ctx.plan = graph, plan
@@ -168,7 +168,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
         dskip = torch.empty(n, HD, dtype=torch.float32, device=dev) if has_skip else None
         _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
-                  int(act_elu), hagg.data_ptr(), HD, f.data_ptr(), lse.data_ptr(), rec.data_ptr(), ldrec,
+                  int(act_elu), hagg.data_ptr(), HD, f.data_ptr(), H, lse.data_ptr(), rec.data_ptr(), ldrec,
                   _ptr(dskip), HD, st)
 
         # partial dWh / dg for EVERY source from this rank's destination rows
@@ -177,8 +177,8 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
         scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, wh_full.data_ptr(), HD,
-                  g_full.data_ptr(), rec.data_ptr(), ldrec, None, 1.0, alpha,
-                  a_dst.data_ptr(), dwh_part.data_ptr(), HD, dg_part.data_ptr(), edge_dz.data_ptr(),
+                  g_full.data_ptr(), H, rec.data_ptr(), ldrec, None, 1.0, alpha,
+                  a_dst.data_ptr(), dwh_part.data_ptr(), HD, dg_part.data_ptr(), H, edge_dz.data_ptr(),
                   *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), st)
         del rec
         dg_loc = reduce_rows(dg_part, plan).contiguous()
@@ -188,7 +188,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
         dwh_own = plan.rows(dwh_part)
         _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), a_src.data_ptr(),
-                  None, 1.0, dwh_own.data_ptr(), HD, df.data_ptr(), *hubs.args(scratch), st)
+                  None, 1.0, dwh_own.data_ptr(), HD, df.data_ptr(), H, *hubs.args(scratch), st)
         del edge_dz
 
         da_src = torch.empty(H, Dp, dtype=torch.float32, device=dev)

@@ -222,6 +222,23 @@ def test_hub_rows_split_into_segments(seg_len):
     _check_head(d, head, x, y)
 
 
+@pytest.mark.parametrize("name", ["sp_head_hub", "sp_head_wide", "sp_head_skip_last"])
+def test_explicit_and_folded_forms_agree(name, monkeypatch):
+    """Without dropout the layer runs in the folded form (logits and their gradients as extra GEMM
+    columns); the explicit kernels (logits pass, dWh update, da reduction) must give the same numbers."""
+    import pygat_b200.functional as Fn
+    d = load(name)
+    adj = dense_adj(d).to(DEV)
+    res = {}
+    for fold in (True, False):
+        monkeypatch.setattr(Fn, "FOLD_LOGITS", fold)
+        head, x, y = _run_head(d, "sparse", adj)
+        _check_head(d, head, x, y)
+        res[fold] = (y, x.grad, head.W.grad, head.a.grad)
+    for a, b in zip(res[True], res[False]):
+        assert rel_err(a, b) < 2e-6
+
+
 def test_dense_and_sparse_classes_agree():
     d = load("sp_head_basic")
     adj = dense_adj(d).to(DEV)
