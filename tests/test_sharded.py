@@ -59,9 +59,10 @@ def test_sharded_layer_world1_equals_single_gpu():
     plan = ShardPlan([0, n], 0)
     y1 = sharded_gat_layer(x, plan.local_graph(rowptr, col, seg_len=128), plan, Ws, a_s, a_d, None, 0.2, True)
     y1.backward(gout)
-    assert torch.equal(y0, y1)
+    # the single-GPU layer runs the folded form, the sharded one the explicit kernels: same math, re-associated
+    assert (y0 - y1).abs().max().item() <= 2e-6 * y0.abs().max().item()
     for a, b in zip(g0, [p.grad for p in Ws + a_s + a_d]):
-        assert (a - b).abs().max().item() <= 1e-6 * b.abs().max().item()
+        assert (a - b).abs().max().item() <= 3e-6 * b.abs().max().item()
 
 
 @pytest.mark.gpu
