@@ -123,8 +123,10 @@ GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* 
  *
  *  prep    per destination row i, one contiguous RECORD of ldrec = gatk_attn_bwd_record_ld(H, Dp)
  *          floats:  [ dhp_i = dL/dh'_i = gout_i * ELU'(out_i)  |  (f_i, lse_i, c_i, 0) per head ]
- *          with c[i,h] = dhp_i . hagg_i (the softmax-backward row term); out may be NULL if
- *          !act_elu; dhp2 (optional) receives a second copy of dhp (it is also dL/d(skip)).
+ *          with c[i,h] = dhp_i . hagg_i (the softmax-backward row term).  out (the activated output)
+ *          is needed only when a skip term was added before the ELU; with out == NULL the
+ *          derivative is taken from hagg itself.  dhp2 (optional) receives a second copy of dhp
+ *          (it is also dL/d(skip)).
  *  fused   per SOURCE row j over the transposed pattern (scatter-free): gathers record i once
  *          per edge and uses it for both  dz_ij = alpha_ij (keep/(1-p) dhp_i.Wh_j - c_i)
  *          LeakyReLU'(f_i+g_j)  and  dwh_j = sum_i alpha~_ij dhp_i + dg_j a_dst,  dg_j = sum_i

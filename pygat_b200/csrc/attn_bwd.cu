@@ -40,16 +40,24 @@ __global__ void attn_bwd_prep_kernel(int64_t n, int H, int lph, int V, const flo
     if (slot < V) {
       const int off = slot * 4;
       float4 go = ldg4_stream(gout + row * ldgo + off);
+      const float4 hg = ldg4_stream(hagg + row * ldh + off);
       if (act_elu) {
-        const float4 o = ldg4_stream(out + row * ldo + off);
-        go.x *= o.x > 0.f ? 1.f : o.x + 1.f;
-        go.y *= o.y > 0.f ? 1.f : o.y + 1.f;
-        go.z *= o.z > 0.f ? 1.f : o.z + 1.f;
-        go.w *= o.w > 0.f ? 1.f : o.w + 1.f;
+        if (out) {  // ELU'(h') from the activated output: out > 0 ? 1 : out + 1
+          const float4 o = ldg4_stream(out + row * ldo + off);
+          go.x *= o.x > 0.f ? 1.f : o.x + 1.f;
+          go.y *= o.y > 0.f ? 1.f : o.y + 1.f;
+          go.z *= o.z > 0.f ? 1.f : o.z + 1.f;
+          go.w *= o.w > 0.f ? 1.f : o.w + 1.f;
+        } else {    // no skip term: h' is hagg itself, ELU'(h) = h > 0 ? 1 : exp(h); saves reading `out`
+          go.x *= hg.x > 0.f ? 1.f : expf(hg.x);
+          go.y *= hg.y > 0.f ? 1.f : expf(hg.y);
+          go.z *= hg.z > 0.f ? 1.f : expf(hg.z);
+          go.w *= hg.w > 0.f ? 1.f : expf(hg.w);
+        }
       }
       stg4(rec + row * ldrec + off, go);
       if (dhp2) stg4(dhp2 + row * lddhp2 + off, go);
-      part[v] = dot4(go, ldg4_stream(hagg + row * ldh + off));
+      part[v] = dot4(go, hg);
     }
   }
   head_reduce<NV>(part, lph);
@@ -467,9 +475,8 @@ extern "C" int gatk_attn_bwd_prep(int64_t n, int H, int Dp, const float* gout, i
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
   GATK_REQUIRE(gout && hagg && f && lse && rec, "null pointer argument");
-  GATK_REQUIRE(!act_elu || out, "out is required when act_elu is set");
   GATK_REQUIRE(ldgo % 4 == 0 && ldh % 4 == 0 && ldrec % 4 == 0 && ldrec >= (int64_t)H * Dp + 4 * H &&
-                   (!act_elu || ldo % 4 == 0) && (!dhp2 || lddhp2 % 4 == 0),
+                   (!out || ldo % 4 == 0) && (!dhp2 || lddhp2 % 4 == 0),
                "leading dims must be multiples of 4 floats (record: >= H*Dp + 4*H)");
   if (n == 0) return 0;
   const int lph = Dp / 4, V = H * lph;

@@ -157,7 +157,7 @@ class GatLayerFunction(torch.autograd.Function):
         edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
 
         # ---- K3 prep: per-destination records [dh' | f, lse, c] -------------------------------------
-        _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
+        _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if (act_elu and has_skip) else None, HD,
                   int(act_elu), hagg.data_ptr(), HD, f.data_ptr(), H, lse.data_ptr(), rec.data_ptr(), ldrec,
                   dz_rows.data_ptr() + 4 * HD if has_skip else None, M_out, st)
 
@@ -285,7 +285,7 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
         rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
         edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
-        _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
+        _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if (act_elu and has_skip) else None, HD,
                   int(act_elu), hagg.data_ptr(), HD, f_ptr, Mz, lse.data_ptr(), rec.data_ptr(), ldrec,
                   dz_rows.data_ptr() + 4 * HD if has_skip else None, Mz, st)
         scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)

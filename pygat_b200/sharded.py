@@ -167,7 +167,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
         rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
         dskip = torch.empty(n, HD, dtype=torch.float32, device=dev) if has_skip else None
-        _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if act_elu else None, HD,
+        _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if (act_elu and has_skip) else None, HD,
                   int(act_elu), hagg.data_ptr(), HD, f.data_ptr(), H, lse.data_ptr(), rec.data_ptr(), ldrec,
                   _ptr(dskip), HD, st)
 
