@@ -25,6 +25,9 @@ import os
 # The folded form needs no logits pass, no da reduction and no dWh read-modify-write; GATK_FOLD=0 keeps
 # the explicit kernels even without dropout (used by the tests to compare the two forms).
 FOLD_LOGITS = os.environ.get("GATK_FOLD", "1") != "0"
+# The aggregate-first form (neighbour sum before the projection) for narrow first-layer inputs; GATK_AGG_FIRST=0
+# keeps the project-first kernels (the tests compare the forms).
+AGG_FIRST = os.environ.get("GATK_AGG_FIRST", "1") != "0"
 
 
 def padded_width(d: int) -> int:
@@ -308,6 +311,114 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         return dx, dw_full, None, None, None, None, None, None
 
 
+def agg_first_geometry(f_in: int, H: int, Dp: int):
+    """(Fp, ok): padded input width and whether the aggregate-first form applies and pays: at most 8
+    heads, accumulators fit the register file, and the input row is narrower than the projected row."""
+    Fp = (f_in + 3) // 4 * 4
+    hp = 1 if H <= 1 else 2 if H <= 2 else 4 if H <= 4 else 8
+    ns = 1 if Fp <= 128 else 2 if Fp <= 256 else 4
+    ok = H <= 8 and Fp <= 512 and hp * ns <= 16 and Fp < H * Dp
+    return Fp, ok
+
+
+class GatLayerAggFirstFunction(torch.autograd.Function):
+    """The layer with the neighbour sum taken BEFORE the projection (see csrc/attn_x.cu):
+
+        fg   = x [W a_src | W a_dst]                      thin GEMM, logits are linear in the input
+        xagg = softmax-weighted neighbour sum of x        gatk_attn_x_fwd, gathers F_in-wide rows
+        out  = act( xagg_h W_h  (+ x S_h) )               H per-head GEMMs on the aggregated rows
+
+    Same math as layers.py:134-170 up to fp32 re-association (sum_j alpha_ij (x_j W) = (sum_j alpha_ij x_j) W).
+    Used when no dropout sits between projection and logits, the input needs no gradient (a first layer)
+    and F_in < H*D: the edge passes then move F_in/(H*D) of the bytes (1/5 at the products shape)."""
+
+    @staticmethod
+    def forward(ctx, x, w_ext, w_uv, graph: Graph, H: int, Dp: int, has_skip: bool, alpha: float, act_elu: bool):
+        _require_cuda(x, "input features")
+        dev = x.device
+        n, f_in = x.shape
+        if graph.n_dst != n or graph.n_src != n:
+            raise RuntimeError(f"adjacency is {graph.n_dst}x{graph.n_src} but the input has {n} rows")
+        HD = H * Dp
+        M_out = HD * (2 if has_skip else 1)
+        Muv = w_uv.shape[1]
+        Fp = (f_in + 3) // 4 * 4
+        assert w_ext.shape == (f_in, M_out) and Muv >= 2 * H and Muv % 4 == 0
+        xp = x.contiguous() if Fp == f_in else torch.nn.functional.pad(x, (0, Fp - f_in))
+        w_ext = w_ext.contiguous()
+        w_uv = w_uv.contiguous()
+        st = _stream()
+        fg = torch.empty(n, Muv, dtype=torch.float32, device=dev)
+        _gemm(0, 0, n, Muv, f_in, xp, Fp, w_uv, Muv, fg, Muv)
+        need_grad = any(ctx.needs_input_grad[1:3])
+        xagg = torch.empty(n, H * Fp, dtype=torch.float32, device=dev)
+        lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        hubs = graph.hubs
+        scratch = _x_scratch(0, H, Fp, hubs.n_seg, dev)
+        _lib.call("gatk_attn_x_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xp.data_ptr(), Fp,
+                  fg.data_ptr(), fg.data_ptr() + 4 * H, Muv, float(alpha), xagg.data_ptr(), H * Fp, _ptr(lse),
+                  *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+        out = torch.empty(n, HD, dtype=torch.float32, device=dev)
+        for h in range(H):
+            _gemm(0, 0, n, Dp, f_in, xagg, H * Fp, w_ext, M_out, out, HD, a_off=h * Fp, b_off=h * Dp, c_off=h * Dp)
+        if has_skip:
+            _gemm(0, 0, n, HD, f_in, xp, Fp, w_ext, M_out, out, HD, accumulate=1, b_off=HD)
+        if act_elu:
+            _lib.call("gatk_elu_fwd", n, HD, out.data_ptr(), HD, st)
+        if need_grad:
+            ctx.graph = graph
+            ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu), f_in, Fp)
+            ctx.save_for_backward(xp, w_ext, fg, lse, xagg, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        xp, w_ext, fg, lse, xagg, out = ctx.saved_tensors
+        graph = ctx.graph
+        H, Dp, has_skip, alpha, act_elu, f_in, Fp = ctx.cfg
+        dev = xp.device
+        n = xp.shape[0]
+        HD = H * Dp
+        M_out = HD * (2 if has_skip else 1)
+        Muv = fg.shape[1]
+        st = _stream()
+        gout = gout.contiguous()
+        if act_elu:
+            dhp = torch.empty(n, HD, dtype=torch.float32, device=dev)
+            _lib.call("gatk_elu_bwd", n, HD, gout.data_ptr(), HD, out.data_ptr(), HD, dhp.data_ptr(), HD, st)
+        else:
+            dhp = gout
+        # value path: dW_h = xagg_h^T dh'_h, dS = x^T dh';  dxagg_h = dh'_h W_h^T feeds the softmax backward
+        dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
+        dxagg = (torch.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
+        for h in range(H):
+            _gemm(1, 0, f_in, Dp, n, xagg, H * Fp, dhp, HD, dw_ext, M_out, a_off=h * Fp, b_off=h * Dp, c_off=h * Dp)
+            _gemm(0, 1, n, f_in, Dp, dhp, HD, w_ext, M_out, dxagg, H * Fp, a_off=h * Dp, b_off=h * Dp, c_off=h * Fp)
+        if has_skip:
+            _gemm(1, 0, f_in, HD, n, xp, Fp, dhp, HD, dw_ext, M_out, c_off=HD)
+        # logit path: ds per stored entry, df per destination, dg per source (transposed sum of ds)
+        ds = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        dfg = (torch.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
+        hubs = graph.hubs
+        scratch = _x_scratch(1, H, Fp, hubs.n_seg, dev)
+        _lib.call("gatk_attn_x_bwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xp.data_ptr(), Fp,
+                  fg.data_ptr(), fg.data_ptr() + 4 * H, Muv, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
+                  dxagg.data_ptr(), H * Fp, ds.data_ptr(), dfg.data_ptr(), Muv,
+                  *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+        tptr, _trow, perm, thubs = graph.transpose()[:4]
+        _lib.call("gatk_edge_tsum", graph.n_src, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(),
+                  dfg.data_ptr() + 4 * H, Muv, thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
+        dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
+        _gemm(1, 0, f_in, Muv, n, xp, Fp, dfg, Muv, dw_uv, Muv)
+        return None, dw_ext, dw_uv, None, None, None, None, None, None
+
+
+def _x_scratch(which: int, H: int, Fp: int, n_seg: int, dev):
+    if not n_seg:
+        return None
+    return torch.empty(_lib.query("gatk_attn_x_scratch_floats", which, H, Fp, n_seg), dtype=torch.float32, device=dev)
+
+
 class HeadCombineFunction(torch.autograd.Function):
     """[N, H*Dp] -> torch.cat of the unpadded heads (mode 0, models.py:32) or their mean
     (mode 1, models.py:34)."""
@@ -352,10 +463,13 @@ def pack_heads(Ws: Sequence[torch.Tensor], a_srcs: Sequence[torch.Tensor], a_dst
 
 def gat_layer(x: torch.Tensor, graph: Graph, Ws, a_srcs, a_dsts, skips, alpha: float, concat: bool,
               p: float = 0.0, training: bool = False, masks: Optional[LayerMasks] = None,
-              combine: str = "cat") -> torch.Tensor:
+              combine: str = "cat", form: str = "auto") -> torch.Tensor:
     """All heads of one GAT layer.  concat=True applies ELU inside each head (layers.py:50-53);
     combine="cat" -> [N, H*D] (models.py:32), "mean" -> [N, D] (models.py:34),
-    "none" -> the padded [N, H*Dp] rows."""
+    "none" -> the padded [N, H*Dp] rows.
+    form: "auto" picks among the three algebraically equal forms of the layer -- "explicit" (projection,
+    logits pass, attention; the only one valid with dropout), "folded" (logits as projection columns) and
+    "agg_first" (neighbour sum before the projection; narrow inputs that need no gradient)."""
     H = len(Ws)
     if x.dtype != torch.float32:
         x = x.float()
@@ -363,15 +477,22 @@ def gat_layer(x: torch.Tensor, graph: Graph, Ws, a_srcs, a_dsts, skips, alpha: f
     p_eff = float(p) if training else 0.0
     if p_eff > 0.0 and masks is None:
         masks = random_masks(x.shape[0], x.shape[1], H, Dp, graph.nnz, p_eff, x.device)
-    if p_eff == 0.0 and FOLD_LOGITS:
-        # f = x (W a_src), g = x (W a_dst): 2H extra columns of the projection (see GatLayerFoldedFunction)
+    use_agg_first = (p_eff == 0.0 and FOLD_LOGITS and AGG_FIRST and form in ("auto", "agg_first")
+                     and not (x.requires_grad and torch.is_grad_enabled())
+                     and (agg_first_geometry(x.shape[1], H, Dp)[1] or form == "agg_first"))
+    if p_eff == 0.0 and FOLD_LOGITS and form != "explicit":
+        # f = x (W a_src), g = x (W a_dst): linear in the input (see GatLayerFoldedFunction)
         w3 = w_ext[:, : H * Dp].reshape(x.shape[1], H, Dp)
-        cols = [w_ext, (w3 * a_src).sum(-1), (w3 * a_dst).sum(-1)]
+        uv = [(w3 * a_src).sum(-1), (w3 * a_dst).sum(-1)]
         pad = (-2 * H) % 4
         if pad:
-            cols.append(w_ext.new_zeros(x.shape[1], pad))
-        rows = GatLayerFoldedFunction.apply(x, torch.cat(cols, dim=1), graph, H, Dp, skips is not None,
-                                            float(alpha), bool(concat))
+            uv.append(w_ext.new_zeros(x.shape[1], pad))
+        if use_agg_first:
+            rows = GatLayerAggFirstFunction.apply(x, w_ext, torch.cat(uv, dim=1), graph, H, Dp, skips is not None,
+                                                  float(alpha), bool(concat))
+        else:
+            rows = GatLayerFoldedFunction.apply(x, torch.cat([w_ext] + uv, dim=1), graph, H, Dp, skips is not None,
+                                                float(alpha), bool(concat))
     else:
         rows = GatLayerFunction.apply(x, w_ext, a_src, a_dst, graph, H, Dp, skips is not None, float(alpha),
                                       bool(concat), p_eff, masks)

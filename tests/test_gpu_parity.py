@@ -362,6 +362,83 @@ def test_power_law_layer_matches_oracle(H, D, f_in):
         assert rel_err(Ad[k].grad, Ao[k].grad) < TOL, k
 
 
+@pytest.mark.parametrize("H,D,f_in,skip,concat,seg_len", [
+    (8, 64, 100, False, True, 128),    # products first layer
+    (4, 256, 50, True, True, 64),      # PPI first layer (input padded 50 -> 52, skip projection)
+    (8, 64, 32, False, False, 100000), # one float4 slot per lane quarter, no hub path
+    (2, 16, 7, True, False, 32),       # odd width, two heads
+    (3, 8, 20, False, True, 128),      # H padded to 4, 2H not a multiple of 4
+    (4, 64, 200, False, True, 128),    # two slots per lane
+    (1, 40, 12, False, True, 128),     # single head
+])
+def test_aggregate_first_form_matches_oracle(H, D, f_in, skip, concat, seg_len):
+    """The aggregate-first form (neighbour sum before the projection, csrc/attn_x.cu) against the oracle's
+    project-first restatement of layers.py:125-173: outputs and every parameter gradient."""
+    n = 5000
+    rowptr, col = power_law_csr(n, 18.0, seed=11, exponent=0.7)
+    x, Ws, As, gout = _layer_inputs(n, f_in, H, D, 3)
+    g = torch.Generator().manual_seed(9)
+    Ss = [torch.randn(f_in, D, generator=g) * O.xavier_std(f_in, D) for _ in range(H)] if skip else None
+    adj = O.PatternAdj(rowptr, col)
+    Wo = [w.clone().requires_grad_(True) for w in Ws]
+    Ao = [a.clone().requires_grad_(True) for a in As]
+    So = [s.clone().requires_grad_(True) for s in Ss] if skip else [None] * H
+    edge = adj.nonzero().t()
+    yo = torch.cat([O.sparse_head(x, w, a, edge, 0.2, concat, s, 0.0, faithful=False) for w, a, s in zip(Wo, Ao, So)], 1)
+    yo.backward(gout)
+
+    graph = Graph.from_csr(rowptr.to(DEV), col.to(DEV), seg_len=seg_len)
+    assert (graph.hubs.n_hub > 0) == (seg_len < 1000)
+    Wd = [w.to(DEV).requires_grad_(True) for w in Ws]
+    Ad = [a.to(DEV).requires_grad_(True) for a in As]
+    Sd = [s.to(DEV).requires_grad_(True) for s in Ss] if skip else None
+    before = _lib.call_count
+    y = gat_layer(x.to(DEV), graph, Wd, [a[0, :D] for a in Ad], [a[0, D:] for a in Ad], Sd, 0.2, concat,
+                  form="agg_first")
+    y.backward(gout.to(DEV))
+    assert _lib.call_count > before
+    assert rel_err(y, yo) < TOL
+    for k in range(H):
+        assert rel_err(Wd[k].grad, Wo[k].grad) < TOL, k
+        assert rel_err(Ad[k].grad, Ao[k].grad) < TOL, k
+        if skip:
+            assert rel_err(Sd[k].grad, So[k].grad) < TOL, k
+
+
+def test_aggregate_first_is_the_default_for_narrow_first_layers(monkeypatch):
+    """gat_layer picks the aggregate-first form only when it is valid (no dropout, input without gradient)
+    and pays (input row narrower than the projected row); it agrees with the folded form to fp32 rounding."""
+    import pygat_b200.functional as Fn
+    used = []
+    orig = Fn.GatLayerAggFirstFunction.apply
+    monkeypatch.setattr(Fn.GatLayerAggFirstFunction, "apply", staticmethod(lambda *a: (used.append(1), orig(*a))[1]))
+    n, H, D, f_in = 3000, 8, 64, 100
+    rowptr, col = power_law_csr(n, 12.0, seed=4, exponent=0.7, device=DEV)
+    graph = Graph.from_csr(rowptr, col, seg_len=128)
+    x, Ws, As, gout = _layer_inputs(n, f_in, H, D, 5)
+    x, gout = x.to(DEV), gout.to(DEV)
+    res = {}
+    for form in ("auto", "folded"):
+        Wd = [w.to(DEV).requires_grad_(True) for w in Ws]
+        Ad = [a.to(DEV).requires_grad_(True) for a in As]
+        y = gat_layer(x, graph, Wd, [a[0, :D] for a in Ad], [a[0, D:] for a in Ad], None, 0.2, True, form=form)
+        y.backward(gout)
+        res[form] = [y] + [w.grad for w in Wd] + [a.grad for a in Ad]
+    assert len(used) == 1
+    for a, b in zip(res["auto"], res["folded"]):
+        assert rel_err(a, b) < 3e-6
+    # an input that needs a gradient, a wide input, or dropout keep the project-first kernels
+    Wd = [w.to(DEV).requires_grad_(True) for w in Ws]
+    gat_layer(x.clone().requires_grad_(True), graph, Wd, [a[0, :D].to(DEV) for a in As], [a[0, D:].to(DEV) for a in As],
+              None, 0.2, True)
+    xw = torch.randn(n, 600, device=DEV)
+    Ww = [torch.randn(600, D, device=DEV) * 0.05 for _ in range(H)]
+    gat_layer(xw, graph, Ww, [a[0, :D].to(DEV) for a in As], [a[0, D:].to(DEV) for a in As], None, 0.2, True)
+    gat_layer(x, graph, Wd, [a[0, :D].to(DEV) for a in As], [a[0, D:].to(DEV) for a in As], None, 0.2, True,
+              p=0.5, training=True)
+    assert len(used) == 1
+
+
 def test_products_shape_invariants_at_full_size():
     """ogbn-products shape (N=2.45M, ~62M stored entries, 8 heads x 64): properties that need no
     oracle.  (1) attention rows sum to one, so constant source features come back unchanged;
