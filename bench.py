@@ -39,9 +39,10 @@ def algorithmic_bytes(n, e, H, D, f_in, need_dx=False):
     """Bytes each kernel's algorithm must move (no-reuse gather model: every stored entry moves its
     neighbour row once per pass; fp32, 4-byte col ids, 8-byte rowptr).
 
-    `layer_survey` is SURVEY.md section 8(d)'s model of the layer (three row gathers per edge: K2,
-    a destination-pass K3 and a source-pass K4); `layer` is the sum over the kernels this engine
-    actually runs, whose backward gathers each row once instead of twice."""
+    `layer_survey` is SURVEY.md section 8(d)'s model of the layer (three H*D-wide row gathers per edge: K2,
+    a destination-pass K3 and a source-pass K4).  `layer_project_first` sums the kernels of this engine's
+    project-first (folded) form, whose backward gathers each row once; `layer_agg_first` sums the kernels of
+    the aggregate-first form, which gathers the F_in-wide INPUT row twice."""
     k2 = e * H * (4 * D + 4) + 4 * e + n * H * (4 * D + 12) + 8 * n
     k3_survey = e * H * (4 * D + 4 + 4) + 4 * e + n * H * (8 * D + 16)
     k4_survey = e * H * (4 * D + 4 + 12) + 8 * e + n * H * (4 * D + 4)
@@ -50,10 +51,27 @@ def algorithmic_bytes(n, e, H, D, f_in, need_dx=False):
     prep = n * H * (16 * D + 4)                      # gout, out, hagg read; dhp write; c write
     fused = e * H * (4 * D + 16 + 4) + 8 * e + n * H * (8 * D + 8)   # record gather (dh' + f,lse,c,pad), dz write, trow+perm
     finish = 4 * e * H + 4 * n * H + 8 * n            # dz read, df write (folded form: no dWh update, no da pass)
+    # aggregate-first form
+    Fp = (f_in + 3) // 4 * 4
+    HD = H * D
+    x_fwd = e * (4 * Fp + 4 * H + 4) + n * (4 * H * Fp + 8 * H + 8)            # x_j, g_j, col; xagg write, f, lse
+    x_bwd = e * (4 * Fp + 4 * H + 4 + 4 * H) + n * (8 * H * Fp + 12 * H + 8)   # x_j, g_j, col, ds write; xagg, dxagg, f, lse, df
+    tsum = e * (4 * H + 4) + n * (4 * H + 8)                                    # ds through perm; dg write
+    elu_f = 8 * n * HD
+    elu_b = 12 * n * HD
+    gemm_x = (4 * n * Fp + 8 * n * H                      # fg = x [u|v]
+              + 4 * n * H * Fp + 4 * n * HD                # out_h = xagg_h W_h
+              + 4 * n * H * Fp + 4 * n * HD                # dW_h = xagg_h^T dh'_h
+              + 4 * n * HD + 4 * n * H * Fp                # dxagg_h = dh'_h W_h^T
+              + 4 * n * Fp + 8 * n * H)                    # d[u|v] = x^T [df|dg]
+    agg = x_fwd + x_bwd + tsum + elu_f + elu_b + gemm_x
     return {"gatk_attn_fwd": k2, "gatk_attn_bwd_prep": prep, "gatk_attn_bwd_fused": fused,
             "gatk_attn_bwd_finish": finish, "projection_fwd": k1, "projection_bwd": k5,
+            "gatk_attn_x_fwd": x_fwd, "gatk_attn_x_bwd": x_bwd, "gatk_edge_tsum": tsum,
+            "gatk_elu_fwd": elu_f, "gatk_elu_bwd": elu_b, "gemm_agg_first": gemm_x,
             "layer_survey": k2 + k3_survey + k4_survey + k1 + k5,
-            "layer": k2 + prep + fused + finish + k1 + k5}
+            "layer_project_first": k2 + prep + fused + finish + k1 + k5,
+            "layer_agg_first": agg}
 
 
 def measured_peak():
@@ -194,6 +212,7 @@ def run_ours(args):
         clocks.start()
     _lib.timer = _lib.KernelTimer()
     calls0 = _lib.call_count
+    launches0 = _lib.query("gatk_launch_count")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -204,7 +223,7 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1) / args.steps
     kern = _lib.timer.summary()
     _lib.timer = None
-    launches = runner.launches_per_step * args.steps
+    launches = _lib.query("gatk_launch_count") - launches0
     calls = _lib.call_count - calls0
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
@@ -229,7 +248,8 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     ab = algorithmic_bytes(n, e_total, H, D, f_in)
     per_kernel = {}
-    for name in ("gatk_attn_fwd", "gatk_attn_bwd_fused", "gatk_attn_bwd_prep", "gatk_attn_bwd_finish"):
+    for name in ("gatk_attn_fwd", "gatk_attn_bwd_fused", "gatk_attn_bwd_prep", "gatk_attn_bwd_finish",
+                 "gatk_attn_x_fwd", "gatk_attn_x_bwd", "gatk_edge_tsum", "gatk_elu_fwd", "gatk_elu_bwd"):
         if name in kern:
             gbs = ab[name] / world / (kern[name]["ms_avg"] * 1e-3) / 1e9
             per_kernel[name] = {"ms": round(kern[name]["ms_avg"], 4), "algorithmic_GB": round(ab[name] / world / 1e9, 3),
@@ -241,9 +261,12 @@ def run_ours(args):
     if dom and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
     roofline = None
+    form = "agg_first" if "gatk_attn_x_fwd" in kern else "project_first"
+    ab["layer"] = ab["layer_" + form]
     if dom:
         roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["achieved_GBs"], "peak": peak,
                     "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "form": form,
                     "layer_frac": round(ab["layer"] / world / (ms * 1e-3) / 1e9 / peak, 4),
                     "layer_algorithmic_GB": round(ab["layer"] / 1e9, 2),
                     "layer_frac_survey_model": round(ab["layer_survey"] / world / (ms * 1e-3) / 1e9 / peak, 4),

@@ -38,6 +38,8 @@ extern "C" {
 
 GATK_API int gatk_version(void);
 GATK_API const char* gatk_last_error(void);
+/* Kernels launched by the library in this process so far (every launch is counted). */
+GATK_API int64_t gatk_launch_count(void);
 /* Number of SMs of the current device (grid sizing), <0 on error. */
 GATK_API int gatk_sm_count(void);
 

@@ -18,6 +18,7 @@ P = c_void_p  # every device pointer / stream crosses the ABI as void*
 PROTOTYPES = {
     "gatk_version": (c_int, []),
     "gatk_last_error": (c_char_p, []),
+    "gatk_launch_count": (c_int64, []),
     "gatk_sm_count": (c_int, []),
     "gatk_scan_workspace_bytes": (c_size_t, [c_int64]),
     "gatk_csr_from_dense_rowptr": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P, c_size_t, P]),
@@ -108,8 +109,9 @@ timer: "KernelTimer | None" = None  # set by bench.py around its timed region
 call_count = 0                      # entry-point invocations (every one launches >= 1 kernel)
 
 
-def call(name: str, *args):
-    """Invoke an int-returning entry point; non-zero -> GatkError(gatk_last_error())."""
+def call(name: str, *args, label: "str | None" = None):
+    """Invoke an int-returning entry point; non-zero -> GatkError(gatk_last_error()).
+    label: key the optional KernelTimer files this call under (default: the entry point's name)."""
     global call_count
     lib = load()
     call_count += 1
@@ -119,7 +121,7 @@ def call(name: str, *args):
         e0.record()
         rc = getattr(lib, name)(*args)
         e1.record()
-        timer.records.append((name, e0, e1))
+        timer.records.append((label or name, e0, e1))
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:

@@ -25,7 +25,7 @@
 
 namespace gatk {
 
-constexpr int XW = 8;  // warps per CTA
+constexpr int XW = 4;  // warps per CTA (small CTAs: the staging buffers set how many fit on an SM)
 
 struct XArgs {
   int64_t n_dst;
@@ -66,9 +66,10 @@ template <> struct Log2<4> { static constexpr int v = 2; };
 template <> struct Log2<8> { static constexpr int v = 3; };
 
 // Butterfly "reduce-scatter" over the warp: on entry every lane holds NVAL partial values; on exit
-// v[0] of lane l holds (NVAL == 32) the warp-wide sum of value l, or (NVAL < 32) the sum of value
-// (l >> (5 - log2 NVAL)) -- each step halves the values a lane carries.
-template <int NVAL>
+// v[0] of lane l holds (NVAL == 32) the warp-wide reduction of value l, or (NVAL < 32) that of value
+// (l >> (5 - log2 NVAL)) -- each step halves the values a lane carries (NVAL-1 + 5-log2 NVAL shuffles
+// instead of 5*NVAL).
+template <int NVAL, bool MAX = false>
 __device__ __forceinline__ void butterfly_scatter(float (&v)[NVAL], int lane) {
   int o = 16;
 #pragma unroll
@@ -78,180 +79,280 @@ __device__ __forceinline__ void butterfly_scatter(float (&v)[NVAL], int lane) {
     for (int i = 0; i < n; ++i) {
       const float send = up ? v[i] : v[i + n];
       const float keep = up ? v[i + n] : v[i];
-      v[i] = keep + __shfl_xor_sync(FULL, send, o);
+      const float r = __shfl_xor_sync(FULL, send, o);
+      v[i] = MAX ? fmaxf(keep, r) : keep + r;
     }
   }
-  for (; o >= 1; o >>= 1) v[0] += __shfl_xor_sync(FULL, v[0], o);
+  for (; o >= 1; o >>= 1) {
+    const float r = __shfl_xor_sync(FULL, v[0], o);
+    v[0] = MAX ? fmaxf(v[0], r) : v[0] + r;
+  }
+}
+
+// ---- per-warp staging in shared memory -------------------------------------------------------------
+// A warp works on CHUNKS of up to `chunk` stored entries of one destination row.  The neighbour rows
+// x_j of a chunk are copied to shared memory with cp.async (16 bytes per lane, one instruction per
+// row), so the number of row gathers in flight is set by the staging buffer (chunk rows per warp), not
+// by registers; the per-edge scalars (forward: softmax weights, backward: g_j) and the next chunk's
+// column ids are fetched while the copies are in flight.
+__host__ __device__ __forceinline__ int x_chunk_for(int Fp) {
+  int c = 32;
+  while (c > 1 && c * Fp * 4 > 16384) c >>= 1;
+  return c;
+}
+__host__ __device__ __forceinline__ int x_warp_smem_floats(int Fp, int HP, int chunk) { return chunk * Fp + 32 * HP + 32 + 8; }
+
+struct WarpStage {
+  float* rows;   // [chunk][Fp]
+  float* es;     // [32][HP] per-edge scalars
+  int* cols;     // [32]
+  float* scale;  // [8]
+  __device__ __forceinline__ void init(float* base, int warp, int Fp, int HP, int chunk) {
+    float* p = base + (size_t)warp * x_warp_smem_floats(Fp, HP, chunk);
+    rows = p;
+    es = p + chunk * Fp;
+    cols = reinterpret_cast<int*>(es + 32 * HP);
+    scale = es + 32 * HP + 32;
+  }
+};
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct Chunk {
+  int row, cnt;
+  int64_t base;
+  bool first, last, ok;
+};
+
+// Enumerates the chunks a warp processes, one chunk AHEAD of the compute (warp-uniform state).  HUB: the
+// chunks of one hub segment; otherwise the rows of dynamically claimed work items (hub rows skipped, empty
+// rows yielded as a chunk of 0 entries so their outputs get written).
+template <bool HUB>
+struct ChunkIter {
+  int cur, nxt, n_work, step, chunk, row, rend;
+  int64_t beg, base, end;
+  bool open;
+  __device__ __forceinline__ void init(const XArgs& a, int lane, int seg, int chunk_) {
+    chunk = chunk_;
+    if (HUB) {
+      int r;
+      hub_locate(seg, a.hub_rows, a.hub_seg_ptr, a.n_hub, a.rowptr, a.seg_len, r, beg, end);
+      row = r;
+      rend = r;
+      base = beg;
+      open = true;
+      cur = nxt = n_work = step = 0;
+    } else {
+      n_work = a.item_ptr ? a.n_items : (int)a.n_dst;
+      step = a.item_ptr ? 1 : GRAB;
+      cur = warp_grab(a.counter, lane, step);
+      nxt = warp_grab(a.counter, lane, step);
+      row = rend = 0;
+      open = false;
+      beg = base = end = 0;
+    }
+  }
+  __device__ __forceinline__ Chunk next(const XArgs& a, int lane) {
+    Chunk c;
+    c.ok = false;
+    c.row = 0; c.cnt = 0; c.base = 0; c.first = c.last = false;
+    while (true) {
+      if (open) {
+        const int64_t rem = end - base;
+        c.row = row;
+        c.base = base;
+        c.cnt = rem < chunk ? (int)rem : chunk;
+        c.first = base == beg;
+        base += chunk;
+        c.last = base >= end;
+        c.ok = true;
+        if (c.last) {
+          open = false;
+          ++row;
+        }
+        return c;
+      }
+      if (HUB) return c;
+      if (row >= rend) {
+        if (cur >= n_work) return c;
+        if (a.item_ptr) {
+          row = a.item_ptr[cur];
+          rend = a.item_ptr[cur + 1];
+        } else {
+          row = cur;
+          rend = cur + GRAB < a.n_dst ? cur + GRAB : (int)a.n_dst;
+        }
+        cur = nxt;
+        nxt = warp_grab(a.counter, lane, step);
+        continue;
+      }
+      beg = a.rowptr[row];
+      end = a.rowptr[row + 1];
+      if (end - beg > a.seg_len) {  // hub: handled by the segment kernels
+        ++row;
+        continue;
+      }
+      base = beg;
+      open = true;
+    }
+  }
+};
+
+// cp.async the cnt neighbour rows of the staged column ids into the row buffer (lanes = float4 slots).
+template <int NS>
+__device__ __forceinline__ void x_issue_rows(const XArgs& a, const WarpStage& w, int cnt, const int (&loff)[NS],
+                                             const bool (&act)[NS]) {
+#pragma unroll 4
+  for (int t = 0; t < cnt; ++t) {
+    const float* xj = a.x + (int64_t)w.cols[t] * a.ldx;
+    float* dst = w.rows + t * a.Fp;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (act[s]) cp_async16(dst + loff[s], xj + loff[s]);
+  }
+  cp_async_commit();
 }
 
 // =====================================================================================================
 // forward: xagg_ih = sum_j softmax_j(LeakyReLU(f_ih + g_jh)) x_j,  lse_ih
+// Every lane carries the running (max, sum) of head  lane >> (5 - log2 HP).
 // =====================================================================================================
-template <int HP, int NS>
-__device__ __forceinline__ void x_fwd_segment(const XArgs& a, int row, int64_t beg, int64_t end, int lane,
-                                              const int (&loff)[NS], float4 (&acc)[HP][NS], float& m_reg, float& l_reg,
-                                              int* col_s, float* p_s, float* scale_s) {
-  constexpr int U = NS == 1 ? 8 : (NS == 2 ? 4 : 2);
-  const int H = a.H;
-  const float f_reg = lane < H ? __ldg(a.f + (int64_t)row * a.ldfg + lane) : 0.f;
-  m_reg = -INFINITY;
-  l_reg = 0.f;
-#pragma unroll
-  for (int h = 0; h < HP; ++h)
-#pragma unroll
-    for (int s = 0; s < NS; ++s) acc[h][s] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  for (int64_t base = beg; base < end; base += 32) {
-    const int cnt = (end - base) < 32 ? (int)(end - base) : 32;
-    const bool valid = lane < cnt;
-    const int j = valid ? __ldg(a.col + base + lane) : 0;
-    col_s[lane] = j;
-    const float* gj = a.g + (int64_t)j * a.ldfg;
-    float gv[HP];
-#pragma unroll
-    for (int h = 0; h < HP; ++h) gv[h] = (valid && h < H) ? __ldg(gj + h) : 0.f;
-#pragma unroll
-    for (int h = 0; h < HP; ++h) {
-      if (h < H) {
-        const float z = __shfl_sync(FULL, f_reg, h) + gv[h];
-        float s = z > 0.f ? z : a.alpha * z;
-        s = valid ? s : -INFINITY;
-        const float cmax = warp_max(s);
-        const float m_old = __shfl_sync(FULL, m_reg, h);
-        const float m_new = fmaxf(m_old, cmax);
-        const float pe = valid ? expf(s - m_new) : 0.f;
-        const float csum = warp_sum(pe);
-        if (lane == h) {
-          const float sc = (m_old == -INFINITY) ? 0.f : expf(m_old - m_new);
-          l_reg = l_reg * sc + csum;
-          m_reg = m_new;
-          scale_s[h] = sc;
-        }
-        p_s[lane * HP + h] = pe;
-      }
-    }
-    __syncwarp();
-    if (base != beg) {
-      float sc[HP];
-      lds_vec<HP>(scale_s, sc);
-#pragma unroll
-      for (int h = 0; h < HP; ++h)
-#pragma unroll
-        for (int s = 0; s < NS; ++s) scale4(acc[h][s], sc[h]);
-    }
-    int t = 0;
-    for (; t + U <= cnt; t += U) {
-      float4 xv[U][NS];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float* xj = a.x + (int64_t)col_s[t + u] * a.ldx;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) xv[u][s] = ldg4(xj + loff[s]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float p[HP];
-        lds_vec<HP>(p_s + (t + u) * HP, p);
-#pragma unroll
-        for (int h = 0; h < HP; ++h)
-#pragma unroll
-          for (int s = 0; s < NS; ++s) fma4(acc[h][s], p[h], xv[u][s]);
-      }
-    }
-    for (; t < cnt; ++t) {
-      const float* xj = a.x + (int64_t)col_s[t] * a.ldx;
-      float p[HP];
-      lds_vec<HP>(p_s + t * HP, p);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const float4 xv = ldg4(xj + loff[s]);
-#pragma unroll
-        for (int h = 0; h < HP; ++h) fma4(acc[h][s], p[h], xv);
-      }
-    }
-    __syncwarp();
-  }
-}
-
 template <int HP, int NS, bool HUB>
-__global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a) {
-  __shared__ int col_sm[XW][32];
-  __shared__ __align__(16) float p_sm[XW][32 * HP];
-  __shared__ __align__(16) float scale_sm[XW][HP < 4 ? 4 : HP];
+__global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, const int chunk) {
+  extern __shared__ __align__(16) float x_smem[];
+  constexpr int SH = 5 - Log2<HP>::v;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int* col_s = col_sm[warp];
-  float* p_s = p_sm[warp];
-  float* scale_s = scale_sm[warp];
+  const int H = a.H;
+  const int hq = lane >> SH;
+  const bool hq_writer = (lane & ((1 << SH) - 1)) == 0 && hq < H;
+  WarpStage w;
+  w.init(x_smem, warp, a.Fp, HP, chunk);
   int loff[NS];
   bool act[NS];
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     act[s] = lane + 32 * s < a.S;
-    loff[s] = act[s] ? (lane + 32 * s) * 4 : 0;  // idle lanes re-read slot 0 (never stored)
+    loff[s] = act[s] ? (lane + 32 * s) * 4 : 0;
   }
-  for (int i = lane; i < 32 * HP; i += 32) p_s[i] = 0.f;  // padded heads stay zero
-  __syncwarp();
+  const int seg = blockIdx.x * XW + warp;
+  if (HUB && seg >= a.n_hub_seg) return;
+  ChunkIter<HUB> it;
+  it.init(a, lane, seg, chunk);
+
   float4 acc[HP][NS];
-  float m_reg, l_reg;
-
-  if (HUB) {
-    const int seg = blockIdx.x * XW + warp;
-    if (seg >= a.n_hub_seg) return;
-    int row;
-    int64_t beg, end;
-    hub_locate(seg, a.hub_rows, a.hub_seg_ptr, a.n_hub, a.rowptr, a.seg_len, row, beg, end);
-    x_fwd_segment<HP, NS>(a, row, beg, end, lane, loff, acc, m_reg, l_reg, col_s, p_s, scale_s);
-    float* sc = a.scratch + (int64_t)seg * xfwd_scratch_stride(a.H, a.Fp);
+  float fv[HP];
+  float m_reg = -INFINITY, l_reg = 0.f;
+  Chunk c = it.next(a, lane);
+  int j = (c.ok && lane < c.cnt) ? __ldg(a.col + c.base + lane) : 0;
+  while (c.ok) {
+    const Chunk n = it.next(a, lane);
+    w.cols[lane] = j;
+    __syncwarp();
+    x_issue_rows<NS>(a, w, c.cnt, loff, act);
+    const int jn = (n.ok && lane < n.cnt) ? __ldg(a.col + n.base + lane) : 0;  // next chunk's columns
+    const bool valid = lane < c.cnt;
+    // ---- softmax terms of this chunk (lanes = edges) while the row copies are in flight
+    const float* gj = a.g + (int64_t)j * a.ldfg;
+    float gv[HP];
 #pragma unroll
-    for (int h = 0; h < HP; ++h)
-      if (h < a.H)
+    for (int h = 0; h < HP; ++h) gv[h] = (valid && h < H) ? __ldg(gj + h) : 0.f;
+    if (c.first) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s)
-          if (act[s]) stg4(sc + h * a.Fp + loff[s], acc[h][s]);
-    if (lane < a.H) {
-      sc[a.H * a.Fp + lane] = m_reg;
-      sc[a.H * a.Fp + a.H + lane] = l_reg;
+      for (int h = 0; h < HP; ++h) fv[h] = h < H ? __ldg(a.f + (int64_t)c.row * a.ldfg + h) : 0.f;
+      m_reg = -INFINITY;
+      l_reg = 0.f;
+#pragma unroll
+      for (int h = 0; h < HP; ++h)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[h][s] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    return;
-  }
-
-  const int n_work = a.item_ptr ? a.n_items : (int)a.n_dst;
-  const int step = a.item_ptr ? 1 : GRAB;
-  int cur = warp_grab(a.counter, lane, step);
-  while (cur < n_work) {
-    const int nxt = warp_grab(a.counter, lane, step);
-    int rbeg, rend;
-    if (a.item_ptr) {
-      rbeg = a.item_ptr[cur];
-      rend = a.item_ptr[cur + 1];
-    } else {
-      rbeg = cur;
-      rend = cur + GRAB < a.n_dst ? cur + GRAB : (int)a.n_dst;
+    float sv[HP], red[HP];
+#pragma unroll
+    for (int h = 0; h < HP; ++h) {
+      const float z = fv[h] + gv[h];
+      sv[h] = (valid && h < H) ? (z > 0.f ? z : a.alpha * z) : -INFINITY;
+      red[h] = sv[h];
     }
-    for (int row = rbeg; row < rend; ++row) {
-      const int64_t beg = a.rowptr[row], end = a.rowptr[row + 1];
-      if (end - beg > a.seg_len) continue;  // hub: handled by the segment kernels
-      x_fwd_segment<HP, NS>(a, row, beg, end, lane, loff, acc, m_reg, l_reg, col_s, p_s, scale_s);
-      float* dst = a.xagg + (int64_t)row * a.ldxa;
+    butterfly_scatter<HP, true>(red, lane);  // red[0]: chunk max of head hq
+    const float m_new = fmaxf(m_reg, red[0]);
+    const float sc = (m_reg == -INFINITY) ? 0.f : expf(m_reg - m_new);
+    m_reg = m_new;
+    float pe[HP];
 #pragma unroll
-      for (int h = 0; h < HP; ++h) {
-        if (h < a.H) {
-          const float l = __shfl_sync(FULL, l_reg, h);
+    for (int h = 0; h < HP; ++h) {
+      const float mh = __shfl_sync(FULL, m_new, h << SH);
+      pe[h] = (valid && h < H) ? expf(sv[h] - mh) : 0.f;
+      red[h] = pe[h];
+    }
+    butterfly_scatter<HP, false>(red, lane);  // red[0]: chunk sum of head hq
+    l_reg = l_reg * sc + red[0];
+    sts_vec<HP>(w.es + lane * HP, pe);
+    if ((lane & ((1 << SH) - 1)) == 0) w.scale[hq] = sc;
+    cp_async_wait_all();
+    __syncwarp();
+    if (!c.first) {
+      float scv[HP];
+      lds_vec<HP>(w.scale, scv);
 #pragma unroll
-          for (int s = 0; s < NS; ++s) {
-            float4 r = acc[h][s];
-            if (l > 0.f) {
-              r.x /= l; r.y /= l; r.z /= l; r.w /= l;
-            } else {
-              r = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int h = 0; h < HP; ++h)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) scale4(acc[h][s], scv[h]);
+    }
+    // ---- weighted sum of the staged rows (lanes = float4 slots)
+#pragma unroll 4
+    for (int t = 0; t < c.cnt; ++t) {
+      float p[HP];
+      lds_vec<HP>(w.es + t * HP, p);
+      const float* xr = w.rows + t * a.Fp;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + loff[s]);
+#pragma unroll
+        for (int h = 0; h < HP; ++h) fma4(acc[h][s], p[h], xv);
+      }
+    }
+    if (c.last) {
+      if (HUB) {
+        float* scr = a.scratch + (int64_t)seg * xfwd_scratch_stride(H, a.Fp);
+#pragma unroll
+        for (int h = 0; h < HP; ++h)
+          if (h < H)
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+              if (act[s]) stg4(scr + h * a.Fp + loff[s], acc[h][s]);
+        if (hq_writer) {
+          scr[H * a.Fp + hq] = m_reg;
+          scr[H * a.Fp + H + hq] = l_reg;
+        }
+      } else {
+        float* dst = a.xagg + (int64_t)c.row * a.ldxa;
+#pragma unroll
+        for (int h = 0; h < HP; ++h) {
+          if (h < H) {
+            const float l = __shfl_sync(FULL, l_reg, h << SH);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+              float4 r = acc[h][s];
+              if (l > 0.f) {
+                r.x /= l; r.y /= l; r.z /= l; r.w /= l;
+              } else {
+                r = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              if (act[s]) stg4(dst + h * a.Fp + loff[s], r);
             }
-            if (act[s]) stg4(dst + h * a.Fp + loff[s], r);
           }
         }
+        if (a.lse && hq_writer) a.lse[(int64_t)c.row * H + hq] = l_reg > 0.f ? m_reg + logf(l_reg) : 0.f;
       }
-      if (a.lse && lane < a.H) a.lse[(int64_t)row * a.H + lane] = l_reg > 0.f ? m_reg + logf(l_reg) : 0.f;
     }
-    cur = nxt;
+    __syncwarp();  // the staging buffers are rewritten by the next chunk
+    c = n;
+    j = jn;
   }
 }
 
@@ -287,97 +388,16 @@ __global__ void attn_x_fwd_hub_merge_kernel(const XArgs a) {
 // =====================================================================================================
 // backward: ds_ijh, df_ih from (x, xagg, dxagg, f, g, lse)
 // =====================================================================================================
-template <int HP, int NS>
-__device__ __forceinline__ float x_bwd_segment(const XArgs& a, int row, int64_t beg, int64_t end, int lane,
-                                               const int (&loff)[NS], const bool (&act)[NS], int* col_s) {
+template <int HP, int NS, bool HUB>
+__global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const XArgs a, const int chunk) {
+  extern __shared__ __align__(16) float x_smem[];
   constexpr int EPG = 32 / HP;  // edges per group: one (edge, head) pair per lane after the butterfly
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int H = a.H;
   const int my_h = lane & (HP - 1), my_e = lane / HP;
   const bool head_ok = my_h < H;
-
-  // row state: dxagg_i in registers, c_ih = dxagg_ih . xagg_ih, f_ih, lse_ih for this lane's head
-  float4 dxa[HP][NS];
-  float cp[HP];
-  const float* dxr = a.dxagg + (int64_t)row * a.ldd;
-  const float* xar = a.xagg + (int64_t)row * a.ldxa;
-#pragma unroll
-  for (int h = 0; h < HP; ++h) {
-    cp[h] = 0.f;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      if (h < H && act[s]) {
-        dxa[h][s] = ldg4_stream(dxr + h * a.Fp + loff[s]);
-        cp[h] += dot4(dxa[h][s], ldg4_stream(xar + h * a.Fp + loff[s]));
-      } else {
-        dxa[h][s] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  }
-  butterfly_scatter<HP>(cp, lane);
-  const float c_my = __shfl_sync(FULL, cp[0], my_h << (5 - Log2<HP>::v));
-  const float f_my = head_ok ? __ldg(a.f + (int64_t)row * a.ldfg + my_h) : 0.f;
-  const float lse_my = head_ok ? __ldg(a.lse + (int64_t)row * H + my_h) : 0.f;
-  float df_acc = 0.f;
-
-  for (int64_t base = beg; base < end; base += 32) {
-    const int cnt = (end - base) < 32 ? (int)(end - base) : 32;
-    col_s[lane] = lane < cnt ? __ldg(a.col + base + lane) : 0;
-    __syncwarp();
-    // software pipeline over groups of EPG edges: the loads of group k+1 are issued before the math of k
-    float4 xv[EPG][NS], xn[EPG][NS];
-    float gv, gn;
-    auto issue = [&](int t, float4 (&dst)[EPG][NS], float& gdst) {
-#pragma unroll
-      for (int u = 0; u < EPG; ++u) {
-        const int tt = t + u < cnt ? t + u : cnt - 1;
-        const float* xj = a.x + (int64_t)col_s[tt] * a.ldx;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) dst[u][s] = ldg4(xj + loff[s]);
-      }
-      const int ee = t + my_e;
-      gdst = (ee < cnt && head_ok) ? __ldg(a.g + (int64_t)col_s[ee] * a.ldfg + my_h) : 0.f;
-    };
-    issue(0, xv, gv);
-    for (int t = 0; t < cnt; t += EPG) {
-      if (t + EPG < cnt) issue(t + EPG, xn, gn);
-      float part[32];
-#pragma unroll
-      for (int u = 0; u < EPG; ++u)
-#pragma unroll
-        for (int h = 0; h < HP; ++h) {
-          float d = dot4(dxa[h][0], xv[u][0]);
-#pragma unroll
-          for (int s = 1; s < NS; ++s) d += dot4(dxa[h][s], xv[u][s]);
-          part[u * HP + h] = d;
-        }
-      butterfly_scatter<32>(part, lane);
-      const int ee = t + my_e;
-      const float z = f_my + gv;
-      const float s = z > 0.f ? z : a.alpha * z;
-      const float al = expf(s - lse_my);
-      const float dsv = al * (part[0] - c_my) * (z > 0.f ? 1.f : a.alpha);
-      if (ee < cnt && head_ok) {
-        a.ds[(base + ee) * H + my_h] = dsv;
-        df_acc += dsv;
-      }
-#pragma unroll
-      for (int u = 0; u < EPG; ++u)
-#pragma unroll
-        for (int s = 0; s < NS; ++s) xv[u][s] = xn[u][s];
-      gv = gn;
-    }
-    __syncwarp();
-  }
-#pragma unroll
-  for (int o = HP; o < 32; o <<= 1) df_acc += __shfl_xor_sync(FULL, df_acc, o);
-  return df_acc;  // lanes < H: df of head `lane`
-}
-
-template <int HP, int NS, bool HUB>
-__global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const XArgs a) {
-  __shared__ int col_sm[XW][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int* col_s = col_sm[warp];
+  WarpStage w;
+  w.init(x_smem, warp, a.Fp, HP, chunk);
   int loff[NS];
   bool act[NS];
 #pragma unroll
@@ -385,36 +405,95 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const XArgs a) {
     act[s] = lane + 32 * s < a.S;
     loff[s] = act[s] ? (lane + 32 * s) * 4 : 0;
   }
-  if (HUB) {
-    const int seg = blockIdx.x * XW + warp;
-    if (seg >= a.n_hub_seg) return;
-    int row;
-    int64_t beg, end;
-    hub_locate(seg, a.hub_rows, a.hub_seg_ptr, a.n_hub, a.rowptr, a.seg_len, row, beg, end);
-    const float d = x_bwd_segment<HP, NS>(a, row, beg, end, lane, loff, act, col_s);
-    if (lane < a.H) a.scratch[(int64_t)seg * a.H + lane] = d;
-    return;
-  }
-  const int n_work = a.item_ptr ? a.n_items : (int)a.n_dst;
-  const int step = a.item_ptr ? 1 : GRAB;
-  int cur = warp_grab(a.counter, lane, step);
-  while (cur < n_work) {
-    const int nxt = warp_grab(a.counter, lane, step);
-    int rbeg, rend;
-    if (a.item_ptr) {
-      rbeg = a.item_ptr[cur];
-      rend = a.item_ptr[cur + 1];
-    } else {
-      rbeg = cur;
-      rend = cur + GRAB < a.n_dst ? cur + GRAB : (int)a.n_dst;
+  const int seg = blockIdx.x * XW + warp;
+  if (HUB && seg >= a.n_hub_seg) return;
+  ChunkIter<HUB> it;
+  it.init(a, lane, seg, chunk);
+
+  float4 dxa[HP][NS];
+  float c_my = 0.f, f_my = 0.f, lse_my = 0.f, df_acc = 0.f;
+  Chunk c = it.next(a, lane);
+  int j = (c.ok && lane < c.cnt) ? __ldg(a.col + c.base + lane) : 0;
+  while (c.ok) {
+    const Chunk n = it.next(a, lane);
+    w.cols[lane] = j;
+    __syncwarp();
+    x_issue_rows<NS>(a, w, c.cnt, loff, act);
+    const int jn = (n.ok && lane < n.cnt) ? __ldg(a.col + n.base + lane) : 0;
+    // g_j of the chunk's edges (lanes = edges) -> staged for the (edge, head) lanes
+    {
+      const bool valid = lane < c.cnt;
+      const float* gj = a.g + (int64_t)j * a.ldfg;
+      float gv[HP];
+#pragma unroll
+      for (int h = 0; h < HP; ++h) gv[h] = (valid && h < H) ? __ldg(gj + h) : 0.f;
+      if (c.first) {
+        // row state: dxagg_i in registers, c_ih = dxagg_ih . xagg_ih, f_ih, lse_ih for this lane's head
+        float cp[HP];
+        const float* dxr = a.dxagg + (int64_t)c.row * a.ldd;
+        const float* xar = a.xagg + (int64_t)c.row * a.ldxa;
+#pragma unroll
+        for (int h = 0; h < HP; ++h) {
+          cp[h] = 0.f;
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            if (h < H && act[s]) {
+              dxa[h][s] = ldg4_stream(dxr + h * a.Fp + loff[s]);
+              cp[h] += dot4(dxa[h][s], ldg4_stream(xar + h * a.Fp + loff[s]));
+            } else {
+              dxa[h][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+        f_my = head_ok ? __ldg(a.f + (int64_t)c.row * a.ldfg + my_h) : 0.f;
+        lse_my = head_ok ? __ldg(a.lse + (int64_t)c.row * H + my_h) : 0.f;
+        butterfly_scatter<HP>(cp, lane);
+        c_my = __shfl_sync(FULL, cp[0], my_h << (5 - Log2<HP>::v));
+        df_acc = 0.f;
+      }
+      sts_vec<HP>(w.es + lane * HP, gv);
     }
-    for (int row = rbeg; row < rend; ++row) {
-      const int64_t beg = a.rowptr[row], end = a.rowptr[row + 1];
-      if (end - beg > a.seg_len) continue;
-      const float d = x_bwd_segment<HP, NS>(a, row, beg, end, lane, loff, act, col_s);
-      if (lane < a.H) a.df[(int64_t)row * a.lddf + lane] = d;
+    cp_async_wait_all();
+    __syncwarp();
+    for (int t = 0; t < c.cnt; t += EPG) {
+      float part[32];
+#pragma unroll
+      for (int u = 0; u < EPG; ++u) {
+        const float* xr = w.rows + (t + u < c.cnt ? t + u : t) * a.Fp;
+        float4 xv[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) xv[s] = *reinterpret_cast<const float4*>(xr + loff[s]);
+#pragma unroll
+        for (int h = 0; h < HP; ++h) {
+          float d = dot4(dxa[h][0], xv[0]);
+#pragma unroll
+          for (int s = 1; s < NS; ++s) d += dot4(dxa[h][s], xv[s]);
+          part[u * HP + h] = d;
+        }
+      }
+      butterfly_scatter<32>(part, lane);
+      const int ee = t + my_e;
+      const float z = f_my + w.es[(ee & 31) * HP + my_h];
+      const float sl = z > 0.f ? z : a.alpha * z;
+      const float al = expf(sl - lse_my);
+      const float dsv = al * (part[0] - c_my) * (z > 0.f ? 1.f : a.alpha);
+      if (ee < c.cnt && head_ok) {
+        a.ds[(c.base + ee) * H + my_h] = dsv;
+        df_acc += dsv;
+      }
     }
-    cur = nxt;
+    if (c.last) {
+      float d = df_acc;
+#pragma unroll
+      for (int o = HP; o < 32; o <<= 1) d += __shfl_xor_sync(FULL, d, o);
+      if (lane < H) {
+        if (HUB) a.scratch[(int64_t)seg * H + lane] = d;
+        else a.df[(int64_t)c.row * a.lddf + lane] = d;
+      }
+    }
+    __syncwarp();
+    c = n;
+    j = jn;
   }
 }
 
@@ -534,18 +613,22 @@ static int check_x_geom(int H, int S, int* hp, int* ns) {
 
 template <int HP, int NS>
 static int launch_x_fwd(const XArgs& a, cudaStream_t st) {
+  const int chunk = x_chunk_for(a.Fp);
+  const size_t smem = (size_t)XW * x_warp_smem_floats(a.Fp, HP, chunk) * sizeof(float);
   if (a.n_hub_seg > 0) {
-    attn_x_fwd_kernel<HP, NS, true><<<(a.n_hub_seg + XW - 1) / XW, XW * 32, 0, st>>>(a);
+    if (smem > 48 * 1024)
+      GATK_CHECK_CUDA(cudaFuncSetAttribute(attn_x_fwd_kernel<HP, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_x_fwd_kernel<HP, NS, true><<<(a.n_hub_seg + XW - 1) / XW, XW * 32, smem, st>>>(a, chunk);
     GATK_CHECK_LAUNCH();
     attn_x_fwd_hub_merge_kernel<<<a.n_hub, 128, 0, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   if (a.n_dst > 0) {
     int grid = 0;
-    if (int rc = persistent_grid(attn_x_fwd_kernel<HP, NS, false>, XW * 32, 0, &grid)) return rc;
+    if (int rc = persistent_grid(attn_x_fwd_kernel<HP, NS, false>, XW * 32, smem, &grid)) return rc;
     const int64_t need = a.item_ptr ? (a.n_items + XW - 1) / XW : (a.n_dst + (int64_t)XW * GRAB - 1) / ((int64_t)XW * GRAB);
     if (need < grid) grid = (int)need;
-    attn_x_fwd_kernel<HP, NS, false><<<grid, XW * 32, 0, st>>>(a);
+    attn_x_fwd_kernel<HP, NS, false><<<grid, XW * 32, smem, st>>>(a, chunk);
     GATK_CHECK_LAUNCH();
   }
   return 0;
@@ -553,18 +636,22 @@ static int launch_x_fwd(const XArgs& a, cudaStream_t st) {
 
 template <int HP, int NS>
 static int launch_x_bwd(const XArgs& a, cudaStream_t st) {
+  const int chunk = x_chunk_for(a.Fp);
+  const size_t smem = (size_t)XW * x_warp_smem_floats(a.Fp, HP, chunk) * sizeof(float);
   if (a.n_hub_seg > 0) {
-    attn_x_bwd_kernel<HP, NS, true><<<(a.n_hub_seg + XW - 1) / XW, XW * 32, 0, st>>>(a);
+    if (smem > 48 * 1024)
+      GATK_CHECK_CUDA(cudaFuncSetAttribute(attn_x_bwd_kernel<HP, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_x_bwd_kernel<HP, NS, true><<<(a.n_hub_seg + XW - 1) / XW, XW * 32, smem, st>>>(a, chunk);
     GATK_CHECK_LAUNCH();
     attn_x_bwd_hub_merge_kernel<<<(a.n_hub * a.H + 127) / 128, 128, 0, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   if (a.n_dst > 0) {
     int grid = 0;
-    if (int rc = persistent_grid(attn_x_bwd_kernel<HP, NS, false>, XW * 32, 0, &grid)) return rc;
+    if (int rc = persistent_grid(attn_x_bwd_kernel<HP, NS, false>, XW * 32, smem, &grid)) return rc;
     const int64_t need = a.item_ptr ? (a.n_items + XW - 1) / XW : (a.n_dst + (int64_t)XW * GRAB - 1) / ((int64_t)XW * GRAB);
     if (need < grid) grid = (int)need;
-    attn_x_bwd_kernel<HP, NS, false><<<grid, XW * 32, 0, st>>>(a);
+    attn_x_bwd_kernel<HP, NS, false><<<grid, XW * 32, smem, st>>>(a, chunk);
     GATK_CHECK_LAUNCH();
   }
   return 0;

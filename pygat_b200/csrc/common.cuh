@@ -19,7 +19,13 @@ void set_error(const char* fmt, ...);
     }                                                                                      \
   } while (0)
 
-#define GATK_CHECK_LAUNCH() GATK_CHECK_CUDA(cudaGetLastError())
+void note_launch();  // every kernel launch of the library is counted (gatk_launch_count)
+
+#define GATK_CHECK_LAUNCH()               \
+  do {                                    \
+    gatk::note_launch();                  \
+    GATK_CHECK_CUDA(cudaGetLastError());  \
+  } while (0)
 
 #define GATK_REQUIRE(cond, ...)       \
   do {                                \

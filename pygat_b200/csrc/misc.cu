@@ -2,11 +2,15 @@
 // attention core: dropout masks, logits, da reduction, head combine, SpecialSpmm.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace gatk {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -201,6 +205,7 @@ __global__ void spmm_coo_bwd_kernel(const int64_t* __restrict__ row, const int64
 using namespace gatk;
 
 extern "C" int gatk_version(void) { return GATK_VERSION; }
+extern "C" int64_t gatk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* gatk_last_error(void) { return g_err; }
 extern "C" int gatk_sm_count(void) {
   int dev = 0, n = 0;

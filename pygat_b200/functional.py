@@ -48,12 +48,12 @@ class LayerMasks:
     keep_att: Optional[torch.Tensor] = None
 
 
-def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=0, a_off=0, b_off=0, c_off=0):
+def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=0, a_off=0, b_off=0, c_off=0, label=None):
     """C[M,N] (+)= op(A) op(B) on raw pointers; *_off are element offsets into the tensors."""
     ws_bytes = _lib.query("gatk_gemm_workspace_bytes", ta, tb, M, N, K)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=C.device) if ws_bytes else None
     _lib.call("gatk_gemm", ta, tb, M, N, K, A.data_ptr() + 4 * a_off, lda, B.data_ptr() + 4 * b_off, ldb,
-              C.data_ptr() + 4 * c_off, ldc, accumulate, _ptr(ws), ws_bytes, _stream())
+              C.data_ptr() + 4 * c_off, ldc, accumulate, _ptr(ws), ws_bytes, _stream(), label=label)
 
 
 def _hub_scratch(which: int, H: int, Dp: int, n_seg: int, dev):
@@ -349,7 +349,7 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         w_uv = w_uv.contiguous()
         st = _stream()
         fg = torch.empty(n, Muv, dtype=torch.float32, device=dev)
-        _gemm(0, 0, n, Muv, f_in, xp, Fp, w_uv, Muv, fg, Muv)
+        _gemm(0, 0, n, Muv, f_in, xp, Fp, w_uv, Muv, fg, Muv, label="gemm:logits")
         need_grad = any(ctx.needs_input_grad[1:3])
         xagg = torch.empty(n, H * Fp, dtype=torch.float32, device=dev)
         lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
@@ -360,9 +360,10 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         out = torch.empty(n, HD, dtype=torch.float32, device=dev)
         for h in range(H):
-            _gemm(0, 0, n, Dp, f_in, xagg, H * Fp, w_ext, M_out, out, HD, a_off=h * Fp, b_off=h * Dp, c_off=h * Dp)
+            _gemm(0, 0, n, Dp, f_in, xagg, H * Fp, w_ext, M_out, out, HD, a_off=h * Fp, b_off=h * Dp, c_off=h * Dp,
+                  label="gemm:project")
         if has_skip:
-            _gemm(0, 0, n, HD, f_in, xp, Fp, w_ext, M_out, out, HD, accumulate=1, b_off=HD)
+            _gemm(0, 0, n, HD, f_in, xp, Fp, w_ext, M_out, out, HD, accumulate=1, b_off=HD, label="gemm:skip")
         if act_elu:
             _lib.call("gatk_elu_fwd", n, HD, out.data_ptr(), HD, st)
         if need_grad:
@@ -392,10 +393,12 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
         dxagg = (torch.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
         for h in range(H):
-            _gemm(1, 0, f_in, Dp, n, xagg, H * Fp, dhp, HD, dw_ext, M_out, a_off=h * Fp, b_off=h * Dp, c_off=h * Dp)
-            _gemm(0, 1, n, f_in, Dp, dhp, HD, w_ext, M_out, dxagg, H * Fp, a_off=h * Dp, b_off=h * Dp, c_off=h * Fp)
+            _gemm(1, 0, f_in, Dp, n, xagg, H * Fp, dhp, HD, dw_ext, M_out, a_off=h * Fp, b_off=h * Dp, c_off=h * Dp,
+                  label="gemm:dW")
+            _gemm(0, 1, n, f_in, Dp, dhp, HD, w_ext, M_out, dxagg, H * Fp, a_off=h * Dp, b_off=h * Dp, c_off=h * Fp,
+                  label="gemm:dxagg")
         if has_skip:
-            _gemm(1, 0, f_in, HD, n, xp, Fp, dhp, HD, dw_ext, M_out, c_off=HD)
+            _gemm(1, 0, f_in, HD, n, xp, Fp, dhp, HD, dw_ext, M_out, c_off=HD, label="gemm:dskip")
         # logit path: ds per stored entry, df per destination, dg per source (transposed sum of ds)
         ds = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
         dfg = (torch.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
@@ -409,7 +412,7 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         _lib.call("gatk_edge_tsum", graph.n_src, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(),
                   dfg.data_ptr() + 4 * H, Muv, thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
         dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
-        _gemm(1, 0, f_in, Muv, n, xp, Fp, dfg, Muv, dw_uv, Muv)
+        _gemm(1, 0, f_in, Muv, n, xp, Fp, dfg, Muv, dw_uv, Muv, label="gemm:dlogits")
         return None, dw_ext, dw_uv, None, None, None, None, None, None
 
 
