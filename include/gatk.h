@@ -171,11 +171,14 @@ GATK_API int gatk_da_reduce(int64_t n, int H, int Dp, const float* wh, int64_t l
  * The same layer as K1-K5 (layers.py:134-170, models.py:29-35) with the neighbour sum taken BEFORE the
  * projection:  h'_ih = (sum_j alpha_ijh x_j) W_h.  Valid when no dropout sits between the projection and
  * the logits; pays when the input row is narrower than the projected row (F_in < H*D: the products shape
- * gathers 400 B instead of 2 KiB per stored entry).  f = x (W a_src), g = x (W a_dst) come from a thin GEMM.
+ * gathers 400 B instead of 2 KiB per stored entry).
  *
+ *  logits_pack  f = x u, g = x v with [u | v] = [W a_src | W a_dst] (uv is [F, >= 2H], u in columns 0..H-1,
+ *          v in H..2H-1) and the GATHER ROWS  xg_i = [x_i (F floats, zero padded to Fp = 4*ceil(F/4)) |
+ *          g_i (H floats) | zero pad]  with row pitch gatk_xg_pitch(Fp, H) (a multiple of 32 floats: rows are
+ *          128-byte aligned, so a stored entry costs one DRAM access for both x_j and g_j).
  *  x_fwd   per destination row: softmax_j LeakyReLU(f_i + g_j) (online, max-subtracted) and
- *          xagg[i, h*Fp:(h+1)*Fp] = sum_j alpha_ijh x_j;  lse[i,h] = m + log l.  Fp = input width padded to
- *          a multiple of 4 floats (x rows 16-byte aligned, pad columns zero).  The caller then projects:
+ *          xagg[i, h*Fp:(h+1)*Fp] = sum_j alpha_ijh x_j;  lse[i,h] = m + log l.  The caller then projects:
  *          out_h = xagg_h W_h (+ x S_h) through gatk_gemm and applies gatk_elu_fwd.
  *  x_bwd   per destination row, given dxagg_ih = dh'_ih W_h^T (gatk_gemm):  c_ih = dxagg_ih . xagg_ih,
  *          ds_ijh = alpha_ijh (dxagg_ih . x_j - c_ih) LeakyReLU'(f_ih + g_jh)  ->  ds [E, H] in CSR edge order,
@@ -184,19 +187,22 @@ GATK_API int gatk_da_reduce(int64_t n, int H, int Dp, const float* wh, int64_t l
  *  edge_tsum  dg[j,h] = sum_i ds_ijh: segmented sum along the transposed pattern (tptr, perm from
  *          gatk_csr_transpose); sources with more than long_len entries are listed in long_rows.
  * Hub rows (longer than seg_len) as in gatk_attn_fwd; scratch floats: gatk_attn_x_scratch_floats(which, ...)
- * with which = 0 (x_fwd), 1 (x_bwd).  H <= 8, Fp <= 512, H*ceil(Fp/128) <= 16. */
+ * with which = 0 (x_fwd), 1 (x_bwd).  H <= 8, Fp <= 512, H_pow2 * ceil((Fp/4 + ceil(H/4)) / 32) <= 16. */
+GATK_API int64_t gatk_xg_pitch(int Fp, int H);
+GATK_API int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t ldx, const float* uv, int64_t lduv,
+                              float* xg, int64_t ldxg, float* f, int64_t ldf, void* stream);
 GATK_API size_t gatk_attn_x_scratch_floats(int which, int H, int Fp, int n_hub_seg);
 GATK_API int gatk_attn_x_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
-                             const float* x, int64_t ldx, const float* f, const float* g, int64_t ldfg, float alpha,
+                             const float* xg, int64_t ldxg, const float* f, int64_t ldf, float alpha,
                              float* xagg, int64_t ldxa, float* lse, int seg_len, const int32_t* hub_rows,
                              const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
                              int32_t* counter, const int32_t* item_ptr, int n_items, void* stream);
 GATK_API int gatk_attn_x_bwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
-                             const float* x, int64_t ldx, const float* f, const float* g, int64_t ldfg,
-                             const float* lse, float alpha, const float* xagg, int64_t ldxa, const float* dxagg,
-                             int64_t ldd, float* ds, float* df, int64_t lddf, int seg_len, const int32_t* hub_rows,
-                             const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
-                             int32_t* counter, const int32_t* item_ptr, int n_items, void* stream);
+                             const float* xg, int64_t ldxg, const float* f, int64_t ldf, const float* lse, float alpha,
+                             const float* xagg, int64_t ldxa, const float* dxagg, int64_t ldd, float* ds, float* df,
+                             int64_t lddf, int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
+                             int n_hub_seg, float* hub_scratch, int32_t* counter, const int32_t* item_ptr,
+                             int n_items, void* stream);
 GATK_API int gatk_edge_tsum(int64_t n_src, const int64_t* tptr, const int32_t* perm, int H, const float* ds,
                             float* dg, int64_t lddg, int long_len, const int32_t* long_rows, int n_long,
                             void* stream);

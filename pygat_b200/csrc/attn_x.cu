@@ -18,25 +18,29 @@
 // so the backward edge pass is destination-major as well and gathers x_j once more; nothing
 // H*D wide is ever gathered.
 //
-// Lane geometry: an x row is S = Fp/4 float4 slots, lane l owns slots l, l+32, ... (NS per lane).
-// Softmax terms are computed with lanes = edges (forward) or lanes = (edge, head) pairs (backward,
-// after a transposing butterfly reduction of the 32 partial dot products of an edge group).
+// Data layout: the source-side logit half g_j rides BEHIND the input row, xg_j = [x_j (Fp floats, zero
+// padded) | g_j (H floats) | pad] with 128-byte aligned rows (gatk_logits_pack builds it), so a stored
+// entry costs ONE random DRAM access.  A warp works on chunks of up to 32 stored entries of one
+// destination row: the chunk's rows are copied to shared memory with cp.async (one 16-byte-per-lane
+// instruction per row), so the gathers in flight are bounded by the staging buffer, not by registers,
+// and the column ids of the next chunk are fetched one chunk ahead.  Forward: softmax terms with
+// lanes = edges, weighted sum with lanes = float4 slots (packed FFMA2).  Backward: lanes = edges, every
+// lane dots ITS row against dxagg_i broadcast from shared memory -- no cross-lane reduction per edge.
 #include "attn_common.cuh"
 
 namespace gatk {
 
-constexpr int XW = 4;  // warps per CTA (small CTAs: the staging buffers set how many fit on an SM)
+constexpr int XW = 2;  // warps per CTA (small CTAs: the staging buffers set how many fit on an SM)
 
 struct XArgs {
   int64_t n_dst;
   const int64_t* rowptr;
   const int32_t* col;
-  int H, S, Fp;
-  const float* x;
-  int64_t ldx;
+  int H, S, Fp, Sx, RS;  // heads; x slots; 4*S; slots copied per row (x + g); smem row pitch (floats)
+  const float* xg;
+  int64_t ldxg;
   const float* f;
-  const float* g;
-  int64_t ldfg;
+  int64_t ldf;
   float alpha;
   float* xagg;
   int64_t ldxa;
@@ -64,6 +68,7 @@ template <> struct Log2<1> { static constexpr int v = 0; };
 template <> struct Log2<2> { static constexpr int v = 1; };
 template <> struct Log2<4> { static constexpr int v = 2; };
 template <> struct Log2<8> { static constexpr int v = 3; };
+template <> struct Log2<16> { static constexpr int v = 4; };
 
 // Butterfly "reduce-scatter" over the warp: on entry every lane holds NVAL partial values; on exit
 // v[0] of lane l holds (NVAL == 32) the warp-wide reduction of value l, or (NVAL < 32) that of value
@@ -90,31 +95,14 @@ __device__ __forceinline__ void butterfly_scatter(float (&v)[NVAL], int lane) {
 }
 
 // ---- per-warp staging in shared memory -------------------------------------------------------------
-// A warp works on CHUNKS of up to `chunk` stored entries of one destination row.  The neighbour rows
-// x_j of a chunk are copied to shared memory with cp.async (16 bytes per lane, one instruction per
-// row), so the number of row gathers in flight is set by the staging buffer (chunk rows per warp), not
-// by registers; the per-edge scalars (forward: softmax weights, backward: g_j) and the next chunk's
-// column ids are fetched while the copies are in flight.
-__host__ __device__ __forceinline__ int x_chunk_for(int Fp) {
+__host__ __device__ __forceinline__ int x_row_pitch(int Sx) { return (Sx | 1) * 4; }  // odd number of 16-byte units: lane-per-row reads are conflict free
+__host__ __device__ __forceinline__ int x_chunk_for(int RS) {
   int c = 32;
-  while (c > 1 && c * Fp * 4 > 16384) c >>= 1;
+  while (c > 4 && c * RS * 4 > 14336) c >>= 1;
   return c;
 }
-__host__ __device__ __forceinline__ int x_warp_smem_floats(int Fp, int HP, int chunk) { return chunk * Fp + 32 * HP + 32 + 8; }
-
-struct WarpStage {
-  float* rows;   // [chunk][Fp]
-  float* es;     // [32][HP] per-edge scalars
-  int* cols;     // [32]
-  float* scale;  // [8]
-  __device__ __forceinline__ void init(float* base, int warp, int Fp, int HP, int chunk) {
-    float* p = base + (size_t)warp * x_warp_smem_floats(Fp, HP, chunk);
-    rows = p;
-    es = p + chunk * Fp;
-    cols = reinterpret_cast<int*>(es + 32 * HP);
-    scale = es + 32 * HP + 32;
-  }
-};
+__host__ __device__ __forceinline__ int xfwd_warp_floats(int RS, int HP, int chunk) { return chunk * RS + 64 * HP + 32 + 8; }
+__host__ __device__ __forceinline__ int xbwd_warp_floats(int RS, int H, int Fp, int chunk) { return chunk * RS + H * Fp + 32; }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -122,6 +110,13 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// acc += p * x on a float4 with two packed FFMA2 (pp = {p, p})
+__device__ __forceinline__ void fma4_pp(float4& acc, const float2 pp, const float4& x) {
+  const float2 lo = __ffma2_rn(pp, make_float2(x.x, x.y), make_float2(acc.x, acc.y));
+  const float2 hi = __ffma2_rn(pp, make_float2(x.z, x.w), make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 
 struct Chunk {
   int row, cnt;
@@ -203,14 +198,14 @@ struct ChunkIter {
   }
 };
 
-// cp.async the cnt neighbour rows of the staged column ids into the row buffer (lanes = float4 slots).
+// cp.async the cnt neighbour rows [x_j | g_j] of the staged column ids into the row buffer (lanes = slots).
 template <int NS>
-__device__ __forceinline__ void x_issue_rows(const XArgs& a, const WarpStage& w, int cnt, const int (&loff)[NS],
+__device__ __forceinline__ void x_issue_rows(const XArgs& a, float* rows, const int* cols, int cnt, const int (&loff)[NS],
                                              const bool (&act)[NS]) {
 #pragma unroll 4
   for (int t = 0; t < cnt; ++t) {
-    const float* xj = a.x + (int64_t)w.cols[t] * a.ldx;
-    float* dst = w.rows + t * a.Fp;
+    const float* xj = a.xg + (int64_t)cols[t] * a.ldxg;
+    float* dst = rows + t * a.RS;
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       if (act[s]) cp_async16(dst + loff[s], xj + loff[s]);
@@ -229,14 +224,18 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int H = a.H;
   const int hq = lane >> SH;
-  const bool hq_writer = (lane & ((1 << SH) - 1)) == 0 && hq < H;
-  WarpStage w;
-  w.init(x_smem, warp, a.Fp, HP, chunk);
+  const bool hq_lead = (lane & ((1 << SH) - 1)) == 0;
+  const bool hq_writer = hq_lead && hq < H;
+  float* rows = x_smem + (size_t)warp * xfwd_warp_floats(a.RS, HP, chunk);
+  float2* es2 = reinterpret_cast<float2*>(rows + chunk * a.RS);  // [32][HP] {p, p}
+  int* cols = reinterpret_cast<int*>(rows + chunk * a.RS + 64 * HP);
+  float* scale = rows + chunk * a.RS + 64 * HP + 32;
   int loff[NS];
-  bool act[NS];
+  bool act[NS], act_x[NS];
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    act[s] = lane + 32 * s < a.S;
+    act[s] = lane + 32 * s < a.Sx;     // copied / accumulated (x and g slots)
+    act_x[s] = lane + 32 * s < a.S;    // stored (x slots)
     loff[s] = act[s] ? (lane + 32 * s) * 4 : 0;
   }
   const int seg = blockIdx.x * XW + warp;
@@ -251,19 +250,14 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
   int j = (c.ok && lane < c.cnt) ? __ldg(a.col + c.base + lane) : 0;
   while (c.ok) {
     const Chunk n = it.next(a, lane);
-    w.cols[lane] = j;
+    cols[lane] = j;
     __syncwarp();
-    x_issue_rows<NS>(a, w, c.cnt, loff, act);
+    x_issue_rows<NS>(a, rows, cols, c.cnt, loff, act);
     const int jn = (n.ok && lane < n.cnt) ? __ldg(a.col + n.base + lane) : 0;  // next chunk's columns
     const bool valid = lane < c.cnt;
-    // ---- softmax terms of this chunk (lanes = edges) while the row copies are in flight
-    const float* gj = a.g + (int64_t)j * a.ldfg;
-    float gv[HP];
-#pragma unroll
-    for (int h = 0; h < HP; ++h) gv[h] = (valid && h < H) ? __ldg(gj + h) : 0.f;
     if (c.first) {
 #pragma unroll
-      for (int h = 0; h < HP; ++h) fv[h] = h < H ? __ldg(a.f + (int64_t)c.row * a.ldfg + h) : 0.f;
+      for (int h = 0; h < HP; ++h) fv[h] = h < H ? __ldg(a.f + (int64_t)c.row * a.ldf + h) : 0.f;
       m_reg = -INFINITY;
       l_reg = 0.f;
 #pragma unroll
@@ -271,6 +265,11 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
 #pragma unroll
         for (int s = 0; s < NS; ++s) acc[h][s] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    cp_async_wait_all();
+    __syncwarp();
+    // ---- softmax terms of this chunk (lanes = edges); g_j sits behind x_j in the staged row
+    float gv[HP];
+    lds_vec<HP>(rows + (valid ? lane : 0) * a.RS + a.Fp, gv);
     float sv[HP], red[HP];
 #pragma unroll
     for (int h = 0; h < HP; ++h) {
@@ -291,13 +290,13 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
     }
     butterfly_scatter<HP, false>(red, lane);  // red[0]: chunk sum of head hq
     l_reg = l_reg * sc + red[0];
-    sts_vec<HP>(w.es + lane * HP, pe);
-    if ((lane & ((1 << SH) - 1)) == 0) w.scale[hq] = sc;
-    cp_async_wait_all();
+#pragma unroll
+    for (int h = 0; h < HP; ++h) es2[lane * HP + h] = make_float2(pe[h], pe[h]);
+    if (hq_lead) scale[hq] = sc;
     __syncwarp();
     if (!c.first) {
       float scv[HP];
-      lds_vec<HP>(w.scale, scv);
+      lds_vec<HP>(scale, scv);
 #pragma unroll
       for (int h = 0; h < HP; ++h)
 #pragma unroll
@@ -306,14 +305,23 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
     // ---- weighted sum of the staged rows (lanes = float4 slots)
 #pragma unroll 4
     for (int t = 0; t < c.cnt; ++t) {
-      float p[HP];
-      lds_vec<HP>(w.es + t * HP, p);
-      const float* xr = w.rows + t * a.Fp;
+      float2 pp[HP];
+      if constexpr (HP >= 2) {
+#pragma unroll
+        for (int h = 0; h < HP; h += 2) {
+          const float4 q = *reinterpret_cast<const float4*>(es2 + t * HP + h);
+          pp[h] = make_float2(q.x, q.y);
+          pp[h + 1] = make_float2(q.z, q.w);
+        }
+      } else {
+        pp[0] = es2[t];
+      }
+      const float* xr = rows + t * a.RS;
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const float4 xv = *reinterpret_cast<const float4*>(xr + loff[s]);
 #pragma unroll
-        for (int h = 0; h < HP; ++h) fma4(acc[h][s], p[h], xv);
+        for (int h = 0; h < HP; ++h) fma4_pp(acc[h][s], pp[h], xv);
       }
     }
     if (c.last) {
@@ -324,26 +332,23 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
           if (h < H)
 #pragma unroll
             for (int s = 0; s < NS; ++s)
-              if (act[s]) stg4(scr + h * a.Fp + loff[s], acc[h][s]);
+              if (act_x[s]) stg4(scr + h * a.Fp + loff[s], acc[h][s]);
         if (hq_writer) {
           scr[H * a.Fp + hq] = m_reg;
           scr[H * a.Fp + H + hq] = l_reg;
         }
       } else {
         float* dst = a.xagg + (int64_t)c.row * a.ldxa;
+        const float inv_mine = l_reg > 0.f ? 1.f / l_reg : 0.f;
 #pragma unroll
         for (int h = 0; h < HP; ++h) {
           if (h < H) {
-            const float l = __shfl_sync(FULL, l_reg, h << SH);
+            const float inv = __shfl_sync(FULL, inv_mine, h << SH);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
               float4 r = acc[h][s];
-              if (l > 0.f) {
-                r.x /= l; r.y /= l; r.z /= l; r.w /= l;
-              } else {
-                r = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-              if (act[s]) stg4(dst + h * a.Fp + loff[s], r);
+              scale4(r, inv);
+              if (act_x[s]) stg4(dst + h * a.Fp + loff[s], r);
             }
           }
         }
@@ -386,110 +391,118 @@ __global__ void attn_x_fwd_hub_merge_kernel(const XArgs a) {
 }
 
 // =====================================================================================================
-// backward: ds_ijh, df_ih from (x, xagg, dxagg, f, g, lse)
+// backward: ds_ijh, df_ih from (xg, xagg, dxagg, f, lse).  Lanes = edges: every lane dots its staged
+// row against dxagg_i, which all lanes read (broadcast) from shared memory.
 // =====================================================================================================
-template <int HP, int NS, bool HUB>
+template <int HP, bool HUB>
 __global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const XArgs a, const int chunk) {
   extern __shared__ __align__(16) float x_smem[];
-  constexpr int EPG = 32 / HP;  // edges per group: one (edge, head) pair per lane after the butterfly
+  constexpr int SH = 5 - Log2<HP>::v;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int H = a.H;
-  const int my_h = lane & (HP - 1), my_e = lane / HP;
-  const bool head_ok = my_h < H;
-  WarpStage w;
-  w.init(x_smem, warp, a.Fp, HP, chunk);
-  int loff[NS];
-  bool act[NS];
-#pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    act[s] = lane + 32 * s < a.S;
-    loff[s] = act[s] ? (lane + 32 * s) * 4 : 0;
-  }
+  const int H = a.H, S = a.S, Fp = a.Fp;
+  const int hq = lane >> SH;
+  const bool hq_writer = (lane & ((1 << SH) - 1)) == 0 && hq < H;
+  float* rows = x_smem + (size_t)warp * xbwd_warp_floats(a.RS, H, Fp, chunk);
+  float* dxs = rows + chunk * a.RS;  // [H][Fp] dxagg_i
+  int* cols = reinterpret_cast<int*>(dxs + H * Fp);
   const int seg = blockIdx.x * XW + warp;
   if (HUB && seg >= a.n_hub_seg) return;
   ChunkIter<HUB> it;
   it.init(a, lane, seg, chunk);
+  const int n_copy = (a.Sx + 31) >> 5;  // copy instructions per row
 
-  float4 dxa[HP][NS];
-  float c_my = 0.f, f_my = 0.f, lse_my = 0.f, df_acc = 0.f;
+  float cv[HP], fv[HP], lv[HP];
+  float df_acc = 0.f;  // running df of head hq
   Chunk c = it.next(a, lane);
   int j = (c.ok && lane < c.cnt) ? __ldg(a.col + c.base + lane) : 0;
   while (c.ok) {
     const Chunk n = it.next(a, lane);
-    w.cols[lane] = j;
+    cols[lane] = j;
     __syncwarp();
-    x_issue_rows<NS>(a, w, c.cnt, loff, act);
+#pragma unroll 4
+    for (int t = 0; t < c.cnt; ++t) {
+      const float* xj = a.xg + (int64_t)cols[t] * a.ldxg;
+      float* dst = rows + t * a.RS;
+      for (int s = 0; s < n_copy; ++s) {
+        const int slot = lane + 32 * s;
+        if (slot < a.Sx) cp_async16(dst + slot * 4, xj + slot * 4);
+      }
+    }
+    cp_async_commit();
     const int jn = (n.ok && lane < n.cnt) ? __ldg(a.col + n.base + lane) : 0;
-    // g_j of the chunk's edges (lanes = edges) -> staged for the (edge, head) lanes
-    {
-      const bool valid = lane < c.cnt;
-      const float* gj = a.g + (int64_t)j * a.ldfg;
-      float gv[HP];
+    if (c.first) {
+      // row state (lanes = slots): dxagg_i -> shared memory, c_ih = dxagg_ih . xagg_ih; f_ih, lse_ih
+      float cp[HP];
 #pragma unroll
-      for (int h = 0; h < HP; ++h) gv[h] = (valid && h < H) ? __ldg(gj + h) : 0.f;
-      if (c.first) {
-        // row state: dxagg_i in registers, c_ih = dxagg_ih . xagg_ih, f_ih, lse_ih for this lane's head
-        float cp[HP];
-        const float* dxr = a.dxagg + (int64_t)c.row * a.ldd;
-        const float* xar = a.xagg + (int64_t)c.row * a.ldxa;
+      for (int h = 0; h < HP; ++h) cp[h] = 0.f;
+      const float* dxr = a.dxagg + (int64_t)c.row * a.ldd;
+      const float* xar = a.xagg + (int64_t)c.row * a.ldxa;
+      for (int slot = lane; slot < S; slot += 32) {
 #pragma unroll
         for (int h = 0; h < HP; ++h) {
-          cp[h] = 0.f;
-#pragma unroll
-          for (int s = 0; s < NS; ++s) {
-            if (h < H && act[s]) {
-              dxa[h][s] = ldg4_stream(dxr + h * a.Fp + loff[s]);
-              cp[h] += dot4(dxa[h][s], ldg4_stream(xar + h * a.Fp + loff[s]));
-            } else {
-              dxa[h][s] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+          if (h < H) {
+            const float4 d = ldg4_stream(dxr + h * Fp + slot * 4);
+            cp[h] += dot4(d, ldg4_stream(xar + h * Fp + slot * 4));
+            *reinterpret_cast<float4*>(dxs + h * Fp + slot * 4) = d;
           }
         }
-        f_my = head_ok ? __ldg(a.f + (int64_t)c.row * a.ldfg + my_h) : 0.f;
-        lse_my = head_ok ? __ldg(a.lse + (int64_t)c.row * H + my_h) : 0.f;
-        butterfly_scatter<HP>(cp, lane);
-        c_my = __shfl_sync(FULL, cp[0], my_h << (5 - Log2<HP>::v));
-        df_acc = 0.f;
       }
-      sts_vec<HP>(w.es + lane * HP, gv);
+#pragma unroll
+      for (int h = 0; h < HP; ++h) {
+        fv[h] = h < H ? __ldg(a.f + (int64_t)c.row * a.ldf + h) : 0.f;
+        lv[h] = h < H ? __ldg(a.lse + (int64_t)c.row * H + h) : 0.f;
+      }
+      butterfly_scatter<HP>(cp, lane);
+#pragma unroll
+      for (int h = 0; h < HP; ++h) cv[h] = __shfl_sync(FULL, cp[0], h << SH);
+      df_acc = 0.f;
     }
     cp_async_wait_all();
     __syncwarp();
-    for (int t = 0; t < c.cnt; t += EPG) {
-      float part[32];
+    // ---- dalpha_eh = dxagg_ih . x_e for this lane's edge e
+    const bool valid = lane < c.cnt;
+    const float* xr = rows + (valid ? lane : 0) * a.RS;
+    float2 acc2[HP];
 #pragma unroll
-      for (int u = 0; u < EPG; ++u) {
-        const float* xr = w.rows + (t + u < c.cnt ? t + u : t) * a.Fp;
-        float4 xv[NS];
+    for (int h = 0; h < HP; ++h) acc2[h] = make_float2(0.f, 0.f);
+#pragma unroll 2
+    for (int k = 0; k < S; ++k) {
+      const float4 xq = *reinterpret_cast<const float4*>(xr + 4 * k);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) xv[s] = *reinterpret_cast<const float4*>(xr + loff[s]);
-#pragma unroll
-        for (int h = 0; h < HP; ++h) {
-          float d = dot4(dxa[h][0], xv[0]);
-#pragma unroll
-          for (int s = 1; s < NS; ++s) d += dot4(dxa[h][s], xv[s]);
-          part[u * HP + h] = d;
+      for (int h = 0; h < HP; ++h) {
+        if (h < H) {
+          const float4 dq = *reinterpret_cast<const float4*>(dxs + h * Fp + 4 * k);
+          acc2[h] = __ffma2_rn(make_float2(dq.x, dq.y), make_float2(xq.x, xq.y), acc2[h]);
+          acc2[h] = __ffma2_rn(make_float2(dq.z, dq.w), make_float2(xq.z, xq.w), acc2[h]);
         }
       }
-      butterfly_scatter<32>(part, lane);
-      const int ee = t + my_e;
-      const float z = f_my + w.es[(ee & 31) * HP + my_h];
+    }
+    float gv[HP], dsv[HP];
+    lds_vec<HP>(xr + Fp, gv);
+#pragma unroll
+    for (int h = 0; h < HP; ++h) {
+      const float z = fv[h] + gv[h];
       const float sl = z > 0.f ? z : a.alpha * z;
-      const float al = expf(sl - lse_my);
-      const float dsv = al * (part[0] - c_my) * (z > 0.f ? 1.f : a.alpha);
-      if (ee < c.cnt && head_ok) {
-        a.ds[(c.base + ee) * H + my_h] = dsv;
-        df_acc += dsv;
+      const float al = expf(sl - lv[h]);
+      const float v = al * ((acc2[h].x + acc2[h].y) - cv[h]) * (z > 0.f ? 1.f : a.alpha);
+      dsv[h] = (valid && h < H) ? v : 0.f;
+    }
+    if (valid) {
+      float* dp = a.ds + (c.base + lane) * H;
+      if (HP >= 4 && H == HP) {
+#pragma unroll
+        for (int h = 0; h < HP; h += 4) stg4(dp + h, make_float4(dsv[h], dsv[h + 1], dsv[h + 2], dsv[h + 3]));
+      } else {
+#pragma unroll
+        for (int h = 0; h < HP; ++h)
+          if (h < H) dp[h] = dsv[h];
       }
     }
-    if (c.last) {
-      float d = df_acc;
-#pragma unroll
-      for (int o = HP; o < 32; o <<= 1) d += __shfl_xor_sync(FULL, d, o);
-      if (lane < H) {
-        if (HUB) a.scratch[(int64_t)seg * H + lane] = d;
-        else a.df[(int64_t)c.row * a.lddf + lane] = d;
-      }
+    butterfly_scatter<HP>(dsv, lane);  // dsv[0]: this chunk's sum of head hq
+    df_acc += dsv[0];
+    if (c.last && hq_writer) {
+      if (HUB) a.scratch[(int64_t)seg * H + hq] = df_acc;
+      else a.df[(int64_t)c.row * a.lddf + hq] = df_acc;
     }
     __syncwarp();
     c = n;
@@ -587,12 +600,68 @@ __global__ void elu_bwd_kernel(int64_t n, int c4, const float* __restrict__ gout
   stg4(dhp + r * ldd + c, gv);
 }
 
-static int check_x_geom(int H, int S, int* hp, int* ns) {
+// =====================================================================================================
+// f_i = x_i . u_h, g_i = x_i . v_h  (u = W a_src, v = W a_dst: layers.py:141-144 folded into the input) and
+// the gather rows xg_i = [x_i | 0.. | g_i | 0..].  Warp per row, lanes = float4 slots, [u|v] transposed in
+// shared memory.
+// =====================================================================================================
+template <int HP, bool VEC>
+__global__ void __launch_bounds__(256) logits_pack_kernel(int64_t n, int F, int H, const float* __restrict__ x, int64_t ldx,
+                                                          const float* __restrict__ uv, int64_t lduv, int Fp, int P,
+                                                          float* __restrict__ xg, float* __restrict__ f, int64_t ldf) {
+  extern __shared__ __align__(16) float uvs[];  // [2*HP][Fp]
+  constexpr int C2 = 2 * HP;
+  constexpr int SHC = 5 - Log2<C2>::v;
+  for (int i = threadIdx.x; i < C2 * Fp; i += blockDim.x) {
+    const int c = i / Fp, k = i - c * Fp;
+    const int h = c < HP ? c : c - HP;
+    uvs[i] = (k < F && h < H) ? uv[(int64_t)k * lduv + (c < HP ? h : H + h)] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int S = Fp >> 2;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
+    const float* xr = x + row * ldx;
+    float* gr = xg + row * P;
+    float part[C2];
+#pragma unroll
+    for (int c = 0; c < C2; ++c) part[c] = 0.f;
+    for (int slot = lane; slot < S; slot += 32) {
+      float4 v;
+      if (VEC) {
+        v = ldg4_stream(xr + slot * 4);
+      } else {
+        const int k = slot * 4;
+        v.x = k < F ? __ldg(xr + k) : 0.f;
+        v.y = k + 1 < F ? __ldg(xr + k + 1) : 0.f;
+        v.z = k + 2 < F ? __ldg(xr + k + 2) : 0.f;
+        v.w = k + 3 < F ? __ldg(xr + k + 3) : 0.f;
+      }
+      stg4(gr + slot * 4, v);
+#pragma unroll
+      for (int c = 0; c < C2; ++c) part[c] += dot4(v, *reinterpret_cast<const float4*>(uvs + c * Fp + slot * 4));
+    }
+    butterfly_scatter<C2>(part, lane);  // lane (c << SHC) holds column c
+    if ((lane & ((1 << SHC) - 1)) == 0) {
+      const int c = lane >> SHC;
+      if (c < H) f[row * ldf + c] = part[0];
+    }
+    for (int t0 = 0; t0 < P - Fp; t0 += 32) {  // g behind the input row, zero padding after it
+      const int t = t0 + lane;
+      const float gval = __shfl_sync(FULL, part[0], ((HP + (t < HP ? t : 0)) << SHC) & 31);
+      if (t < P - Fp) gr[Fp + t] = t < H ? gval : 0.f;
+    }
+  }
+}
+
+static int check_x_geom(int H, int Fp, int* hp, int* ns, int* sx) {
   GATK_REQUIRE(H >= 1 && H <= 8, "aggregate-first form: H=%d out of range [1,8]", H);
-  GATK_REQUIRE(S >= 1 && S <= 128, "aggregate-first form: %d float4 slots per input row out of range [1,128]", S);
+  GATK_REQUIRE(Fp >= 4 && Fp % 4 == 0 && Fp <= 512, "aggregate-first form: Fp=%d must be a multiple of 4 in [4,512]", Fp);
   *hp = H <= 1 ? 1 : (H <= 2 ? 2 : (H <= 4 ? 4 : 8));
-  *ns = S <= 32 ? 1 : (S <= 64 ? 2 : 4);
-  GATK_REQUIRE(*hp * *ns <= 16, "aggregate-first form: H=%d x %d floats per row needs too many accumulators", H, 4 * S);
+  *sx = Fp / 4 + (H + 3) / 4;
+  *ns = *sx <= 32 ? 1 : (*sx <= 64 ? 2 : (*sx <= 128 ? 4 : 5));
+  GATK_REQUIRE(*ns <= 4 && *hp * *ns <= 16, "aggregate-first form: H=%d x Fp=%d needs too many accumulators", H, Fp);
   return 0;
 }
 
@@ -610,48 +679,52 @@ static int check_x_geom(int H, int S, int* hp, int* ns) {
     case 8 * 8 + 1: { constexpr int HP = 8, NS = 1; CALL; } break;           \
     default:        { constexpr int HP = 8, NS = 2; CALL; } break;           \
   }
+#define HP_DISPATCH(hp, CALL)                          \
+  switch (hp) {                                        \
+    case 1: { constexpr int HP = 1; CALL; } break;     \
+    case 2: { constexpr int HP = 2; CALL; } break;     \
+    case 4: { constexpr int HP = 4; CALL; } break;     \
+    default: { constexpr int HP = 8; CALL; } break;    \
+  }
 
-template <int HP, int NS>
-static int launch_x_fwd(const XArgs& a, cudaStream_t st) {
-  const int chunk = x_chunk_for(a.Fp);
-  const size_t smem = (size_t)XW * x_warp_smem_floats(a.Fp, HP, chunk) * sizeof(float);
+template <typename KH, typename KM>
+static int launch_x(KH hub_kernel, KM main_kernel, const XArgs& a, int chunk, size_t smem, cudaStream_t st) {
   if (a.n_hub_seg > 0) {
     if (smem > 48 * 1024)
-      GATK_CHECK_CUDA(cudaFuncSetAttribute(attn_x_fwd_kernel<HP, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_x_fwd_kernel<HP, NS, true><<<(a.n_hub_seg + XW - 1) / XW, XW * 32, smem, st>>>(a, chunk);
-    GATK_CHECK_LAUNCH();
-    attn_x_fwd_hub_merge_kernel<<<a.n_hub, 128, 0, st>>>(a);
+      GATK_CHECK_CUDA(cudaFuncSetAttribute(hub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hub_kernel<<<(a.n_hub_seg + XW - 1) / XW, XW * 32, smem, st>>>(a, chunk);
     GATK_CHECK_LAUNCH();
   }
   if (a.n_dst > 0) {
     int grid = 0;
-    if (int rc = persistent_grid(attn_x_fwd_kernel<HP, NS, false>, XW * 32, smem, &grid)) return rc;
+    if (int rc = persistent_grid(main_kernel, XW * 32, smem, &grid)) return rc;
     const int64_t need = a.item_ptr ? (a.n_items + XW - 1) / XW : (a.n_dst + (int64_t)XW * GRAB - 1) / ((int64_t)XW * GRAB);
     if (need < grid) grid = (int)need;
-    attn_x_fwd_kernel<HP, NS, false><<<grid, XW * 32, smem, st>>>(a, chunk);
+    main_kernel<<<grid, XW * 32, smem, st>>>(a, chunk);
     GATK_CHECK_LAUNCH();
   }
   return 0;
 }
 
 template <int HP, int NS>
-static int launch_x_bwd(const XArgs& a, cudaStream_t st) {
-  const int chunk = x_chunk_for(a.Fp);
-  const size_t smem = (size_t)XW * x_warp_smem_floats(a.Fp, HP, chunk) * sizeof(float);
-  if (a.n_hub_seg > 0) {
-    if (smem > 48 * 1024)
-      GATK_CHECK_CUDA(cudaFuncSetAttribute(attn_x_bwd_kernel<HP, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_x_bwd_kernel<HP, NS, true><<<(a.n_hub_seg + XW - 1) / XW, XW * 32, smem, st>>>(a, chunk);
-    GATK_CHECK_LAUNCH();
-    attn_x_bwd_hub_merge_kernel<<<(a.n_hub * a.H + 127) / 128, 128, 0, st>>>(a);
+static int launch_x_fwd(const XArgs& a, cudaStream_t st) {
+  const int chunk = x_chunk_for(a.RS);
+  const size_t smem = (size_t)XW * xfwd_warp_floats(a.RS, HP, chunk) * sizeof(float);
+  if (int rc = launch_x(attn_x_fwd_kernel<HP, NS, true>, attn_x_fwd_kernel<HP, NS, false>, a, chunk, smem, st)) return rc;
+  if (a.n_hub_seg > 0) {  // stream order: the merge only needs the segment kernel, which ran first
+    attn_x_fwd_hub_merge_kernel<<<a.n_hub, 128, 0, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
-  if (a.n_dst > 0) {
-    int grid = 0;
-    if (int rc = persistent_grid(attn_x_bwd_kernel<HP, NS, false>, XW * 32, smem, &grid)) return rc;
-    const int64_t need = a.item_ptr ? (a.n_items + XW - 1) / XW : (a.n_dst + (int64_t)XW * GRAB - 1) / ((int64_t)XW * GRAB);
-    if (need < grid) grid = (int)need;
-    attn_x_bwd_kernel<HP, NS, false><<<grid, XW * 32, smem, st>>>(a, chunk);
+  return 0;
+}
+
+template <int HP>
+static int launch_x_bwd(const XArgs& a, cudaStream_t st) {
+  const int chunk = x_chunk_for(a.RS);
+  const size_t smem = (size_t)XW * xbwd_warp_floats(a.RS, a.H, a.Fp, chunk) * sizeof(float);
+  if (int rc = launch_x(attn_x_bwd_kernel<HP, true>, attn_x_bwd_kernel<HP, false>, a, chunk, smem, st)) return rc;
+  if (a.n_hub_seg > 0) {
+    attn_x_bwd_hub_merge_kernel<<<(a.n_hub * a.H + 127) / 128, 128, 0, st>>>(a);
     GATK_CHECK_LAUNCH();
   }
   return 0;
@@ -667,57 +740,91 @@ extern "C" size_t gatk_attn_x_scratch_floats(int which, int H, int Fp, int n_hub
   return (size_t)n_hub_seg * H;
 }
 
+extern "C" int64_t gatk_xg_pitch(int Fp, int H) { return ((int64_t)Fp + 4 * ((H + 3) / 4) + 31) / 32 * 32; }
+
+extern "C" int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t ldx, const float* uv, int64_t lduv,
+                                float* xg, int64_t ldxg, float* f, int64_t ldf, void* stream) {
+  GATK_REQUIRE(F >= 1 && H >= 1 && H <= 8, "bad sizes F=%d H=%d", F, H);
+  const int Fp = (F + 3) / 4 * 4;
+  GATK_REQUIRE(Fp <= 512, "F=%d too wide for the aggregate-first form", F);
+  GATK_REQUIRE(x && uv && xg && f && ldx >= F && lduv >= 2 * H && ldf >= H, "bad arguments");
+  GATK_REQUIRE(ldxg == gatk_xg_pitch(Fp, H) && ((uintptr_t)xg & 127) == 0, "xg must have pitch gatk_xg_pitch(Fp, H) and 128-byte alignment");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int hp = H <= 1 ? 1 : (H <= 2 ? 2 : (H <= 4 ? 4 : 8));
+  const bool vec = (F % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)x & 15) == 0);
+  const size_t smem = (size_t)2 * hp * Fp * sizeof(float);
+  int64_t blocks = (n + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+#define PACK_LAUNCH(HPV, V) logits_pack_kernel<HPV, V><<<(unsigned)blocks, 256, smem, st>>>(n, F, H, x, ldx, uv, lduv, Fp, (int)ldxg, xg, f, ldf)
+  if (vec) {
+    HP_DISPATCH(hp, PACK_LAUNCH(HP, true));
+  } else {
+    HP_DISPATCH(hp, PACK_LAUNCH(HP, false));
+  }
+#undef PACK_LAUNCH
+  GATK_CHECK_LAUNCH();
+  return 0;
+}
+
+static int fill_xargs(XArgs& a, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp, int sx,
+                      const float* xg, int64_t ldxg, const float* f, int64_t ldf, float alpha, int seg_len,
+                      const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
+                      int32_t* counter, const int32_t* item_ptr, int n_items) {
+  if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
+  GATK_REQUIRE(n_dst < (1LL << 31), "n_dst too large for one shard");
+  GATK_REQUIRE(rowptr && col && xg && f && counter, "null pointer argument");
+  GATK_REQUIRE(ldxg % 4 == 0 && ldxg >= 4 * sx && ((uintptr_t)xg & 15) == 0 && ldf >= H,
+               "xg rows must be 16-byte aligned with pitch >= Fp + 4*ceil(H/4); ldf >= H");
+  a.n_dst = n_dst; a.rowptr = rowptr; a.col = col; a.H = H; a.S = Fp / 4; a.Fp = Fp; a.Sx = sx; a.RS = x_row_pitch(sx);
+  a.xg = xg; a.ldxg = ldxg; a.f = f; a.ldf = ldf; a.alpha = alpha;
+  a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub; a.n_hub_seg = n_hub_seg;
+  a.scratch = hub_scratch; a.counter = counter; a.item_ptr = item_ptr; a.n_items = n_items;
+  return 0;
+}
+
 extern "C" int gatk_attn_x_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
-                               const float* x, int64_t ldx, const float* f, const float* g, int64_t ldfg, float alpha,
+                               const float* xg, int64_t ldxg, const float* f, int64_t ldf, float alpha,
                                float* xagg, int64_t ldxa, float* lse, int seg_len, const int32_t* hub_rows,
                                const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
                                int32_t* counter, const int32_t* item_ptr, int n_items, void* stream) {
-  GATK_REQUIRE(Fp >= 4 && Fp % 4 == 0, "Fp=%d must be a positive multiple of 4", Fp);
-  int hp, ns;
-  if (int rc = check_x_geom(H, Fp / 4, &hp, &ns)) return rc;
-  if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
-  GATK_REQUIRE(n_dst < (1LL << 31), "n_dst too large for one shard");
-  GATK_REQUIRE(rowptr && col && x && f && g && xagg && counter, "null pointer argument");
-  GATK_REQUIRE(ldx % 4 == 0 && ldx >= Fp && ldxa % 4 == 0 && ldxa >= (int64_t)H * Fp && ldfg >= H,
-               "leading dims: ldx, ldxa multiples of 4 floats, ldx >= Fp, ldxa >= H*Fp, ldfg >= H");
-  GATK_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)xagg & 15) == 0, "x and xagg must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
+  int hp, ns, sx;
+  if (int rc = check_x_geom(H, Fp, &hp, &ns, &sx)) return rc;
   XArgs a = {};
-  a.n_dst = n_dst; a.rowptr = rowptr; a.col = col; a.H = H; a.S = Fp / 4; a.Fp = Fp; a.x = x; a.ldx = ldx;
-  a.f = f; a.g = g; a.ldfg = ldfg; a.alpha = alpha; a.xagg = xagg; a.ldxa = ldxa; a.lse = lse;
-  a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub; a.n_hub_seg = n_hub_seg;
-  a.scratch = hub_scratch; a.counter = counter; a.item_ptr = item_ptr; a.n_items = n_items;
+  if (int rc = fill_xargs(a, n_dst, rowptr, col, H, Fp, sx, xg, ldxg, f, ldf, alpha, seg_len, hub_rows, hub_seg_ptr,
+                          n_hub, n_hub_seg, hub_scratch, counter, item_ptr, n_items))
+    return rc;
+  GATK_REQUIRE(xagg && ldxa % 4 == 0 && ldxa >= (int64_t)H * Fp && ((uintptr_t)xagg & 15) == 0,
+               "xagg must be 16-byte aligned with pitch >= H*Fp (multiple of 4 floats)");
+  a.xagg = xagg; a.ldxa = ldxa; a.lse = lse;
+  cudaStream_t st = (cudaStream_t)stream;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
   X_DISPATCH(hp, ns, return (launch_x_fwd<HP, NS>(a, st)));
   return 0;
 }
 
 extern "C" int gatk_attn_x_bwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
-                               const float* x, int64_t ldx, const float* f, const float* g, int64_t ldfg,
-                               const float* lse, float alpha, const float* xagg, int64_t ldxa, const float* dxagg,
-                               int64_t ldd, float* ds, float* df, int64_t lddf, int seg_len, const int32_t* hub_rows,
-                               const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
-                               int32_t* counter, const int32_t* item_ptr, int n_items, void* stream) {
-  GATK_REQUIRE(Fp >= 4 && Fp % 4 == 0, "Fp=%d must be a positive multiple of 4", Fp);
-  int hp, ns;
-  if (int rc = check_x_geom(H, Fp / 4, &hp, &ns)) return rc;
-  if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
-  GATK_REQUIRE(n_dst < (1LL << 31), "n_dst too large for one shard");
-  GATK_REQUIRE(rowptr && col && x && f && g && lse && xagg && dxagg && ds && df && counter, "null pointer argument");
-  GATK_REQUIRE(ldx % 4 == 0 && ldx >= Fp && ldxa % 4 == 0 && ldxa >= (int64_t)H * Fp && ldd % 4 == 0 &&
-                   ldd >= (int64_t)H * Fp && ldfg >= H && lddf >= H,
-               "leading dims: ldx, ldxa, ldd multiples of 4 floats and wide enough, ldfg, lddf >= H");
-  GATK_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)xagg & 15) == 0 && ((uintptr_t)dxagg & 15) == 0,
-               "x, xagg and dxagg must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
+                               const float* xg, int64_t ldxg, const float* f, int64_t ldf, const float* lse, float alpha,
+                               const float* xagg, int64_t ldxa, const float* dxagg, int64_t ldd, float* ds, float* df,
+                               int64_t lddf, int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
+                               int n_hub_seg, float* hub_scratch, int32_t* counter, const int32_t* item_ptr,
+                               int n_items, void* stream) {
+  int hp, ns, sx;
+  if (int rc = check_x_geom(H, Fp, &hp, &ns, &sx)) return rc;
   XArgs a = {};
-  a.n_dst = n_dst; a.rowptr = rowptr; a.col = col; a.H = H; a.S = Fp / 4; a.Fp = Fp; a.x = x; a.ldx = ldx;
-  a.f = f; a.g = g; a.ldfg = ldfg; a.alpha = alpha; a.xagg = const_cast<float*>(xagg); a.ldxa = ldxa;
-  a.lse = const_cast<float*>(lse); a.dxagg = dxagg; a.ldd = ldd; a.ds = ds; a.df = df; a.lddf = lddf;
-  a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub; a.n_hub_seg = n_hub_seg;
-  a.scratch = hub_scratch; a.counter = counter; a.item_ptr = item_ptr; a.n_items = n_items;
+  if (int rc = fill_xargs(a, n_dst, rowptr, col, H, Fp, sx, xg, ldxg, f, ldf, alpha, seg_len, hub_rows, hub_seg_ptr,
+                          n_hub, n_hub_seg, hub_scratch, counter, item_ptr, n_items))
+    return rc;
+  GATK_REQUIRE(lse && xagg && dxagg && ds && df, "null pointer argument");
+  GATK_REQUIRE(ldxa % 4 == 0 && ldxa >= (int64_t)H * Fp && ldd % 4 == 0 && ldd >= (int64_t)H * Fp && lddf >= H &&
+                   ((uintptr_t)xagg & 15) == 0 && ((uintptr_t)dxagg & 15) == 0 && ((uintptr_t)ds & 15) == 0,
+               "xagg / dxagg: 16-byte aligned, pitch >= H*Fp (multiple of 4 floats); ds 16-byte aligned; lddf >= H");
+  a.xagg = const_cast<float*>(xagg); a.ldxa = ldxa; a.lse = const_cast<float*>(lse);
+  a.dxagg = dxagg; a.ldd = ldd; a.ds = ds; a.df = df; a.lddf = lddf;
+  cudaStream_t st = (cudaStream_t)stream;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
-  X_DISPATCH(hp, ns, return (launch_x_bwd<HP, NS>(a, st)));
+  HP_DISPATCH(hp, return (launch_x_bwd<HP>(a, st)));
   return 0;
 }
 

@@ -324,9 +324,10 @@ def agg_first_geometry(f_in: int, H: int, Dp: int):
 class GatLayerAggFirstFunction(torch.autograd.Function):
     """The layer with the neighbour sum taken BEFORE the projection (see csrc/attn_x.cu):
 
-        fg   = x [W a_src | W a_dst]                      thin GEMM, logits are linear in the input
-        xagg = softmax-weighted neighbour sum of x        gatk_attn_x_fwd, gathers F_in-wide rows
-        out  = act( xagg_h W_h  (+ x S_h) )               H per-head GEMMs on the aggregated rows
+        f, xg = x [W a_src], [x | x (W a_dst)]            gatk_logits_pack: logits are linear in the input; the
+                                                          source half g rides behind the input row it is gathered with
+        xagg  = softmax-weighted neighbour sum of x       gatk_attn_x_fwd, gathers F_in-wide rows
+        out   = act( xagg_h W_h  (+ x S_h) )              H per-head GEMMs on the aggregated rows
 
     Same math as layers.py:134-170 up to fp32 re-association (sum_j alpha_ij (x_j W) = (sum_j alpha_ij x_j) W).
     Used when no dropout sits between projection and logits, the input needs no gradient (a first layer)
@@ -344,44 +345,46 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         Muv = w_uv.shape[1]
         Fp = (f_in + 3) // 4 * 4
         assert w_ext.shape == (f_in, M_out) and Muv >= 2 * H and Muv % 4 == 0
-        xp = x.contiguous() if Fp == f_in else torch.nn.functional.pad(x, (0, Fp - f_in))
+        x = x.contiguous()
         w_ext = w_ext.contiguous()
         w_uv = w_uv.contiguous()
         st = _stream()
-        fg = torch.empty(n, Muv, dtype=torch.float32, device=dev)
-        _gemm(0, 0, n, Muv, f_in, xp, Fp, w_uv, Muv, fg, Muv, label="gemm:logits")
+        P = _lib.query("gatk_xg_pitch", Fp, H)
+        xg = torch.empty(n, P, dtype=torch.float32, device=dev)
+        f = torch.empty(n, H, dtype=torch.float32, device=dev)
+        _lib.call("gatk_logits_pack", n, f_in, H, x.data_ptr(), f_in, w_uv.data_ptr(), Muv, xg.data_ptr(), P,
+                  f.data_ptr(), H, st)
         need_grad = any(ctx.needs_input_grad[1:3])
         xagg = torch.empty(n, H * Fp, dtype=torch.float32, device=dev)
         lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
         hubs = graph.hubs
         scratch = _x_scratch(0, H, Fp, hubs.n_seg, dev)
-        _lib.call("gatk_attn_x_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xp.data_ptr(), Fp,
-                  fg.data_ptr(), fg.data_ptr() + 4 * H, Muv, float(alpha), xagg.data_ptr(), H * Fp, _ptr(lse),
+        _lib.call("gatk_attn_x_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
+                  f.data_ptr(), H, float(alpha), xagg.data_ptr(), H * Fp, _ptr(lse),
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         out = torch.empty(n, HD, dtype=torch.float32, device=dev)
         for h in range(H):
             _gemm(0, 0, n, Dp, f_in, xagg, H * Fp, w_ext, M_out, out, HD, a_off=h * Fp, b_off=h * Dp, c_off=h * Dp,
                   label="gemm:project")
         if has_skip:
-            _gemm(0, 0, n, HD, f_in, xp, Fp, w_ext, M_out, out, HD, accumulate=1, b_off=HD, label="gemm:skip")
+            _gemm(0, 0, n, HD, f_in, xg, P, w_ext, M_out, out, HD, accumulate=1, b_off=HD, label="gemm:skip")
         if act_elu:
             _lib.call("gatk_elu_fwd", n, HD, out.data_ptr(), HD, st)
         if need_grad:
             ctx.graph = graph
-            ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu), f_in, Fp)
-            ctx.save_for_backward(xp, w_ext, fg, lse, xagg, out)
+            ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu), f_in, Fp, Muv)
+            ctx.save_for_backward(xg, w_ext, f, lse, xagg, out)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        xp, w_ext, fg, lse, xagg, out = ctx.saved_tensors
+        xg, w_ext, f, lse, xagg, out = ctx.saved_tensors
         graph = ctx.graph
-        H, Dp, has_skip, alpha, act_elu, f_in, Fp = ctx.cfg
-        dev = xp.device
-        n = xp.shape[0]
+        H, Dp, has_skip, alpha, act_elu, f_in, Fp, Muv = ctx.cfg
+        dev = xg.device
+        n, P = xg.shape
         HD = H * Dp
         M_out = HD * (2 if has_skip else 1)
-        Muv = fg.shape[1]
         st = _stream()
         gout = gout.contiguous()
         if act_elu:
@@ -398,21 +401,21 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
             _gemm(0, 1, n, f_in, Dp, dhp, HD, w_ext, M_out, dxagg, H * Fp, a_off=h * Dp, b_off=h * Dp, c_off=h * Fp,
                   label="gemm:dxagg")
         if has_skip:
-            _gemm(1, 0, f_in, HD, n, xp, Fp, dhp, HD, dw_ext, M_out, c_off=HD, label="gemm:dskip")
+            _gemm(1, 0, f_in, HD, n, xg, P, dhp, HD, dw_ext, M_out, c_off=HD, label="gemm:dskip")
         # logit path: ds per stored entry, df per destination, dg per source (transposed sum of ds)
         ds = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
         dfg = (torch.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
         hubs = graph.hubs
         scratch = _x_scratch(1, H, Fp, hubs.n_seg, dev)
-        _lib.call("gatk_attn_x_bwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xp.data_ptr(), Fp,
-                  fg.data_ptr(), fg.data_ptr() + 4 * H, Muv, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
+        _lib.call("gatk_attn_x_bwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
+                  f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
                   dxagg.data_ptr(), H * Fp, ds.data_ptr(), dfg.data_ptr(), Muv,
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         tptr, _trow, perm, thubs = graph.transpose()[:4]
         _lib.call("gatk_edge_tsum", graph.n_src, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(),
                   dfg.data_ptr() + 4 * H, Muv, thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
         dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
-        _gemm(1, 0, f_in, Muv, n, xp, Fp, dfg, Muv, dw_uv, Muv, label="gemm:dlogits")
+        _gemm(1, 0, f_in, Muv, n, xg, P, dfg, Muv, dw_uv, Muv, label="gemm:dlogits")
         return None, dw_ext, dw_uv, None, None, None, None, None, None
 
 
