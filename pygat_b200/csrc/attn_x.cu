@@ -26,6 +26,8 @@
 // and the column ids of the next chunk are fetched one chunk ahead.  Forward: softmax terms with
 // lanes = edges, weighted sum with lanes = float4 slots (packed FFMA2).  Backward: lanes = edges, every
 // lane dots ITS row against dxagg_i broadcast from shared memory -- no cross-lane reduction per edge.
+#include <stdlib.h>
+
 #include "attn_common.cuh"
 
 namespace gatk {
@@ -101,7 +103,11 @@ __host__ __device__ __forceinline__ int x_chunk_for(int RS) {
   while (c > 4 && c * RS * 4 > 14336) c >>= 1;
   return c;
 }
-__host__ __device__ __forceinline__ int xfwd_warp_floats(int RS, int HP, int chunk) { return chunk * RS + 64 * HP + 32 + 8; }
+__host__ __device__ __forceinline__ int xfwd_warp_floats(int RS, int HP, int chunk) { return chunk * RS + 32 * HP + 32 + 8; }
+// backward (tensor-core kernel): row pitch = 16 (mod 32) floats, so the two rows a quarter-warp touches per
+// 128-bit fragment load sit in different bank halves
+__host__ __device__ __forceinline__ int xmma_row_pitch(int Sx) { return (4 * Sx + 15) / 32 * 32 + 16; }
+__host__ __device__ __forceinline__ int xmma_warp_floats(int RS) { return 32 * RS + 32; }
 __host__ __device__ __forceinline__ int xbwd_warp_floats(int RS, int H, int Fp, int chunk) { return chunk * RS + H * Fp + 32; }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
@@ -227,9 +233,9 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
   const bool hq_lead = (lane & ((1 << SH) - 1)) == 0;
   const bool hq_writer = hq_lead && hq < H;
   float* rows = x_smem + (size_t)warp * xfwd_warp_floats(a.RS, HP, chunk);
-  float2* es2 = reinterpret_cast<float2*>(rows + chunk * a.RS);  // [32][HP] {p, p}
-  int* cols = reinterpret_cast<int*>(rows + chunk * a.RS + 64 * HP);
-  float* scale = rows + chunk * a.RS + 64 * HP + 32;
+  float* es = rows + chunk * a.RS;  // [32][HP] softmax weights of the chunk's edges
+  int* cols = reinterpret_cast<int*>(es + 32 * HP);
+  float* scale = es + 32 * HP + 32;
   int loff[NS];
   bool act[NS], act_x[NS];
 #pragma unroll
@@ -290,8 +296,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
     }
     butterfly_scatter<HP, false>(red, lane);  // red[0]: chunk sum of head hq
     l_reg = l_reg * sc + red[0];
-#pragma unroll
-    for (int h = 0; h < HP; ++h) es2[lane * HP + h] = make_float2(pe[h], pe[h]);
+    sts_vec<HP>(es + lane * HP, pe);
     if (hq_lead) scale[hq] = sc;
     __syncwarp();
     if (!c.first) {
@@ -303,25 +308,19 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
         for (int s = 0; s < NS; ++s) scale4(acc[h][s], scv[h]);
     }
     // ---- weighted sum of the staged rows (lanes = float4 slots)
+    {
+      const float* ep = es;
+      const float* xr = rows;
 #pragma unroll 4
-    for (int t = 0; t < c.cnt; ++t) {
-      float2 pp[HP];
-      if constexpr (HP >= 2) {
+      for (int t = 0; t < c.cnt; ++t, ep += HP, xr += a.RS) {
+        float p[HP];
+        lds_vec<HP>(ep, p);
 #pragma unroll
-        for (int h = 0; h < HP; h += 2) {
-          const float4 q = *reinterpret_cast<const float4*>(es2 + t * HP + h);
-          pp[h] = make_float2(q.x, q.y);
-          pp[h + 1] = make_float2(q.z, q.w);
+        for (int s = 0; s < NS; ++s) {
+          const float4 xv = *reinterpret_cast<const float4*>(xr + loff[s]);
+#pragma unroll
+          for (int h = 0; h < HP; ++h) fma4_pp(acc[h][s], make_float2(p[h], p[h]), xv);
         }
-      } else {
-        pp[0] = es2[t];
-      }
-      const float* xr = rows + t * a.RS;
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const float4 xv = *reinterpret_cast<const float4*>(xr + loff[s]);
-#pragma unroll
-        for (int h = 0; h < HP; ++h) fma4_pp(acc[h][s], pp[h], xv);
       }
     }
     if (c.last) {
@@ -503,6 +502,164 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const XArgs a, cons
     if (c.last && hq_writer) {
       if (HUB) a.scratch[(int64_t)seg * H + hq] = df_acc;
       else a.df[(int64_t)c.row * a.lddf + hq] = df_acc;
+    }
+    __syncwarp();
+    c = n;
+    j = jn;
+  }
+}
+
+// =====================================================================================================
+// backward on the tensor cores (Fp <= 128).  The per-edge dots dalpha[e][h] = sum_k x_e[k] dxagg_i[h][k] of
+// a chunk are one small GEMM  [32 edges x Fp] x [Fp x 8 heads]:  mma.sync m16n8k8 tf32 with the 3xTF32
+// error-compensated split (x = hi + lo, hi = tf32 truncation; hi*hi + lo*hi + hi*lo), A fragments read from
+// the staged rows with 128-bit loads (the k index is permuted so a lane's four k's are adjacent in memory),
+// B fragments (dxagg_i, constant over the row) held in registers.  After the MMAs lane (g, t) owns
+// dalpha of edges {g, g+8, g+16, g+24} x heads {2t, 2t+1}.
+// =====================================================================================================
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+
+template <int KPMAX, bool HUB>
+__global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) {
+  extern __shared__ __align__(16) float x_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int H = a.H, Fp = a.Fp, RS = a.RS;
+  const int KP = (Fp + 15) >> 4;  // pairs of k-steps
+  const int h0 = 2 * tg, h1 = 2 * tg + 1;
+  float* rows = x_smem + (size_t)warp * xmma_warp_floats(RS);
+  int* cols = reinterpret_cast<int*>(rows + 32 * RS);
+  for (int i = lane; i < 32 * RS; i += 32) rows[i] = 0.f;  // stale lanes of the MMA must hold finite numbers
+  __syncwarp();
+  const int seg = blockIdx.x * XW + warp;
+  if (HUB && seg >= a.n_hub_seg) return;
+  ChunkIter<HUB> it;
+  it.init(a, lane, seg, 32);
+  const int n_copy = (a.Sx + 31) >> 5;
+
+  uint32_t bhi[KPMAX][4], blo[KPMAX][4];
+  float f0 = 0.f, f1 = 0.f, l0 = 0.f, l1 = 0.f, c0 = 0.f, c1 = 0.f, df0 = 0.f, df1 = 0.f;
+  Chunk c = it.next(a, lane);
+  int j = (c.ok && lane < c.cnt) ? __ldg(a.col + c.base + lane) : 0;
+  while (c.ok) {
+    const Chunk n = it.next(a, lane);
+    cols[lane] = j;
+    __syncwarp();
+#pragma unroll 4
+    for (int t = 0; t < c.cnt; ++t) {
+      const float* xj = a.xg + (int64_t)cols[t] * a.ldxg;
+      float* dst = rows + t * RS;
+      for (int s = 0; s < n_copy; ++s) {
+        const int slot = lane + 32 * s;
+        if (slot < a.Sx) cp_async16(dst + slot * 4, xj + slot * 4);
+      }
+    }
+    cp_async_commit();
+    const int jn = (n.ok && lane < n.cnt) ? __ldg(a.col + n.base + lane) : 0;
+    if (c.first) {
+      // row state: B fragments of dxagg_i (head g, features 16kp + 4tg .. +3), c_ih = dxagg_ih . xagg_ih
+      const float* dxr = a.dxagg + (int64_t)c.row * a.ldd + g * Fp + 4 * tg;
+      const float* xar = a.xagg + (int64_t)c.row * a.ldxa + g * Fp + 4 * tg;
+      float cp = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < KPMAX; ++kp) {
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kp < KP && g < H && 16 * kp + 4 * tg < Fp) {
+          d = ldg4_stream(dxr + 16 * kp);
+          cp += dot4(d, ldg4_stream(xar + 16 * kp));
+        }
+        split_tf32(d.x, bhi[kp][0], blo[kp][0]);
+        split_tf32(d.y, bhi[kp][1], blo[kp][1]);
+        split_tf32(d.z, bhi[kp][2], blo[kp][2]);
+        split_tf32(d.w, bhi[kp][3], blo[kp][3]);
+      }
+      cp += __shfl_xor_sync(FULL, cp, 1);
+      cp += __shfl_xor_sync(FULL, cp, 2);  // lanes (g, *) hold c of head g
+      c0 = __shfl_sync(FULL, cp, 4 * h0);
+      c1 = __shfl_sync(FULL, cp, 4 * h1);
+      f0 = h0 < H ? __ldg(a.f + (int64_t)c.row * a.ldf + h0) : 0.f;
+      f1 = h1 < H ? __ldg(a.f + (int64_t)c.row * a.ldf + h1) : 0.f;
+      l0 = h0 < H ? __ldg(a.lse + (int64_t)c.row * H + h0) : 0.f;
+      l1 = h1 < H ? __ldg(a.lse + (int64_t)c.row * H + h1) : 0.f;
+      df0 = df1 = 0.f;
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    const int n_mt = c.cnt > 16 ? 2 : 1;
+    float acc[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[mt][q] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < KPMAX; ++kp) {
+      if (kp < KP) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt < n_mt) {
+            const float4 ag = *reinterpret_cast<const float4*>(rows + (16 * mt + g) * RS + 16 * kp + 4 * tg);
+            const float4 a8 = *reinterpret_cast<const float4*>(rows + (16 * mt + g + 8) * RS + 16 * kp + 4 * tg);
+            uint32_t gh[4], gl[4], eh[4], el[4];
+            split_tf32(ag.x, gh[0], gl[0]); split_tf32(ag.y, gh[1], gl[1]);
+            split_tf32(ag.z, gh[2], gl[2]); split_tf32(ag.w, gh[3], gl[3]);
+            split_tf32(a8.x, eh[0], el[0]); split_tf32(a8.y, eh[1], el[1]);
+            split_tf32(a8.z, eh[2], el[2]); split_tf32(a8.w, eh[3], el[3]);
+            // k-step 2kp: logical k = tg -> feature +0, tg+4 -> +1;  k-step 2kp+1: +2, +3
+            mma_tf32(acc[mt], gl[0], el[0], gl[1], el[1], bhi[kp][0], bhi[kp][1]);
+            mma_tf32(acc[mt], gh[0], eh[0], gh[1], eh[1], blo[kp][0], blo[kp][1]);
+            mma_tf32(acc[mt], gh[0], eh[0], gh[1], eh[1], bhi[kp][0], bhi[kp][1]);
+            mma_tf32(acc[mt], gl[2], el[2], gl[3], el[3], bhi[kp][2], bhi[kp][3]);
+            mma_tf32(acc[mt], gh[2], eh[2], gh[3], eh[3], blo[kp][2], blo[kp][3]);
+            mma_tf32(acc[mt], gh[2], eh[2], gh[3], eh[3], bhi[kp][2], bhi[kp][3]);
+          }
+        }
+      }
+    }
+    // ---- ds for this lane's (edge, head) pairs: acc[mt][0..1] = edge 16mt+g, heads h0,h1; [2..3] = edge 16mt+g+8
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int e = 16 * mt + g + 8 * half;
+        if (e < c.cnt) {
+          const float2 gq = *reinterpret_cast<const float2*>(rows + e * RS + Fp + h0);
+          const float z0 = f0 + gq.x, z1 = f1 + gq.y;
+          const float s0 = z0 > 0.f ? z0 : a.alpha * z0, s1 = z1 > 0.f ? z1 : a.alpha * z1;
+          const float v0 = expf(s0 - l0) * (acc[mt][2 * half] - c0) * (z0 > 0.f ? 1.f : a.alpha);
+          const float v1 = expf(s1 - l1) * (acc[mt][2 * half + 1] - c1) * (z1 > 0.f ? 1.f : a.alpha);
+          float* dp = a.ds + (c.base + e) * H + h0;
+          if (h1 < H && (H & 1) == 0) {
+            *reinterpret_cast<float2*>(dp) = make_float2(v0, v1);
+            df0 += v0;
+            df1 += v1;
+          } else {
+            if (h0 < H) { dp[0] = v0; df0 += v0; }
+            if (h1 < H) { dp[1] = v1; df1 += v1; }
+          }
+        }
+      }
+    }
+    if (c.last) {
+      float d0 = df0, d1 = df1;
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        d0 += __shfl_xor_sync(FULL, d0, o);
+        d1 += __shfl_xor_sync(FULL, d1, o);
+      }
+      if (g == 0) {
+        float* dst = HUB ? a.scratch + (int64_t)seg * H : a.df + (int64_t)c.row * a.lddf;
+        if (h0 < H) dst[h0] = d0;
+        if (h1 < H) dst[h1] = d1;
+      }
     }
     __syncwarp();
     c = n;
@@ -718,6 +875,39 @@ static int launch_x_fwd(const XArgs& a, cudaStream_t st) {
   return 0;
 }
 
+template <typename KH, typename KM>
+static int launch_x_mma(KH hub_kernel, KM main_kernel, const XArgs& a, size_t smem, cudaStream_t st) {
+  if (a.n_hub_seg > 0) {
+    if (smem > 48 * 1024)
+      GATK_CHECK_CUDA(cudaFuncSetAttribute(hub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hub_kernel<<<(a.n_hub_seg + XW - 1) / XW, XW * 32, smem, st>>>(a);
+    GATK_CHECK_LAUNCH();
+  }
+  if (a.n_dst > 0) {
+    int grid = 0;
+    if (int rc = persistent_grid(main_kernel, XW * 32, smem, &grid)) return rc;
+    const int64_t need = a.item_ptr ? (a.n_items + XW - 1) / XW : (a.n_dst + (int64_t)XW * GRAB - 1) / ((int64_t)XW * GRAB);
+    if (need < grid) grid = (int)need;
+    main_kernel<<<grid, XW * 32, smem, st>>>(a);
+    GATK_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+static int launch_x_bwd_mma(XArgs a, cudaStream_t st) {
+  a.RS = xmma_row_pitch(a.Sx);
+  const size_t smem = (size_t)XW * xmma_warp_floats(a.RS) * sizeof(float);
+  int rc;
+  if (a.Fp <= 64) rc = launch_x_mma(attn_x_bwd_mma_kernel<4, true>, attn_x_bwd_mma_kernel<4, false>, a, smem, st);
+  else rc = launch_x_mma(attn_x_bwd_mma_kernel<8, true>, attn_x_bwd_mma_kernel<8, false>, a, smem, st);
+  if (rc) return rc;
+  if (a.n_hub_seg > 0) {
+    attn_x_bwd_hub_merge_kernel<<<(a.n_hub * a.H + 127) / 128, 128, 0, st>>>(a);
+    GATK_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
 template <int HP>
 static int launch_x_bwd(const XArgs& a, cudaStream_t st) {
   const int chunk = x_chunk_for(a.RS);
@@ -824,6 +1014,8 @@ extern "C" int gatk_attn_x_bwd(int64_t n_dst, const int64_t* rowptr, const int32
   a.dxagg = dxagg; a.ldd = ldd; a.ds = ds; a.df = df; a.lddf = lddf;
   cudaStream_t st = (cudaStream_t)stream;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
+  static const bool simt_only = getenv("GATK_XBWD_SIMT") != nullptr;
+  if (Fp <= 128 && !simt_only) return launch_x_bwd_mma(a, st);
   HP_DISPATCH(hp, return (launch_x_bwd<HP>(a, st)));
   return 0;
 }
