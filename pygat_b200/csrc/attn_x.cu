@@ -103,12 +103,12 @@ __host__ __device__ __forceinline__ int x_chunk_for(int RS) {
   while (c > 4 && c * RS * 4 > 14336) c >>= 1;
   return c;
 }
-__host__ __device__ __forceinline__ int xfwd_warp_floats(int RS, int HP, int chunk) { return chunk * RS + 32 * HP + 32 + 8; }
+__host__ __device__ __forceinline__ int xfwd_warp_floats(int RS, int HP, int chunk) { return chunk * RS + 32 * HP + 8 + 4; }
 // backward (tensor-core kernel): row pitch = 16 (mod 32) floats, so the two rows a quarter-warp touches per
 // 128-bit fragment load sit in different bank halves
 __host__ __device__ __forceinline__ int xmma_row_pitch(int Sx) { return (4 * Sx + 15) / 32 * 32 + 16; }
-__host__ __device__ __forceinline__ int xmma_warp_floats(int RS) { return 32 * RS + 32; }
-__host__ __device__ __forceinline__ int xbwd_warp_floats(int RS, int H, int Fp, int chunk) { return chunk * RS + H * Fp + 32; }
+__host__ __device__ __forceinline__ int xmma_warp_floats(int RS) { return 32 * RS + 4; }
+__host__ __device__ __forceinline__ int xbwd_warp_floats(int RS, int H, int Fp, int chunk) { return chunk * RS + H * Fp + 4; }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -204,19 +204,40 @@ struct ChunkIter {
   }
 };
 
-// cp.async the cnt neighbour rows [x_j | g_j] of the staged column ids into the row buffer (lanes = slots).
-template <int NS>
-__device__ __forceinline__ void x_issue_rows(const XArgs& a, float* rows, const int* cols, int cnt, const int (&loff)[NS],
-                                             const bool (&act)[NS]) {
-#pragma unroll 4
-  for (int t = 0; t < cnt; ++t) {
-    const float* xj = a.xg + (int64_t)cols[t] * a.ldxg;
-    float* dst = rows + t * a.RS;
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-      if (act[s]) cp_async16(dst + loff[s], xj + loff[s]);
+// Stage the cnt neighbour rows [x_j | g_j] of a chunk: lane t issues ONE bulk copy (TMA, cp.async.bulk) of row
+// cols[t] straight into the warp's row buffer; completion is tracked by the warp's mbarrier (expect_tx =
+// cnt * row bytes).  One instruction per lane for the whole chunk -- the gather costs no issue slots and
+// no registers, and up to 32 rows per warp are in flight.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
   }
-  cp_async_commit();
+}
+__device__ __forceinline__ void x_issue_rows(const XArgs& a, float* rows, int j, int cnt, int lane, int RS, unsigned bar) {
+  if (cnt > 0) {
+    const unsigned row_bytes = (unsigned)a.Sx * 16u;
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (unsigned)cnt) : "memory");
+    __syncwarp();
+    if (lane < cnt) {
+      const float* src = a.xg + (int64_t)j * a.ldxg;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(rows + lane * RS)),
+                   "l"(src), "r"(row_bytes), "r"(bar)
+                   : "memory");
+    }
+  }
 }
 
 // =====================================================================================================
@@ -234,8 +255,12 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
   const bool hq_writer = hq_lead && hq < H;
   float* rows = x_smem + (size_t)warp * xfwd_warp_floats(a.RS, HP, chunk);
   float* es = rows + chunk * a.RS;  // [32][HP] softmax weights of the chunk's edges
-  int* cols = reinterpret_cast<int*>(es + 32 * HP);
-  float* scale = es + 32 * HP + 32;
+  float* scale = es + 32 * HP;
+  const unsigned bar = smem_u32(scale + 8);
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  unsigned phase = 0;
   int loff[NS];
   bool act[NS], act_x[NS];
 #pragma unroll
@@ -256,9 +281,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
   int j = (c.ok && lane < c.cnt) ? __ldg(a.col + c.base + lane) : 0;
   while (c.ok) {
     const Chunk n = it.next(a, lane);
-    cols[lane] = j;
-    __syncwarp();
-    x_issue_rows<NS>(a, rows, cols, c.cnt, loff, act);
+    x_issue_rows(a, rows, j, c.cnt, lane, a.RS, bar);
     const int jn = (n.ok && lane < n.cnt) ? __ldg(a.col + n.base + lane) : 0;  // next chunk's columns
     const bool valid = lane < c.cnt;
     if (c.first) {
@@ -271,8 +294,10 @@ __global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, cons
 #pragma unroll
         for (int s = 0; s < NS; ++s) acc[h][s] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    cp_async_wait_all();
-    __syncwarp();
+    if (c.cnt > 0) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+    }
     // ---- softmax terms of this chunk (lanes = edges); g_j sits behind x_j in the staged row
     float gv[HP];
     lds_vec<HP>(rows + (valid ? lane : 0) * a.RS + a.Fp, gv);
@@ -403,12 +428,15 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const XArgs a, cons
   const bool hq_writer = (lane & ((1 << SH) - 1)) == 0 && hq < H;
   float* rows = x_smem + (size_t)warp * xbwd_warp_floats(a.RS, H, Fp, chunk);
   float* dxs = rows + chunk * a.RS;  // [H][Fp] dxagg_i
-  int* cols = reinterpret_cast<int*>(dxs + H * Fp);
+  const unsigned bar = smem_u32(dxs + H * Fp);
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  unsigned phase = 0;
   const int seg = blockIdx.x * XW + warp;
   if (HUB && seg >= a.n_hub_seg) return;
   ChunkIter<HUB> it;
   it.init(a, lane, seg, chunk);
-  const int n_copy = (a.Sx + 31) >> 5;  // copy instructions per row
 
   float cv[HP], fv[HP], lv[HP];
   float df_acc = 0.f;  // running df of head hq
@@ -416,18 +444,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const XArgs a, cons
   int j = (c.ok && lane < c.cnt) ? __ldg(a.col + c.base + lane) : 0;
   while (c.ok) {
     const Chunk n = it.next(a, lane);
-    cols[lane] = j;
-    __syncwarp();
-#pragma unroll 4
-    for (int t = 0; t < c.cnt; ++t) {
-      const float* xj = a.xg + (int64_t)cols[t] * a.ldxg;
-      float* dst = rows + t * a.RS;
-      for (int s = 0; s < n_copy; ++s) {
-        const int slot = lane + 32 * s;
-        if (slot < a.Sx) cp_async16(dst + slot * 4, xj + slot * 4);
-      }
-    }
-    cp_async_commit();
+    x_issue_rows(a, rows, j, c.cnt, lane, a.RS, bar);
     const int jn = (n.ok && lane < n.cnt) ? __ldg(a.col + n.base + lane) : 0;
     if (c.first) {
       // row state (lanes = slots): dxagg_i -> shared memory, c_ih = dxagg_ih . xagg_ih; f_ih, lse_ih
@@ -456,7 +473,10 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const XArgs a, cons
       for (int h = 0; h < HP; ++h) cv[h] = __shfl_sync(FULL, cp[0], h << SH);
       df_acc = 0.f;
     }
-    cp_async_wait_all();
+    if (c.cnt > 0) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+    }
     __syncwarp();
     // ---- dalpha_eh = dxagg_ih . x_e for this lane's edge e
     const bool valid = lane < c.cnt;
@@ -537,14 +557,17 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
   const int KP = (Fp + 15) >> 4;  // pairs of k-steps
   const int h0 = 2 * tg, h1 = 2 * tg + 1;
   float* rows = x_smem + (size_t)warp * xmma_warp_floats(RS);
-  int* cols = reinterpret_cast<int*>(rows + 32 * RS);
+  const unsigned bar = smem_u32(rows + 32 * RS);
   for (int i = lane; i < 32 * RS; i += 32) rows[i] = 0.f;  // stale lanes of the MMA must hold finite numbers
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic zero fill before the async-proxy copies
   __syncwarp();
+  unsigned phase = 0;
   const int seg = blockIdx.x * XW + warp;
   if (HUB && seg >= a.n_hub_seg) return;
   ChunkIter<HUB> it;
   it.init(a, lane, seg, 32);
-  const int n_copy = (a.Sx + 31) >> 5;
 
   uint32_t bhi[KPMAX][4], blo[KPMAX][4];
   float f0 = 0.f, f1 = 0.f, l0 = 0.f, l1 = 0.f, c0 = 0.f, c1 = 0.f, df0 = 0.f, df1 = 0.f;
@@ -552,18 +575,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
   int j = (c.ok && lane < c.cnt) ? __ldg(a.col + c.base + lane) : 0;
   while (c.ok) {
     const Chunk n = it.next(a, lane);
-    cols[lane] = j;
-    __syncwarp();
-#pragma unroll 4
-    for (int t = 0; t < c.cnt; ++t) {
-      const float* xj = a.xg + (int64_t)cols[t] * a.ldxg;
-      float* dst = rows + t * RS;
-      for (int s = 0; s < n_copy; ++s) {
-        const int slot = lane + 32 * s;
-        if (slot < a.Sx) cp_async16(dst + slot * 4, xj + slot * 4);
-      }
-    }
-    cp_async_commit();
+    x_issue_rows(a, rows, j, c.cnt, lane, RS, bar);
     const int jn = (n.ok && lane < n.cnt) ? __ldg(a.col + n.base + lane) : 0;
     if (c.first) {
       // row state: B fragments of dxagg_i (head g, features 16kp + 4tg .. +3), c_ih = dxagg_ih . xagg_ih
@@ -592,8 +604,10 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
       l1 = h1 < H ? __ldg(a.lse + (int64_t)c.row * H + h1) : 0.f;
       df0 = df1 = 0.f;
     }
-    cp_async_wait_all();
-    __syncwarp();
+    if (c.cnt > 0) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+    }
     const int n_mt = c.cnt > 16 ? 2 : 1;
     float acc[2][4];
 #pragma unroll
