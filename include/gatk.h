@@ -85,6 +85,15 @@ GATK_API int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, 
               const float* B, int64_t ldb, float* C, int64_t ldc, int accumulate,
               void* ws, size_t ws_bytes, void* stream);
 
+/* Batched (per-head) products: for b in [0, batches)  C_b = op(A_b) op(B_b)  with A_b = A + b*a_bs, B_b = B + b*b_bs,
+ * C_b = C + b*c_bs (element offsets: the batches are column blocks of the same matrices, or separate matrices).
+ * epilogue 1 applies ELU to C (F.elu, layers.py:51,170).  Never accumulates.  One launch of the tcgen05 kernels
+ * covers all batches when  (!transA, K <= 512)  or  (transA, !transB, K >= 2048, M, N <= 512). */
+GATK_API size_t gatk_gemm_batched_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches);
+GATK_API int gatk_gemm_batched(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A,
+                               int64_t lda, int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, float* C, int64_t ldc,
+                               int64_t c_bs, int epilogue, void* ws, size_t ws_bytes, void* stream);
+
 /* Attention-logit halves f_i = Wh_i . a[:D], g_j = Wh_j . a[D:] (layers.py:60-61, :141-144),
  * after the post-projection dropout (layers.py:37,136) applied IN PLACE to wh when
  * keep_wh != NULL (keep_wh is [n, H*Dp] dense).  a_src / a_dst are [H, Dp]. */

@@ -32,6 +32,9 @@ PROTOTYPES = {
     "gatk_gemm_uses_tensor_cores": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int]),
     "gatk_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int,
                           P, c_size_t, P]),
+    "gatk_gemm_batched_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int64, c_int64, c_int]),
+    "gatk_gemm_batched": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int, P, c_int64, c_int64, P, c_int64, c_int64,
+                                  P, c_int64, c_int64, c_int, P, c_size_t, P]),
     "gatk_logits_fwd": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_float, P, P, P, P, P]),
     "gatk_hub_scratch_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gatk_attn_fwd": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, P, c_int64, P, c_float, c_float,

@@ -152,6 +152,13 @@ bool gemm_long_tc_eligible(int transA, int64_t M, int64_t N, int64_t K, const fl
 int gemm_long_tc_launch(int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                         int64_t ldb, float* C, int64_t ldc, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t gemm_batched_tc_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches);
+int gemm_batched_path(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A, int64_t lda,
+                      int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, const float* C, int64_t ldc, int64_t c_bs);
+int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A, int64_t lda,
+                           int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, float* C, int64_t ldc, int64_t c_bs,
+                           int epilogue, void* ws, size_t ws_bytes, cudaStream_t st);
+
 static bool tc_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -227,6 +234,35 @@ extern "C" int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K
   if (splits > 1) {
     splitk_reduce_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(M, N, splits, part, C, ldc, accumulate);
     GATK_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int gatk_elu_fwd(int64_t n, int64_t cols, float* buf, int64_t ld, void* stream);
+
+extern "C" size_t gatk_gemm_batched_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches) {
+  const size_t one = gatk_gemm_workspace_bytes(transA, transB, M, N, K);
+  const size_t bat = tc_enabled() ? gemm_batched_tc_workspace_bytes(transA, transB, M, N, K, batches) : 0;
+  return one > bat ? one : bat;
+}
+
+extern "C" int gatk_gemm_batched(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A,
+                                 int64_t lda, int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, float* C, int64_t ldc,
+                                 int64_t c_bs, int epilogue, void* ws, size_t ws_bytes, void* stream) {
+  GATK_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batches >= 0, "negative GEMM size");
+  GATK_REQUIRE(epilogue == 0 || epilogue == 1, "epilogue must be 0 (none) or 1 (ELU)");
+  if (M == 0 || N == 0 || batches == 0) return 0;
+  GATK_REQUIRE(A && B && C, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int path = tc_enabled() ? gemm_batched_path(transA, transB, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs) : 0;
+  if (path && ws && ws_bytes >= gemm_batched_tc_workspace_bytes(transA, transB, M, N, K, batches))
+    return gemm_batched_tc_launch(path, transB, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, epilogue, ws,
+                                  ws_bytes, st);
+  for (int b = 0; b < batches; ++b) {  // shapes the batched tensor-core kernels do not take: one product per batch
+    if (int rc = gatk_gemm(transA, transB, M, N, K, A + b * a_bs, lda, B + b * b_bs, ldb, C + b * c_bs, ldc, 0, ws, ws_bytes, stream))
+      return rc;
+    if (epilogue == 1)
+      if (int rc = gatk_elu_fwd(M, N, C + b * c_bs, ldc, stream)) return rc;
   }
   return 0;
 }

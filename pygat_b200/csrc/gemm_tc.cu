@@ -633,6 +633,617 @@ static int make_map_box32(CUtensorMap* map, const void* base, int64_t rows, int6
 }  // namespace tn
 
 
+// =====================================================================================================
+// Batched (per-head) products for the aggregate-first form of the layer (functional.GatLayerAggFirstFunction):
+//   NN / NT   C_b[M,N] = A_b[M,K] op(B_b)        out_h = xagg_h W_h,  dxagg_h = dh'_h W_h^T   (K <= 512)
+//   TN        C_b[Mo,No] = A_b^T[Mo,K] B_b[K,No]  dW_h = xagg_h^T dh'_h                         (K = nodes)
+// with A_b = A + b*a_bs (a COLUMN block of the same rows), C_b = C + b*c_bs.  One launch covers all heads:
+// the operands are described to TMA as 3-D tensors (columns of a batch, rows, batch), so K / N tails of a
+// batch are zero-filled on load and clipped on store even though the next head's columns follow in memory.
+// Same 3xTF32 scheme and warp roles as the kernels above; the tile width is 64 when a head is 64 wide.
+// =====================================================================================================
+namespace bt {
+
+using namespace tc;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_i(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// F.elu computes exp(x) - 1 (not expm1); the fast exponential is accurate to ~2 ulp of exp, i.e. ~1e-7 absolute here
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+
+template <int BN>
+struct Cfg {
+  static constexpr int TILE_A = BLOCK_M * BLOCK_K * 4;  // 16 KiB
+  static constexpr int TILE_B = BN * BLOCK_K * 4;
+  static constexpr int STAGE = 2 * TILE_A + 2 * TILE_B;  // Ahi, Alo, Bhi, Blo
+  static constexpr int SMEM = STAGES * STAGE + 2 * CSTAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_TN = STAGES * STAGE + 1024 + 256;
+  static constexpr int TMEM = 4 * BN;  // 2 stages x (main, correction)
+  static constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  static constexpr uint32_t IDESC_MN = IDESC_K | (1u << 15) | (1u << 16);
+};
+
+// ---- NN / NT, K <= 512: C_b = A_b op(B_b), optional ELU epilogue (F.elu, layers.py:51,170)
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                           const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c,
+                           int m_tiles, int n_tiles, int batches, int k_blocks, int npad, int epilogue) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* cstage = smem + STAGES * C::STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cstage + 2 * CSTAGE_BYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto split_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_m = n_tiles * batches;
+  const int total_tiles = m_tiles * per_m;
+  auto decode = [&](int tile, int& m0, int& n0, int& b) {
+    const int mt = tile / per_m, r = tile - mt * per_m;
+    b = r / n_tiles;
+    m0 = mt * BLOCK_M;
+    n0 = (r - b * n_tiles) * BN;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(split_bar(s), 4);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring r;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m0, n0, b;
+        decode(tile, m0, n0, b);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(r.stage), r.phase ^ 1);
+          const uint32_t st = smem_base + r.stage * C::STAGE;
+          mbar_expect_tx(full_bar(r.stage), C::TILE_A + 2 * C::TILE_B);
+          tma_load_3d(st, &map_a, full_bar(r.stage), kb * BLOCK_K, m0, b);
+          tma_load_2d(st + 2 * C::TILE_A, &map_bhi, full_bar(r.stage), kb * BLOCK_K, b * npad + n0);
+          tma_load_2d(st + 2 * C::TILE_A + C::TILE_B, &map_blo, full_bar(r.stage), kb * BLOCK_K, b * npad + n0);
+          r.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    Ring r;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * 2 * BN;
+      const uint32_t tmem_c = tmem_d + BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(r.stage), r.phase);
+        mbar_wait(split_bar(r.stage), r.phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_base + r.stage * C::STAGE;
+          const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + C::TILE_A);
+          const uint64_t b_hi = umma_desc(st + 2 * C::TILE_A), b_lo = umma_desc(st + 2 * C::TILE_A + C::TILE_B);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma_tf32_i(tmem_c, a_lo + adv, b_hi + adv, C::IDESC_K, (kb | k) != 0);
+            umma_tf32_i(tmem_c, a_hi + adv, b_lo + adv, C::IDESC_K, 1);
+            umma_tf32_i(tmem_d, a_hi + adv, b_hi + adv, C::IDESC_K, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(r.stage));
+          if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        r.advance();
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    Ring r;
+    const int t = threadIdx.x - 128;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(r.stage), r.phase);
+        float4* hi = reinterpret_cast<float4*>(smem + r.stage * C::STAGE);
+        float4* lo = reinterpret_cast<float4*>(smem + r.stage * C::STAGE + C::TILE_A);
+#pragma unroll
+        for (int i = 0; i < C::TILE_A / 16 / 128; ++i) {
+          const int idx = t + i * 128;
+          float4 v = hi[idx];
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          hi[idx] = h;
+          lo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(r.stage));
+        r.advance();
+      }
+    }
+  } else if (warp >= 8) {
+    const int ew = warp - 8;
+    const int row = ew * 32 + lane;
+    const bool issuer = threadIdx.x == 256;
+    int it = 0, chunk_id = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int m0, n0, b;
+      decode(tile, m0, n0, b);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c, ++chunk_id) {
+        uint32_t v[32], w[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 2 * BN + c * 32;
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + BN, w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+          if (epilogue == 1) x = elu_f(x);
+          v[j] = __float_as_uint(x);
+        }
+        uint8_t* buf = cstage + (chunk_id & 1) * CSTAGE_BYTES;
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          *reinterpret_cast<uint4*>(buf + row * 128 + ((j ^ (row & 7)) << 4)) = q;
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          tma_store_3d(&map_c, smem_u32(buf), n0 + c * 32, m0, b);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM));
+  }
+}
+
+// ---- TN: C_b[Mo,No] = A_b^T B_b, reduction over the rows (nodes), deterministic split-K partials
+template <int BN>
+__global__ void __launch_bounds__(tn::TN_THREADS, 1)
+gemm_tn_batched_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       float* __restrict__ part, int Mo, int No, int m_tiles, int n_tiles, int batches, int splits,
+                       int kb_total, int kb_per_split) {
+  using C = Cfg<BN>;
+  using tn::BOX_BYTES;
+  using tn::PROMOTE;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto split_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = m_tiles * n_tiles;
+  const int items = batches * tiles * splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(split_bar(s), 4);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  // item -> (batch, split, m tile, n tile); the splits of a batch are adjacent
+  auto decode = [&](int item, int& b, int& m0, int& n0, int& kb0, int& kb1, int& sp) {
+    b = item / (tiles * splits);
+    const int r = item - b * tiles * splits;
+    sp = r / tiles;
+    const int t = r - sp * tiles;
+    m0 = (t / n_tiles) * BLOCK_M;
+    n0 = (t % n_tiles) * BN;
+    kb0 = sp * kb_per_split;
+    kb1 = kb0 + kb_per_split < kb_total ? kb0 + kb_per_split : kb_total;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring r;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int b, m0, n0, kb0, kb1, sp;
+        decode(item, b, m0, n0, kb0, kb1, sp);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(r.stage), r.phase ^ 1);
+          const uint32_t st = smem_base + r.stage * C::STAGE;
+          mbar_expect_tx(full_bar(r.stage), C::TILE_A + C::TILE_B);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tma_load_3d(st + q * BOX_BYTES, &map_a, full_bar(r.stage), m0 + q * 32, kb * BLOCK_K, b);
+#pragma unroll
+          for (int q = 0; q < BN / 32; ++q)
+            tma_load_3d(st + 2 * C::TILE_A + q * BOX_BYTES, &map_b, full_bar(r.stage), n0 + q * 32, kb * BLOCK_K, b);
+          r.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    Ring r;
+    int drain = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int b, m0, n0, kb0, kb1, sp;
+      decode(item, b, m0, n0, kb0, kb1, sp);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int rel = kb - kb0;
+        const int acc = drain & 1;
+        if (rel % PROMOTE == 0) {
+          mbar_wait(tempty_bar(acc), ((drain >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t tmem_d = tmem_base + acc * 2 * BN;
+        const uint32_t tmem_c = tmem_d + BN;
+        mbar_wait(full_bar(r.stage), r.phase);
+        mbar_wait(split_bar(r.stage), r.phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_base + r.stage * C::STAGE;
+          const uint32_t fresh = (rel % PROMOTE) == 0 ? 0u : 1u;
+          const uint64_t a_hi = tn::umma_desc_mn(st), a_lo = tn::umma_desc_mn(st + C::TILE_A);
+          const uint64_t b_hi = tn::umma_desc_mn(st + 2 * C::TILE_A), b_lo = tn::umma_desc_mn(st + 2 * C::TILE_A + C::TILE_B);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 1024 >> 4);
+            umma_tf32_i(tmem_c, a_lo + adv, b_hi + adv, C::IDESC_MN, fresh | (uint32_t)(k != 0));
+            umma_tf32_i(tmem_c, a_hi + adv, b_lo + adv, C::IDESC_MN, 1);
+            umma_tf32_i(tmem_d, a_hi + adv, b_hi + adv, C::IDESC_MN, fresh | (uint32_t)(k != 0));
+          }
+          umma_commit(empty_bar(r.stage));
+          if ((rel + 1) % PROMOTE == 0 || kb == kb1 - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if ((rel + 1) % PROMOTE == 0 || kb == kb1 - 1) ++drain;
+        r.advance();
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    Ring r;
+    const int t = threadIdx.x - 128;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int b, m0, n0, kb0, kb1, sp;
+      decode(item, b, m0, n0, kb0, kb1, sp);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(r.stage), r.phase);
+        uint8_t* st = smem + r.stage * C::STAGE;
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {
+          float4* hi = reinterpret_cast<float4*>(st + (op ? 2 * C::TILE_A : 0));
+          float4* lo = reinterpret_cast<float4*>(st + (op ? 2 * C::TILE_A + C::TILE_B : C::TILE_A));
+          const int n16 = (op ? C::TILE_B : C::TILE_A) / 16 / 128;
+#pragma unroll
+          for (int i = 0; i < n16; ++i) {
+            const int idx = t + i * 128;
+            float4 v = hi[idx];
+            float4 h;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            hi[idx] = h;
+            lo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(r.stage));
+        r.advance();
+      }
+    }
+  } else if (warp >= 8) {
+    constexpr int HALF = BN / 2;  // columns per epilogue warp group
+    const int quarter = warp & 3;
+    const int half = (warp - 8) >> 2;
+    const int row = quarter * 32 + lane;
+    int drain = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int b, m0, n0, kb0, kb1, sp;
+      decode(item, b, m0, n0, kb0, kb1, sp);
+      float racc[HALF];
+#pragma unroll
+      for (int j = 0; j < HALF; ++j) racc[j] = 0.f;
+      const int n_drains = (kb1 - kb0 + PROMOTE - 1) / PROMOTE;
+      for (int d = 0; d < n_drains; ++d, ++drain) {
+        const int acc = drain & 1;
+        mbar_wait(tfull_bar(acc), (drain >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 2 * BN + half * HALF;
+#pragma unroll
+        for (int c = 0; c < HALF / 32; ++c) {
+          uint32_t v[32], w[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld32(taddr + BN + c * 32, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      const int gm = m0 + row;
+      if (gm < Mo) {
+        float* dst = part + (((int64_t)b * splits + sp) * Mo + gm) * No + n0 + half * HALF;
+#pragma unroll
+        for (int j = 0; j < HALF; ++j)
+          if (n0 + half * HALF + j < No) dst[j] = racc[j];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM));
+  }
+}
+
+// B_b (row-major [K,N] or, transposed, [N,K]) -> K-major hi / lo copies [batch][Npad][Kpad], zero padded
+__global__ void split_transpose_b_batched_kernel(const float* __restrict__ B, int64_t ldb, int64_t b_bs, int K, int N,
+                                                 int Kpad, int Npad, int batches, int b_is_nk, float* __restrict__ bhi,
+                                                 float* __restrict__ blo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)Npad * Kpad;
+  if (i >= per * batches) return;
+  const int b = (int)(i / per);
+  const int64_t r = i - b * per;
+  const int n = (int)(r / Kpad), k = (int)(r % Kpad);
+  const float* Bb = B + b * b_bs;
+  float v = (n < N && k < K) ? (b_is_nk ? Bb[(int64_t)n * ldb + k] : Bb[(int64_t)k * ldb + n]) : 0.f;
+  float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  bhi[i] = h;
+  blo[i] = v - h;
+}
+
+__global__ void splitk_reduce_batched_kernel(int Mo, int No, int splits, int batches, const float* __restrict__ part,
+                                             float* __restrict__ C, int64_t ldc, int64_t c_bs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)Mo * No;
+  if (i >= per * batches) return;
+  const int b = (int)(i / per);
+  const int64_t r = i - b * per;
+  const float* p = part + (int64_t)b * splits * per + r;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += p[(int64_t)z * per];
+  C[b * c_bs + (r / No) * ldc + (r % No)] = s;
+}
+
+// 3-D fp32 tensor (cols of one batch, rows, batch): box = box_cols x box_rows x 1
+static int make_map_3d(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t batches, int64_t ld,
+                       int64_t bs, int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_fn();
+  GATK_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)(batches > 1 ? bs : ld) * sizeof(float)};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GATK_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed (%d) cols=%lld rows=%lld batches=%lld ld=%lld bs=%lld",
+               (int)rc, (long long)cols, (long long)rows, (long long)batches, (long long)ld, (long long)bs);
+  return 0;
+}
+
+static int make_map_b(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  GATK_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GATK_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled (weights) failed (%d)", (int)rc);
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static void tn_plan(int64_t Mo, int64_t No, int64_t K, int batches, int bn, int* mt, int* nt, int* sp, int* kbt, int* kbs) {
+  *mt = (int)((Mo + BLOCK_M - 1) / BLOCK_M);
+  *nt = (int)((No + bn - 1) / bn);
+  *kbt = (int)((K + BLOCK_K - 1) / BLOCK_K);
+  int s = sm_count() / (*mt * *nt * batches);
+  if (s < 1) s = 1;
+  const int max_s = (*kbt + tn::PROMOTE - 1) / tn::PROMOTE;
+  if (s > max_s) s = max_s;
+  *kbs = (*kbt + s - 1) / s;
+  *sp = (*kbt + *kbs - 1) / *kbs;
+}
+
+}  // namespace bt
+
+// which tensor-core path a batched product takes: 1 = NN/NT (K <= 512), 2 = TN, 0 = none
+static int batched_path(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A, int64_t lda,
+                        int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, const float* C, int64_t ldc, int64_t c_bs) {
+  if (batches < 1 || batches > 64) return 0;
+  if ((lda & 3) || (a_bs & 3) || (A && !bt::aligned16(A))) return 0;
+  if (!transA) {
+    if (M < 1024 || N < 8 || N > 4096 || K < 1 || K > 512 || M >= (1LL << 31) - 256) return 0;
+    if ((ldc & 3) || (c_bs & 3) || (C && !bt::aligned16(C))) return 0;
+    return 1;
+  }
+  if (transB) return 0;
+  if (K < 2048 || M < 8 || N < 8 || M > 512 || N > 512 || K >= (1LL << 31) - 64) return 0;
+  if ((ldb & 3) || (b_bs & 3) || (B && !bt::aligned16(B))) return 0;
+  return 2;
+}
+
+size_t gemm_batched_tc_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches) {
+  if (!transA) {
+    const int bn = N <= 64 ? 64 : 128;
+    const int64_t Kpad = (K + tc::BLOCK_K - 1) / tc::BLOCK_K * tc::BLOCK_K;
+    const int64_t Npad = (N + bn - 1) / bn * bn;
+    return (size_t)(2 * batches * Npad * Kpad * sizeof(float) + 256);
+  }
+  if (transB) return 0;
+  int mt, nt, sp, kbt, kbs;
+  bt::tn_plan(M, N, K, batches, N <= 64 ? 64 : 128, &mt, &nt, &sp, &kbt, &kbs);
+  return (size_t)batches * sp * M * N * sizeof(float);
+}
+
+int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A, int64_t lda,
+                           int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, float* C, int64_t ldc, int64_t c_bs,
+                           int epilogue, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace bt;
+  GATK_REQUIRE(ws && ws_bytes >= gemm_batched_tc_workspace_bytes(path == 2, transB, M, N, K, batches),
+               "batched GEMM workspace too small");
+  const int bn = N <= 64 ? 64 : 128;
+  if (path == 1) {
+    const int Kpad = (int)((K + BLOCK_K - 1) / BLOCK_K * BLOCK_K);
+    const int Npad = (int)((N + bn - 1) / bn * bn);
+    float* bhi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    float* blo = bhi + (size_t)batches * Npad * Kpad;
+    const int64_t total = (int64_t)batches * Npad * Kpad;
+    split_transpose_b_batched_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, ldb, b_bs, (int)K, (int)N, Kpad, Npad,
+                                                                                       batches, transB ? 1 : 0, bhi, blo);
+    GATK_CHECK_LAUNCH();
+    CUtensorMap map_a, map_bhi, map_blo, map_c;
+    if (int rc = make_map_3d(&map_a, A, K, M, batches, lda, a_bs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_b(&map_bhi, bhi, (int64_t)batches * Npad, Kpad, bn)) return rc;
+    if (int rc = make_map_b(&map_blo, blo, (int64_t)batches * Npad, Kpad, bn)) return rc;
+    if (int rc = make_map_3d(&map_c, C, N, M, batches, ldc, c_bs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = Npad / bn, k_blocks = Kpad / BLOCK_K;
+    const int64_t tiles = (int64_t)m_tiles * n_tiles * batches;
+    GATK_REQUIRE(tiles < (1LL << 31), "too many tiles");
+    int grid = sm_count();
+    if (tiles < grid) grid = (int)tiles;
+    if (bn == 64) {
+      static bool configured = false;
+      if (!configured) {
+        GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_batched_tf32x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
+        configured = true;
+      }
+      gemm_batched_tf32x3_kernel<64><<<grid, NUM_THREADS, Cfg<64>::SMEM, st>>>(map_a, map_bhi, map_blo, map_c, m_tiles, n_tiles,
+                                                                               batches, k_blocks, Npad, epilogue);
+    } else {
+      static bool configured = false;
+      if (!configured) {
+        GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_batched_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
+        configured = true;
+      }
+      gemm_batched_tf32x3_kernel<128><<<grid, NUM_THREADS, Cfg<128>::SMEM, st>>>(map_a, map_bhi, map_blo, map_c, m_tiles, n_tiles,
+                                                                                 batches, k_blocks, Npad, epilogue);
+    }
+    GATK_CHECK_LAUNCH();
+    return 0;
+  }
+  // TN: here M = Mo (columns of A_b), N = No (columns of B_b), K = rows
+  int mt, nt, sp, kbt, kbs;
+  tn_plan(M, N, K, batches, bn, &mt, &nt, &sp, &kbt, &kbs);
+  CUtensorMap map_a, map_b;
+  if (int rc = make_map_3d(&map_a, A, M, K, batches, lda, a_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_map_3d(&map_b, B, N, K, batches, ldb, b_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  const int items = mt * nt * sp * batches;
+  int grid = sm_count();
+  if (items < grid) grid = items;
+  float* part = static_cast<float*>(ws);
+  if (bn == 64) {
+    static bool configured = false;
+    if (!configured) {
+      GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_batched_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_TN));
+      configured = true;
+    }
+    gemm_tn_batched_kernel<64><<<grid, tn::TN_THREADS, Cfg<64>::SMEM_TN, st>>>(map_a, map_b, part, (int)M, (int)N, mt, nt, batches, sp, kbt, kbs);
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_batched_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_TN));
+      configured = true;
+    }
+    gemm_tn_batched_kernel<128><<<grid, tn::TN_THREADS, Cfg<128>::SMEM_TN, st>>>(map_a, map_b, part, (int)M, (int)N, mt, nt, batches, sp, kbt, kbs);
+  }
+  GATK_CHECK_LAUNCH();
+  const int64_t total = (int64_t)batches * M * N;
+  splitk_reduce_batched_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((int)M, (int)N, sp, batches, part, C, ldc, c_bs);
+  GATK_CHECK_LAUNCH();
+  return 0;
+}
+
+int gemm_batched_path(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A, int64_t lda,
+                      int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, const float* C, int64_t ldc, int64_t c_bs) {
+  return batched_path(transA, transB, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs);
+}
+
 bool gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
                       const float* C, int64_t ldc, int accumulate) {
   if (transA || transB || accumulate) return false;

@@ -56,6 +56,14 @@ def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=0, a_off=0, b_off=
               C.data_ptr() + 4 * c_off, ldc, accumulate, _ptr(ws), ws_bytes, _stream(), label=label)
 
 
+def _gemm_batched(ta, tb, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, epilogue=0, label=None):
+    """C_b = op(A_b) op(B_b) for the `batches` column blocks A_b = A + b*a_bs, ... (one launch for all heads)."""
+    ws_bytes = _lib.query("gatk_gemm_batched_workspace_bytes", ta, tb, M, N, K, batches)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=C.device) if ws_bytes else None
+    _lib.call("gatk_gemm_batched", ta, tb, M, N, K, batches, A.data_ptr(), lda, a_bs, B.data_ptr(), ldb, b_bs,
+              C.data_ptr(), ldc, c_bs, epilogue, _ptr(ws), ws_bytes, _stream(), label=label)
+
+
 def _hub_scratch(which: int, H: int, Dp: int, n_seg: int, dev):
     if not n_seg:
         return None
@@ -363,13 +371,13 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
                   f.data_ptr(), H, float(alpha), xagg.data_ptr(), H * Fp, _ptr(lse),
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         out = torch.empty(n, HD, dtype=torch.float32, device=dev)
-        for h in range(H):
-            _gemm(0, 0, n, Dp, f_in, xagg, H * Fp, w_ext, M_out, out, HD, a_off=h * Fp, b_off=h * Dp, c_off=h * Dp,
-                  label="gemm:project")
+        fuse_elu = act_elu and not has_skip  # ELU rides in the projection's epilogue unless a skip term is added first
+        _gemm_batched(0, 0, n, Dp, f_in, H, xagg, H * Fp, Fp, w_ext, M_out, Dp, out, HD, Dp, epilogue=int(fuse_elu),
+                      label="gemm:project")
         if has_skip:
             _gemm(0, 0, n, HD, f_in, xg, P, w_ext, M_out, out, HD, accumulate=1, b_off=HD, label="gemm:skip")
-        if act_elu:
-            _lib.call("gatk_elu_fwd", n, HD, out.data_ptr(), HD, st)
+            if act_elu:
+                _lib.call("gatk_elu_fwd", n, HD, out.data_ptr(), HD, st)
         if need_grad:
             ctx.graph = graph
             ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu), f_in, Fp, Muv)
@@ -395,11 +403,8 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         # value path: dW_h = xagg_h^T dh'_h, dS = x^T dh';  dxagg_h = dh'_h W_h^T feeds the softmax backward
         dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
         dxagg = (torch.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
-        for h in range(H):
-            _gemm(1, 0, f_in, Dp, n, xagg, H * Fp, dhp, HD, dw_ext, M_out, a_off=h * Fp, b_off=h * Dp, c_off=h * Dp,
-                  label="gemm:dW")
-            _gemm(0, 1, n, f_in, Dp, dhp, HD, w_ext, M_out, dxagg, H * Fp, a_off=h * Dp, b_off=h * Dp, c_off=h * Fp,
-                  label="gemm:dxagg")
+        _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp, label="gemm:dW")
+        _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp, label="gemm:dxagg")
         if has_skip:
             _gemm(1, 0, f_in, HD, n, xg, P, dhp, HD, dw_ext, M_out, c_off=HD, label="gemm:dskip")
         # logit path: ds per stored entry, df per destination, dg per source (transposed sum of ds)

@@ -161,6 +161,54 @@ def test_tensor_core_weight_gradient_gemm(M, N, K, padb):
     assert torch.equal(outs[0], outs[1])  # split-K partials are reduced in a fixed order
 
 
+@pytest.mark.parametrize("kind,M,N,K,batches,elu", [
+    ("nn", 5000, 64, 100, 8, True),      # out_h = ELU(xagg_h W_h)
+    ("nn", 3000, 256, 52, 4, False),     # PPI first layer, 4 x 256
+    ("nt", 5000, 100, 64, 8, False),     # dxagg_h = dh'_h W_h^T: batches adjacent in C, N not a multiple of 32
+    ("nt", 2500, 52, 256, 4, False),
+    ("tn", 100, 64, 30000, 8, False),    # dW_h = xagg_h^T dh'_h
+    ("tn", 52, 256, 9000, 4, False),
+    ("nn", 300, 24, 40, 3, True),        # small: per-batch fallback
+])
+def test_batched_per_head_gemms(kind, M, N, K, batches, elu):
+    """gatk_gemm_batched (one tcgen05 launch for all heads; 3-D TMA descriptors clip each head's column block)
+    against fp64 products, including untouched padding columns."""
+    g = torch.Generator().manual_seed(M + N + K + batches)
+    if kind == "tn":   # A [K, batches*M], B [K, batches*N] -> C [M, batches*N]
+        A = torch.randn(K, batches * M, generator=g)
+        B = torch.randn(K, batches * N, generator=g)
+        ref = torch.cat([A[:, b * M:(b + 1) * M].double().t() @ B[:, b * N:(b + 1) * N].double() for b in range(batches)], 1)
+        ta, tb, lda, a_bs, ldb, b_bs = 1, 0, batches * M, M, batches * N, N
+        rows_c = M
+    else:              # A [M, batches*K]; B: nn [K, batches*N] / nt [N, batches*K]
+        A = torch.randn(M, batches * K, generator=g)
+        ta, lda, a_bs = 0, batches * K, K
+        if kind == "nn":
+            B = torch.randn(K, batches * N, generator=g) * 0.2
+            ref = torch.cat([A[:, b * K:(b + 1) * K].double() @ B[:, b * N:(b + 1) * N].double() for b in range(batches)], 1)
+            tb, ldb, b_bs = 0, batches * N, N
+        else:
+            B = torch.randn(N, batches * K, generator=g) * 0.2
+            ref = torch.cat([A[:, b * K:(b + 1) * K].double() @ B[:, b * K:(b + 1) * K].double().t() for b in range(batches)], 1)
+            tb, ldb, b_bs = 1, batches * K, K
+        rows_c = M
+    if elu:
+        ref = torch.nn.functional.elu(ref)
+    dA, dB = A.to(DEV), B.to(DEV)
+    C = torch.full((rows_c, batches * N + 4), 7.0, device=DEV)
+    ws_bytes = _lib.query("gatk_gemm_batched_workspace_bytes", ta, tb, M, N, K, batches)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=DEV)
+    outs = []
+    for _ in range(2):
+        _lib.call("gatk_gemm_batched", ta, tb, M, N, K, batches, dA.data_ptr(), lda, a_bs, dB.data_ptr(), ldb, b_bs,
+                  C.data_ptr(), batches * N + 4, N, int(elu), ws.data_ptr(), ws_bytes, _stream())
+        torch.cuda.synchronize()
+        outs.append(C.clone())
+    assert rel_err(C[:, :batches * N], ref) < 3e-6
+    assert torch.all(C[:, batches * N:] == 7.0)
+    assert torch.equal(outs[0], outs[1])
+
+
 # ------------------------------------------------------------------------------ heads
 def _run_head(d, kind, adj_arg, masks=None):
     cls = layers.SpGraphAttentionLayer if kind == "sparse" else layers.GraphAttentionLayer
