@@ -18,7 +18,9 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .functional import (HeadCombineFunction, LayerMasks, _gemm, _hub_scratch, pack_heads)
+from . import functional as Fn
+from .functional import (HeadCombineFunction, LayerMasks, _gemm, _gemm_batched, _hub_scratch, _x_scratch,
+                         agg_first_geometry, pack_heads)
 from .graph import Graph, _ptr, _stream
 from .synth import shard_rows_by_nnz
 
@@ -217,13 +219,121 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         return dx, dw_ext, da_src, da_dst, None, None, None, None, None, None, None
 
 
+class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
+    """functional.GatLayerAggFirstFunction on a destination-row shard (narrow first-layer inputs, no dropout).
+
+    What crosses NVLink per layer:
+      forward   all-gather of the GATHER ROWS xg = [x | g] (F_in + H floats per node, padded to 128 bytes): every
+                rank packs its own rows (gatk_logits_pack) and gathers the others'; nothing is recomputed;
+      backward  reduce-scatter of the per-source logit gradients dg [N, H] and one all-reduce of the
+                parameter-sized gradients (dW, d[W a_src | W a_dst]).
+    Everything H*D wide (aggregated rows, outputs, their gradients) stays on the rank that owns the rows."""
+
+    @staticmethod
+    def forward(ctx, x, w_ext, w_uv, graph: Graph, plan: ShardPlan, H: int, Dp: int, has_skip: bool, alpha: float,
+                act_elu: bool):
+        dev = x.device
+        n, f_in = x.shape
+        assert n == plan.n_local == graph.n_dst and graph.n_src == plan.n_total
+        N = plan.n_total
+        HD = H * Dp
+        M_out = HD * (2 if has_skip else 1)
+        Muv = w_uv.shape[1]
+        Fp = (f_in + 3) // 4 * 4
+        x, w_ext, w_uv = x.contiguous(), w_ext.contiguous(), w_uv.contiguous()
+        st = _stream()
+        P = _lib.query("gatk_xg_pitch", Fp, H)
+        xg_full = torch.empty(N, P, dtype=torch.float32, device=dev)
+        xg_loc = plan.rows(xg_full)
+        f = torch.empty(n, H, dtype=torch.float32, device=dev)
+        _lib.call("gatk_logits_pack", n, f_in, H, x.data_ptr(), f_in, w_uv.data_ptr(), Muv, xg_loc.data_ptr(), P,
+                  f.data_ptr(), H, st)
+        gather_rows(xg_full, plan)
+        need_grad = any(ctx.needs_input_grad[1:3])
+        xagg = torch.empty(n, H * Fp, dtype=torch.float32, device=dev)
+        lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        hubs = graph.hubs
+        scratch = _x_scratch(0, H, Fp, hubs.n_seg, dev)
+        _lib.call("gatk_attn_x_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg_full.data_ptr(), P,
+                  f.data_ptr(), H, float(alpha), xagg.data_ptr(), H * Fp, _ptr(lse),
+                  *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+        out = torch.empty(n, HD, dtype=torch.float32, device=dev)
+        fuse_elu = act_elu and not has_skip
+        _gemm_batched(0, 0, n, Dp, f_in, H, xagg, H * Fp, Fp, w_ext, M_out, Dp, out, HD, Dp, epilogue=int(fuse_elu))
+        if has_skip:
+            _gemm(0, 0, n, HD, f_in, xg_loc, P, w_ext, M_out, out, HD, accumulate=1, b_off=HD)
+            if act_elu:
+                _lib.call("gatk_elu_fwd", n, HD, out.data_ptr(), HD, st)
+        if need_grad:
+            ctx.graph, ctx.plan = graph, plan
+            ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu), f_in, Fp, Muv)
+            ctx.save_for_backward(xg_full, w_ext, f, lse, xagg, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        xg_full, w_ext, f, lse, xagg, out = ctx.saved_tensors
+        graph, plan = ctx.graph, ctx.plan
+        H, Dp, has_skip, alpha, act_elu, f_in, Fp, Muv = ctx.cfg
+        dev = xg_full.device
+        N, P = xg_full.shape
+        n = plan.n_local
+        HD = H * Dp
+        M_out = HD * (2 if has_skip else 1)
+        st = _stream()
+        gout = gout.contiguous()
+        xg_loc = plan.rows(xg_full)
+        if act_elu:
+            dhp = torch.empty(n, HD, dtype=torch.float32, device=dev)
+            _lib.call("gatk_elu_bwd", n, HD, gout.data_ptr(), HD, out.data_ptr(), HD, dhp.data_ptr(), HD, st)
+        else:
+            dhp = gout
+        dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
+        dxagg = (torch.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
+        _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp)
+        _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp)
+        if has_skip:
+            _gemm(1, 0, f_in, HD, n, xg_loc, P, dhp, HD, dw_ext, M_out, c_off=HD)
+        ds = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        dfg = (torch.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
+        hubs = graph.hubs
+        scratch = _x_scratch(1, H, Fp, hubs.n_seg, dev)
+        _lib.call("gatk_attn_x_bwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg_full.data_ptr(), P,
+                  f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
+                  dxagg.data_ptr(), H * Fp, ds.data_ptr(), dfg.data_ptr(), Muv,
+                  *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+        # dg: partial sums for EVERY source from this rank's stored entries, reduced to the rows' owners
+        tptr, _trow, perm, thubs = graph.transpose()[:4]
+        dg_part = torch.empty(N, H, dtype=torch.float32, device=dev)
+        _lib.call("gatk_edge_tsum", N, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(), dg_part.data_ptr(), H,
+                  thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
+        dfg[:, H:2 * H] = reduce_rows(dg_part, plan)
+        dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
+        _gemm(1, 0, f_in, Muv, n, xg_loc, P, dfg, Muv, dw_uv, Muv)
+        if plan.world > 1:
+            allreduce_([dw_ext, dw_uv], plan)
+        return None, dw_ext, dw_uv, None, None, None, None, None, None, None
+
+
 def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, a_srcs, a_dsts, skips, alpha: float,
-                      concat: bool, combine: str = "cat") -> torch.Tensor:
+                      concat: bool, combine: str = "cat", form: str = "auto") -> torch.Tensor:
     """All heads of one GAT layer on this rank's destination rows (see functional.gat_layer)."""
     H = len(Ws)
+    x_local = x_local.float()
     w_ext, a_src, a_dst, D, Dp = pack_heads(Ws, a_srcs, a_dsts, skips)
-    rows = ShardedGatLayerFunction.apply(x_local.float(), w_ext, a_src, a_dst, graph, plan, H, Dp, skips is not None,
-                                         float(alpha), bool(concat))
+    agg_first = (Fn.AGG_FIRST and form in ("auto", "agg_first")
+                 and not (x_local.requires_grad and torch.is_grad_enabled())
+                 and (agg_first_geometry(x_local.shape[1], H, Dp)[1] or form == "agg_first"))
+    if agg_first:
+        w3 = w_ext[:, : H * Dp].reshape(x_local.shape[1], H, Dp)
+        uv = [(w3 * a_src).sum(-1), (w3 * a_dst).sum(-1)]
+        if (-2 * H) % 4:
+            uv.append(w_ext.new_zeros(x_local.shape[1], (-2 * H) % 4))
+        rows = ShardedGatLayerAggFirstFunction.apply(x_local, w_ext, torch.cat(uv, dim=1), graph, plan, H, Dp,
+                                                     skips is not None, float(alpha), bool(concat))
+    else:
+        rows = ShardedGatLayerFunction.apply(x_local, w_ext, a_src, a_dst, graph, plan, H, Dp, skips is not None,
+                                             float(alpha), bool(concat))
     if combine == "none" or (combine == "cat" and D == Dp):
         return rows
     return HeadCombineFunction.apply(rows, H, D, Dp, 1 if combine == "mean" else 0)

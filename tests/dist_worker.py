@@ -99,16 +99,29 @@ def run_nccl(rank, world):
         # first-layer case: the input needs no gradient, so no dWh rows are exchanged at all
         for p in Ws + a_s + a_d + (Ss or []):
             p.grad = None
+        # (narrow inputs take the aggregate-first form here while the single-GPU reference above ran the folded
+        # form: two fp32 re-associations, each held to 1e-5 against the oracle in test_gpu_parity.py, so they
+        # may differ from each other by up to the sum)
         y2 = sharded_gat_layer(plan.rows(x).clone(), graph, plan, Ws, a_s, a_d, Ss, 0.2, concat)
         y2.backward(plan.rows(gout))
         assert rel(y2, plan.rows(y_ref)) < 1e-5
         for got, want in zip([w.grad for w in Ws], ref["dW"]):
+            assert rel(got, want) < 2e-5, rel(got, want)
+        for got, want in zip([a.grad for a in a_s + a_d], ref["da"]):
+            assert rel(got, want) < 2e-5, rel(got, want)
+        if skip:
+            for got, want in zip([s.grad for s in Ss], ref["dS"]):
+                assert rel(got, want) < 2e-5
+        # and the project-first sharded kernels on the same no-gradient input
+        for p in Ws + a_s + a_d + (Ss or []):
+            p.grad = None
+        y3 = sharded_gat_layer(plan.rows(x).clone(), graph, plan, Ws, a_s, a_d, Ss, 0.2, concat, form="project_first")
+        y3.backward(plan.rows(gout))
+        assert rel(y3, plan.rows(y_ref)) < 1e-5
+        for got, want in zip([w.grad for w in Ws], ref["dW"]):
             assert rel(got, want) < 1e-5, rel(got, want)
         for got, want in zip([a.grad for a in a_s + a_d], ref["da"]):
             assert rel(got, want) < 1e-5, rel(got, want)
-        if skip:
-            for got, want in zip([s.grad for s in Ss], ref["dS"]):
-                assert rel(got, want) < 1e-5
     torch.cuda.synchronize()
 
 
