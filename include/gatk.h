@@ -184,8 +184,8 @@ GATK_API int gatk_da_reduce(int64_t n, int H, int Dp, const float* wh, int64_t l
  *
  *  logits_pack  f = x u, g = x v with [u | v] = [W a_src | W a_dst] (uv is [F, >= 2H], u in columns 0..H-1,
  *          v in H..2H-1) and the GATHER ROWS  xg_i = [x_i (F floats, zero padded to Fp = 4*ceil(F/4)) |
- *          g_i (H floats) | zero pad]  with row pitch gatk_xg_pitch(Fp, H) (a multiple of 32 floats: rows are
- *          128-byte aligned, so a stored entry costs one DRAM access for both x_j and g_j).
+ *          g_i (H floats) | zero pad]  with row pitch >= gatk_xg_pitch(Fp, H) = Fp + 4*ceil(H/4) floats (rows
+ *          16-byte aligned for the bulk copies; a stored entry costs one gather for both x_j and g_j).
  *  x_fwd   per destination row: softmax_j LeakyReLU(f_i + g_j) (online, max-subtracted) and
  *          xagg[i, h*Fp:(h+1)*Fp] = sum_j alpha_ijh x_j;  lse[i,h] = m + log l.  The caller then projects:
  *          out_h = xagg_h W_h (+ x S_h) through gatk_gemm and applies gatk_elu_fwd.

@@ -133,6 +133,28 @@ def call(name: str, *args, label: "str | None" = None):
         raise GatkError(f"{name} failed ({rc}): {lib.gatk_last_error().decode(errors='replace')}")
 
 
+class timed:
+    """Context manager filing a non-library region (a collective, a torch op) under `label` in the KernelTimer."""
+
+    def __init__(self, label: str):
+        self.label = label
+
+    def __enter__(self):
+        if timer is not None:
+            import torch
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if timer is not None:
+            import torch
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            timer.records.append((self.label, self.e0, e1))
+        return False
+
+
 def query(name: str, *args):
     """Invoke a size/value query (no error code)."""
     return getattr(load(), name)(*args)

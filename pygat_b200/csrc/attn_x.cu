@@ -107,7 +107,7 @@ __host__ __device__ __forceinline__ int xfwd_warp_floats(int RS, int HP, int chu
 // backward (tensor-core kernel): row pitch = 16 (mod 32) floats, so the two rows a quarter-warp touches per
 // 128-bit fragment load sit in different bank halves
 __host__ __device__ __forceinline__ int xmma_row_pitch(int Sx) { return (4 * Sx + 15) / 32 * 32 + 16; }
-__host__ __device__ __forceinline__ int xmma_warp_floats(int RS) { return 32 * RS + 4; }
+__host__ __device__ __forceinline__ int xmma_warp_floats(int RS, int H, int Fp) { return 64 * RS + 2 * H * Fp + 4; }
 __host__ __device__ __forceinline__ int xbwd_warp_floats(int RS, int H, int Fp, int chunk) { return chunk * RS + H * Fp + 4; }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
@@ -556,64 +556,120 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
   const int H = a.H, Fp = a.Fp, RS = a.RS;
   const int KP = (Fp + 15) >> 4;  // pairs of k-steps
   const int h0 = 2 * tg, h1 = 2 * tg + 1;
-  float* rows = x_smem + (size_t)warp * xmma_warp_floats(RS);
-  const unsigned bar = smem_u32(rows + 32 * RS);
-  for (int i = lane; i < 32 * RS; i += 32) rows[i] = 0.f;  // stale lanes of the MMA must hold finite numbers
-  if (lane == 0) mbar_init(bar, 1);
+  // per warp: two row buffers (the next chunk's rows land while this chunk is computed), one staging area for
+  // the row state (dxagg_i, xagg_i) of the next destination row, two mbarriers
+  float* rowbuf = x_smem + (size_t)warp * xmma_warp_floats(RS, H, Fp);
+  float* dxs = rowbuf + 64 * RS;
+  float* xas = dxs + H * Fp;
+  const unsigned bar0 = smem_u32(xas + H * Fp);
+  for (int i = lane; i < 64 * RS; i += 32) rowbuf[i] = 0.f;  // stale lanes of the MMA must hold finite numbers
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+  }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic zero fill before the async-proxy copies
   __syncwarp();
-  unsigned phase = 0;
+  unsigned phases = 0;  // bit b: parity the next wait on barrier b expects
   const int seg = blockIdx.x * XW + warp;
   if (HUB && seg >= a.n_hub_seg) return;
   ChunkIter<HUB> it;
   it.init(a, lane, seg, 32);
+  const unsigned row_bytes = (unsigned)a.Sx * 16u, st_bytes = (unsigned)(H * Fp) * 4u;
+
+  // copies of one chunk: its neighbour rows and, for the first chunk of a destination row, the row state
+  auto issue = [&](const Chunk& ch, int jcol, int buf) {
+    if (ch.cnt > 0) {
+      const unsigned bar = bar0 + 8 * buf;
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                     "r"(row_bytes * (unsigned)ch.cnt + (ch.first ? 2 * st_bytes : 0u))
+                     : "memory");
+      __syncwarp();
+      if (lane < ch.cnt) {
+        const float* src = a.xg + (int64_t)jcol * a.ldxg;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(rowbuf + (buf * 32 + lane) * RS)),
+                     "l"(src), "r"(row_bytes), "r"(bar)
+                     : "memory");
+      }
+      if (ch.first && lane < 2) {
+        const float* src = lane == 0 ? a.dxagg + (int64_t)ch.row * a.ldd : a.xagg + (int64_t)ch.row * a.ldxa;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(lane == 0 ? dxs : xas)),
+                     "l"(src), "r"(st_bytes), "r"(bar)
+                     : "memory");
+      }
+    }
+  };
+  auto cols_of = [&](const Chunk& ch) { return (ch.ok && lane < ch.cnt) ? __ldg(a.col + ch.base + lane) : 0; };
 
   uint32_t bhi[KPMAX][4], blo[KPMAX][4];
   float f0 = 0.f, f1 = 0.f, l0 = 0.f, l1 = 0.f, c0 = 0.f, c1 = 0.f, df0 = 0.f, df1 = 0.f;
+  float nf0 = 0.f, nf1 = 0.f, nl0 = 0.f, nl1 = 0.f;  // f, lse of the NEXT destination row (prefetched)
+  auto prefetch_fl = [&](const Chunk& ch) {
+    if (ch.ok && ch.first) {
+      nf0 = h0 < H ? __ldg(a.f + (int64_t)ch.row * a.ldf + h0) : 0.f;
+      nf1 = h1 < H ? __ldg(a.f + (int64_t)ch.row * a.ldf + h1) : 0.f;
+      nl0 = h0 < H ? __ldg(a.lse + (int64_t)ch.row * H + h0) : 0.f;
+      nl1 = h1 < H ? __ldg(a.lse + (int64_t)ch.row * H + h1) : 0.f;
+    }
+  };
   Chunk c = it.next(a, lane);
-  int j = (c.ok && lane < c.cnt) ? __ldg(a.col + c.base + lane) : 0;
+  {
+    const int jc = cols_of(c);
+    if (c.ok) issue(c, jc, 0);
+    prefetch_fl(c);
+  }
+  Chunk n = it.next(a, lane);
+  int jn = cols_of(n);
+  int p = 0;
   while (c.ok) {
-    const Chunk n = it.next(a, lane);
-    x_issue_rows(a, rows, j, c.cnt, lane, RS, bar);
-    const int jn = (n.ok && lane < n.cnt) ? __ldg(a.col + n.base + lane) : 0;
-    if (c.first) {
-      // row state: B fragments of dxagg_i (head g, features 16kp + 4tg .. +3), c_ih = dxagg_ih . xagg_ih
-      const float* dxr = a.dxagg + (int64_t)c.row * a.ldd + g * Fp + 4 * tg;
-      const float* xar = a.xagg + (int64_t)c.row * a.ldxa + g * Fp + 4 * tg;
-      float cp = 0.f;
-#pragma unroll
-      for (int kp = 0; kp < KPMAX; ++kp) {
-        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kp < KP && g < H && 16 * kp + 4 * tg < Fp) {
-          d = ldg4_stream(dxr + 16 * kp);
-          cp += dot4(d, ldg4_stream(xar + 16 * kp));
-        }
-        split_tf32(d.x, bhi[kp][0], blo[kp][0]);
-        split_tf32(d.y, bhi[kp][1], blo[kp][1]);
-        split_tf32(d.z, bhi[kp][2], blo[kp][2]);
-        split_tf32(d.w, bhi[kp][3], blo[kp][3]);
-      }
-      cp += __shfl_xor_sync(FULL, cp, 1);
-      cp += __shfl_xor_sync(FULL, cp, 2);  // lanes (g, *) hold c of head g
-      c0 = __shfl_sync(FULL, cp, 4 * h0);
-      c1 = __shfl_sync(FULL, cp, 4 * h1);
-      f0 = h0 < H ? __ldg(a.f + (int64_t)c.row * a.ldf + h0) : 0.f;
-      f1 = h1 < H ? __ldg(a.f + (int64_t)c.row * a.ldf + h1) : 0.f;
-      l0 = h0 < H ? __ldg(a.lse + (int64_t)c.row * H + h0) : 0.f;
-      l1 = h1 < H ? __ldg(a.lse + (int64_t)c.row * H + h1) : 0.f;
-      df0 = df1 = 0.f;
-    }
+    const Chunk nn = it.next(a, lane);
+    const int jnn = cols_of(nn);  // column ids two chunks ahead
+    const float* rows = rowbuf + p * 32 * RS;
     if (c.cnt > 0) {
-      mbar_wait(bar, phase);
-      phase ^= 1;
+      mbar_wait(bar0 + 8 * p, (phases >> p) & 1u);
+      phases ^= 1u << p;
     }
+    if (c.first) {
+      f0 = nf0; f1 = nf1; l0 = nl0; l1 = nl1;
+      df0 = df1 = 0.f;
+      if (c.cnt > 0) {
+        // row state from the staging area: B fragments of dxagg_i (head g, features 16kp + 4tg .. +3),
+        // c_ih = dxagg_ih . xagg_ih
+        float cp = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < KPMAX; ++kp) {
+          float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kp < KP && g < H && 16 * kp + 4 * tg < Fp) {
+            d = *reinterpret_cast<const float4*>(dxs + g * Fp + 16 * kp + 4 * tg);
+            cp += dot4(d, *reinterpret_cast<const float4*>(xas + g * Fp + 16 * kp + 4 * tg));
+          }
+          split_tf32(d.x, bhi[kp][0], blo[kp][0]);
+          split_tf32(d.y, bhi[kp][1], blo[kp][1]);
+          split_tf32(d.z, bhi[kp][2], blo[kp][2]);
+          split_tf32(d.w, bhi[kp][3], blo[kp][3]);
+        }
+        cp += __shfl_xor_sync(FULL, cp, 1);
+        cp += __shfl_xor_sync(FULL, cp, 2);  // lanes (g, *) hold c of head g
+        c0 = __shfl_sync(FULL, cp, 4 * h0);
+        c1 = __shfl_sync(FULL, cp, 4 * h1);
+      }
+    }
+    __syncwarp();  // the staging area and the other row buffer are free: start the next chunk's copies
+    if (n.ok) issue(n, jn, p ^ 1);
+    prefetch_fl(n);
     const int n_mt = c.cnt > 16 ? 2 : 1;
-    float acc[2][4];
+    // three independent accumulators per 16-edge tile (hi*hi, lo*hi, hi*lo): the MMAs of a k-step do not
+    // wait on each other, and the small compensation terms are summed apart from the main product
+    float acc[2][3][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[mt][q] = 0.f;
+      for (int t3 = 0; t3 < 3; ++t3)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[mt][t3][q] = 0.f;
 #pragma unroll
     for (int kp = 0; kp < KPMAX; ++kp) {
       if (kp < KP) {
@@ -628,17 +684,21 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
             split_tf32(a8.x, eh[0], el[0]); split_tf32(a8.y, eh[1], el[1]);
             split_tf32(a8.z, eh[2], el[2]); split_tf32(a8.w, eh[3], el[3]);
             // k-step 2kp: logical k = tg -> feature +0, tg+4 -> +1;  k-step 2kp+1: +2, +3
-            mma_tf32(acc[mt], gl[0], el[0], gl[1], el[1], bhi[kp][0], bhi[kp][1]);
-            mma_tf32(acc[mt], gh[0], eh[0], gh[1], eh[1], blo[kp][0], blo[kp][1]);
-            mma_tf32(acc[mt], gh[0], eh[0], gh[1], eh[1], bhi[kp][0], bhi[kp][1]);
-            mma_tf32(acc[mt], gl[2], el[2], gl[3], el[3], bhi[kp][2], bhi[kp][3]);
-            mma_tf32(acc[mt], gh[2], eh[2], gh[3], eh[3], blo[kp][2], blo[kp][3]);
-            mma_tf32(acc[mt], gh[2], eh[2], gh[3], eh[3], bhi[kp][2], bhi[kp][3]);
+            mma_tf32(acc[mt][0], gh[0], eh[0], gh[1], eh[1], bhi[kp][0], bhi[kp][1]);
+            mma_tf32(acc[mt][1], gl[0], el[0], gl[1], el[1], bhi[kp][0], bhi[kp][1]);
+            mma_tf32(acc[mt][2], gh[0], eh[0], gh[1], eh[1], blo[kp][0], blo[kp][1]);
+            mma_tf32(acc[mt][0], gh[2], eh[2], gh[3], eh[3], bhi[kp][2], bhi[kp][3]);
+            mma_tf32(acc[mt][1], gl[2], el[2], gl[3], el[3], bhi[kp][2], bhi[kp][3]);
+            mma_tf32(acc[mt][2], gh[2], eh[2], gh[3], eh[3], blo[kp][2], blo[kp][3]);
           }
         }
       }
     }
-    // ---- ds for this lane's (edge, head) pairs: acc[mt][0..1] = edge 16mt+g, heads h0,h1; [2..3] = edge 16mt+g+8
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[mt][0][q] += acc[mt][1][q] + acc[mt][2][q];
+    // ---- ds for this lane's (edge, head) pairs: acc[mt][0][0..1] = edge 16mt+g, heads h0,h1; [2..3] = edge 16mt+g+8
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
@@ -648,8 +708,8 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
           const float2 gq = *reinterpret_cast<const float2*>(rows + e * RS + Fp + h0);
           const float z0 = f0 + gq.x, z1 = f1 + gq.y;
           const float s0 = z0 > 0.f ? z0 : a.alpha * z0, s1 = z1 > 0.f ? z1 : a.alpha * z1;
-          const float v0 = expf(s0 - l0) * (acc[mt][2 * half] - c0) * (z0 > 0.f ? 1.f : a.alpha);
-          const float v1 = expf(s1 - l1) * (acc[mt][2 * half + 1] - c1) * (z1 > 0.f ? 1.f : a.alpha);
+          const float v0 = expf(s0 - l0) * (acc[mt][0][2 * half] - c0) * (z0 > 0.f ? 1.f : a.alpha);
+          const float v1 = expf(s1 - l1) * (acc[mt][0][2 * half + 1] - c1) * (z1 > 0.f ? 1.f : a.alpha);
           float* dp = a.ds + (c.base + e) * H + h0;
           if (h1 < H && (H & 1) == 0) {
             *reinterpret_cast<float2*>(dp) = make_float2(v0, v1);
@@ -677,7 +737,9 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
     }
     __syncwarp();
     c = n;
-    j = jn;
+    n = nn;
+    jn = jnn;
+    p ^= 1;
   }
 }
 
@@ -791,6 +853,11 @@ __global__ void __launch_bounds__(256) logits_pack_kernel(int64_t n, int F, int 
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int S = Fp >> 2;
+  const bool one_slot = S <= 32;  // a lane owns ONE slot: its [u|v] fragment stays in registers for the whole kernel
+  float4 uvr[C2];
+#pragma unroll
+  for (int c = 0; c < C2; ++c)
+    uvr[c] = (one_slot && lane < S) ? *reinterpret_cast<const float4*>(uvs + c * Fp + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
     const float* xr = x + row * ldx;
@@ -810,8 +877,13 @@ __global__ void __launch_bounds__(256) logits_pack_kernel(int64_t n, int F, int 
         v.w = k + 3 < F ? __ldg(xr + k + 3) : 0.f;
       }
       stg4(gr + slot * 4, v);
+      if (one_slot) {
 #pragma unroll
-      for (int c = 0; c < C2; ++c) part[c] += dot4(v, *reinterpret_cast<const float4*>(uvs + c * Fp + slot * 4));
+        for (int c = 0; c < C2; ++c) part[c] += dot4(v, uvr[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C2; ++c) part[c] += dot4(v, *reinterpret_cast<const float4*>(uvs + c * Fp + slot * 4));
+      }
     }
     butterfly_scatter<C2>(part, lane);  // lane (c << SHC) holds column c
     if ((lane & ((1 << SHC) - 1)) == 0) {
@@ -910,7 +982,7 @@ static int launch_x_mma(KH hub_kernel, KM main_kernel, const XArgs& a, size_t sm
 
 static int launch_x_bwd_mma(XArgs a, cudaStream_t st) {
   a.RS = xmma_row_pitch(a.Sx);
-  const size_t smem = (size_t)XW * xmma_warp_floats(a.RS) * sizeof(float);
+  const size_t smem = (size_t)XW * xmma_warp_floats(a.RS, a.H, a.Fp) * sizeof(float);
   int rc;
   if (a.Fp <= 64) rc = launch_x_mma(attn_x_bwd_mma_kernel<4, true>, attn_x_bwd_mma_kernel<4, false>, a, smem, st);
   else rc = launch_x_mma(attn_x_bwd_mma_kernel<8, true>, attn_x_bwd_mma_kernel<8, false>, a, smem, st);
@@ -944,7 +1016,7 @@ extern "C" size_t gatk_attn_x_scratch_floats(int which, int H, int Fp, int n_hub
   return (size_t)n_hub_seg * H;
 }
 
-extern "C" int64_t gatk_xg_pitch(int Fp, int H) { return ((int64_t)Fp + 4 * ((H + 3) / 4) + 31) / 32 * 32; }
+extern "C" int64_t gatk_xg_pitch(int Fp, int H) { return (int64_t)Fp + 4 * ((H + 3) / 4); }
 
 extern "C" int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t ldx, const float* uv, int64_t lduv,
                                 float* xg, int64_t ldxg, float* f, int64_t ldf, void* stream) {
@@ -952,7 +1024,8 @@ extern "C" int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t
   const int Fp = (F + 3) / 4 * 4;
   GATK_REQUIRE(Fp <= 512, "F=%d too wide for the aggregate-first form", F);
   GATK_REQUIRE(x && uv && xg && f && ldx >= F && lduv >= 2 * H && ldf >= H, "bad arguments");
-  GATK_REQUIRE(ldxg == gatk_xg_pitch(Fp, H) && ((uintptr_t)xg & 127) == 0, "xg must have pitch gatk_xg_pitch(Fp, H) and 128-byte alignment");
+  GATK_REQUIRE(ldxg >= gatk_xg_pitch(Fp, H) && ldxg % 4 == 0 && ((uintptr_t)xg & 15) == 0,
+               "xg must be 16-byte aligned with pitch >= gatk_xg_pitch(Fp, H), a multiple of 4 floats");
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int hp = H <= 1 ? 1 : (H <= 2 ? 2 : (H <= 4 ? 4 : 8));

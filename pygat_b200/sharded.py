@@ -38,8 +38,9 @@ class ShardPlan:
         self.n_total = self.bounds[-1]
 
     @staticmethod
-    def by_nnz(rowptr: torch.Tensor, rank: int, world: int, group=None) -> "ShardPlan":
-        return ShardPlan(shard_rows_by_nnz(rowptr, world), rank, group)
+    def by_nnz(rowptr: torch.Tensor, rank: int, world: int, group=None, row_cost: int = 0) -> "ShardPlan":
+        """row_cost: per-row work expressed in stored entries (see synth.shard_rows_by_nnz)."""
+        return ShardPlan(shard_rows_by_nnz(rowptr, world, row_cost), rank, group)
 
     def rows(self, full: torch.Tensor, r: Optional[int] = None) -> torch.Tensor:
         r = self.rank if r is None else r
@@ -248,7 +249,8 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         f = torch.empty(n, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_logits_pack", n, f_in, H, x.data_ptr(), f_in, w_uv.data_ptr(), Muv, xg_loc.data_ptr(), P,
                   f.data_ptr(), H, st)
-        gather_rows(xg_full, plan)
+        with _lib.timed("comm:allgather_xg"):
+            gather_rows(xg_full, plan)
         need_grad = any(ctx.needs_input_grad[1:3])
         xagg = torch.empty(n, H * Fp, dtype=torch.float32, device=dev)
         lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
@@ -307,11 +309,13 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         dg_part = torch.empty(N, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_edge_tsum", N, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(), dg_part.data_ptr(), H,
                   thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
-        dfg[:, H:2 * H] = reduce_rows(dg_part, plan)
+        with _lib.timed("comm:reduce_dg"):
+            dfg[:, H:2 * H] = reduce_rows(dg_part, plan)
         dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
         _gemm(1, 0, f_in, Muv, n, xg_loc, P, dfg, Muv, dw_uv, Muv)
         if plan.world > 1:
-            allreduce_([dw_ext, dw_uv], plan)
+            with _lib.timed("comm:allreduce_dw"):
+                allreduce_([dw_ext, dw_uv], plan)
         return None, dw_ext, dw_uv, None, None, None, None, None, None, None
 
 
@@ -361,6 +365,9 @@ def allreduce_gradients(params, n_local_nodes: int, group=None):
 
 
 # ---------------------------------------------------------------------- bench harness (bench.py --gpus N)
+ROW_COST = 25  # measured on one GPU at the products shape: row-proportional kernels ~7.0 ns/row, edge passes ~0.275 ns/entry
+
+
 class ShardedLayerBench:
     """The bench.py workload on `world` GPUs: the whole synthetic graph is generated identically on
     every rank (same seed) and each rank keeps its destination-row shard."""
@@ -370,7 +377,7 @@ class ShardedLayerBench:
         n, H, D, f_in = cfg["n"], cfg["H"], cfg["D"], cfg["f_in"]
         rowptr, col = power_law_csr(n, cfg["avg_deg"], seed=72, exponent=cfg["exponent"], device=dev)
         self.e_total = int(col.numel())
-        self.plan = ShardPlan.by_nnz(rowptr, rank, world)
+        self.plan = ShardPlan.by_nnz(rowptr, rank, world, row_cost=ROW_COST)
         self.graph = self.plan.local_graph(rowptr, col)
         del rowptr, col
         self.graph.transpose()

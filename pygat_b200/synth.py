@@ -32,13 +32,16 @@ def power_law_csr(n: int, avg_deg: float, seed: int, exponent: float = 0.5, devi
     return rowptr, col
 
 
-def shard_rows_by_nnz(rowptr: torch.Tensor, world: int):
-    """Contiguous destination-row ranges with ~equal stored entries (power-law graphs are not
-    balanced by row count).  Returns world+1 row boundaries (python ints)."""
+def shard_rows_by_nnz(rowptr: torch.Tensor, world: int, row_cost: int = 0):
+    """Contiguous destination-row ranges of ~equal COST, cost(row) = stored entries + row_cost (power-law
+    graphs are balanced neither by row count nor, once per-row work matters, by entries alone: at the
+    products shape the per-row kernels -- projections, ELU, the aggregated-row traffic -- weigh as much as
+    ~25 stored entries per row).  Returns world+1 row boundaries (python ints)."""
     n = rowptr.numel() - 1
-    total = int(rowptr[-1].item())
+    cum = rowptr + row_cost * torch.arange(n + 1, device=rowptr.device, dtype=torch.int64)
+    total = int(cum[-1].item())
     targets = torch.arange(1, world, device=rowptr.device, dtype=torch.int64) * total // world
-    cuts = torch.searchsorted(rowptr, targets).clamp_(max=n).tolist()
+    cuts = torch.searchsorted(cum, targets).clamp_(max=n).tolist()
     return [0] + [int(c) for c in cuts] + [n]
 
 

@@ -36,6 +36,13 @@ def test_shard_plan_local_graph_shapes():
     b = shard_rows_by_nnz(rowptr, 4)
     assert len(b) == 5 and b[0] == 0 and b[-1] == 300
     assert shard_rows_by_nnz(rowptr, 1) == [0, 300]
+    # cost-balanced cuts: entries + row_cost per row; a large row cost tends to equal row counts
+    c = shard_rows_by_nnz(rowptr, 4, row_cost=10_000)
+    assert c[0] == 0 and c[-1] == 300 and max(c[i + 1] - c[i] for i in range(4)) - min(c[i + 1] - c[i] for i in range(4)) <= 2
+    cost = lambda lo, hi, rc: int(rowptr[hi] - rowptr[lo]) + rc * (hi - lo)
+    d = shard_rows_by_nnz(rowptr, 4, row_cost=25)
+    costs = [cost(d[i], d[i + 1], 25) for i in range(4)]
+    assert max(costs) - min(costs) <= int((rowptr[1:] - rowptr[:-1]).max()) + 25
 
 
 @pytest.mark.gpu
