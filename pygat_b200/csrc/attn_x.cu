@@ -845,6 +845,7 @@ __global__ void __launch_bounds__(256) logits_pack_kernel(int64_t n, int F, int 
   extern __shared__ __align__(16) float uvs[];  // [2*HP][Fp]
   constexpr int C2 = 2 * HP;
   constexpr int SHC = 5 - Log2<C2>::v;
+  constexpr int R = 4;  // rows per warp iteration: one read of the [u|v] fragment serves R rows
   for (int i = threadIdx.x; i < C2 * Fp; i += blockDim.x) {
     const int c = i / Fp, k = i - c * Fp;
     const int h = c < HP ? c : c - HP;
@@ -853,47 +854,54 @@ __global__ void __launch_bounds__(256) logits_pack_kernel(int64_t n, int F, int 
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int S = Fp >> 2;
-  const bool one_slot = S <= 32;  // a lane owns ONE slot: its [u|v] fragment stays in registers for the whole kernel
-  float4 uvr[C2];
-#pragma unroll
-  for (int c = 0; c < C2; ++c)
-    uvr[c] = (one_slot && lane < S) ? *reinterpret_cast<const float4*>(uvs + c * Fp + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
-    const float* xr = x + row * ldx;
-    float* gr = xg + row * P;
-    float part[C2];
+  for (int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; row0 < n; row0 += warps * R) {
+    float part[R][C2];
 #pragma unroll
-    for (int c = 0; c < C2; ++c) part[c] = 0.f;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < C2; ++c) part[r][c] = 0.f;
     for (int slot = lane; slot < S; slot += 32) {
-      float4 v;
-      if (VEC) {
-        v = ldg4_stream(xr + slot * 4);
-      } else {
-        const int k = slot * 4;
-        v.x = k < F ? __ldg(xr + k) : 0.f;
-        v.y = k + 1 < F ? __ldg(xr + k + 1) : 0.f;
-        v.z = k + 2 < F ? __ldg(xr + k + 2) : 0.f;
-        v.w = k + 3 < F ? __ldg(xr + k + 3) : 0.f;
+      float4 v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + r < n ? row0 + r : n - 1;
+        const float* xr = x + row * ldx;
+        if (VEC) {
+          v[r] = ldg4_stream(xr + slot * 4);
+        } else {
+          const int k = slot * 4;
+          v[r].x = k < F ? __ldg(xr + k) : 0.f;
+          v[r].y = k + 1 < F ? __ldg(xr + k + 1) : 0.f;
+          v[r].z = k + 2 < F ? __ldg(xr + k + 2) : 0.f;
+          v[r].w = k + 3 < F ? __ldg(xr + k + 3) : 0.f;
+        }
       }
-      stg4(gr + slot * 4, v);
-      if (one_slot) {
 #pragma unroll
-        for (int c = 0; c < C2; ++c) part[c] += dot4(v, uvr[c]);
-      } else {
+      for (int r = 0; r < R; ++r)
+        if (row0 + r < n) stg4(xg + (row0 + r) * P + slot * 4, v[r]);
 #pragma unroll
-        for (int c = 0; c < C2; ++c) part[c] += dot4(v, *reinterpret_cast<const float4*>(uvs + c * Fp + slot * 4));
+      for (int c = 0; c < C2; ++c) {
+        const float4 q = *reinterpret_cast<const float4*>(uvs + c * Fp + slot * 4);
+#pragma unroll
+        for (int r = 0; r < R; ++r) part[r][c] += dot4(v[r], q);
       }
     }
-    butterfly_scatter<C2>(part, lane);  // lane (c << SHC) holds column c
-    if ((lane & ((1 << SHC) - 1)) == 0) {
-      const int c = lane >> SHC;
-      if (c < H) f[row * ldf + c] = part[0];
-    }
-    for (int t0 = 0; t0 < P - Fp; t0 += 32) {  // g behind the input row, zero padding after it
-      const int t = t0 + lane;
-      const float gval = __shfl_sync(FULL, part[0], ((HP + (t < HP ? t : 0)) << SHC) & 31);
-      if (t < P - Fp) gr[Fp + t] = t < H ? gval : 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+      butterfly_scatter<C2>(part[r], lane);  // lane (c << SHC) holds column c
+      if (row < n) {
+        if ((lane & ((1 << SHC) - 1)) == 0) {
+          const int c = lane >> SHC;
+          if (c < H) f[row * ldf + c] = part[r][0];
+        }
+      }
+      for (int t0 = 0; t0 < P - Fp; t0 += 32) {  // g behind the input row, zero padding after it
+        const int t = t0 + lane;
+        const float gval = __shfl_sync(FULL, part[r][0], ((HP + (t < HP ? t : 0)) << SHC) & 31);
+        if (row < n && t < P - Fp) xg[row * P + Fp + t] = t < H ? gval : 0.f;
+      }
     }
   }
 }
@@ -1031,7 +1039,7 @@ extern "C" int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t
   const int hp = H <= 1 ? 1 : (H <= 2 ? 2 : (H <= 4 ? 4 : 8));
   const bool vec = (F % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)x & 15) == 0);
   const size_t smem = (size_t)2 * hp * Fp * sizeof(float);
-  int64_t blocks = (n + 7) / 8;
+  int64_t blocks = (n + 31) / 32;  // 8 warps x 4 rows per iteration
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
 #define PACK_LAUNCH(HPV, V) logits_pack_kernel<HPV, V><<<(unsigned)blocks, 256, smem, st>>>(n, F, H, x, ldx, uv, lduv, Fp, (int)ldxg, xg, f, ldf)

@@ -668,13 +668,27 @@ __device__ __forceinline__ void umma_tf32_i(uint32_t tmem_d, uint64_t adesc, uin
 // F.elu computes exp(x) - 1 (not expm1); the fast exponential is accurate to ~2 ulp of exp, i.e. ~1e-7 absolute here
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
+template <int NST>
+struct RingN {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == NST) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
 template <int BN>
 struct Cfg {
   static constexpr int TILE_A = BLOCK_M * BLOCK_K * 4;  // 16 KiB
   static constexpr int TILE_B = BN * BLOCK_K * 4;
   static constexpr int STAGE = 2 * TILE_A + 2 * TILE_B;  // Ahi, Alo, Bhi, Blo
-  static constexpr int SMEM = STAGES * STAGE + 2 * CSTAGE_BYTES + 1024 + 256;
-  static constexpr int SMEM_TN = STAGES * STAGE + 1024 + 256;
+  // these products are HBM-bound: the ring depth sets the bytes in flight per SM (one 16 KiB A tile per stage)
+  static constexpr int NST = BN == 64 ? 4 : 3;
+  static constexpr int SMEM = NST * STAGE + 2 * CSTAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_TN = NST * STAGE + 1024 + 256;
   static constexpr int TMEM = 4 * BN;  // 2 stages x (main, correction)
   static constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
   static constexpr uint32_t IDESC_MN = IDESC_K | (1u << 15) | (1u << 16);
@@ -689,15 +703,15 @@ gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* cstage = smem + STAGES * C::STAGE;
+  uint8_t* cstage = smem + C::NST * C::STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(cstage + 2 * CSTAGE_BYTES);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto split_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  auto split_bar = [&](int s) { return bar0 + 8u * (C::NST + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * C::NST + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * C::NST + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * C::NST + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::NST + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_m = n_tiles * batches;
@@ -710,7 +724,7 @@ gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < C::NST; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(split_bar(s), 4);
       mbar_init(empty_bar(s), 1);
@@ -733,7 +747,7 @@ gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
 
   if (warp == 0) {
     if (lane == 0) {
-      Ring r;
+      RingN<C::NST> r;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int m0, n0, b;
         decode(tile, m0, n0, b);
@@ -749,7 +763,7 @@ gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
       }
     }
   } else if (warp == 1) {
-    Ring r;
+    RingN<C::NST> r;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -781,7 +795,7 @@ gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    Ring r;
+    RingN<C::NST> r;
     const int t = threadIdx.x - 128;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < k_blocks; ++kb) {
@@ -871,21 +885,21 @@ gemm_tn_batched_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   using tn::PROMOTE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NST * C::STAGE);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto split_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  auto split_bar = [&](int s) { return bar0 + 8u * (C::NST + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * C::NST + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * C::NST + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * C::NST + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::NST + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = m_tiles * n_tiles;
   const int items = batches * tiles * splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < C::NST; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(split_bar(s), 4);
       mbar_init(empty_bar(s), 1);
@@ -920,7 +934,7 @@ gemm_tn_batched_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      Ring r;
+      RingN<C::NST> r;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         int b, m0, n0, kb0, kb1, sp;
         decode(item, b, m0, n0, kb0, kb1, sp);
@@ -938,7 +952,7 @@ gemm_tn_batched_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       }
     }
   } else if (warp == 1) {
-    Ring r;
+    RingN<C::NST> r;
     int drain = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int b, m0, n0, kb0, kb1, sp;
@@ -976,7 +990,7 @@ gemm_tn_batched_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    Ring r;
+    RingN<C::NST> r;
     const int t = threadIdx.x - 128;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int b, m0, n0, kb0, kb1, sp;
