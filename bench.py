@@ -51,24 +51,24 @@ def algorithmic_bytes(n, e, H, D, f_in, need_dx=False):
     prep = n * H * (16 * D + 4)                      # gout, out, hagg read; dhp write; c write
     fused = e * H * (4 * D + 16 + 4) + 8 * e + n * H * (8 * D + 8)   # record gather (dh' + f,lse,c,pad), dz write, trow+perm
     finish = 4 * e * H + 4 * n * H + 8 * n            # dz read, df write (folded form: no dWh update, no da pass)
-    # aggregate-first form
+    # aggregate-first form: gather rows xg = [x (Fp) | g (H)] of pitch P floats
     Fp = (f_in + 3) // 4 * 4
+    P = Fp + 4 * ((H + 3) // 4)
     HD = H * D
-    x_fwd = e * (4 * Fp + 4 * H + 4) + n * (4 * H * Fp + 8 * H + 8)            # x_j, g_j, col; xagg write, f, lse
-    x_bwd = e * (4 * Fp + 4 * H + 4 + 4 * H) + n * (8 * H * Fp + 12 * H + 8)   # x_j, g_j, col, ds write; xagg, dxagg, f, lse, df
-    tsum = e * (4 * H + 4) + n * (4 * H + 8)                                    # ds through perm; dg write
-    elu_f = 8 * n * HD
+    pack = n * (4 * f_in + 4 * P + 4 * H)                                        # x read; xg, f written
+    x_fwd = e * (4 * P + 4) + n * (4 * H * Fp + 8 * H + 8)                       # xg_j, col; xagg write, f, lse
+    x_bwd = e * (4 * P + 4 + 4 * H) + n * (8 * H * Fp + 12 * H + 8)              # xg_j, col, ds write; xagg, dxagg, f, lse, df
+    tsum = e * (4 * H + 4) + n * (4 * H + 8)                                     # ds through perm; dg write
     elu_b = 12 * n * HD
-    gemm_x = (4 * n * Fp + 8 * n * H                      # fg = x [u|v]
-              + 4 * n * H * Fp + 4 * n * HD                # out_h = xagg_h W_h
-              + 4 * n * H * Fp + 4 * n * HD                # dW_h = xagg_h^T dh'_h
-              + 4 * n * HD + 4 * n * H * Fp                # dxagg_h = dh'_h W_h^T
-              + 4 * n * Fp + 8 * n * H)                    # d[u|v] = x^T [df|dg]
-    agg = x_fwd + x_bwd + tsum + elu_f + elu_b + gemm_x
+    g_proj = 4 * n * H * Fp + 4 * n * HD                                         # out_h = ELU(xagg_h W_h)
+    g_dw = 4 * n * H * Fp + 4 * n * HD                                           # dW_h = xagg_h^T dh'_h
+    g_dx = 4 * n * HD + 4 * n * H * Fp                                           # dxagg_h = dh'_h W_h^T
+    g_dl = 4 * n * f_in + 8 * n * H                                              # d[u|v] = x^T [df|dg]
+    agg = pack + x_fwd + x_bwd + tsum + elu_b + g_proj + g_dw + g_dx + g_dl
     return {"gatk_attn_fwd": k2, "gatk_attn_bwd_prep": prep, "gatk_attn_bwd_fused": fused,
             "gatk_attn_bwd_finish": finish, "projection_fwd": k1, "projection_bwd": k5,
-            "gatk_attn_x_fwd": x_fwd, "gatk_attn_x_bwd": x_bwd, "gatk_edge_tsum": tsum,
-            "gatk_elu_fwd": elu_f, "gatk_elu_bwd": elu_b, "gemm_agg_first": gemm_x,
+            "gatk_logits_pack": pack, "gatk_attn_x_fwd": x_fwd, "gatk_attn_x_bwd": x_bwd, "gatk_edge_tsum": tsum,
+            "gatk_elu_bwd": elu_b, "gemm:project": g_proj, "gemm:dW": g_dw, "gemm:dxagg": g_dx, "gemm:dlogits": g_dl,
             "layer_survey": k2 + k3_survey + k4_survey + k1 + k5,
             "layer_project_first": k2 + prep + fused + finish + k1 + k5,
             "layer_agg_first": agg}
@@ -249,7 +249,8 @@ def run_ours(args):
     ab = algorithmic_bytes(n, e_total, H, D, f_in)
     per_kernel = {}
     for name in ("gatk_attn_fwd", "gatk_attn_bwd_fused", "gatk_attn_bwd_prep", "gatk_attn_bwd_finish",
-                 "gatk_attn_x_fwd", "gatk_attn_x_bwd", "gatk_edge_tsum", "gatk_elu_fwd", "gatk_elu_bwd"):
+                 "gatk_logits_pack", "gatk_attn_x_fwd", "gatk_attn_x_bwd", "gatk_edge_tsum", "gatk_elu_bwd",
+                 "gemm:project", "gemm:dW", "gemm:dxagg", "gemm:dlogits"):
         if name in kern:
             gbs = ab[name] / world / (kern[name]["ms_avg"] * 1e-3) / 1e9
             per_kernel[name] = {"ms": round(kern[name]["ms_avg"], 4), "algorithmic_GB": round(ab[name] / world / 1e9, 3),

@@ -107,7 +107,7 @@ __host__ __device__ __forceinline__ int xfwd_warp_floats(int RS, int HP, int chu
 // backward (tensor-core kernel): row pitch = 16 (mod 32) floats, so the two rows a quarter-warp touches per
 // 128-bit fragment load sit in different bank halves
 __host__ __device__ __forceinline__ int xmma_row_pitch(int Sx) { return (4 * Sx + 15) / 32 * 32 + 16; }
-__host__ __device__ __forceinline__ int xmma_warp_floats(int RS, int H, int Fp) { return 64 * RS + 2 * H * Fp + 4; }
+__host__ __device__ __forceinline__ int xmma_warp_floats(int RS, int H, int Fp, int chunk) { return 2 * chunk * RS + 2 * H * Fp + 4; }
 __host__ __device__ __forceinline__ int xbwd_warp_floats(int RS, int H, int Fp, int chunk) { return chunk * RS + H * Fp + 4; }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
@@ -548,8 +548,9 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
-template <int KPMAX, bool HUB>
+template <int KPMAX, int MT, bool HUB>  // MT: 16-edge MMA tiles per chunk (chunk = 16*MT stored entries)
 __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) {
+  constexpr int CH = 16 * MT;
   extern __shared__ __align__(16) float x_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tg = lane & 3;
@@ -558,11 +559,11 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
   const int h0 = 2 * tg, h1 = 2 * tg + 1;
   // per warp: two row buffers (the next chunk's rows land while this chunk is computed), one staging area for
   // the row state (dxagg_i, xagg_i) of the next destination row, two mbarriers
-  float* rowbuf = x_smem + (size_t)warp * xmma_warp_floats(RS, H, Fp);
-  float* dxs = rowbuf + 64 * RS;
+  float* rowbuf = x_smem + (size_t)warp * xmma_warp_floats(RS, H, Fp, CH);
+  float* dxs = rowbuf + 2 * CH * RS;
   float* xas = dxs + H * Fp;
   const unsigned bar0 = smem_u32(xas + H * Fp);
-  for (int i = lane; i < 64 * RS; i += 32) rowbuf[i] = 0.f;  // stale lanes of the MMA must hold finite numbers
+  for (int i = lane; i < 2 * CH * RS; i += 32) rowbuf[i] = 0.f;  // stale lanes of the MMA must hold finite numbers
   if (lane == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
   const int seg = blockIdx.x * XW + warp;
   if (HUB && seg >= a.n_hub_seg) return;
   ChunkIter<HUB> it;
-  it.init(a, lane, seg, 32);
+  it.init(a, lane, seg, CH);
   const unsigned row_bytes = (unsigned)a.Sx * 16u, st_bytes = (unsigned)(H * Fp) * 4u;
 
   // copies of one chunk: its neighbour rows and, for the first chunk of a destination row, the row state
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
       if (lane < ch.cnt) {
         const float* src = a.xg + (int64_t)jcol * a.ldxg;
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(rowbuf + (buf * 32 + lane) * RS)),
+                         smem_u32(rowbuf + (buf * CH + lane) * RS)),
                      "l"(src), "r"(row_bytes), "r"(bar)
                      : "memory");
       }
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
   while (c.ok) {
     const Chunk nn = it.next(a, lane);
     const int jnn = cols_of(nn);  // column ids two chunks ahead
-    const float* rows = rowbuf + p * 32 * RS;
+    const float* rows = rowbuf + p * CH * RS;
     if (c.cnt > 0) {
       mbar_wait(bar0 + 8 * p, (phases >> p) & 1u);
       phases ^= 1u << p;
@@ -660,12 +661,12 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
     __syncwarp();  // the staging area and the other row buffer are free: start the next chunk's copies
     if (n.ok) issue(n, jn, p ^ 1);
     prefetch_fl(n);
-    const int n_mt = c.cnt > 16 ? 2 : 1;
+    const int n_mt = (MT > 1 && c.cnt > 16) ? 2 : 1;
     // three independent accumulators per 16-edge tile (hi*hi, lo*hi, hi*lo): the MMAs of a k-step do not
     // wait on each other, and the small compensation terms are summed apart from the main product
-    float acc[2][3][4];
+    float acc[MT][3][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int t3 = 0; t3 < 3; ++t3)
 #pragma unroll
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
     for (int kp = 0; kp < KPMAX; ++kp) {
       if (kp < KP) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
           if (mt < n_mt) {
             const float4 ag = *reinterpret_cast<const float4*>(rows + (16 * mt + g) * RS + 16 * kp + 4 * tg);
             const float4 a8 = *reinterpret_cast<const float4*>(rows + (16 * mt + g + 8) * RS + 16 * kp + 4 * tg);
@@ -695,12 +696,12 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
       }
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[mt][0][q] += acc[mt][1][q] + acc[mt][2][q];
     // ---- ds for this lane's (edge, head) pairs: acc[mt][0][0..1] = edge 16mt+g, heads h0,h1; [2..3] = edge 16mt+g+8
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int e = 16 * mt + g + 8 * half;
@@ -959,7 +960,9 @@ static int launch_x(KH hub_kernel, KM main_kernel, const XArgs& a, int chunk, si
 
 template <int HP, int NS>
 static int launch_x_fwd(const XArgs& a, cudaStream_t st) {
-  const int chunk = x_chunk_for(a.RS);
+  static const int chunk_env = getenv("GATK_XFWD_CHUNK") ? atoi(getenv("GATK_XFWD_CHUNK")) : 0;
+  int chunk = x_chunk_for(a.RS);
+  if (chunk_env == 8 || chunk_env == 16) chunk = chunk_env < chunk ? chunk_env : chunk;
   const size_t smem = (size_t)XW * xfwd_warp_floats(a.RS, HP, chunk) * sizeof(float);
   if (int rc = launch_x(attn_x_fwd_kernel<HP, NS, true>, attn_x_fwd_kernel<HP, NS, false>, a, chunk, smem, st)) return rc;
   if (a.n_hub_seg > 0) {  // stream order: the merge only needs the segment kernel, which ran first
@@ -990,10 +993,17 @@ static int launch_x_mma(KH hub_kernel, KM main_kernel, const XArgs& a, size_t sm
 
 static int launch_x_bwd_mma(XArgs a, cudaStream_t st) {
   a.RS = xmma_row_pitch(a.Sx);
-  const size_t smem = (size_t)XW * xmma_warp_floats(a.RS, a.H, a.Fp) * sizeof(float);
+  static const int mt_env = getenv("GATK_XBWD_MT") ? atoi(getenv("GATK_XBWD_MT")) : 1;
+  const int mt = mt_env == 2 ? 2 : 1;
+  const size_t smem = (size_t)XW * xmma_warp_floats(a.RS, a.H, a.Fp, 16 * mt) * sizeof(float);
   int rc;
-  if (a.Fp <= 64) rc = launch_x_mma(attn_x_bwd_mma_kernel<4, true>, attn_x_bwd_mma_kernel<4, false>, a, smem, st);
-  else rc = launch_x_mma(attn_x_bwd_mma_kernel<8, true>, attn_x_bwd_mma_kernel<8, false>, a, smem, st);
+  if (a.Fp <= 64) {
+    rc = mt == 2 ? launch_x_mma(attn_x_bwd_mma_kernel<4, 2, true>, attn_x_bwd_mma_kernel<4, 2, false>, a, smem, st)
+                 : launch_x_mma(attn_x_bwd_mma_kernel<4, 1, true>, attn_x_bwd_mma_kernel<4, 1, false>, a, smem, st);
+  } else {
+    rc = mt == 2 ? launch_x_mma(attn_x_bwd_mma_kernel<8, 2, true>, attn_x_bwd_mma_kernel<8, 2, false>, a, smem, st)
+                 : launch_x_mma(attn_x_bwd_mma_kernel<8, 1, true>, attn_x_bwd_mma_kernel<8, 1, false>, a, smem, st);
+  }
   if (rc) return rc;
   if (a.n_hub_seg > 0) {
     attn_x_bwd_hub_merge_kernel<<<(a.n_hub * a.H + 127) / 128, 128, 0, st>>>(a);

@@ -261,7 +261,8 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         out = torch.empty(n, HD, dtype=torch.float32, device=dev)
         fuse_elu = act_elu and not has_skip
-        _gemm_batched(0, 0, n, Dp, f_in, H, xagg, H * Fp, Fp, w_ext, M_out, Dp, out, HD, Dp, epilogue=int(fuse_elu))
+        _gemm_batched(0, 0, n, Dp, f_in, H, xagg, H * Fp, Fp, w_ext, M_out, Dp, out, HD, Dp, epilogue=int(fuse_elu),
+                      label="gemm:project")
         if has_skip:
             _gemm(0, 0, n, HD, f_in, xg_loc, P, w_ext, M_out, out, HD, accumulate=1, b_off=HD)
             if act_elu:
@@ -292,8 +293,8 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
             dhp = gout
         dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
         dxagg = (torch.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
-        _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp)
-        _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp)
+        _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp, label="gemm:dW")
+        _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp, label="gemm:dxagg")
         if has_skip:
             _gemm(1, 0, f_in, HD, n, xg_loc, P, dhp, HD, dw_ext, M_out, c_off=HD)
         ds = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
@@ -312,7 +313,7 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         with _lib.timed("comm:reduce_dg"):
             dfg[:, H:2 * H] = reduce_rows(dg_part, plan)
         dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
-        _gemm(1, 0, f_in, Muv, n, xg_loc, P, dfg, Muv, dw_uv, Muv)
+        _gemm(1, 0, f_in, Muv, n, xg_loc, P, dfg, Muv, dw_uv, Muv, label="gemm:dlogits")
         if plan.world > 1:
             with _lib.timed("comm:allreduce_dw"):
                 allreduce_([dw_ext, dw_uv], plan)
