@@ -195,18 +195,19 @@ GATK_API int gatk_da_reduce(int64_t n, int H, int Dp, const float* wh, int64_t l
  *          for layers whose input needs no gradient.)
  *  edge_tsum  dg[j,h] = sum_i ds_ijh: segmented sum along the transposed pattern (tptr, perm from
  *          gatk_csr_transpose); sources with more than long_len entries are listed in long_rows.
+ * n_src: rows of xg (sources; col indexes them), n_dst: destination rows of this shard.
  * Hub rows (longer than seg_len) as in gatk_attn_fwd; scratch floats: gatk_attn_x_scratch_floats(which, ...)
  * with which = 0 (x_fwd), 1 (x_bwd).  H <= 8, Fp <= 512, H_pow2 * ceil((Fp/4 + ceil(H/4)) / 32) <= 16. */
 GATK_API int64_t gatk_xg_pitch(int Fp, int H);
 GATK_API int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t ldx, const float* uv, int64_t lduv,
                               float* xg, int64_t ldxg, float* f, int64_t ldf, void* stream);
 GATK_API size_t gatk_attn_x_scratch_floats(int which, int H, int Fp, int n_hub_seg);
-GATK_API int gatk_attn_x_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
+GATK_API int gatk_attn_x_fwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
                              const float* xg, int64_t ldxg, const float* f, int64_t ldf, float alpha,
                              float* xagg, int64_t ldxa, float* lse, int seg_len, const int32_t* hub_rows,
                              const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
                              int32_t* counter, const int32_t* item_ptr, int n_items, void* stream);
-GATK_API int gatk_attn_x_bwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
+GATK_API int gatk_attn_x_bwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
                              const float* xg, int64_t ldxg, const float* f, int64_t ldf, const float* lse, float alpha,
                              const float* xagg, int64_t ldxa, const float* dxagg, int64_t ldd, float* ds, float* df,
                              int64_t lddf, int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,

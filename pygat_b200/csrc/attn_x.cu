@@ -26,6 +26,7 @@
 // and the column ids of the next chunk are fetched one chunk ahead.  Forward: softmax terms with
 // lanes = edges, weighted sum with lanes = float4 slots (packed FFMA2).  Backward: lanes = edges, every
 // lane dots ITS row against dxagg_i broadcast from shared memory -- no cross-lane reduction per edge.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "attn_common.cuh"
@@ -34,7 +35,10 @@ namespace gatk {
 
 constexpr int XW = 2;  // warps per CTA (small CTAs: the staging buffers set how many fit on an SM)
 
-struct XArgs {
+struct alignas(64) XArgs {
+  CUtensorMap xmap;  // the gather rows as a 2-D tensor (box = RS floats x 1 row) for TMA tile::gather4
+  int use_g4;        // rows are staged four per instruction through xmap (row pitch in shared memory = RS)
+  int64_t n_src;
   int64_t n_dst;
   const int64_t* rowptr;
   const int32_t* col;
@@ -97,17 +101,21 @@ __device__ __forceinline__ void butterfly_scatter(float (&v)[NVAL], int lane) {
 }
 
 // ---- per-warp staging in shared memory -------------------------------------------------------------
-__host__ __device__ __forceinline__ int x_row_pitch(int Sx) { return (Sx | 1) * 4; }  // odd number of 16-byte units: lane-per-row reads are conflict free
+// row pitch of the staged rows: a multiple of 8 floats, so that groups of four rows (TMA tile::gather4
+// destinations) start on 128-byte boundaries
+__host__ __device__ __forceinline__ int x_row_pitch(int Sx) { return (4 * Sx + 7) / 8 * 8; }
 __host__ __device__ __forceinline__ int x_chunk_for(int RS) {
   int c = 32;
   while (c > 4 && c * RS * 4 > 14336) c >>= 1;
   return c;
 }
-__host__ __device__ __forceinline__ int xfwd_warp_floats(int RS, int HP, int chunk) { return chunk * RS + 32 * HP + 8 + 4; }
+__host__ __device__ __forceinline__ int xfwd_warp_floats(int RS, int HP, int chunk) { return chunk * RS + 32 * HP + 32; }  // multiples of 128 bytes
 // backward (tensor-core kernel): row pitch = 16 (mod 32) floats, so the two rows a quarter-warp touches per
 // 128-bit fragment load sit in different bank halves
 __host__ __device__ __forceinline__ int xmma_row_pitch(int Sx) { return (4 * Sx + 15) / 32 * 32 + 16; }
-__host__ __device__ __forceinline__ int xmma_warp_floats(int RS, int H, int Fp, int chunk) { return 2 * chunk * RS + 2 * H * Fp + 4; }
+__host__ __device__ __forceinline__ int xmma_warp_floats(int RS, int H, int Fp, int chunk) {
+  return 2 * chunk * RS + (2 * H * Fp + 31) / 32 * 32 + 32;  // every piece a multiple of 128 bytes
+}
 __host__ __device__ __forceinline__ int xbwd_warp_floats(int RS, int H, int Fp, int chunk) { return chunk * RS + H * Fp + 4; }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
@@ -224,8 +232,24 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         : "memory");
   }
 }
+// Four rows per instruction (TMA tile::gather4): lane q stages entries 4q..4q+3; entries past cnt re-read row 0.
+__device__ __forceinline__ void x_gather4(const XArgs& a, float* dst, int r0, int r1, int r2, int r3, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(&a.xmap), "r"(bar), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
 __device__ __forceinline__ void x_issue_rows(const XArgs& a, float* rows, int j, int cnt, int lane, int RS, unsigned bar) {
-  if (cnt > 0) {
+  if (cnt > 0 && a.use_g4) {
+    const int ngrp = (cnt + 3) >> 2;
+    const int r0 = __shfl_sync(FULL, j, (4 * lane) & 31), r1 = __shfl_sync(FULL, j, (4 * lane + 1) & 31);
+    const int r2 = __shfl_sync(FULL, j, (4 * lane + 2) & 31), r3 = __shfl_sync(FULL, j, (4 * lane + 3) & 31);
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(ngrp * 16 * RS)) : "memory");
+    __syncwarp();
+    if (lane < ngrp) x_gather4(a, rows + lane * 4 * RS, r0, r1, r2, r3, bar);
+  } else if (cnt > 0) {
     const unsigned row_bytes = (unsigned)a.Sx * 16u;
     if (lane == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (unsigned)cnt) : "memory");
@@ -245,8 +269,8 @@ __device__ __forceinline__ void x_issue_rows(const XArgs& a, float* rows, int j,
 // Every lane carries the running (max, sum) of head  lane >> (5 - log2 HP).
 // =====================================================================================================
 template <int HP, int NS, bool HUB>
-__global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const XArgs a, const int chunk) {
-  extern __shared__ __align__(16) float x_smem[];
+__global__ void __launch_bounds__(XW * 32) attn_x_fwd_kernel(const __grid_constant__ XArgs a, const int chunk) {
+  extern __shared__ __align__(128) float x_smem[];
   constexpr int SH = 5 - Log2<HP>::v;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int H = a.H;
@@ -419,8 +443,8 @@ __global__ void attn_x_fwd_hub_merge_kernel(const XArgs a) {
 // row against dxagg_i, which all lanes read (broadcast) from shared memory.
 // =====================================================================================================
 template <int HP, bool HUB>
-__global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const XArgs a, const int chunk) {
-  extern __shared__ __align__(16) float x_smem[];
+__global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const __grid_constant__ XArgs a, const int chunk) {
+  extern __shared__ __align__(128) float x_smem[];
   constexpr int SH = 5 - Log2<HP>::v;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int H = a.H, S = a.S, Fp = a.Fp;
@@ -549,9 +573,9 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 }
 
 template <int KPMAX, int MT, bool HUB>  // MT: 16-edge MMA tiles per chunk (chunk = 16*MT stored entries)
-__global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) {
+__global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_constant__ XArgs a) {
   constexpr int CH = 16 * MT;
-  extern __shared__ __align__(16) float x_smem[];
+  extern __shared__ __align__(128) float x_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tg = lane & 3;
   const int H = a.H, Fp = a.Fp, RS = a.RS;
@@ -562,7 +586,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
   float* rowbuf = x_smem + (size_t)warp * xmma_warp_floats(RS, H, Fp, CH);
   float* dxs = rowbuf + 2 * CH * RS;
   float* xas = dxs + H * Fp;
-  const unsigned bar0 = smem_u32(xas + H * Fp);
+  const unsigned bar0 = smem_u32(rowbuf + 2 * CH * RS + (2 * H * Fp + 31) / 32 * 32);
   for (int i = lane; i < 2 * CH * RS; i += 32) rowbuf[i] = 0.f;  // stale lanes of the MMA must hold finite numbers
   if (lane == 0) {
     mbar_init(bar0, 1);
@@ -582,22 +606,35 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const XArgs a) 
   auto issue = [&](const Chunk& ch, int jcol, int buf) {
     if (ch.cnt > 0) {
       const unsigned bar = bar0 + 8 * buf;
-      if (lane == 0)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                     "r"(row_bytes * (unsigned)ch.cnt + (ch.first ? 2 * st_bytes : 0u))
-                     : "memory");
-      __syncwarp();
-      if (lane < ch.cnt) {
-        const float* src = a.xg + (int64_t)jcol * a.ldxg;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(rowbuf + (buf * CH + lane) * RS)),
-                     "l"(src), "r"(row_bytes), "r"(bar)
-                     : "memory");
+      float* rb = rowbuf + buf * CH * RS;
+      const unsigned st_tx = ch.first ? 2 * st_bytes : 0u;
+      if (a.use_g4) {
+        const int ngrp = (ch.cnt + 3) >> 2;
+        const int r0 = __shfl_sync(FULL, jcol, (4 * lane) & 31), r1 = __shfl_sync(FULL, jcol, (4 * lane + 1) & 31);
+        const int r2 = __shfl_sync(FULL, jcol, (4 * lane + 2) & 31), r3 = __shfl_sync(FULL, jcol, (4 * lane + 3) & 31);
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(ngrp * 16 * RS) + st_tx)
+                       : "memory");
+        __syncwarp();
+        if (lane < ngrp) x_gather4(a, rb + lane * 4 * RS, r0, r1, r2, r3, bar);
+      } else {
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                       "r"(row_bytes * (unsigned)ch.cnt + st_tx)
+                       : "memory");
+        __syncwarp();
+        if (lane < ch.cnt) {
+          const float* src = a.xg + (int64_t)jcol * a.ldxg;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_u32(rb + lane * RS)),
+                       "l"(src), "r"(row_bytes), "r"(bar)
+                       : "memory");
+        }
       }
-      if (ch.first && lane < 2) {
-        const float* src = lane == 0 ? a.dxagg + (int64_t)ch.row * a.ldd : a.xagg + (int64_t)ch.row * a.ldxa;
+      if (ch.first && lane >= 30) {  // the row state rides on the same barrier (lanes that issue no row copies)
+        const float* src = lane == 30 ? a.dxagg + (int64_t)ch.row * a.ldd : a.xagg + (int64_t)ch.row * a.ldxa;
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(lane == 0 ? dxs : xas)),
+                         smem_u32(lane == 30 ? dxs : xas)),
                      "l"(src), "r"(st_bytes), "r"(bar)
                      : "memory");
       }
@@ -939,6 +976,37 @@ static int check_x_geom(int H, int Fp, int* hp, int* ns, int* sx) {
     default: { constexpr int HP = 8; CALL; } break;    \
   }
 
+typedef CUresult (*XEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Describe xg [n_src, ldxg] to TMA with a box of RS floats x 1 row (tile::gather4 stacks four such rows, so RS is
+// the row pitch in shared memory; columns past ldxg are zero filled).  Rows wider than 256 floats, or a driver
+// without the entry point, keep the per-row bulk copies.
+static void make_xg_map(XArgs& a) {
+  a.use_g4 = 0;
+  static const bool off = getenv("GATK_NO_GATHER4") != nullptr;
+  if (off || a.RS > 256 || (a.RS & 7) || a.n_src <= 0) return;
+  static XEncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<XEncodeTiledFn>(p);
+  }
+  if (!fn) return;
+  cuuint64_t dims[2] = {(cuuint64_t)a.ldxg, (cuuint64_t)a.n_src};
+  cuuint64_t strides[1] = {(cuuint64_t)a.ldxg * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)a.RS, 1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(&a.xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.xg), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  a.use_g4 = rc == CUDA_SUCCESS ? 1 : 0;
+}
+
 template <typename KH, typename KM>
 static int launch_x(KH hub_kernel, KM main_kernel, const XArgs& a, int chunk, size_t smem, cudaStream_t st) {
   if (a.n_hub_seg > 0) {
@@ -959,7 +1027,8 @@ static int launch_x(KH hub_kernel, KM main_kernel, const XArgs& a, int chunk, si
 }
 
 template <int HP, int NS>
-static int launch_x_fwd(const XArgs& a, cudaStream_t st) {
+static int launch_x_fwd(XArgs a, cudaStream_t st) {
+  make_xg_map(a);
   static const int chunk_env = getenv("GATK_XFWD_CHUNK") ? atoi(getenv("GATK_XFWD_CHUNK")) : 0;
   int chunk = x_chunk_for(a.RS);
   if (chunk_env == 8 || chunk_env == 16) chunk = chunk_env < chunk ? chunk_env : chunk;
@@ -993,6 +1062,7 @@ static int launch_x_mma(KH hub_kernel, KM main_kernel, const XArgs& a, size_t sm
 
 static int launch_x_bwd_mma(XArgs a, cudaStream_t st) {
   a.RS = xmma_row_pitch(a.Sx);
+  make_xg_map(a);
   static const int mt_env = getenv("GATK_XBWD_MT") ? atoi(getenv("GATK_XBWD_MT")) : 1;
   const int mt = mt_env == 2 ? 2 : 1;
   const size_t smem = (size_t)XW * xmma_warp_floats(a.RS, a.H, a.Fp, 16 * mt) * sizeof(float);
@@ -1063,7 +1133,7 @@ extern "C" int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t
   return 0;
 }
 
-static int fill_xargs(XArgs& a, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp, int sx,
+static int fill_xargs(XArgs& a, int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp, int sx,
                       const float* xg, int64_t ldxg, const float* f, int64_t ldf, float alpha, int seg_len,
                       const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
                       int32_t* counter, const int32_t* item_ptr, int n_items) {
@@ -1072,6 +1142,8 @@ static int fill_xargs(XArgs& a, int64_t n_dst, const int64_t* rowptr, const int3
   GATK_REQUIRE(rowptr && col && xg && f && counter, "null pointer argument");
   GATK_REQUIRE(ldxg % 4 == 0 && ldxg >= 4 * sx && ((uintptr_t)xg & 15) == 0 && ldf >= H,
                "xg rows must be 16-byte aligned with pitch >= Fp + 4*ceil(H/4); ldf >= H");
+  GATK_REQUIRE(n_src >= 0 && n_src < (1LL << 31), "n_src out of range");
+  a.use_g4 = 0; a.n_src = n_src;
   a.n_dst = n_dst; a.rowptr = rowptr; a.col = col; a.H = H; a.S = Fp / 4; a.Fp = Fp; a.Sx = sx; a.RS = x_row_pitch(sx);
   a.xg = xg; a.ldxg = ldxg; a.f = f; a.ldf = ldf; a.alpha = alpha;
   a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub; a.n_hub_seg = n_hub_seg;
@@ -1079,7 +1151,7 @@ static int fill_xargs(XArgs& a, int64_t n_dst, const int64_t* rowptr, const int3
   return 0;
 }
 
-extern "C" int gatk_attn_x_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
+extern "C" int gatk_attn_x_fwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
                                const float* xg, int64_t ldxg, const float* f, int64_t ldf, float alpha,
                                float* xagg, int64_t ldxa, float* lse, int seg_len, const int32_t* hub_rows,
                                const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
@@ -1087,7 +1159,7 @@ extern "C" int gatk_attn_x_fwd(int64_t n_dst, const int64_t* rowptr, const int32
   int hp, ns, sx;
   if (int rc = check_x_geom(H, Fp, &hp, &ns, &sx)) return rc;
   XArgs a = {};
-  if (int rc = fill_xargs(a, n_dst, rowptr, col, H, Fp, sx, xg, ldxg, f, ldf, alpha, seg_len, hub_rows, hub_seg_ptr,
+  if (int rc = fill_xargs(a, n_src, n_dst, rowptr, col, H, Fp, sx, xg, ldxg, f, ldf, alpha, seg_len, hub_rows, hub_seg_ptr,
                           n_hub, n_hub_seg, hub_scratch, counter, item_ptr, n_items))
     return rc;
   GATK_REQUIRE(xagg && ldxa % 4 == 0 && ldxa >= (int64_t)H * Fp && ((uintptr_t)xagg & 15) == 0,
@@ -1099,7 +1171,7 @@ extern "C" int gatk_attn_x_fwd(int64_t n_dst, const int64_t* rowptr, const int32
   return 0;
 }
 
-extern "C" int gatk_attn_x_bwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
+extern "C" int gatk_attn_x_bwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
                                const float* xg, int64_t ldxg, const float* f, int64_t ldf, const float* lse, float alpha,
                                const float* xagg, int64_t ldxa, const float* dxagg, int64_t ldd, float* ds, float* df,
                                int64_t lddf, int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
@@ -1108,7 +1180,7 @@ extern "C" int gatk_attn_x_bwd(int64_t n_dst, const int64_t* rowptr, const int32
   int hp, ns, sx;
   if (int rc = check_x_geom(H, Fp, &hp, &ns, &sx)) return rc;
   XArgs a = {};
-  if (int rc = fill_xargs(a, n_dst, rowptr, col, H, Fp, sx, xg, ldxg, f, ldf, alpha, seg_len, hub_rows, hub_seg_ptr,
+  if (int rc = fill_xargs(a, n_src, n_dst, rowptr, col, H, Fp, sx, xg, ldxg, f, ldf, alpha, seg_len, hub_rows, hub_seg_ptr,
                           n_hub, n_hub_seg, hub_scratch, counter, item_ptr, n_items))
     return rc;
   GATK_REQUIRE(lse && xagg && dxagg && ds && df, "null pointer argument");

@@ -367,7 +367,7 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
         hubs = graph.hubs
         scratch = _x_scratch(0, H, Fp, hubs.n_seg, dev)
-        _lib.call("gatk_attn_x_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
+        _lib.call("gatk_attn_x_fwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
                   f.data_ptr(), H, float(alpha), xagg.data_ptr(), H * Fp, _ptr(lse),
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         out = torch.empty(n, HD, dtype=torch.float32, device=dev)
@@ -412,7 +412,7 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         dfg = (torch.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
         hubs = graph.hubs
         scratch = _x_scratch(1, H, Fp, hubs.n_seg, dev)
-        _lib.call("gatk_attn_x_bwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
+        _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
                   f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
                   dxagg.data_ptr(), H * Fp, ds.data_ptr(), dfg.data_ptr(), Muv,
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
