@@ -191,10 +191,12 @@ GATK_API int gatk_da_reduce(int64_t n, int H, int Dp, const float* wh, int64_t l
  *          out_h = xagg_h W_h (+ x S_h) through gatk_gemm and applies gatk_elu_fwd.
  *  x_bwd   per destination row, given dxagg_ih = dh'_ih W_h^T (gatk_gemm):  c_ih = dxagg_ih . xagg_ih,
  *          ds_ijh = alpha_ijh (dxagg_ih . x_j - c_ih) LeakyReLU'(f_ih + g_jh)  ->  ds [E, H] in CSR edge order,
- *          df[i,h] = sum_j ds_ijh.  (dW_h = xagg_h^T dh'_h is a gatk_gemm; dx is not produced: the form is
- *          for layers whose input needs no gradient.)
+ *          df[i,h] = sum_j ds_ijh.  With iperm (int32 [E], CSR entry -> position in the transposed pattern, the
+ *          inverse of gatk_csr_transpose's perm) ds is written in TRANSPOSED order, so that edge_tsum streams
+ *          it (perm = NULL there) instead of gathering 32-byte pieces.  (dW_h = xagg_h^T dh'_h is a gatk_gemm;
+ *          dx is not produced: the form is for layers whose input needs no gradient.)
  *  edge_tsum  dg[j,h] = sum_i ds_ijh: segmented sum along the transposed pattern (tptr, perm from
- *          gatk_csr_transpose); sources with more than long_len entries are listed in long_rows.
+ *          gatk_csr_transpose; perm = NULL when ds is already in transposed order); sources with more than long_len entries are listed in long_rows.
  * n_src: rows of xg (sources; col indexes them), n_dst: destination rows of this shard.
  * Hub rows (longer than seg_len) as in gatk_attn_fwd; scratch floats: gatk_attn_x_scratch_floats(which, ...)
  * with which = 0 (x_fwd), 1 (x_bwd).  H <= 8, Fp <= 512, H_pow2 * ceil((Fp/4 + ceil(H/4)) / 32) <= 16. */
@@ -209,8 +211,8 @@ GATK_API int gatk_attn_x_fwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr
                              int32_t* counter, const int32_t* item_ptr, int n_items, void* stream);
 GATK_API int gatk_attn_x_bwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
                              const float* xg, int64_t ldxg, const float* f, int64_t ldf, const float* lse, float alpha,
-                             const float* xagg, int64_t ldxa, const float* dxagg, int64_t ldd, float* ds, float* df,
-                             int64_t lddf, int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
+                             const float* xagg, int64_t ldxa, const float* dxagg, int64_t ldd, float* ds,
+                             const int32_t* iperm, float* df, int64_t lddf, int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                              int n_hub_seg, float* hub_scratch, int32_t* counter, const int32_t* item_ptr,
                              int n_items, void* stream);
 GATK_API int gatk_edge_tsum(int64_t n_src, const int64_t* tptr, const int32_t* perm, int H, const float* ds,

@@ -56,7 +56,7 @@ PROTOTYPES = {
     "gatk_attn_x_fwd": (c_int, [c_int64, c_int64, P, P, c_int, c_int, P, c_int64, P, c_int64, c_float, P, c_int64, P,
                                 c_int, P, P, c_int, c_int, P, P, P, c_int, P]),
     "gatk_attn_x_bwd": (c_int, [c_int64, c_int64, P, P, c_int, c_int, P, c_int64, P, c_int64, P, c_float, P, c_int64, P,
-                                c_int64, P, P, c_int64, c_int, P, P, c_int, c_int, P, P, P, c_int, P]),
+                                c_int64, P, P, P, c_int64, c_int, P, P, c_int, c_int, P, P, P, c_int, P]),
     "gatk_edge_tsum": (c_int, [c_int64, P, P, c_int, P, P, c_int64, c_int, P, c_int, P]),
     "gatk_elu_fwd": (c_int, [c_int64, c_int64, P, c_int64, P]),
     "gatk_elu_bwd": (c_int, [c_int64, c_int64, P, c_int64, P, c_int64, P, c_int64, P]),

@@ -54,6 +54,7 @@ struct alignas(64) XArgs {
   const float* dxagg;
   int64_t ldd;
   float* ds;
+  const int32_t* iperm;  // CSR entry -> position in the transposed pattern (NULL: ds stays in CSR order)
   float* df;
   int64_t lddf;
   int seg_len;
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const __grid_consta
       dsv[h] = (valid && h < H) ? v : 0.f;
     }
     if (valid) {
-      float* dp = a.ds + (c.base + lane) * H;
+      float* dp = a.ds + (a.iperm ? (int64_t)__ldg(a.iperm + c.base + lane) : c.base + lane) * H;
       if (HP >= 4 && H == HP) {
 #pragma unroll
         for (int h = 0; h < HP; h += 4) stg4(dp + h, make_float4(dsv[h], dsv[h + 1], dsv[h + 2], dsv[h + 3]));
@@ -645,6 +646,14 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
   uint32_t bhi[KPMAX][4], blo[KPMAX][4];
   float f0 = 0.f, f1 = 0.f, l0 = 0.f, l1 = 0.f, c0 = 0.f, c1 = 0.f, df0 = 0.f, df1 = 0.f;
   float nf0 = 0.f, nf1 = 0.f, nl0 = 0.f, nl1 = 0.f;  // f, lse of the NEXT destination row (prefetched)
+  int64_t ipos[2 * MT], npos[2 * MT];              // where this lane's ds entries go (this chunk / the next one)
+  auto prefetch_pos = [&](const Chunk& ch) {
+#pragma unroll
+    for (int q = 0; q < 2 * MT; ++q) {
+      const int e = 16 * (q >> 1) + g + 8 * (q & 1);
+      npos[q] = (ch.ok && e < ch.cnt) ? (a.iperm ? (int64_t)__ldg(a.iperm + ch.base + e) : ch.base + e) : 0;
+    }
+  };
   auto prefetch_fl = [&](const Chunk& ch) {
     if (ch.ok && ch.first) {
       nf0 = h0 < H ? __ldg(a.f + (int64_t)ch.row * a.ldf + h0) : 0.f;
@@ -658,6 +667,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
     const int jc = cols_of(c);
     if (c.ok) issue(c, jc, 0);
     prefetch_fl(c);
+    prefetch_pos(c);
   }
   Chunk n = it.next(a, lane);
   int jn = cols_of(n);
@@ -670,6 +680,8 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
       mbar_wait(bar0 + 8 * p, (phases >> p) & 1u);
       phases ^= 1u << p;
     }
+#pragma unroll
+    for (int q = 0; q < 2 * MT; ++q) ipos[q] = npos[q];
     if (c.first) {
       f0 = nf0; f1 = nf1; l0 = nl0; l1 = nl1;
       df0 = df1 = 0.f;
@@ -698,6 +710,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
     __syncwarp();  // the staging area and the other row buffer are free: start the next chunk's copies
     if (n.ok) issue(n, jn, p ^ 1);
     prefetch_fl(n);
+    prefetch_pos(n);
     const int n_mt = (MT > 1 && c.cnt > 16) ? 2 : 1;
     // three independent accumulators per 16-edge tile (hi*hi, lo*hi, hi*lo): the MMAs of a k-step do not
     // wait on each other, and the small compensation terms are summed apart from the main product
@@ -748,7 +761,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
           const float s0 = z0 > 0.f ? z0 : a.alpha * z0, s1 = z1 > 0.f ? z1 : a.alpha * z1;
           const float v0 = expf(s0 - l0) * (acc[mt][0][2 * half] - c0) * (z0 > 0.f ? 1.f : a.alpha);
           const float v1 = expf(s1 - l1) * (acc[mt][0][2 * half + 1] - c1) * (z1 > 0.f ? 1.f : a.alpha);
-          float* dp = a.ds + (c.base + e) * H + h0;
+          float* dp = a.ds + ipos[2 * mt + half] * H + h0;
           if (h1 < H && (H & 1) == 0) {
             *reinterpret_cast<float2*>(dp) = make_float2(v0, v1);
             df0 += v0;
@@ -811,12 +824,13 @@ __global__ void __launch_bounds__(256) edge_tsum_kernel(int64_t n_src, const int
     if (my_h < H) {
       int64_t t = beg + my_e;
       for (; t + 3 * EPG < end; t += 4 * EPG) {
-        const int e0 = __ldg(perm + t), e1 = __ldg(perm + t + EPG), e2 = __ldg(perm + t + 2 * EPG), e3 = __ldg(perm + t + 3 * EPG);
-        const float v0 = __ldg(ds + (int64_t)e0 * H + my_h), v1 = __ldg(ds + (int64_t)e1 * H + my_h);
-        const float v2 = __ldg(ds + (int64_t)e2 * H + my_h), v3 = __ldg(ds + (int64_t)e3 * H + my_h);
+        const int64_t e0 = perm ? __ldg(perm + t) : t, e1 = perm ? __ldg(perm + t + EPG) : t + EPG;
+        const int64_t e2 = perm ? __ldg(perm + t + 2 * EPG) : t + 2 * EPG, e3 = perm ? __ldg(perm + t + 3 * EPG) : t + 3 * EPG;
+        const float v0 = __ldg(ds + e0 * H + my_h), v1 = __ldg(ds + e1 * H + my_h);
+        const float v2 = __ldg(ds + e2 * H + my_h), v3 = __ldg(ds + e3 * H + my_h);
         acc += (v0 + v1) + (v2 + v3);
       }
-      for (; t < end; t += EPG) acc += __ldg(ds + (int64_t)__ldg(perm + t) * H + my_h);
+      for (; t < end; t += EPG) acc += __ldg(ds + (perm ? (int64_t)__ldg(perm + t) : t) * H + my_h);
     }
 #pragma unroll
     for (int o = HP; o < 32; o <<= 1) acc += __shfl_xor_sync(FULL, acc, o);
@@ -833,7 +847,7 @@ __global__ void __launch_bounds__(256) edge_tsum_long_kernel(const int32_t* __re
   const int64_t beg = tptr[j], end = tptr[j + 1];
   for (int h = 0; h < H; ++h) {
     float acc = 0.f;
-    for (int64_t t = beg + threadIdx.x; t < end; t += 256) acc += __ldg(ds + (int64_t)__ldg(perm + t) * H + h);
+    for (int64_t t = beg + threadIdx.x; t < end; t += 256) acc += __ldg(ds + (perm ? (int64_t)__ldg(perm + t) : t) * H + h);
     red[threadIdx.x] = acc;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -1173,8 +1187,8 @@ extern "C" int gatk_attn_x_fwd(int64_t n_src, int64_t n_dst, const int64_t* rowp
 
 extern "C" int gatk_attn_x_bwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
                                const float* xg, int64_t ldxg, const float* f, int64_t ldf, const float* lse, float alpha,
-                               const float* xagg, int64_t ldxa, const float* dxagg, int64_t ldd, float* ds, float* df,
-                               int64_t lddf, int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
+                               const float* xagg, int64_t ldxa, const float* dxagg, int64_t ldd, float* ds,
+                               const int32_t* iperm, float* df, int64_t lddf, int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                                int n_hub_seg, float* hub_scratch, int32_t* counter, const int32_t* item_ptr,
                                int n_items, void* stream) {
   int hp, ns, sx;
@@ -1188,7 +1202,7 @@ extern "C" int gatk_attn_x_bwd(int64_t n_src, int64_t n_dst, const int64_t* rowp
                    ((uintptr_t)xagg & 15) == 0 && ((uintptr_t)dxagg & 15) == 0 && ((uintptr_t)ds & 15) == 0,
                "xagg / dxagg: 16-byte aligned, pitch >= H*Fp (multiple of 4 floats); ds 16-byte aligned; lddf >= H");
   a.xagg = const_cast<float*>(xagg); a.ldxa = ldxa; a.lse = const_cast<float*>(lse);
-  a.dxagg = dxagg; a.ldd = ldd; a.ds = ds; a.df = df; a.lddf = lddf;
+  a.dxagg = dxagg; a.ldd = ldd; a.ds = ds; a.iperm = iperm; a.df = df; a.lddf = lddf;
   cudaStream_t st = (cudaStream_t)stream;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
   static const bool simt_only = getenv("GATK_XBWD_SIMT") != nullptr;

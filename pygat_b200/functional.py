@@ -414,7 +414,7 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         scratch = _x_scratch(1, H, Fp, hubs.n_seg, dev)
         _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
                   f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
-                  dxagg.data_ptr(), H * Fp, ds.data_ptr(), dfg.data_ptr(), Muv,
+                  dxagg.data_ptr(), H * Fp, ds.data_ptr(), None, dfg.data_ptr(), Muv,
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         tptr, _trow, perm, thubs = graph.transpose()[:4]
         _lib.call("gatk_edge_tsum", graph.n_src, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(),

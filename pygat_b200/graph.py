@@ -90,6 +90,7 @@ class Graph:
         self.hubs = HubPartition(self.rowptr, self.seg_len)
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._t: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, HubPartition]] = None
+        self._iperm: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ constructors
     @staticmethod
@@ -144,6 +145,15 @@ class Graph:
             del ws
             self._t = (tptr, trow, perm, HubPartition(tptr, self.seg_len))
         return self._t
+
+    def inverse_perm(self) -> torch.Tensor:
+        """int32 [E]: CSR entry -> its position in the transposed pattern (inverse of transpose()[2])."""
+        if self._iperm is None:
+            perm = self.transpose()[2]
+            ip = torch.empty_like(perm)
+            ip[perm.long()] = torch.arange(self.nnz, dtype=torch.int32, device=self.device)
+            self._iperm = ip
+        return self._iperm
 
     def edge_index(self) -> torch.Tensor:
         """(2, E) int64 in adj.nonzero().t() order (layers.py:129)."""

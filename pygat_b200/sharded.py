@@ -303,7 +303,7 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         scratch = _x_scratch(1, H, Fp, hubs.n_seg, dev)
         _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg_full.data_ptr(), P,
                   f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
-                  dxagg.data_ptr(), H * Fp, ds.data_ptr(), dfg.data_ptr(), Muv,
+                  dxagg.data_ptr(), H * Fp, ds.data_ptr(), None, dfg.data_ptr(), Muv,
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         # dg: partial sums for EVERY source from this rank's stored entries, reduced to the rows' owners
         tptr, _trow, perm, thubs = graph.transpose()[:4]
