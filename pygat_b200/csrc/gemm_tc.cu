@@ -16,6 +16,7 @@
 //   warps 4-7   splitter: A tile -> (Ahi in place, Alo) in smem, generic->async proxy fence
 //   warps 8-11  epilogue: tcgen05.ld -> swizzled smem staging -> TMA store (clips M/N tails)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -665,6 +666,40 @@ __device__ __forceinline__ void umma_tf32_i(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand read from tensor memory (lane = row of the tile, one fp32 column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// 32 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // F.elu computes exp(x) - 1 (not expm1); the fast exponential is accurate to ~2 ulp of exp, i.e. ~1e-7 absolute here
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
@@ -680,6 +715,8 @@ struct RingN {
   }
 };
 
+constexpr int BT_THREADS = 512;  // warps 0-2 producer / MMA / TMEM, 4-7 splitter, 8-15 two epilogue warpgroups
+
 template <int BN>
 struct Cfg {
   static constexpr int TILE_A = BLOCK_M * BLOCK_K * 4;  // 16 KiB
@@ -692,30 +729,81 @@ struct Cfg {
   static constexpr int TMEM = 4 * BN;  // 2 stages x (main, correction)
   static constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
   static constexpr uint32_t IDESC_MN = IDESC_K | (1u << 15) | (1u << 16);
+  static constexpr uint32_t IDESC_MN2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24) | (1u << 15) | (1u << 16);
 };
 
 // ---- NN / NT, K <= 512: C_b = A_b op(B_b), optional ELU epilogue (F.elu, layers.py:51,170)
+//
+// ncu on the first version (A split into hi / lo copies in shared memory, both read back by every MMA) showed
+// the kernel bound by shared-memory bandwidth, not HBM: per 32-wide k-block the SM moved 168 KiB through
+// shared memory (TMA fill 32, splitter 16 read + 32 written, 12 MMAs x (4 KiB A + 2 KiB B), store staging 16)
+// = 1344 cycles at 128 B/cycle against the 1356 measured.  Here the A operand goes to TENSOR MEMORY instead:
+// splitter thread r reads row r of the raw tile once, splits it in registers and writes hi / lo into lane r
+// of TMEM (tcgen05.st); the MMAs read A from TMEM and only the weights from shared memory (~70 KiB per
+// k-block), which puts the kernel back under the HBM roof.
+//
+// TMEM (512 columns): accumulators first, then NST x 64 columns of A (32 hi + 32 lo per stage).
+//   BN = 64 : 2 accumulator stages x (hi*hi | compensation) x 64               = 256 columns
+//   BN = 128: 2 accumulator stages x 128, all three products in ONE accumulator = 256 columns (the separate
+//             compensation accumulator only matters for long reductions; this variant takes K <= 128)
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+struct CfgTA {
+  static constexpr int TILE_A = BLOCK_M * BLOCK_K * 4;  // 16 KiB, raw fp32
+  static constexpr int TILE_B = BN * BLOCK_K * 4;
+  // Three rings.  The raw A tiles are the only HBM stream and a slot is free again as soon as the splitter
+  // has read it, so that ring is deep (bytes in flight per SM = NSA x 16 KiB: with 4 the kernel sat at
+  // 4.6 TB/s, latency bound); the weights come from L2 and their slots are held until the MMAs retire.
+  static constexpr int NSA = BN == 64 ? 8 : 6;   // raw A tiles in shared memory
+  static constexpr int NSB = BN == 64 ? 3 : 2;   // (Bhi, Blo) pairs in shared memory
+  static constexpr int NTA = 4;                  // (Ahi, Alo) in tensor memory
+  // store staging: BN = 64: one swizzled 128 x 32 chunk per epilogue warpgroup; BN = 128: ONE dense 128 x box_n tile
+  static constexpr int CS_BYTES = BN == 64 ? 2 * CSTAGE_BYTES : BLOCK_M * BN * 4;
+  static constexpr bool MERGED = BN == 128;
+  static constexpr int ACC_COLS = MERGED ? BN : 2 * BN;  // per accumulator stage
+  static constexpr int TMEM_A = 2 * ACC_COLS;            // first A column
+  static constexpr int TMEM = 512;
+  static constexpr int OFF_B = NSA * TILE_A;
+  static constexpr int OFF_C = OFF_B + NSB * 2 * TILE_B;
+  static constexpr int OFF_BAR = OFF_C + CS_BYTES;
+  static constexpr int NBAR = 2 * NSA + 2 * NSB + 2 * NTA + 4;
+  static constexpr int SMEM = OFF_BAR + 8 * NBAR + 16 + 1024;
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  static constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  static_assert(TMEM_A + NTA * 2 * BLOCK_K <= TMEM, "tensor memory budget");
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(BT_THREADS, 1)
 gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                            const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c,
-                           int m_tiles, int n_tiles, int batches, int k_blocks, int npad, int epilogue) {
-  using C = Cfg<BN>;
+                           int m_tiles, int n_tiles, int batches, int k_blocks, int npad, int epilogue, int contiguous, int box_n) {
+  using C = CfgTA<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* cstage = smem + C::NST * C::STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cstage + 2 * CSTAGE_BYTES);
+  uint8_t* cstage = smem + C::OFF_C;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   const uint32_t bar0 = smem_u32(bars);
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto split_bar = [&](int s) { return bar0 + 8u * (C::NST + s); };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * C::NST + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * C::NST + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * C::NST + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::NST + 4);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };                                   // TMA -> splitter
+  auto a_empty = [&](int s) { return bar0 + 8u * (C::NSA + s); };                       // splitter -> TMA
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * C::NSA + s); };                    // TMA -> MMA
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * C::NSA + C::NSB + s); };          // MMA retired -> TMA
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * C::NSA + 2 * C::NSB + s); };       // splitter -> MMA
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * C::NSA + 2 * C::NSB + C::NTA + s); };  // MMA retired -> splitter
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * C::NSA + 2 * C::NSB + 2 * C::NTA + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * C::NSA + 2 * C::NSB + 2 * C::NTA + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches stay uniform
+  const int lane = threadIdx.x & 31;
   const int per_m = n_tiles * batches;
   const int total_tiles = m_tiles * per_m;
+  // tile order: strided (tile = blockIdx.x + i gridDim.x: the heads of a row block run on neighbouring SMs at the
+  // same time) or contiguous (one CTA walks the heads of its row blocks one after the other)
+  const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_begin = contiguous ? blockIdx.x * per_cta : blockIdx.x;
+  const int tile_end = contiguous ? min(total_tiles, tile_begin + per_cta) : total_tiles;
+  const int tile_step = contiguous ? 1 : gridDim.x;
   auto decode = [&](int tile, int& m0, int& n0, int& b) {
     const int mt = tile / per_m, r = tile - mt * per_m;
     b = r / n_tiles;
@@ -724,14 +812,21 @@ gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::NST; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(split_bar(s), 4);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < C::NSA; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 4);
+    }
+    for (int s = 0; s < C::NSB; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < C::NTA; ++s) {
+      mbar_init(t_full(s), 4);
+      mbar_init(t_empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -746,124 +841,216 @@ gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) {
-    if (lane == 0) {
-      RingN<C::NST> r;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // ---- A producer: the HBM stream
+    if (elect_one()) {
+      RingN<C::NSA> r;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         int m0, n0, b;
         decode(tile, m0, n0, b);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(r.stage), r.phase ^ 1);
-          const uint32_t st = smem_base + r.stage * C::STAGE;
-          mbar_expect_tx(full_bar(r.stage), C::TILE_A + 2 * C::TILE_B);
-          tma_load_3d(st, &map_a, full_bar(r.stage), kb * BLOCK_K, m0, b);
-          tma_load_2d(st + 2 * C::TILE_A, &map_bhi, full_bar(r.stage), kb * BLOCK_K, b * npad + n0);
-          tma_load_2d(st + 2 * C::TILE_A + C::TILE_B, &map_blo, full_bar(r.stage), kb * BLOCK_K, b * npad + n0);
+          mbar_wait(a_empty(r.stage), r.phase ^ 1);
+          mbar_expect_tx(a_full(r.stage), C::TILE_A);
+          tma_load_3d(smem_base + r.stage * C::TILE_A, &map_a, a_full(r.stage), kb * BLOCK_K, m0, b);
+          r.advance();
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ---- B producer: pre-split K-major weights, L2 resident
+    if (elect_one()) {
+      RingN<C::NSB> r;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        int m0, n0, b;
+        decode(tile, m0, n0, b);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(b_empty(r.stage), r.phase ^ 1);
+          const uint32_t st = smem_base + C::OFF_B + r.stage * 2 * C::TILE_B;
+          mbar_expect_tx(b_full(r.stage), 2 * C::TILE_B);
+          tma_load_2d(st, &map_bhi, b_full(r.stage), kb * BLOCK_K, b * npad + n0);
+          tma_load_2d(st + C::TILE_B, &map_blo, b_full(r.stage), kb * BLOCK_K, b * npad + n0);
           r.advance();
         }
       }
     }
   } else if (warp == 1) {
-    RingN<C::NST> r;
+    // ---- MMA issuer
+    RingN<C::NSB> rb;
+    RingN<C::NTA> rt;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * 2 * BN;
-      const uint32_t tmem_c = tmem_d + BN;
+      const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;
+      const uint32_t tmem_c = C::MERGED ? tmem_d : tmem_d + BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(full_bar(r.stage), r.phase);
-        mbar_wait(split_bar(r.stage), r.phase);
+        mbar_wait(b_full(rb.stage), rb.phase);  // the weights of this k-block have landed
+        mbar_wait(t_full(rt.stage), rt.phase);  // hi / lo of A are in tensor memory
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t st = smem_base + r.stage * C::STAGE;
-          const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + C::TILE_A);
-          const uint64_t b_hi = umma_desc(st + 2 * C::TILE_A), b_lo = umma_desc(st + 2 * C::TILE_A + C::TILE_B);
+        if (elect_one()) {
+          const uint32_t st = smem_base + C::OFF_B + rb.stage * 2 * C::TILE_B;
+          const uint32_t a_hi = tmem_base + C::TMEM_A + rt.stage * 2 * BLOCK_K, a_lo = a_hi + BLOCK_K;
+          const uint64_t b_hi = umma_desc(st), b_lo = umma_desc(st + C::TILE_B);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            umma_tf32_i(tmem_c, a_lo + adv, b_hi + adv, C::IDESC_K, (kb | k) != 0);
-            umma_tf32_i(tmem_c, a_hi + adv, b_lo + adv, C::IDESC_K, 1);
-            umma_tf32_i(tmem_d, a_hi + adv, b_hi + adv, C::IDESC_K, (kb | k) != 0);
+            if (C::MERGED) {
+              // small products first: they meet a small accumulator
+              umma_tf32_ta(tmem_d, a_lo + k * 8, b_hi + adv, C::IDESC, (kb | k) != 0);
+              umma_tf32_ta(tmem_d, a_hi + k * 8, b_lo + adv, C::IDESC, 1);
+              umma_tf32_ta(tmem_d, a_hi + k * 8, b_hi + adv, C::IDESC, 1);
+            } else {
+              // Bhi and Blo tiles are adjacent in shared memory = one 2 BN-row operand: a single MMA forms
+              // [Ahi Bhi | Ahi Blo] into the adjacent (main | compensation) accumulator columns
+              umma_tf32_ta(tmem_d, a_hi + k * 8, b_hi + adv, C::IDESC2, (kb | k) != 0);
+              umma_tf32_ta(tmem_c, a_lo + k * 8, b_hi + adv, C::IDESC, 1);
+            }
           }
-          umma_commit(empty_bar(r.stage));
+          umma_commit(t_empty(rt.stage));
+          umma_commit(b_empty(rb.stage));
           if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
-        r.advance();
+        rb.advance();
+        rt.advance();
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    RingN<C::NST> r;
-    const int t = threadIdx.x - 128;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // ---- splitter: thread `row` owns row `row` of the tile = TMEM lane `row` (warp w may touch lanes 32 (w % 4) ...)
+    RingN<C::NSA> ra;
+    RingN<C::NTA> rt;
+    const int row = threadIdx.x - 128;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::TMEM_A;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(full_bar(r.stage), r.phase);
-        float4* hi = reinterpret_cast<float4*>(smem + r.stage * C::STAGE);
-        float4* lo = reinterpret_cast<float4*>(smem + r.stage * C::STAGE + C::TILE_A);
+        mbar_wait(a_full(ra.stage), ra.phase);
+        const uint8_t* src = smem + ra.stage * C::TILE_A + row * 128;
+        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < C::TILE_A / 16 / 128; ++i) {
-          const int idx = t + i * 128;
-          float4 v = hi[idx];
-          float4 h;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          hi[idx] = h;
-          lo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        for (int j = 0; j < 8; ++j)  // 16-byte chunk j of the 128-byte row is stored at j ^ (row & 7)
+          v[j] = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t h = __float_as_uint(x[q]) & 0xffffe000u;
+            hi[4 * j + q] = h;
+            lo[4 * j + q] = __float_as_uint(x[q] - __uint_as_float(h));
+          }
         }
-        fence_proxy_async();
+        __syncwarp();  // every lane's loads have returned (their values were consumed above)
+        if (lane == 0) mbar_arrive(a_empty(ra.stage));
+        mbar_wait(t_empty(rt.stage), rt.phase ^ 1);  // the MMAs that read this TMEM slot have retired
+        tc_fence_after();
+        const uint32_t ta = lane_base + rt.stage * 2 * BLOCK_K;
+        tmem_st32(ta, hi);
+        tmem_st32(ta + BLOCK_K, lo);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(split_bar(r.stage));
-        r.advance();
+        if (lane == 0) mbar_arrive(t_full(rt.stage));
+        ra.advance();
+        rt.advance();
       }
     }
   } else if (warp >= 8) {
-    const int ew = warp - 8;
-    const int row = ew * 32 + lane;
-    const bool issuer = threadIdx.x == 256;
-    int it = 0, chunk_id = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      int m0, n0, b;
-      decode(tile, m0, n0, b);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
+    if constexpr (BN == 128) {
+      // ---- epilogue, wide tile: both warpgroups fill ONE dense [128][box_n] staging tile and a single TMA store
+      // writes box_n contiguous floats per row.  (Storing 32-column chunks left 8 partially written sectors per
+      // row and head when a head's column block is not sector aligned (100 floats): ncu showed +2.4 GB of DRAM
+      // read-fill and the store-bound kernel at 3.7 TB/s.)
+      const int ew = warp & 3, grp = (warp - 8) >> 2;
+      const int row = ew * 32 + lane;
+      const bool issuer = threadIdx.x == 256;
+      uint8_t* dst_row = cstage + (size_t)row * box_n * 4;
+      int it = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+        int m0, n0, b;
+        decode(tile, m0, n0, b);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        if (issuer) tma_store_wait_read<0>();  // the previous tile's store has drained the staging tile
+        named_bar_sync(1, 256);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c, ++chunk_id) {
-        uint32_t v[32], w[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 2 * BN + c * 32;
-        tmem_ld32(taddr, v);
-        tmem_ld32(taddr + BN, w);
+        for (int c = grp; c < BN / 32; c += 2) {
+          if (c * 32 >= box_n) break;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * C::ACC_COLS + c * 32, v);
+          if (epilogue == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) + __uint_as_float(w[j]);
-          if (epilogue == 1) x = elu_f(x);
-          v[j] = __float_as_uint(x);
-        }
-        uint8_t* buf = cstage + (chunk_id & 1) * CSTAGE_BYTES;
-        if (issuer) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(elu_f(__uint_as_float(v[j])));
+          }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          *reinterpret_cast<uint4*>(buf + row * 128 + ((j ^ (row & 7)) << 4)) = q;
+          for (int j = 0; j < 8; ++j)
+            if (c * 32 + 4 * j < box_n)
+              *reinterpret_cast<uint4*>(dst_row + (c * 32 + 4 * j) * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
         fence_proxy_async();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (issuer) {
-          tma_store_3d(&map_c, smem_u32(buf), n0 + c * 32, m0, b);
+          tma_store_3d(&map_c, smem_u32(cstage), n0, m0, b);
           tma_store_commit();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
+      // ---- two epilogue warpgroups (warps 8-11, 12-15) take alternate 32-column chunks of every tile
+      const int ew = warp & 3;            // the TMEM lane quarter this warp may read
+      const int grp = (warp - 8) >> 2;
+      const int row = ew * 32 + lane;     // row inside the tile
+      const bool issuer = (threadIdx.x & 127) == 0;
+      uint8_t* buf = cstage + grp * CSTAGE_BYTES;
+      int it = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+        int m0, n0, b;
+        decode(tile, m0, n0, b);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+  #pragma unroll 1
+        for (int c = grp; c < BN / 32; c += 2) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * C::ACC_COLS + c * 32;
+          tmem_ld32(taddr, v);
+          if (!C::MERGED) {
+            uint32_t w[32];
+            tmem_ld32(taddr + BN, w);
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+          }
+          if (epilogue == 1) {
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(elu_f(__uint_as_float(v[j])));
+          }
+          if (issuer) tma_store_wait_read<0>();  // this group's previous store has drained its staging buffer
+          named_bar_sync(1 + grp, 128);
+  #pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<uint4*>(buf + row * 128 + ((j ^ (row & 7)) << 4)) = q;
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + grp, 128);
+          if (issuer) {
+            tma_store_3d(&map_c, smem_u32(buf), n0 + c * 32, m0, b);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -894,7 +1081,8 @@ gemm_tn_batched_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * C::NST + 2 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::NST + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches stay uniform
+  const int lane = threadIdx.x & 31;
   const int tiles = m_tiles * n_tiles;
   const int items = batches * tiles * splits;
 
@@ -933,7 +1121,7 @@ gemm_tn_batched_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       RingN<C::NST> r;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         int b, m0, n0, kb0, kb1, sp;
@@ -969,17 +1157,18 @@ gemm_tn_batched_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         mbar_wait(full_bar(r.stage), r.phase);
         mbar_wait(split_bar(r.stage), r.phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t st = smem_base + r.stage * C::STAGE;
           const uint32_t fresh = (rel % PROMOTE) == 0 ? 0u : 1u;
           const uint64_t a_hi = tn::umma_desc_mn(st), a_lo = tn::umma_desc_mn(st + C::TILE_A);
-          const uint64_t b_hi = tn::umma_desc_mn(st + 2 * C::TILE_A), b_lo = tn::umma_desc_mn(st + 2 * C::TILE_A + C::TILE_B);
+          const uint64_t b_hi = tn::umma_desc_mn(st + 2 * C::TILE_A);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 1024 >> 4);
-            umma_tf32_i(tmem_c, a_lo + adv, b_hi + adv, C::IDESC_MN, fresh | (uint32_t)(k != 0));
-            umma_tf32_i(tmem_c, a_hi + adv, b_lo + adv, C::IDESC_MN, 1);
-            umma_tf32_i(tmem_d, a_hi + adv, b_hi + adv, C::IDESC_MN, fresh | (uint32_t)(k != 0));
+            // the Bhi and Blo boxes are adjacent in shared memory = one 2 BN-wide operand: a single MMA forms
+            // [Ahi Bhi | Ahi Blo] into the adjacent (main | compensation) accumulator columns
+            umma_tf32_i(tmem_d, a_hi + adv, b_hi + adv, C::IDESC_MN2, fresh | (uint32_t)(k != 0));
+            umma_tf32_i(tmem_c, a_lo + adv, b_hi + adv, C::IDESC_MN, 1);
           }
           umma_commit(empty_bar(r.stage));
           if ((rel + 1) % PROMOTE == 0 || kb == kb1 - 1) umma_commit(tfull_bar(acc));
@@ -1154,6 +1343,7 @@ static int batched_path(int transA, int transB, int64_t M, int64_t N, int64_t K,
   if (!transA) {
     if (M < 1024 || N < 8 || N > 4096 || K < 1 || K > 512 || M >= (1LL << 31) - 256) return 0;
     if ((ldc & 3) || (c_bs & 3) || (C && !bt::aligned16(C))) return 0;
+    if (N > 64 && K > 128) return 0;  // the 128-wide tile keeps all three products in one accumulator: short reductions only
     return 1;
   }
   if (transB) return 0;
@@ -1195,28 +1385,36 @@ int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K
     if (int rc = make_map_3d(&map_a, A, K, M, batches, lda, a_bs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_b(&map_bhi, bhi, (int64_t)batches * Npad, Kpad, bn)) return rc;
     if (int rc = make_map_b(&map_blo, blo, (int64_t)batches * Npad, Kpad, bn)) return rc;
-    if (int rc = make_map_3d(&map_c, C, N, M, batches, ldc, c_bs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    const int box_n = bn == 64 ? 32 : (int)(N >= 128 ? 128 : (N + 3) / 4 * 4);  // wide tile: one dense store box per tile
+    if (int rc = make_map_3d(&map_c, C, N, M, batches, ldc, c_bs, box_n, 128,
+                             bn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE))
+      return rc;
     const int m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M), n_tiles = Npad / bn, k_blocks = Kpad / BLOCK_K;
     const int64_t tiles = (int64_t)m_tiles * n_tiles * batches;
     GATK_REQUIRE(tiles < (1LL << 31), "too many tiles");
     int grid = sm_count();
     if (tiles < grid) grid = (int)tiles;
+    static int order = -1;
+    if (order < 0) {
+      const char* e = getenv("GATK_ORDER");
+      order = e ? atoi(e) : 1;
+    }
     if (bn == 64) {
       static bool configured = false;
       if (!configured) {
-        GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_batched_tf32x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
+        GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_batched_tf32x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgTA<64>::SMEM));
         configured = true;
       }
-      gemm_batched_tf32x3_kernel<64><<<grid, NUM_THREADS, Cfg<64>::SMEM, st>>>(map_a, map_bhi, map_blo, map_c, m_tiles, n_tiles,
-                                                                               batches, k_blocks, Npad, epilogue);
+      gemm_batched_tf32x3_kernel<64><<<grid, BT_THREADS, CfgTA<64>::SMEM, st>>>(map_a, map_bhi, map_blo, map_c, m_tiles, n_tiles,
+                                                                               batches, k_blocks, Npad, epilogue, order, box_n);
     } else {
       static bool configured = false;
       if (!configured) {
-        GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_batched_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
+        GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_batched_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgTA<128>::SMEM));
         configured = true;
       }
-      gemm_batched_tf32x3_kernel<128><<<grid, NUM_THREADS, Cfg<128>::SMEM, st>>>(map_a, map_bhi, map_blo, map_c, m_tiles, n_tiles,
-                                                                                 batches, k_blocks, Npad, epilogue);
+      gemm_batched_tf32x3_kernel<128><<<grid, BT_THREADS, CfgTA<128>::SMEM, st>>>(map_a, map_bhi, map_blo, map_c, m_tiles, n_tiles,
+                                                                                 batches, k_blocks, Npad, epilogue, order, box_n);
     }
     GATK_CHECK_LAUNCH();
     return 0;
