@@ -1259,6 +1259,260 @@ gemm_tn_batched_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   }
 }
 
+// ---- TN, 64-wide tile, A through tensor memory.  The first version split both operands into hi / lo copies in
+// shared memory and the MMAs read all four back: 152 KiB of shared-memory traffic per 32-row k-block
+// (~1200 cycles at 128 B/cycle, 1427 measured) against ~880 cycles of HBM time.  Here the raw A box
+// [32 rows x box_m columns] lands unswizzled; splitter thread m reads COLUMN m (consecutive lanes read
+// consecutive words: conflict free), which is row m of A^T, splits it in registers and writes it into TMEM lane
+// m.  Only the narrow B operand is split in shared memory.
+struct CfgTNA {
+  static constexpr int BN = 64;
+  static constexpr int SLOT_A = BLOCK_K * BLOCK_M * 4;  // 16 KiB slot for a [32][box_m <= 128] raw box
+  static constexpr int TILE_B = BN * BLOCK_K * 4;       // 8 KiB
+  static constexpr int NSA = 8;                         // raw A boxes in flight (the HBM stream)
+  static constexpr int NSS = 4;                         // (Bhi, Blo) in shared memory + (Ahi, Alo) in tensor memory
+  static constexpr int OFF_B = NSA * SLOT_A;
+  static constexpr int OFF_BAR = OFF_B + NSS * 2 * TILE_B;
+  static constexpr int NBAR = 2 * NSA + 3 * NSS + 4;
+  static constexpr int SMEM = OFF_BAR + 8 * NBAR + 16 + 1024;
+  static constexpr int TMEM_A = 4 * BN;  // after 2 accumulator stages x (main | compensation)
+  static constexpr int TMEM = 512;
+  // A from tensor memory (K-major by construction), B MN-major (bit 16)
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24) | (1u << 16);
+  static constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24) | (1u << 16);
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+__global__ void __launch_bounds__(tn::TN_THREADS, 1)
+gemm_tn_batched_ta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          float* __restrict__ part, int Mo, int No, int m_tiles, int n_tiles, int batches, int splits,
+                          int kb_total, int kb_per_split, int box_m) {
+  using C = CfgTNA;
+  constexpr int BN = C::BN;
+  using tn::BOX_BYTES;
+  using tn::PROMOTE;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };                                // TMA -> splitter
+  auto a_empty = [&](int s) { return bar0 + 8u * (C::NSA + s); };                    // splitter -> TMA
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * C::NSA + s); };                 // TMA -> splitter
+  auto s_ready = [&](int s) { return bar0 + 8u * (2 * C::NSA + C::NSS + s); };       // splitter -> MMA
+  auto s_empty = [&](int s) { return bar0 + 8u * (2 * C::NSA + 2 * C::NSS + s); };   // MMA retired -> B producer
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * C::NSA + 3 * C::NSS + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * C::NSA + 3 * C::NSS + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int tiles = m_tiles * n_tiles;
+  const int items = batches * tiles * splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NSA; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 4);
+    }
+    for (int s = 0; s < C::NSS; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(s_ready(s), 4);
+      mbar_init(s_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  // item -> (batch, split, m tile, n tile); the splits of a batch are adjacent
+  auto decode = [&](int item, int& b, int& m0, int& n0, int& kb0, int& kb1, int& sp) {
+    b = item / (tiles * splits);
+    const int r = item - b * tiles * splits;
+    sp = r / tiles;
+    const int t = r - sp * tiles;
+    m0 = (t / n_tiles) * BLOCK_M;
+    n0 = (t % n_tiles) * BN;
+    kb0 = sp * kb_per_split;
+    kb1 = kb0 + kb_per_split < kb_total ? kb0 + kb_per_split : kb_total;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      RingN<C::NSA> r;
+      const uint32_t a_bytes = (uint32_t)(BLOCK_K * box_m * 4);
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int b, m0, n0, kb0, kb1, sp;
+        decode(item, b, m0, n0, kb0, kb1, sp);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(a_empty(r.stage), r.phase ^ 1);
+          mbar_expect_tx(a_full(r.stage), a_bytes);
+          tma_load_3d(smem_base + r.stage * C::SLOT_A, &map_a, a_full(r.stage), m0, kb * BLOCK_K, b);
+          r.advance();
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (elect_one()) {
+      RingN<C::NSS> r;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int b, m0, n0, kb0, kb1, sp;
+        decode(item, b, m0, n0, kb0, kb1, sp);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(s_empty(r.stage), r.phase ^ 1);
+          const uint32_t st = smem_base + C::OFF_B + r.stage * 2 * C::TILE_B;
+          mbar_expect_tx(b_full(r.stage), C::TILE_B);
+#pragma unroll
+          for (int q = 0; q < BN / 32; ++q) tma_load_3d(st + q * BOX_BYTES, &map_b, b_full(r.stage), n0 + q * 32, kb * BLOCK_K, b);
+          r.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    RingN<C::NSS> r;
+    int drain = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int b, m0, n0, kb0, kb1, sp;
+      decode(item, b, m0, n0, kb0, kb1, sp);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int rel = kb - kb0;
+        const int acc = drain & 1;
+        if (rel % PROMOTE == 0) {
+          mbar_wait(tempty_bar(acc), ((drain >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t tmem_d = tmem_base + acc * 2 * BN;
+        const uint32_t tmem_c = tmem_d + BN;
+        mbar_wait(s_ready(r.stage), r.phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem_base + C::OFF_B + r.stage * 2 * C::TILE_B;
+          const uint32_t fresh = (rel % PROMOTE) == 0 ? 0u : 1u;
+          const uint32_t a_hi = tmem_base + C::TMEM_A + r.stage * 2 * BLOCK_K, a_lo = a_hi + BLOCK_K;
+          const uint64_t b_hi = tn::umma_desc_mn(st);  // Bhi boxes, then the Blo boxes: one 2 BN-wide operand
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 1024 >> 4);
+            umma_tf32_ta(tmem_d, a_hi + k * 8, b_hi + adv, C::IDESC2, fresh | (uint32_t)(k != 0));
+            umma_tf32_ta(tmem_c, a_lo + k * 8, b_hi + adv, C::IDESC, 1);
+          }
+          umma_commit(s_empty(r.stage));
+          if ((rel + 1) % PROMOTE == 0 || kb == kb1 - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if ((rel + 1) % PROMOTE == 0 || kb == kb1 - 1) ++drain;
+        r.advance();
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    RingN<C::NSA> ra;
+    RingN<C::NSS> rs;
+    const int t = threadIdx.x - 128;       // column of the raw A box = row of A^T = TMEM lane
+    const int tc = t < box_m ? t : 0;      // lanes past the box hold rows that are never stored
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::TMEM_A;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int b, m0, n0, kb0, kb1, sp;
+      decode(item, b, m0, n0, kb0, kb1, sp);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(a_full(ra.stage), ra.phase);
+        const float* src = reinterpret_cast<const float*>(smem + ra.stage * C::SLOT_A) + tc;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float x = src[k * box_m];
+          const uint32_t h = __float_as_uint(x) & 0xffffe000u;
+          hi[k] = h;
+          lo[k] = __float_as_uint(x - __uint_as_float(h));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_empty(ra.stage));
+        // B raw has landed => the MMAs that used this slot (shared-memory B and tensor-memory A) have retired
+        mbar_wait(b_full(rs.stage), rs.phase);
+        tc_fence_after();
+        const uint32_t ta = lane_base + rs.stage * 2 * BLOCK_K;
+        tmem_st32(ta, hi);
+        tmem_st32(ta + BLOCK_K, lo);
+        float4* bh = reinterpret_cast<float4*>(smem + C::OFF_B + rs.stage * 2 * C::TILE_B);
+        float4* bl = reinterpret_cast<float4*>(smem + C::OFF_B + rs.stage * 2 * C::TILE_B + C::TILE_B);
+#pragma unroll
+        for (int i = 0; i < C::TILE_B / 16 / 128; ++i) {
+          const int idx = t + i * 128;
+          float4 v = bh[idx];
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          bh[idx] = h;
+          bl[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        fence_proxy_async();
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_ready(rs.stage));
+        ra.advance();
+        rs.advance();
+      }
+    }
+  } else if (warp >= 8) {
+    constexpr int HALF = BN / 2;  // columns per epilogue warp group
+    const int quarter = warp & 3;
+    const int half = (warp - 8) >> 2;
+    const int row = quarter * 32 + lane;
+    int drain = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int b, m0, n0, kb0, kb1, sp;
+      decode(item, b, m0, n0, kb0, kb1, sp);
+      float racc[HALF];
+#pragma unroll
+      for (int j = 0; j < HALF; ++j) racc[j] = 0.f;
+      const int n_drains = (kb1 - kb0 + PROMOTE - 1) / PROMOTE;
+      for (int d = 0; d < n_drains; ++d, ++drain) {
+        const int acc = drain & 1;
+        mbar_wait(tfull_bar(acc), (drain >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 2 * BN + half * HALF;
+#pragma unroll
+        for (int c = 0; c < HALF / 32; ++c) {
+          uint32_t v[32], w[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld32(taddr + BN + c * 32, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      const int gm = m0 + row;
+      if (gm < Mo) {
+        float* dst = part + (((int64_t)b * splits + sp) * Mo + gm) * No + n0 + half * HALF;
+#pragma unroll
+        for (int j = 0; j < HALF; ++j)
+          if (n0 + half * HALF + j < No) dst[j] = racc[j];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM));
+  }
+}
+
 // B_b (row-major [K,N] or, transposed, [N,K]) -> K-major hi / lo copies [batch][Npad][Kpad], zero padded
 __global__ void split_transpose_b_batched_kernel(const float* __restrict__ B, int64_t ldb, int64_t b_bs, int K, int N,
                                                  int Kpad, int Npad, int batches, int b_is_nk, float* __restrict__ bhi,
@@ -1423,20 +1677,23 @@ int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K
   int mt, nt, sp, kbt, kbs;
   tn_plan(M, N, K, batches, bn, &mt, &nt, &sp, &kbt, &kbs);
   CUtensorMap map_a, map_b;
-  if (int rc = make_map_3d(&map_a, A, M, K, batches, lda, a_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
   if (int rc = make_map_3d(&map_b, B, N, K, batches, ldb, b_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
   const int items = mt * nt * sp * batches;
   int grid = sm_count();
   if (items < grid) grid = items;
   float* part = static_cast<float*>(ws);
   if (bn == 64) {
+    // A through tensor memory: one dense [32 rows][box_m columns] box per k-block
+    const int box_m = (int)(M >= 128 ? 128 : (M + 3) / 4 * 4);
+    if (int rc = make_map_3d(&map_a, A, M, K, batches, lda, a_bs, box_m, 32, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
     static bool configured = false;
     if (!configured) {
-      GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_batched_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_TN));
+      GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_batched_ta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgTNA::SMEM));
       configured = true;
     }
-    gemm_tn_batched_kernel<64><<<grid, tn::TN_THREADS, Cfg<64>::SMEM_TN, st>>>(map_a, map_b, part, (int)M, (int)N, mt, nt, batches, sp, kbt, kbs);
+    gemm_tn_batched_ta_kernel<<<grid, tn::TN_THREADS, CfgTNA::SMEM, st>>>(map_a, map_b, part, (int)M, (int)N, mt, nt, batches, sp, kbt, kbs, box_m);
   } else {
+    if (int rc = make_map_3d(&map_a, A, M, K, batches, lda, a_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     static bool configured = false;
     if (!configured) {
       GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_batched_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_TN));
