@@ -420,7 +420,7 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         _lib.call("gatk_edge_tsum", graph.n_src, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(),
                   dfg.data_ptr() + 4 * H, Muv, thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
         dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
-        _gemm(1, 0, f_in, Muv, n, xg, P, dfg, Muv, dw_uv, Muv, label="gemm:dlogits")
+        _gemm_batched(1, 0, f_in, Muv, n, 1, xg, P, 0, dfg, Muv, 0, dw_uv, Muv, 0, label="gemm:dlogits")  # one "head": the TMEM-A TN kernel
         return None, dw_ext, dw_uv, None, None, None, None, None, None
 
 

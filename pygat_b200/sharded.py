@@ -313,7 +313,7 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         with _lib.timed("comm:reduce_dg"):
             dfg[:, H:2 * H] = reduce_rows(dg_part, plan)
         dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
-        _gemm(1, 0, f_in, Muv, n, xg_loc, P, dfg, Muv, dw_uv, Muv, label="gemm:dlogits")
+        _gemm_batched(1, 0, f_in, Muv, n, 1, xg_loc, P, 0, dfg, Muv, 0, dw_uv, Muv, 0, label="gemm:dlogits")  # one "head": the TMEM-A TN kernel
         if plan.world > 1:
             with _lib.timed("comm:allreduce_dw"):
                 allreduce_([dw_ext, dw_uv], plan)
