@@ -42,6 +42,17 @@ class ShardPlan:
         """row_cost: per-row work expressed in stored entries (see synth.shard_rows_by_nnz)."""
         return ShardPlan(shard_rows_by_nnz(rowptr, world, row_cost), rank, group)
 
+    def cached_xg(self, key, shape, dev):
+        """(buffer, hit): the persistent gathered-rows buffer for the input identified by `key`; hit says its x
+        columns are already complete on every rank (see ShardedGatLayerAggFirstFunction.forward)."""
+        c = getattr(self, "_xg_cache", None)
+        same_buf = c is not None and tuple(c[1].shape) == tuple(shape) and c[1].device == dev
+        if same_buf and c[0] == key:
+            return c[1], True
+        buf = c[1] if same_buf else torch.empty(*shape, dtype=torch.float32, device=dev)
+        self._xg_cache = (key, buf)
+        return buf, False
+
     def rows(self, full: torch.Tensor, r: Optional[int] = None) -> torch.Tensor:
         r = self.rank if r is None else r
         return full[self.bounds[r]:self.bounds[r + 1]]
@@ -81,6 +92,16 @@ def reduce_rows(partial: torch.Tensor, plan: ShardPlan) -> torch.Tensor:
         dist.reduce(plan.rows(partial, r), dst=dist.get_global_rank(plan.group, r) if plan.group else r,
                     group=plan.group)
     return plan.rows(partial)
+
+
+def reduce_rows_async(partial: torch.Tensor, plan: ShardPlan):
+    """reduce_rows without blocking the launching stream: returns (owned rows, work handle or None).  The
+    caller calls work.wait() (a stream-side wait, no host sync) before it reads the rows."""
+    if plan.world == 1 or not _uneven_ok(plan.group):
+        return reduce_rows(partial, plan), None
+    out = torch.empty_like(plan.rows(partial))
+    work = dist.reduce_scatter(out, [plan.rows(partial, r) for r in range(plan.world)], group=plan.group, async_op=True)
+    return out, work
 
 
 def allreduce_(tensors: Sequence[torch.Tensor], plan_or_group=None):
@@ -232,7 +253,7 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_ext, w_uv, graph: Graph, plan: ShardPlan, H: int, Dp: int, has_skip: bool, alpha: float,
-                act_elu: bool):
+                act_elu: bool, x_key=None):
         dev = x.device
         n, f_in = x.shape
         assert n == plan.n_local == graph.n_dst and graph.n_src == plan.n_total
@@ -244,13 +265,26 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         x, w_ext, w_uv = x.contiguous(), w_ext.contiguous(), w_uv.contiguous()
         st = _stream()
         P = _lib.query("gatk_xg_pitch", Fp, H)
-        xg_full = torch.empty(N, P, dtype=torch.float32, device=dev)
+        # The x columns of the gathered rows depend only on the layer INPUT.  A first layer's input is the
+        # dataset's feature matrix: constant across training steps, so its all-gather is done once and kept
+        # (keyed on the input tensor's storage and version counter: any in-place update or a new tensor
+        # gathers again).  Per step only the source logits g [N, H] cross NVLink.
+        cached = plan.cached_xg(x_key, (N, P), dev) if x_key is not None else None
+        hit = cached is not None and cached[1]
+        xg_full = cached[0] if cached is not None else torch.empty(N, P, dtype=torch.float32, device=dev)
         xg_loc = plan.rows(xg_full)
         f = torch.empty(n, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_logits_pack", n, f_in, H, x.data_ptr(), f_in, w_uv.data_ptr(), Muv, xg_loc.data_ptr(), P,
                   f.data_ptr(), H, st)
-        with _lib.timed("comm:allgather_xg"):
-            gather_rows(xg_full, plan)
+        if hit and plan.world > 1:
+            with _lib.timed("comm:allgather_g"):
+                g_all = torch.empty(N, H, dtype=torch.float32, device=dev)
+                plan.rows(g_all).copy_(xg_loc[:, Fp:Fp + H])
+                gather_rows(g_all, plan)
+                xg_full[:, Fp:Fp + H].copy_(g_all)
+        else:
+            with _lib.timed("comm:allgather_xg"):
+                gather_rows(xg_full, plan)
         need_grad = any(ctx.needs_input_grad[1:3])
         xagg = torch.empty(n, H * Fp, dtype=torch.float32, device=dev)
         lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
@@ -293,10 +327,7 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
             dhp = gout
         dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
         dxagg = (torch.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
-        _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp, label="gemm:dW")
         _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp, label="gemm:dxagg")
-        if has_skip:
-            _gemm(1, 0, f_in, HD, n, xg_loc, P, dhp, HD, dw_ext, M_out, c_off=HD)
         ds = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
         dfg = (torch.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
         hubs = graph.hubs
@@ -310,19 +341,29 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         dg_part = torch.empty(N, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_edge_tsum", N, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(), dg_part.data_ptr(), H,
                   thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
-        with _lib.timed("comm:reduce_dg"):
-            dfg[:, H:2 * H] = reduce_rows(dg_part, plan)
+        # the reduce-scatter runs on NCCL's stream while the value-path products (which need nothing from it)
+        # keep this stream busy
+        dg_own, work = reduce_rows_async(dg_part, plan)
+        _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp, label="gemm:dW")
+        if has_skip:
+            _gemm(1, 0, f_in, HD, n, xg_loc, P, dhp, HD, dw_ext, M_out, c_off=HD)
+        with _lib.timed("comm:reduce_dg_wait"):
+            if work is not None:
+                work.wait()
+            dfg[:, H:2 * H] = dg_own
         dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
         _gemm_batched(1, 0, f_in, Muv, n, 1, xg_loc, P, 0, dfg, Muv, 0, dw_uv, Muv, 0, label="gemm:dlogits")  # one "head": the TMEM-A TN kernel
         if plan.world > 1:
             with _lib.timed("comm:allreduce_dw"):
                 allreduce_([dw_ext, dw_uv], plan)
-        return None, dw_ext, dw_uv, None, None, None, None, None, None, None
+        return None, dw_ext, dw_uv, None, None, None, None, None, None, None, None
 
 
 def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, a_srcs, a_dsts, skips, alpha: float,
-                      concat: bool, combine: str = "cat", form: str = "auto") -> torch.Tensor:
-    """All heads of one GAT layer on this rank's destination rows (see functional.gat_layer)."""
+                      concat: bool, combine: str = "cat", form: str = "auto", cache_input_gather: bool = True) -> torch.Tensor:
+    """All heads of one GAT layer on this rank's destination rows (see functional.gat_layer).
+    cache_input_gather: keep the all-gathered input rows of the aggregate-first form while the input tensor is
+    unchanged (same storage, same version counter): a first layer's features are static across steps."""
     H = len(Ws)
     x_local = x_local.float()
     w_ext, a_src, a_dst, D, Dp = pack_heads(Ws, a_srcs, a_dsts, skips)
@@ -334,8 +375,9 @@ def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, 
         uv = [(w3 * a_src).sum(-1), (w3 * a_dst).sum(-1)]
         if (-2 * H) % 4:
             uv.append(w_ext.new_zeros(x_local.shape[1], (-2 * H) % 4))
+        x_key = (x_local.data_ptr(), x_local._version, tuple(x_local.shape)) if cache_input_gather else None
         rows = ShardedGatLayerAggFirstFunction.apply(x_local, w_ext, torch.cat(uv, dim=1), graph, plan, H, Dp,
-                                                     skips is not None, float(alpha), bool(concat))
+                                                     skips is not None, float(alpha), bool(concat), x_key)
     else:
         rows = ShardedGatLayerFunction.apply(x_local, w_ext, a_src, a_dst, graph, plan, H, Dp, skips is not None,
                                              float(alpha), bool(concat))

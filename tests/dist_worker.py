@@ -52,6 +52,18 @@ def run_gloo(rank, world):
     allreduce_gradients(lin.parameters(), sizes[rank])
     for p, m in zip(lin.parameters(), merged):
         assert torch.allclose(p.grad, m, atol=1e-6), (p.grad, m)
+    # kept gather buffer: same key -> hit, new key -> same storage, miss
+    buf, hit = plan.cached_xg(("k", 0), (500, 4), torch.device("cpu"))
+    assert not hit
+    buf2, hit2 = plan.cached_xg(("k", 0), (500, 4), torch.device("cpu"))
+    assert hit2 and buf2.data_ptr() == buf.data_ptr()
+    buf3, hit3 = plan.cached_xg(("k", 1), (500, 4), torch.device("cpu"))
+    assert not hit3 and buf3.data_ptr() == buf.data_ptr()
+    from pygat_b200.sharded import reduce_rows_async
+    got2, work = reduce_rows_async((ref * (rank + 1)).clone(), plan)
+    if work is not None:
+        work.wait()
+    assert torch.equal(got2, plan.rows(ref) * sum(r + 1 for r in range(world)))
     # local graph slices reassemble the global CSR
     g_rows = [int(rowptr[b1] - rowptr[b0]) for b0, b1 in zip(bounds, bounds[1:])]
     assert sum(g_rows) == col.numel()
@@ -112,6 +124,25 @@ def run_nccl(rank, world):
         if skip:
             for got, want in zip([s.grad for s in Ss], ref["dS"]):
                 assert rel(got, want) < 2e-5
+        # cached input gather: the same input tensor again hits the kept all-gathered rows and exchanges only g.
+        # The first call runs with perturbed attention vectors, so the g columns it leaves behind are stale and the
+        # second call must refresh them on every rank; an in-place update of the input must gather again.
+        xs = plan.rows(x).clone()
+        a_bad = [a.detach() * 1.7 for a in a_d]
+        sharded_gat_layer(xs, graph, plan, Ws, a_s, a_bad, Ss, 0.2, concat)
+        assert plan._xg_cache[0] == (xs.data_ptr(), xs._version, tuple(xs.shape))
+        for variant in ("hit", "invalidated"):
+            for p in Ws + a_s + a_d + (Ss or []):
+                p.grad = None
+            if variant == "invalidated":
+                xs.mul_(1.0)
+            y2c = sharded_gat_layer(xs, graph, plan, Ws, a_s, a_d, Ss, 0.2, concat)
+            y2c.backward(plan.rows(gout))
+            assert rel(y2c, plan.rows(y_ref)) < 1e-5, (variant, rel(y2c, plan.rows(y_ref)))
+            for got, want in zip([w.grad for w in Ws], ref["dW"]):
+                assert rel(got, want) < 2e-5, (variant, rel(got, want))
+            for got, want in zip([a.grad for a in a_s + a_d], ref["da"]):
+                assert rel(got, want) < 2e-5, (variant, rel(got, want))
         # and the project-first sharded kernels on the same no-gradient input
         for p in Ws + a_s + a_d + (Ss or []):
             p.grad = None
