@@ -226,10 +226,17 @@ def run_ours(args):
     launches = _lib.query("gatk_launch_count") - launches0
     calls = _lib.call_count - calls0
     clk = clocks.stop() if rank == 0 else None
+    per_rank = None
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        # every rank's per-call times (rank 0's alone hide the load balance: a "comm:" wait is mostly skew)
+        mine = {k: round(v["ms_total"] / args.steps, 4) for k, v in kern.items()}
+        mine["rows"], mine["entries"] = runner.plan.n_local, runner.graph.nnz
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = {k: [g.get(k) for g in gathered] for k in mine}
 
     # ---- end-to-end through the public API with host buffers (pinned H2D of the step's input
     # features, D2H of the step's results: parameter gradients + a checksum of the output)
@@ -292,13 +299,15 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}-shape power-law graph, one hidden GAT layer fwd+bwd",
                    "nodes": n, "edges": e_total, "f_in": f_in, "heads": H, "head_dim": D, "dropout": 0.0,
-                   "parallelism": f"dst-row shards x{world}" if world > 1 else "single GPU",
+                   "parallelism": (f"dst-row shards x{world} (cost-balanced, row_cost={runner.row_cost:.1f} entries); layer-1 "
+                                   "features are static, their all-gather is kept across steps; per step g [N,H] is "
+                                   "all-gathered, dg reduce-scattered, dW all-reduced") if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (Wh alone is %.1f GB)" % (n * H * D * 4 / 1e9)},
         "e2e": {"value": e_total * H / (e2e_ms * 1e-3), "unit": "head-edges/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "input_pipeline": "pinned host -> device copy of step k+1 overlaps step k (double buffered)"},
         "gpu_launches": launches, "abi_calls": calls, "clocks": clk, "roofline": roofline,
-        "kernels": per_kernel, "other_ms_per_step": other,
+        "kernels": per_kernel, "other_ms_per_step": other, "per_rank_ms_per_step": per_rank,
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "epoch_times": epochs,
     }

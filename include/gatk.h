@@ -203,6 +203,17 @@ GATK_API int gatk_da_reduce(int64_t n, int H, int Dp, const float* wh, int64_t l
 GATK_API int64_t gatk_xg_pitch(int Fp, int H);
 GATK_API int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t ldx, const float* uv, int64_t lduv,
                               float* xg, int64_t ldxg, float* f, int64_t ldf, void* stream);
+/* The same kernel as the forward exchange of a destination-row shard group: besides xg (this GPU's own copy of
+ * its rows) every packed row is also written to peer_xg[q] + row*ldxg, q < n_peers <= GATK_MAX_PEERS, pointers
+ * into the other GPUs' gathered-row buffers mapped into this process (CUDA peer / symmetric memory), at the row
+ * that corresponds to local row 0.  whole_rows = 0 pushes only the g columns (the input columns of the peers'
+ * copies are already in place: a static first-layer input), 1 the whole row.  The caller orders the exchange
+ * (a barrier over the group before the rows are overwritten and after this call).  There is no reference
+ * counterpart: the reference is single-device. */
+#define GATK_MAX_PEERS 15
+GATK_API int gatk_logits_pack_push(int64_t n, int F, int H, const float* x, int64_t ldx, const float* uv, int64_t lduv,
+                                   float* xg, int64_t ldxg, float* f, int64_t ldf, int n_peers, float* const* peer_xg,
+                                   int whole_rows, void* stream);
 GATK_API size_t gatk_attn_x_scratch_floats(int which, int H, int Fp, int n_hub_seg);
 GATK_API int gatk_attn_x_fwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
                              const float* xg, int64_t ldxg, const float* f, int64_t ldf, float alpha,

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "gatk_da_reduce": (c_int, [c_int64, c_int, c_int, P, c_int64, P, P, P, P, P, P]),
     "gatk_xg_pitch": (c_int64, [c_int, c_int]),
     "gatk_logits_pack": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_int64, P, c_int64, P, c_int64, P]),
+    "gatk_logits_pack_push": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int, P, c_int, P]),
     "gatk_attn_x_scratch_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gatk_attn_x_fwd": (c_int, [c_int64, c_int64, P, P, c_int, c_int, P, c_int64, P, c_int64, c_float, P, c_int64, P,
                                 c_int, P, P, c_int, c_int, P, P, P, c_int, P]),

@@ -890,10 +890,20 @@ __global__ void elu_bwd_kernel(int64_t n, int c4, const float* __restrict__ gout
 // the gather rows xg_i = [x_i | 0.. | g_i | 0..].  Warp per row, lanes = float4 slots, [u|v] transposed in
 // shared memory.
 // =====================================================================================================
+// Copies of the packed rows on the other GPUs of the shard group (peer-mapped memory, written over NVLink
+// straight from this kernel: the pack IS the all-gather).  base[q] points at the row of peer q's buffer that
+// corresponds to this rank's local row 0; rows != 0 pushes whole rows, else only the g columns.
+struct PackPeers {
+  int n;
+  int rows;
+  float* base[GATK_MAX_PEERS];
+};
+
 template <int HP, bool VEC>
 __global__ void __launch_bounds__(256) logits_pack_kernel(int64_t n, int F, int H, const float* __restrict__ x, int64_t ldx,
                                                           const float* __restrict__ uv, int64_t lduv, int Fp, int P,
-                                                          float* __restrict__ xg, float* __restrict__ f, int64_t ldf) {
+                                                          float* __restrict__ xg, float* __restrict__ f, int64_t ldf,
+                                                          const PackPeers peers) {
   extern __shared__ __align__(16) float uvs[];  // [2*HP][Fp]
   constexpr int C2 = 2 * HP;
   constexpr int SHC = 5 - Log2<C2>::v;
@@ -931,7 +941,11 @@ __global__ void __launch_bounds__(256) logits_pack_kernel(int64_t n, int F, int 
       }
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (row0 + r < n) stg4(xg + (row0 + r) * P + slot * 4, v[r]);
+        if (row0 + r < n) {
+          stg4(xg + (row0 + r) * P + slot * 4, v[r]);
+          if (peers.rows)
+            for (int q = 0; q < peers.n; ++q) stg4(peers.base[q] + (row0 + r) * P + slot * 4, v[r]);
+        }
 #pragma unroll
       for (int c = 0; c < C2; ++c) {
         const float4 q = *reinterpret_cast<const float4*>(uvs + c * Fp + slot * 4);
@@ -952,7 +966,11 @@ __global__ void __launch_bounds__(256) logits_pack_kernel(int64_t n, int F, int 
       for (int t0 = 0; t0 < P - Fp; t0 += 32) {  // g behind the input row, zero padding after it
         const int t = t0 + lane;
         const float gval = __shfl_sync(FULL, part[r][0], ((HP + (t < HP ? t : 0)) << SHC) & 31);
-        if (row < n && t < P - Fp) xg[row * P + Fp + t] = t < H ? gval : 0.f;
+        if (row < n && t < P - Fp) {
+          const float val = t < H ? gval : 0.f;
+          xg[row * P + Fp + t] = val;
+          for (int q = 0; q < peers.n; ++q) peers.base[q][row * P + Fp + t] = val;
+        }
       }
     }
   }
@@ -1131,8 +1149,8 @@ extern "C" int64_t gatk_xg_pitch(int Fp, int H) {
   return (w + al - 1) / al * al;
 }
 
-extern "C" int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t ldx, const float* uv, int64_t lduv,
-                                float* xg, int64_t ldxg, float* f, int64_t ldf, void* stream) {
+static int logits_pack_launch(int64_t n, int F, int H, const float* x, int64_t ldx, const float* uv, int64_t lduv,
+                              float* xg, int64_t ldxg, float* f, int64_t ldf, const PackPeers& peers, void* stream) {
   GATK_REQUIRE(F >= 1 && H >= 1 && H <= 8, "bad sizes F=%d H=%d", F, H);
   const int Fp = (F + 3) / 4 * 4;
   GATK_REQUIRE(Fp <= 512, "F=%d too wide for the aggregate-first form", F);
@@ -1147,7 +1165,7 @@ extern "C" int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t
   int64_t blocks = (n + 31) / 32;  // 8 warps x 4 rows per iteration
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-#define PACK_LAUNCH(HPV, V) logits_pack_kernel<HPV, V><<<(unsigned)blocks, 256, smem, st>>>(n, F, H, x, ldx, uv, lduv, Fp, (int)ldxg, xg, f, ldf)
+#define PACK_LAUNCH(HPV, V) logits_pack_kernel<HPV, V><<<(unsigned)blocks, 256, smem, st>>>(n, F, H, x, ldx, uv, lduv, Fp, (int)ldxg, xg, f, ldf, peers)
   if (vec) {
     HP_DISPATCH(hp, PACK_LAUNCH(HP, true));
   } else {
@@ -1156,6 +1174,29 @@ extern "C" int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t
 #undef PACK_LAUNCH
   GATK_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int gatk_logits_pack(int64_t n, int F, int H, const float* x, int64_t ldx, const float* uv, int64_t lduv,
+                                float* xg, int64_t ldxg, float* f, int64_t ldf, void* stream) {
+  PackPeers none;
+  none.n = 0;
+  none.rows = 0;
+  return logits_pack_launch(n, F, H, x, ldx, uv, lduv, xg, ldxg, f, ldf, none, stream);
+}
+
+extern "C" int gatk_logits_pack_push(int64_t n, int F, int H, const float* x, int64_t ldx, const float* uv, int64_t lduv,
+                                     float* xg, int64_t ldxg, float* f, int64_t ldf, int n_peers, float* const* peer_xg,
+                                     int whole_rows, void* stream) {
+  GATK_REQUIRE(n_peers >= 0 && n_peers <= GATK_MAX_PEERS && (n_peers == 0 || peer_xg), "n_peers=%d (max %d)", n_peers,
+               GATK_MAX_PEERS);
+  PackPeers p;
+  p.n = n_peers;
+  p.rows = whole_rows ? 1 : 0;
+  for (int q = 0; q < n_peers; ++q) {
+    GATK_REQUIRE(peer_xg[q] && ((uintptr_t)peer_xg[q] & 15) == 0, "peer row pointer %d is null or not 16-byte aligned", q);
+    p.base[q] = peer_xg[q];
+  }
+  return logits_pack_launch(n, F, H, x, ldx, uv, lduv, xg, ldxg, f, ldf, p, stream);
 }
 
 static int fill_xargs(XArgs& a, int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp, int sx,

@@ -12,6 +12,7 @@ torch.distributed.  The reference has no distributed code -- everything here is 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -53,6 +54,28 @@ class ShardPlan:
         self._xg_cache = (key, buf)
         return buf, False
 
+    def peer_rows(self, shape, dev):
+        """PeerRows for an [N, P] gathered-row buffer in symmetric memory (every rank's copy mapped into every
+        process), or None when symmetric memory is unavailable / disabled (GATK_PEER_PUSH=0) / the group is too
+        large: the caller then uses the NCCL all-gather.  Collective: every rank of the group must call it."""
+        c = getattr(self, "_peer_rows", None)
+        if c is not None and (c is False or c.shape == tuple(shape)):
+            return c or None
+        ok, made = 1, None
+        if os.environ.get("GATK_PEER_PUSH", "1") == "0" or self.world - 1 > MAX_PEERS or dev.type != "cuda":
+            ok = 0
+        else:
+            try:
+                made = PeerRows(self, tuple(shape), dev)
+            except Exception as exc:  # no fabric / IPC support on this box
+                import warnings
+                warnings.warn(f"symmetric memory unavailable ({exc!r}); using NCCL all-gather")
+                ok = 0
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self._peer_rows = made if int(flag.item()) == 1 else False
+        return self._peer_rows or None
+
     def rows(self, full: torch.Tensor, r: Optional[int] = None) -> torch.Tensor:
         r = self.rank if r is None else r
         return full[self.bounds[r]:self.bounds[r + 1]]
@@ -62,6 +85,35 @@ class ShardPlan:
         e0, e1 = int(rowptr[self.lo].item()), int(rowptr[self.hi].item())
         return Graph((rowptr[self.lo:self.hi + 1] - e0).contiguous(), col[e0:e1].contiguous(),
                      n_src=self.n_total, seg_len=seg_len)
+
+
+MAX_PEERS = 15  # GATK_MAX_PEERS in include/gatk.h
+
+
+class PeerRows:
+    """The gathered rows [N, P] of a shard group in symmetric memory: `buf` is this rank's copy, `ptrs` the other
+    ranks' copies (device pointers valid in THIS process, offset to this rank's first row) for
+    gatk_logits_pack_push, `barrier()` a device-side barrier over the group on the current stream."""
+
+    def __init__(self, plan: "ShardPlan", shape, dev):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+        self.shape = shape
+        n, pitch = shape
+        self.flat = symm_mem.empty(n * pitch, dtype=torch.float32, device=dev)
+        self.hdl = symm_mem.rendezvous(self.flat, plan.group if plan.group is not None else dist.group.WORLD)
+        assert self.hdl.world_size == plan.world and self.hdl.rank == plan.rank
+        self.buf = self.flat.view(n, pitch)
+        peers = [int(self.hdl.buffer_ptrs[q]) + 4 * plan.lo * pitch for q in range(plan.world) if q != plan.rank]
+        self.n_peers = len(peers)
+        self.ptrs = (ctypes.c_void_p * max(self.n_peers, 1))(*peers)
+        self.key = None   # identity of the input whose x columns every copy currently holds
+        self._chan = 0
+
+    def barrier(self):
+        self.hdl.barrier(channel=self._chan)
+        self._chan ^= 1
 
 
 def _uneven_ok(group) -> bool:
@@ -269,22 +321,37 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         # dataset's feature matrix: constant across training steps, so its all-gather is done once and kept
         # (keyed on the input tensor's storage and version counter: any in-place update or a new tensor
         # gathers again).  Per step only the source logits g [N, H] cross NVLink.
-        cached = plan.cached_xg(x_key, (N, P), dev) if x_key is not None else None
-        hit = cached is not None and cached[1]
-        xg_full = cached[0] if cached is not None else torch.empty(N, P, dtype=torch.float32, device=dev)
-        xg_loc = plan.rows(xg_full)
         f = torch.empty(n, H, dtype=torch.float32, device=dev)
-        _lib.call("gatk_logits_pack", n, f_in, H, x.data_ptr(), f_in, w_uv.data_ptr(), Muv, xg_loc.data_ptr(), P,
-                  f.data_ptr(), H, st)
-        if hit and plan.world > 1:
-            with _lib.timed("comm:allgather_g"):
-                g_all = torch.empty(N, H, dtype=torch.float32, device=dev)
-                plan.rows(g_all).copy_(xg_loc[:, Fp:Fp + H])
-                gather_rows(g_all, plan)
-                xg_full[:, Fp:Fp + H].copy_(g_all)
+        peer = plan.peer_rows((N, P), dev) if plan.world > 1 else None
+        if peer is not None:
+            # fused pack + exchange: the pack kernel writes every row (or, when the peers already hold this
+            # input's x columns, just its g columns) into all the other GPUs' copies over NVLink; two device-side
+            # barriers order it against the readers of the previous contents and of the new ones
+            hit = x_key is not None and peer.key == x_key
+            xg_full = peer.buf
+            xg_loc = plan.rows(xg_full)
+            with _lib.timed("comm:pack_push"):
+                peer.barrier()
+                _lib.call("gatk_logits_pack_push", n, f_in, H, x.data_ptr(), f_in, w_uv.data_ptr(), Muv, xg_loc.data_ptr(), P,
+                          f.data_ptr(), H, peer.n_peers, peer.ptrs, 0 if hit else 1, st, label="gatk_logits_pack")
+                peer.barrier()
+            peer.key = x_key
         else:
-            with _lib.timed("comm:allgather_xg"):
-                gather_rows(xg_full, plan)
+            cached = plan.cached_xg(x_key, (N, P), dev) if x_key is not None else None
+            hit = cached is not None and cached[1]
+            xg_full = cached[0] if cached is not None else torch.empty(N, P, dtype=torch.float32, device=dev)
+            xg_loc = plan.rows(xg_full)
+            _lib.call("gatk_logits_pack", n, f_in, H, x.data_ptr(), f_in, w_uv.data_ptr(), Muv, xg_loc.data_ptr(), P,
+                      f.data_ptr(), H, st)
+            if hit and plan.world > 1:
+                with _lib.timed("comm:allgather_g"):
+                    g_all = torch.empty(N, H, dtype=torch.float32, device=dev)
+                    plan.rows(g_all).copy_(xg_loc[:, Fp:Fp + H])
+                    gather_rows(g_all, plan)
+                    xg_full[:, Fp:Fp + H].copy_(g_all)
+            else:
+                with _lib.timed("comm:allgather_xg"):
+                    gather_rows(xg_full, plan)
         need_grad = any(ctx.needs_input_grad[1:3])
         xagg = torch.empty(n, H * Fp, dtype=torch.float32, device=dev)
         lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
@@ -407,36 +474,92 @@ def allreduce_gradients(params, n_local_nodes: int, group=None):
         off += p.numel()
 
 
+def shard_rows_by_cost(rowptr: torch.Tensor, world: int, row_cost: float):
+    """synth.shard_rows_by_nnz with a fractional per-row cost (costs scaled to integers)."""
+    n = rowptr.numel() - 1
+    cum = rowptr * 16 + int(round(row_cost * 16)) * torch.arange(n + 1, device=rowptr.device, dtype=torch.int64)
+    total = int(cum[-1].item())
+    targets = torch.arange(1, world, device=rowptr.device, dtype=torch.int64) * total // world
+    cuts = torch.searchsorted(cum, targets).clamp_(max=n).tolist()
+    return [0] + [int(c) for c in cuts] + [n]
+
+
+def fit_row_cost(rows: torch.Tensor, entries: torch.Tensor, t: torch.Tensor):
+    """row_cost = a / b of the least-squares fit t = a * rows + b * entries (None if not identifiable)."""
+    A = torch.stack([rows.double(), entries.double()], dim=1)
+    if A.shape[0] < 2 or torch.linalg.matrix_rank(A) < 2:
+        return None
+    sol = torch.linalg.lstsq(A, t.double().unsqueeze(1)).solution.flatten()
+    a, b = float(sol[0]), float(sol[1])
+    if not (a > 0 and b > 0):
+        return None
+    return min(max(a / b, 0.0), 1000.0)
+
+
 # ---------------------------------------------------------------------- bench harness (bench.py --gpus N)
 ROW_COST = 25  # measured on one GPU at the products shape: row-proportional kernels ~7.0 ns/row, edge passes ~0.275 ns/entry
 
 
 class ShardedLayerBench:
     """The bench.py workload on `world` GPUs: the whole synthetic graph is generated identically on
-    every rank (same seed) and each rank keeps its destination-row shard."""
+    every rank (same seed) and each rank keeps its destination-row shard.
 
-    def __init__(self, cfg, rank: int, world: int, dev):
+    Shard boundaries equalise cost(row range) = stored entries + row_cost * rows.  row_cost starts from the
+    single-GPU measurement and, with calibrate=True, is re-fitted once from what the ranks actually measure:
+    a few untimed steps give every rank's kernel time t_r (collective waits excluded), least squares over the
+    ranks gives t = a * rows + b * entries, and the shards are cut again with row_cost = a / b.  This is setup
+    work, like the CSR build: it happens before the timed region."""
+
+    def __init__(self, cfg, rank: int, world: int, dev, calibrate: bool = True):
         from .synth import init_layer_params, power_law_csr
         n, H, D, f_in = cfg["n"], cfg["H"], cfg["D"], cfg["f_in"]
+        self.rank, self.world, self.dev = rank, world, dev
         rowptr, col = power_law_csr(n, cfg["avg_deg"], seed=72, exponent=cfg["exponent"], device=dev)
         self.e_total = int(col.numel())
-        self.plan = ShardPlan.by_nnz(rowptr, rank, world, row_cost=ROW_COST)
-        self.graph = self.plan.local_graph(rowptr, col)
-        del rowptr, col
-        self.graph.transpose()
         g = torch.Generator(device=dev).manual_seed(72)
         x = torch.randn(n, f_in, generator=g, device=dev)
         gout = torch.randn(n, H * D, generator=g, device=dev)
-        self.x = self.plan.rows(x).clone()
-        self.gout = self.plan.rows(gout).clone()
-        del x, gout
-        torch.cuda.empty_cache()
         self.Ws, self.a_src, self.a_dst = init_layer_params(f_in, H, D, dev, seed=72)
         self.params = self.Ws + self.a_src + self.a_dst
+        self.row_cost = float(ROW_COST)
+        self._cut(rowptr, col, x, gout)
+        if calibrate and world > 1:
+            fitted = self._fit_row_cost()
+            if fitted is not None and abs(fitted - self.row_cost) > 0.5:
+                self.row_cost = fitted
+                self._cut(rowptr, col, x, gout)
+        del rowptr, col, x, gout
+        torch.cuda.empty_cache()
         hubs = 2 if self.graph.hubs.n_seg else 0
         thubs = 2 if self.graph.transpose()[3].n_seg else 0
         self.launches_per_step = 2 + 1 + (1 + hubs) + 1 + (1 + thubs) + (1 + hubs) + 2 + 2
         self.x_host = None
+
+    def _cut(self, rowptr, col, x, gout):
+        self.plan = ShardPlan(shard_rows_by_cost(rowptr, self.world, self.row_cost), self.rank)
+        self.graph = self.plan.local_graph(rowptr, col)
+        self.graph.transpose()
+        self.x = self.plan.rows(x).clone()
+        self.gout = self.plan.rows(gout).clone()
+
+    def _fit_row_cost(self, steps: int = 3):
+        """Least-squares (a, b) of t_r = a * rows_r + b * entries_r over the ranks -> a / b, or None when the
+        fit is unusable (fewer than 2 distinct shard shapes, non-positive coefficients)."""
+        for _ in range(2):
+            self.step()
+        torch.cuda.synchronize()
+        old = _lib.timer
+        _lib.timer = _lib.KernelTimer()
+        for _ in range(steps):
+            self.step()
+        kern = _lib.timer.summary()
+        _lib.timer = old
+        t = sum(v["ms_total"] for k, v in kern.items() if not k.startswith("comm:")) / steps
+        mine = torch.tensor([float(self.plan.n_local), float(self.graph.nnz), t], dtype=torch.float64, device=self.dev)
+        allr = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allr, mine)
+        m = torch.stack(allr).cpu()
+        return fit_row_cost(m[:, 0], m[:, 1], m[:, 2])
 
     def _layer(self, x):
         return sharded_gat_layer(x, self.graph, self.plan, self.Ws, self.a_src, self.a_dst, None, 0.2, concat=True)

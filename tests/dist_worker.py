@@ -130,7 +130,8 @@ def run_nccl(rank, world):
         xs = plan.rows(x).clone()
         a_bad = [a.detach() * 1.7 for a in a_d]
         sharded_gat_layer(xs, graph, plan, Ws, a_s, a_bad, Ss, 0.2, concat)
-        assert plan._xg_cache[0] == (xs.data_ptr(), xs._version, tuple(xs.shape))
+        kept = getattr(plan, "_peer_rows", None)  # symmetric-memory exchange, or the NCCL path's kept buffer
+        assert (kept.key if kept else plan._xg_cache[0]) == (xs.data_ptr(), xs._version, tuple(xs.shape))
         for variant in ("hit", "invalidated"):
             for p in Ws + a_s + a_d + (Ss or []):
                 p.grad = None

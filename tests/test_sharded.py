@@ -17,11 +17,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _torchrun(mode, nproc, timeout=600):
+def _torchrun(mode, nproc, timeout=600, **extra_env):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(HERE, "dist_worker.py"), mode]
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="2", **extra_env)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert r.returncode == 0 and f"DIST_OK mode={mode} world={nproc}" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
@@ -76,4 +76,20 @@ def test_sharded_layer_world1_equals_single_gpu():
 def test_sharded_layer_matches_single_gpu_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    _torchrun("nccl", 2)
+    _torchrun("nccl", 2)  # forward exchange fused into the pack kernel (peer stores over NVLink) when available
+    _torchrun("nccl", 2, GATK_PEER_PUSH="0")  # and the NCCL all-gather path
+
+
+def test_row_cost_fit_and_fractional_cuts():
+    from pygat_b200.sharded import fit_row_cost, shard_rows_by_cost
+    from pygat_b200.synth import power_law_csr, shard_rows_by_nnz
+    rows = torch.tensor([100., 200., 300., 400.])
+    ent = torch.tensor([4000., 3000., 2500., 2000.])
+    assert abs(fit_row_cost(rows, ent, 7.0 * rows + 0.25 * ent) - 28.0) < 1e-6
+    assert fit_row_cost(rows[:1], ent[:1], torch.tensor([1.0])) is None          # one rank: not identifiable
+    assert fit_row_cost(rows, 10 * rows, 3.0 * rows) is None                     # collinear shard shapes
+    assert fit_row_cost(rows, ent, 1.0 * rows - 0.5 * ent) is None               # negative coefficient: rejected
+    rowptr, _ = power_law_csr(3000, 10.0, seed=1)
+    assert shard_rows_by_cost(rowptr, 4, 25.0) == shard_rows_by_nnz(rowptr, 4, 25)
+    b = shard_rows_by_cost(rowptr, 4, 12.5)
+    assert b[0] == 0 and b[-1] == 3000 and all(x <= y for x, y in zip(b, b[1:]))
