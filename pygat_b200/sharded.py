@@ -48,7 +48,7 @@ class ShardPlan:
         columns are already complete on every rank (see ShardedGatLayerAggFirstFunction.forward)."""
         c = getattr(self, "_xg_cache", None)
         same_buf = c is not None and tuple(c[1].shape) == tuple(shape) and c[1].device == dev
-        if same_buf and c[0] == key:
+        if same_buf and _same_input(c[0], key):
             return c[1], True
         buf = c[1] if same_buf else torch.empty(*shape, dtype=torch.float32, device=dev)
         self._xg_cache = (key, buf)
@@ -88,6 +88,18 @@ class ShardPlan:
 
 
 MAX_PEERS = 15  # GATK_MAX_PEERS in include/gatk.h
+
+
+def _input_key(x: torch.Tensor):
+    """Identity of a layer input for the kept gathered rows: storage address, version counter, shape, and a weak
+    reference to the tensor object (a dead object's storage may have been handed to a different tensor)."""
+    import weakref
+    return (x.data_ptr(), x._version, tuple(x.shape), weakref.ref(x))
+
+
+def _same_input(kept, new) -> bool:
+    return (kept is not None and new is not None and kept[:3] == new[:3] and kept[3]() is not None
+            and (kept[3]() is new[3]() or kept[3]().data_ptr() == new[0]))
 
 
 class PeerRows:
@@ -327,7 +339,7 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
             # fused pack + exchange: the pack kernel writes every row (or, when the peers already hold this
             # input's x columns, just its g columns) into all the other GPUs' copies over NVLink; two device-side
             # barriers order it against the readers of the previous contents and of the new ones
-            hit = x_key is not None and peer.key == x_key
+            hit = _same_input(peer.key, x_key)
             xg_full = peer.buf
             xg_loc = plan.rows(xg_full)
             with _lib.timed("comm:pack_push"):
@@ -442,7 +454,7 @@ def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, 
         uv = [(w3 * a_src).sum(-1), (w3 * a_dst).sum(-1)]
         if (-2 * H) % 4:
             uv.append(w_ext.new_zeros(x_local.shape[1], (-2 * H) % 4))
-        x_key = (x_local.data_ptr(), x_local._version, tuple(x_local.shape)) if cache_input_gather else None
+        x_key = _input_key(x_local) if cache_input_gather else None
         rows = ShardedGatLayerAggFirstFunction.apply(x_local, w_ext, torch.cat(uv, dim=1), graph, plan, H, Dp,
                                                      skips is not None, float(alpha), bool(concat), x_key)
     else:

@@ -53,12 +53,18 @@ def run_gloo(rank, world):
     for p, m in zip(lin.parameters(), merged):
         assert torch.allclose(p.grad, m, atol=1e-6), (p.grad, m)
     # kept gather buffer: same key -> hit, new key -> same storage, miss
-    buf, hit = plan.cached_xg(("k", 0), (500, 4), torch.device("cpu"))
+    from pygat_b200.sharded import _input_key
+    xin = torch.zeros(7, 3)
+    buf, hit = plan.cached_xg(_input_key(xin), (500, 4), torch.device("cpu"))
     assert not hit
-    buf2, hit2 = plan.cached_xg(("k", 0), (500, 4), torch.device("cpu"))
+    buf2, hit2 = plan.cached_xg(_input_key(xin), (500, 4), torch.device("cpu"))
     assert hit2 and buf2.data_ptr() == buf.data_ptr()
-    buf3, hit3 = plan.cached_xg(("k", 1), (500, 4), torch.device("cpu"))
+    xin.add_(1.0)  # in-place update: version counter moves, the kept rows are stale
+    buf3, hit3 = plan.cached_xg(_input_key(xin), (500, 4), torch.device("cpu"))
     assert not hit3 and buf3.data_ptr() == buf.data_ptr()
+    k_dead = _input_key(torch.zeros(7, 3))  # the tensor object is gone: never a hit, whatever reuses its storage
+    plan.cached_xg(k_dead, (500, 4), torch.device("cpu"))
+    assert not plan.cached_xg(k_dead, (500, 4), torch.device("cpu"))[1]
     from pygat_b200.sharded import reduce_rows_async
     got2, work = reduce_rows_async((ref * (rank + 1)).clone(), plan)
     if work is not None:
@@ -131,7 +137,7 @@ def run_nccl(rank, world):
         a_bad = [a.detach() * 1.7 for a in a_d]
         sharded_gat_layer(xs, graph, plan, Ws, a_s, a_bad, Ss, 0.2, concat)
         kept = getattr(plan, "_peer_rows", None)  # symmetric-memory exchange, or the NCCL path's kept buffer
-        assert (kept.key if kept else plan._xg_cache[0]) == (xs.data_ptr(), xs._version, tuple(xs.shape))
+        assert (kept.key if kept else plan._xg_cache[0])[:3] == (xs.data_ptr(), xs._version, tuple(xs.shape))
         for variant in ("hit", "invalidated"):
             for p in Ws + a_s + a_d + (Ss or []):
                 p.grad = None
@@ -158,6 +164,10 @@ def run_nccl(rank, world):
 
 
 def main():
+    import faulthandler
+    # a rank that fails while its peer waits in a collective would otherwise hang the job: dump every thread's
+    # stack and exit instead
+    faulthandler.dump_traceback_later(int(os.environ.get("DIST_WORKER_TIMEOUT", "120")), exit=True)
     mode = sys.argv[1]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo" if mode == "gloo" else "nccl")
@@ -166,8 +176,14 @@ def main():
         dist.barrier()
         if rank == 0:
             print(f"DIST_OK mode={mode} world={world}")
-    finally:
-        dist.destroy_process_group()
+    except BaseException:
+        # report and leave at once: tearing the process group down would wait for the peer's pending collective
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
