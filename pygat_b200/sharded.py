@@ -56,13 +56,13 @@ class ShardPlan:
 
     def peer_rows(self, shape, dev):
         """PeerRows for an [N, P] gathered-row buffer in symmetric memory (every rank's copy mapped into every
-        process), or None when symmetric memory is unavailable or not enabled (GATK_PEER_PUSH=1 turns it on) / the group is too
+        process), or None when symmetric memory is unavailable or switched off (GATK_PEER_PUSH=0) / the group is too
         large: the caller then uses the NCCL all-gather.  Collective: every rank of the group must call it."""
         c = getattr(self, "_peer_rows", None)
         if c is not None and (c is False or c.shape == tuple(shape)):
             return c or None
         ok, made = 1, None
-        if os.environ.get("GATK_PEER_PUSH", "0") != "1" or self.world - 1 > MAX_PEERS or dev.type != "cuda":
+        if os.environ.get("GATK_PEER_PUSH", "1") == "0" or self.world - 1 > MAX_PEERS or dev.type != "cuda":
             ok = 0
         else:
             try:

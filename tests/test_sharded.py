@@ -76,7 +76,7 @@ def test_sharded_layer_world1_equals_single_gpu():
 def test_sharded_layer_matches_single_gpu_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    _torchrun("nccl", 2)  # NCCL exchanges
+    _torchrun("nccl", 2, GATK_PEER_PUSH="0")  # NCCL exchanges only
 
 
 @pytest.mark.gpu
@@ -84,7 +84,7 @@ def test_sharded_layer_peer_push_exchange_nccl():
     """Forward exchange fused into the pack kernel (stores into the peers' symmetric-memory copies over NVLink)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    _torchrun("nccl", 2, GATK_PEER_PUSH="1")
+    _torchrun("nccl", 2, GATK_PEER_PUSH="1")  # the default
 
 
 def test_row_cost_fit_and_fractional_cuts():
