@@ -309,8 +309,10 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
     """functional.GatLayerAggFirstFunction on a destination-row shard (narrow first-layer inputs, no dropout).
 
     What crosses NVLink per layer:
-      forward   all-gather of the GATHER ROWS xg = [x | g] (F_in + H floats per node, padded to 128 bytes): every
-                rank packs its own rows (gatk_logits_pack) and gathers the others'; nothing is recomputed;
+      forward   the GATHER ROWS xg = [x | g] (F_in + H floats per node, 64-byte aligned pitch): every rank packs its
+                own rows and the pack kernel itself writes them into the other ranks' copies (gatk_logits_pack_push
+                over symmetric memory; NCCL all-gather when that is unavailable).  While the input tensor is unchanged
+                only the g columns are exchanged; nothing is recomputed;
       backward  reduce-scatter of the per-source logit gradients dg [N, H] and one all-reduce of the
                 parameter-sized gradients (dW, d[W a_src | W a_dst]).
     Everything H*D wide (aggregated rows, outputs, their gradients) stays on the rank that owns the rows."""
