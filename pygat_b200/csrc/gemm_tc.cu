@@ -641,7 +641,11 @@ static int make_map_box32(CUtensorMap* map, const void* base, int64_t rows, int6
 // with A_b = A + b*a_bs (a COLUMN block of the same rows), C_b = C + b*c_bs.  One launch covers all heads:
 // the operands are described to TMA as 3-D tensors (columns of a batch, rows, batch), so K / N tails of a
 // batch are zero-filled on load and clipped on store even though the next head's columns follow in memory.
-// Same 3xTF32 scheme and warp roles as the kernels above; the tile width is 64 when a head is 64 wide.
+// Same 3xTF32 scheme as the kernels above; the tile width is 64 when a head is 64 wide.  Differences (all
+// ncu-driven): the A operand is split into TENSOR memory (tcgen05.st; the TN kernel transposes
+// it through registers on the way) and read from there by the MMAs; Bhi|Blo are one stacked operand (2 MMAs per
+// k-step); role branches are warp-uniform with one elect.sync per issue block; A, B and the TMEM A slots cycle
+// in separate rings; the wide tile leaves through one dense TMA store.
 // =====================================================================================================
 namespace bt {
 
@@ -717,6 +721,8 @@ struct RingN {
 
 constexpr int BT_THREADS = 512;  // warps 0-2 producer / MMA / TMEM, 4-7 splitter, 8-15 two epilogue warpgroups
 
+// configuration of the shared-memory-operand TN kernel (only the 128-wide tile still uses it: its accumulators
+// fill all 512 TMEM columns, so there is no room for A there)
 template <int BN>
 struct Cfg {
   static constexpr int TILE_A = BLOCK_M * BLOCK_K * 4;  // 16 KiB
