@@ -128,7 +128,20 @@ def cora_adj():
     return adj
 
 
+def v2_cases():
+    """GATv2 flavours (layers.py:179-316): eval mode and p = 0, as for the other parity cases."""
+    sp2, de2 = ref_layers.SpGraphAttentionLayerV2, ref_layers.GraphAttentionLayerV2
+    a96 = rand_graph(96, 3.0, 1)
+    head_case("sp2_head_basic", sp2, 96, 24, 8, a96, True, False, 41)
+    head_case("sp2_head_skip_last", sp2, 96, 24, 7, a96, False, True, 42)
+    head_case("sp2_head_hub", sp2, 300, 12, 16, hub_graph(300, 3), True, True, 43)
+    head_case("de2_head_basic", de2, 96, 24, 8, a96, True, False, 44)
+    head_case("de2_head_skip_last", de2, 96, 24, 7, a96, False, True, 45)
+
+
 def main():
+    if os.environ.get("GOLDEN_ONLY") == "v2":  # add the GATv2 fixtures without rewriting the others
+        return v2_cases()
     sp, de = ref_layers.SpGraphAttentionLayer, ref_layers.GraphAttentionLayer
     a96 = rand_graph(96, 3.0, 1)
     head_case("sp_head_basic", sp, 96, 24, 8, a96, True, False, 11)
@@ -149,6 +162,7 @@ def main():
     gat_case("gat_de_ppi_like", [10, 32, 32, 11], [4, 4, 6], de, blk, True, 33, 0.0, True)
     gat_case("gat_sp_ppi_like", [10, 32, 32, 11], [4, 4, 6], sp, blk, True, 34, 0.0, True)
     gat_case("gat_sp_cora_topology", [16, 8, 7], [8, 1], sp, cora_adj(), False, 72, 0.6, False)
+    v2_cases()
 
 
 if __name__ == "__main__":

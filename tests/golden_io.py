@@ -7,7 +7,9 @@ import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-HEAD_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*_head_*.npz")))
+_ALL_HEADS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*_head_*.npz")))
+HEAD_CASES = [n for n in _ALL_HEADS if n.startswith(("sp_", "de_"))]        # GAT heads: the accelerated path
+V2_HEAD_CASES = [n for n in _ALL_HEADS if n.startswith(("sp2_", "de2_"))]   # GATv2 heads (layers.py:179-316)
 GAT_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "gat_*.npz")))
 
 

@@ -523,3 +523,31 @@ def test_products_shape_invariants_at_full_size():
     lhs = xr.grad.sum(0)
     rhs = torch.cat(Ws, dim=1) @ gout.sum(0)
     assert rel_err(lhs, rhs) < 1e-3
+
+
+# ------------------------------------------------------------------------------ GATv2 flavours
+@pytest.mark.parametrize("name", ["sp2_head_basic", "sp2_head_skip_last", "sp2_head_hub"])
+def test_sparse_v2_heads_match_reference_golden(name):
+    """SpGraphAttentionLayerV2 (layers.py:234-316) is not on the accelerated path yet: torch ops on the device over
+    the engine's cached CSR (O(E*D) instead of the reference's per-call adj.nonzero() and dense N x N backward).
+    Outputs and gradients against the unmodified reference.  (The dense GATv2 class is device-agnostic torch code
+    and is checked against its golden vectors on CPU, tests/test_modules_cpu.py.)"""
+    d = load(name)
+    cls = layers.SpGraphAttentionLayerV2 if name.startswith("sp2_") else layers.GraphAttentionLayerV2
+    two_f, dd = d["W"].shape
+    head = cls(two_f // 2, dd, dropout=d["p"], alpha=d["alpha"], concat=bool(d["concat"]), skip_connection="skip" in d)
+    with torch.no_grad():
+        head.W.copy_(d["W"])
+        head.a.copy_(d["a"])
+        if "skip" in d:
+            head.skip_projection.copy_(d["skip"])
+    head = head.to(DEV)
+    head.train(bool(d["train"]))
+    x = d["x"].to(DEV).requires_grad_(True)
+    y = head(x, dense_adj(d).to(DEV))
+    y.backward(d["gout"].to(DEV))
+    errs = {"y": rel_err(y, d["y"]), "dx": rel_err(x.grad, d["dx"]), "dW": rel_err(head.W.grad, d["dW"]),
+            "da": rel_err(head.a.grad, d["da"])}
+    if "skip" in d:
+        errs["dskip"] = rel_err(head.skip_projection.grad, d["dskip"])
+    assert all(v < 1e-5 for v in errs.values()), errs

@@ -83,3 +83,48 @@ def test_padded_width_and_packing():
     assert torch.equal(a_src[2, :7], heads[2].a[:7, 0]) and torch.equal(a_dst[2, :7], heads[2].a[7:, 0])
     w_ext.sum().backward()  # gradients flow back to the per-head parameters
     assert heads[0].W.grad is not None and heads[2].skip_projection.grad is not None
+
+
+# ------------------------------------------------------------------------------ GATv2 flavours
+V2_SEEDS = {"sp2_head_basic": 41, "sp2_head_skip_last": 42, "sp2_head_hub": 43, "de2_head_basic": 44,
+            "de2_head_skip_last": 45}
+
+
+def _v2_head(d, name, seed=None):
+    cls = layers.SpGraphAttentionLayerV2 if name.startswith("sp2_") else layers.GraphAttentionLayerV2
+    two_f, dd = d["W"].shape
+    if seed is not None:
+        torch.manual_seed(seed)
+    return cls(two_f // 2, dd, dropout=d["p"], alpha=d["alpha"], concat=bool(d["concat"]), skip_connection="skip" in d)
+
+
+@pytest.mark.parametrize("name", sorted(V2_SEEDS))
+def test_v2_head_same_seed_same_parameters_as_reference(name):
+    d = load(name)
+    head = _v2_head(d, name, V2_SEEDS[name])
+    assert torch.equal(head.W.data, d["W"]) and torch.equal(head.a.data, d["a"])  # layers.py:190-195, 246-251
+    if "skip" in d:
+        assert torch.equal(head.skip_projection.data, d["skip"])
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(V2_SEEDS) if n.startswith("de2_")])
+def test_dense_v2_head_matches_reference_golden(name):
+    """The dense GATv2 class is plain torch ops on the caller's device (not on the accelerated path): checked on
+    CPU against the unmodified reference's outputs and gradients (layers.py:203-229)."""
+    from tests.golden_io import dense_adj, rel_err
+    d = load(name)
+    head = _v2_head(d, name)
+    with torch.no_grad():
+        head.W.copy_(d["W"])
+        head.a.copy_(d["a"])
+        if "skip" in d:
+            head.skip_projection.copy_(d["skip"])
+    head.train(bool(d["train"]))
+    x = d["x"].clone().requires_grad_(True)
+    y = head(x, dense_adj(d))
+    y.backward(d["gout"])
+    errs = {"y": rel_err(y, d["y"]), "dx": rel_err(x.grad, d["dx"]), "dW": rel_err(head.W.grad, d["dW"]),
+            "da": rel_err(head.a.grad, d["da"])}
+    if "skip" in d:
+        errs["dskip"] = rel_err(head.skip_projection.grad, d["dskip"])
+    assert all(v < 1e-5 for v in errs.values()), errs
