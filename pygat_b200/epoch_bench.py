@@ -91,20 +91,24 @@ def ppi_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup:
                        layer_type=layers.GraphAttentionLayer, skip_connection=True).to(device)
     opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0)
     loss_fn = torch.nn.BCEWithLogitsLoss(reduction="mean")
-    mine = batches[rank::world]
+    from .sharded import rank_batch_schedule
+    mine = [batches[i] if i is not None else None for i in rank_batch_schedule(len(batches), rank, world)]
 
     def epoch():
         model.train()
         tot = 0.0
-        for feats, labels, adj in mine:
-            out = model(feats, adj)
-            loss = loss_fn(out, labels)
-            opt.zero_grad()
-            loss.backward()
+        for item in mine:  # every rank runs the same number of steps; None = this rank idles in the step
+            opt.zero_grad(set_to_none=True)
+            n_nodes = 0
+            if item is not None:
+                feats, labels, adj = item
+                loss = loss_fn(model(feats, adj), labels)
+                loss.backward()
+                n_nodes = feats.shape[0]
+                tot += loss.item()  # the reference prints the loss of every batch (host sync)
             if world > 1:
-                allreduce_gradients(model.parameters(), feats.shape[0])
+                allreduce_gradients(model.parameters(), n_nodes)
             opt.step()
-            tot += loss.item()  # the reference prints the loss of every batch (host sync)
         return tot
 
     for _ in range(warmup):
@@ -116,5 +120,5 @@ def ppi_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup:
         epoch()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / epochs, {"graphs": len(graphs), "batches_per_rank": len(mine), "epochs": epochs,
+    return e0.elapsed_time(e1) / epochs, {"graphs": len(graphs), "batches_per_rank": sum(m is not None for m in mine), "epochs": epochs,
                                           "nodes": sum(PPI_TRAIN_GRAPH_NODES)}

@@ -472,20 +472,36 @@ def allreduce_gradients(params, n_local_nodes: int, group=None):
     """Make per-rank mean-loss gradients equal the gradient of the mean over ALL ranks' nodes: the
     reference's BCEWithLogitsLoss(reduction='mean') over a merged batch (train_ppi.py:114-119,
     load_data_ppi.py:84-86) weights every node equally, so each rank's gradient is scaled by
-    n_local / n_total before the sum."""
-    params = [p for p in params if p.grad is not None]
+    n_local / n_total before the sum.  A rank that has no graphs in this step (the last step of an epoch when
+    the batches do not divide evenly, see rank_batch_schedule) passes n_local_nodes = 0 and still takes part:
+    its missing gradients count as zeros."""
+    params = list(params)
     if not params:
         return
-    dev = params[0].grad.device
+    dev = params[0].device
     cnt = torch.tensor([float(n_local_nodes)], device=dev)
     dist.all_reduce(cnt, group=group)
-    w = float(n_local_nodes) / float(cnt.item())
-    flat = torch.cat([p.grad.reshape(-1) for p in params]) * w
+    total = float(cnt.item())
+    w = float(n_local_nodes) / total if total > 0 else 0.0
+    flat = torch.cat([(p.grad.reshape(-1) * w) if (p.grad is not None and n_local_nodes > 0)
+                      else torch.zeros(p.numel(), dtype=p.dtype, device=dev) for p in params])
     dist.all_reduce(flat, group=group)
     off = 0
     for p in params:
-        p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+        g = flat[off:off + p.numel()].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
         off += p.numel()
+
+
+def rank_batch_schedule(n_batches: int, rank: int, world: int):
+    """Which batch this rank runs at every step of an epoch under graph-level data parallelism: step s takes
+    batches [s*world, (s+1)*world), one per rank, so every rank runs the SAME number of steps (collectives
+    stay matched); None marks a step in which this rank idles (and all-reduces zeros with weight 0)."""
+    steps = (n_batches + world - 1) // world
+    return [s * world + rank if s * world + rank < n_batches else None for s in range(steps)]
 
 
 def shard_rows_by_cost(rowptr: torch.Tensor, world: int, row_cost: float):

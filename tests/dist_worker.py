@@ -52,6 +52,26 @@ def run_gloo(rank, world):
     allreduce_gradients(lin.parameters(), sizes[rank])
     for p, m in zip(lin.parameters(), merged):
         assert torch.allclose(p.grad, m, atol=1e-6), (p.grad, m)
+    # uneven epochs: 3 batches on 2 ranks = 2 steps, rank 1 idles in the second one but still all-reduces;
+    # every step's gradient equals the merged gradient of the batches that ran in it
+    from pygat_b200.sharded import rank_batch_schedule
+    assert rank_batch_schedule(3, 0, 2) == [0, 2] and rank_batch_schedule(3, 1, 2) == [1, None]
+    assert rank_batch_schedule(10, 3, 4) == [3, 7, None] and rank_batch_schedule(10, 1, 4) == [1, 5, 9]
+    bx = [torch.randn(s, 4, generator=torch.Generator().manual_seed(30 + i)) for i, s in enumerate([6, 9, 4])]
+    by = [torch.rand(s, 3, generator=torch.Generator().manual_seed(40 + i)).round() for i, s in enumerate([6, 9, 4])]
+    for step, idx in enumerate(rank_batch_schedule(3, rank, world) if world == 2 else []):
+        ran = [i for i in (step * world + r for r in range(world)) if i < 3]
+        lin.zero_grad()
+        loss_fn(lin(torch.cat([bx[i] for i in ran])), torch.cat([by[i] for i in ran])).backward()
+        want = [p.grad.clone() for p in lin.parameters()]
+        lin.zero_grad(set_to_none=True)
+        n_nodes = 0
+        if idx is not None:
+            loss_fn(lin(bx[idx]), by[idx]).backward()
+            n_nodes = bx[idx].shape[0]
+        allreduce_gradients(lin.parameters(), n_nodes)
+        for p, m in zip(lin.parameters(), want):
+            assert torch.allclose(p.grad, m, atol=1e-6), (step, p.grad, m)
     # kept gather buffer: same key -> hit, new key -> same storage, miss
     from pygat_b200.sharded import _input_key
     xin = torch.zeros(7, 3)
