@@ -1,0 +1,49 @@
+"""bench.py's output contract that can be checked without a GPU: the reference arm's JSON line and the
+algorithmic-byte model the roofline fractions are computed from."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    env = dict(os.environ, BENCH_CPU_SAMPLE_NODES="1024", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "gat_layer_fwd_bwd_head_edges_per_s"
+    assert d["unit"] == "head-edges/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["nodes"] == 1024 and d["vs_baseline"] is None
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", BENCH_CPU_SAMPLE_NODES="1024")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_algorithmic_bytes_products_shape():
+    sys.path.insert(0, ROOT)
+    import bench
+    n, e, H, D, F = 2_449_029, 61_861_615, 8, 64, 100
+    ab = bench.algorithmic_bytes(n, e, H, D, F)
+    # leading term 12*D + 28 bytes per head-edge for the three-gather model, ~428 GB per layer
+    assert abs(ab["layer_survey"] / 1e9 - 427.8) < 0.5
+    lead = e * H * (12 * D + 28)
+    assert 0.90 < lead / ab["layer_survey"] < 1.0
+    # the aggregate-first form gathers the (F + H)-float input row twice: 2 * E * 432 bytes dominate its 139 GB
+    assert abs(ab["layer_agg_first"] / 1e9 - 139.05) < 0.1
+    assert ab["gatk_attn_x_fwd"] == e * (4 * 108 + 4) + n * (4 * H * F + 8 * H + 8)
+    assert ab["gatk_attn_x_bwd"] == e * (4 * 108 + 4 + 4 * H) + n * (8 * H * F + 12 * H + 8)
+    assert ab["gemm:project"] == ab["gemm:dW"] == ab["gemm:dxagg"] == 4 * n * H * (F + D)
+    parts = ["gatk_logits_pack", "gatk_attn_x_fwd", "gatk_attn_x_bwd", "gatk_edge_tsum", "gatk_elu_bwd", "gemm:project",
+             "gemm:dW", "gemm:dxagg", "gemm:dlogits"]
+    assert sum(ab[k] for k in parts) == ab["layer_agg_first"]
