@@ -22,6 +22,8 @@ Reference lines each function follows (all under /root/reference):
 * ``coo_matmul`` / ``CooMatmul`` layers.py:70-90 (``SpecialSpmmFunction``)
 * ``sparse_head``                layers.py:125-173 (``SpGraphAttentionLayer.forward``)
 * ``dense_head``                 layers.py:32-64  (``GraphAttentionLayer.forward``)
+* ``sparse_head_v2``             layers.py:255-313 (``SpGraphAttentionLayerV2.forward``)
+* ``dense_head_v2``              layers.py:203-229 (``GraphAttentionLayerV2.forward``)
 * ``gat_forward``                models.py:29-35  (``GAT.forward``)
 * ``init_head`` / ``init_gat``   layers.py:21-28, 111-119 and models.py:15-27
 
@@ -177,6 +179,47 @@ def dense_head(x, W, a, adj, alpha, concat=True, skip=None, p=0.0,
     if skip is not None:
         out = out + h.mm(skip)                                 # :48
     return torch.nn.functional.elu(out) if concat else out     # :50-53
+
+
+# --------------------------------------------------------------------------- GATv2 flavours
+def sparse_head_v2(x, W, a, edge, alpha, concat=True, skip=None, faithful=True):
+    """SpGraphAttentionLayerV2.forward (layers.py:255-313) for one head, eval mode / p = 0.
+
+    x (N,F) W (2F,D) a (1,D) edge (2,E).  The score needs a D-wide operation per stored entry,
+    e_ij = a . LeakyReLU(Whi_i + Whj_j) -- it does not split into f_i + g_j -- and the aggregated rows are
+    the FIRST projection of the source, Whi_j (layers.py:295)."""
+    n, f_in = x.shape
+    whi = x.mm(W[:f_in])                                       # :265
+    whj = x.mm(W[f_in:])                                       # :266
+    edge_h = (whi[edge[0]] + whj[edge[1]]).t()                 # :275
+    logit = a.reshape(1, -1).mm(_leaky(edge_h, alpha)).squeeze(0)  # :278
+    row_max = segment_max(logit, edge[0])                      # :280
+    ex = torch.exp(logit - row_max[edge[0]])                   # :281
+    ones = torch.ones(n, 1, dtype=x.dtype)
+    rowsum = coo_matmul(edge, ex, torch.Size([n, n]), ones, faithful)   # :285
+    out = coo_matmul(edge, ex, torch.Size([n, n]), whi, faithful)       # :291
+    out = out.div(rowsum)                                      # :295
+    if skip is not None:
+        out = out + x.mm(skip)                                 # :301
+    return torch.nn.functional.elu(out) if concat else out     # :303-308
+
+
+def dense_head_v2(x, W, a, adj, alpha, concat=True, skip=None):
+    """GraphAttentionLayerV2.forward (layers.py:203-229) for one head, eval mode / p = 0.
+
+    a is (D,1).  As shipped, the score is a per-node COLUMN (N,1) that `torch.where` broadcasts along each
+    row (layers.py:214-217): every stored entry of row i gets the same score, i.e. attention is uniform
+    over a node's neighbourhood, and the aggregated rows are the second projection (layers.py:220)."""
+    f_in = x.shape[1]
+    wh1 = x.mm(W[:f_in])                                       # :207
+    wh2 = x.mm(W[f_in:])                                       # :208
+    e = _leaky(wh1 + wh2, alpha).matmul(a.reshape(-1, 1))      # :212-214
+    att = torch.where(adj > 0, e, torch.full_like(e, NEG_FILL))  # :216-217 (broadcast of the (N,1) column)
+    att = torch.softmax(att, dim=1)                            # :218
+    out = att.matmul(wh2)                                      # :220
+    if skip is not None:
+        out = out + x.mm(skip)                                 # :224
+    return torch.nn.functional.elu(out) if concat else out     # :226-229
 
 
 # --------------------------------------------------------------------------- model

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import gat_oracle as O
-from tests.golden_io import GAT_CASES, HEAD_CASES, dense_adj, gat_params, head_masks, load, rel_err
+from tests.golden_io import GAT_CASES, HEAD_CASES, V2_HEAD_CASES, dense_adj, gat_params, head_masks, load, rel_err
 
 TOL = 2e-6  # same fp32 ops in the same order on the same CPU: only reduction-order noise
 
@@ -23,6 +23,28 @@ def test_head_matches_reference(name):
         y = O.sparse_head(x, W, a, O.edge_list(adj), d["alpha"], bool(d["concat"]), skip, d["p"], **mk)
     else:
         y = O.dense_head(x, W, a, adj, d["alpha"], bool(d["concat"]), skip, d["p"], **mk)
+    y.backward(d["gout"])
+    assert rel_err(y, d["y"]) < TOL
+    assert rel_err(x.grad, d["dx"]) < TOL
+    assert rel_err(W.grad, d["dW"]) < TOL
+    assert rel_err(a.grad, d["da"]) < TOL
+    if skip is not None:
+        assert rel_err(skip.grad, d["dskip"]) < TOL
+
+
+@pytest.mark.parametrize("name", V2_HEAD_CASES)
+def test_v2_head_matches_reference(name):
+    """GATv2 flavours (layers.py:179-316): the checker for the next fused kernel."""
+    d = load(name)
+    adj = dense_adj(d)
+    x = d["x"].clone().requires_grad_(True)
+    W = d["W"].clone().requires_grad_(True)
+    a = d["a"].clone().requires_grad_(True)
+    skip = d["skip"].clone().requires_grad_(True) if "skip" in d else None
+    if name.startswith("sp2_"):
+        y = O.sparse_head_v2(x, W, a, O.edge_list(adj), d["alpha"], bool(d["concat"]), skip)
+    else:
+        y = O.dense_head_v2(x, W, a, adj, d["alpha"], bool(d["concat"]), skip)
     y.backward(d["gout"])
     assert rel_err(y, d["y"]) < TOL
     assert rel_err(x.grad, d["dx"]) < TOL
