@@ -88,7 +88,10 @@ GATK_API int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, 
 /* Batched (per-head) products: for b in [0, batches)  C_b = op(A_b) op(B_b)  with A_b = A + b*a_bs, B_b = B + b*b_bs,
  * C_b = C + b*c_bs (element offsets: the batches are column blocks of the same matrices, or separate matrices).
  * epilogue 1 applies ELU to C (F.elu, layers.py:51,170).  Never accumulates.  One launch of the tcgen05 kernels
- * covers all batches when  (!transA, K <= 512)  or  (transA, !transB, K >= 2048, M, N <= 512). */
+ * (A operand split into tensor memory, fp32 parity through the 3xTF32 scheme) covers all batches when
+ *   !transA:           M >= 1024, K <= 512 and (N <= 64 or K <= 128), pitches / batch strides multiples of 4 floats;
+ *   transA, !transB:   K >= 2048, 8 <= M, N <= 512 (deterministic split-K over all SMs);
+ * other shapes run one gatk_gemm per batch. */
 GATK_API size_t gatk_gemm_batched_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches);
 GATK_API int gatk_gemm_batched(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A,
                                int64_t lda, int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, float* C, int64_t ldc,
