@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from . import _lib
+from . import _lib, _mem
 from .graph import Graph, _ptr, _require_cuda, _stream
 
 
@@ -51,7 +51,7 @@ class LayerMasks:
 def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=0, a_off=0, b_off=0, c_off=0, label=None):
     """C[M,N] (+)= op(A) op(B) on raw pointers; *_off are element offsets into the tensors."""
     ws_bytes = _lib.query("gatk_gemm_workspace_bytes", ta, tb, M, N, K)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=C.device) if ws_bytes else None
+    ws = _mem.empty(ws_bytes, dtype=torch.uint8, device=C.device) if ws_bytes else None
     _lib.call("gatk_gemm", ta, tb, M, N, K, A.data_ptr() + 4 * a_off, lda, B.data_ptr() + 4 * b_off, ldb,
               C.data_ptr() + 4 * c_off, ldc, accumulate, _ptr(ws), ws_bytes, _stream(), label=label)
 
@@ -59,7 +59,7 @@ def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=0, a_off=0, b_off=
 def _gemm_batched(ta, tb, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, epilogue=0, label=None):
     """C_b = op(A_b) op(B_b) for the `batches` column blocks A_b = A + b*a_bs, ... (one launch for all heads)."""
     ws_bytes = _lib.query("gatk_gemm_batched_workspace_bytes", ta, tb, M, N, K, batches)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=C.device) if ws_bytes else None
+    ws = _mem.empty(ws_bytes, dtype=torch.uint8, device=C.device) if ws_bytes else None
     _lib.call("gatk_gemm_batched", ta, tb, M, N, K, batches, A.data_ptr(), lda, a_bs, B.data_ptr(), ldb, b_bs,
               C.data_ptr(), ldc, c_bs, epilogue, _ptr(ws), ws_bytes, _stream(), label=label)
 
@@ -67,7 +67,7 @@ def _gemm_batched(ta, tb, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, 
 def _hub_scratch(which: int, H: int, Dp: int, n_seg: int, dev):
     if not n_seg:
         return None
-    return torch.empty(_lib.query("gatk_hub_scratch_floats", which, H, Dp, n_seg), dtype=torch.float32, device=dev)
+    return _mem.empty(_lib.query("gatk_hub_scratch_floats", which, H, Dp, n_seg), dtype=torch.float32, device=dev)
 
 
 def random_masks(n: int, f_in: int, H: int, Dp: int, nnz: int, p: float, device) -> LayerMasks:
@@ -77,7 +77,7 @@ def random_masks(n: int, f_in: int, H: int, Dp: int, nnz: int, p: float, device)
     sizes = (H * n * f_in, n * H * Dp, nnz * H)
     bufs, off = [], 0
     for sz in sizes:
-        t = torch.empty(sz, dtype=torch.uint8, device=device)
+        t = _mem.empty(sz, dtype=torch.uint8, device=device)
         _lib.call("gatk_dropout_keep_mask", t.data_ptr(), sz, float(p), seed, off, _stream())
         off += (sz + 3) // 4
         bufs.append(t)
@@ -107,11 +107,11 @@ class GatLayerFunction(torch.autograd.Function):
         st = _stream()
 
         # ---- K1: projection (+ skip columns) ---------------------------------------------
-        z = torch.empty(n, M_out, dtype=torch.float32, device=dev)
+        z = _mem.empty(n, M_out, dtype=torch.float32, device=dev)
         if masks.keep_in is None:
             _gemm(0, 0, n, M_out, f_in, x, f_in, w_ext, M_out, z, M_out)
         else:
-            xh = torch.empty_like(x)
+            xh = _mem.empty_like(x)
             for h in range(H):  # every head drops the input with its own mask (layers.py:34,132)
                 _lib.call("gatk_mask_scale", x.data_ptr(), f_in, masks.keep_in[h].data_ptr(), inv_keep,
                           xh.data_ptr(), f_in, n, f_in, st)
@@ -122,17 +122,17 @@ class GatLayerFunction(torch.autograd.Function):
         skip_ptr = z.data_ptr() + 4 * HD if has_skip else None
 
         # ---- logits (and the post-projection dropout, in place) --------------------------
-        f = torch.empty(n, H, dtype=torch.float32, device=dev)
-        g = torch.empty(n, H, dtype=torch.float32, device=dev)
+        f = _mem.empty(n, H, dtype=torch.float32, device=dev)
+        g = _mem.empty(n, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_logits_fwd", n, H, Dp, wh_ptr, M_out, _ptr(masks.keep_wh), inv_keep,
                   a_src.data_ptr(), a_dst.data_ptr(), f.data_ptr(), g.data_ptr(), st)
 
         # ---- K2: fused attention -----------------------------------------------------------
         need_grad = any(ctx.needs_input_grad[:4])
-        out = torch.empty(n, HD, dtype=torch.float32, device=dev)
+        out = _mem.empty(n, HD, dtype=torch.float32, device=dev)
         separate_hagg = need_grad and (has_skip or act_elu)
-        hagg = torch.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
-        lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        hagg = _mem.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
+        lse = _mem.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
         hubs = graph.hubs
         scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_ptr, M_out,
@@ -160,12 +160,12 @@ class GatLayerFunction(torch.autograd.Function):
         tptr, trow, perm, thubs = graph.transpose()
 
         # dZ = [dWh | dSkip]; with a skip projection dL/dh' IS dSkip, so prep writes it there as well.
-        dz_rows = torch.empty(n, M_out, dtype=torch.float32, device=dev)
+        dz_rows = _mem.empty(n, M_out, dtype=torch.float32, device=dev)
         ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
-        rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
-        df = torch.empty(n, H, dtype=torch.float32, device=dev)
-        dg = torch.empty(n, H, dtype=torch.float32, device=dev)
-        edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        rec = _mem.empty(n, ldrec, dtype=torch.float32, device=dev)
+        df = _mem.empty(n, H, dtype=torch.float32, device=dev)
+        dg = _mem.empty(n, H, dtype=torch.float32, device=dev)
+        edge_dz = _mem.empty(graph.nnz, H, dtype=torch.float32, device=dev)
 
         # ---- K3 prep: per-destination records [dh' | f, lse, c] -------------------------------------
         _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if (act_elu and has_skip) else None, HD,
@@ -189,23 +189,23 @@ class GatLayerFunction(torch.autograd.Function):
         del edge_dz
 
         # ---- da ------------------------------------------------------------------------------
-        da_src = torch.empty(H, Dp, dtype=torch.float32, device=dev)
-        da_dst = torch.empty(H, Dp, dtype=torch.float32, device=dev)
-        ws = torch.empty(_lib.query("gatk_da_workspace_floats", H, Dp), dtype=torch.float32, device=dev)
+        da_src = _mem.empty(H, Dp, dtype=torch.float32, device=dev)
+        da_dst = _mem.empty(H, Dp, dtype=torch.float32, device=dev)
+        ws = _mem.empty(_lib.query("gatk_da_workspace_floats", H, Dp), dtype=torch.float32, device=dev)
         _lib.call("gatk_da_reduce", n, H, Dp, z.data_ptr(), M_out, df.data_ptr(), dg.data_ptr(),
                   da_src.data_ptr(), da_dst.data_ptr(), ws.data_ptr(), st)
 
         # ---- K5: projection backward -------------------------------------------------------
         need_dx = ctx.needs_input_grad[0]
-        dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
-        dx = torch.empty(n, f_in, dtype=torch.float32, device=dev) if need_dx else None
+        dw_ext = _mem.empty(f_in, M_out, dtype=torch.float32, device=dev)
+        dx = _mem.empty(n, f_in, dtype=torch.float32, device=dev) if need_dx else None
         if masks.keep_in is None:
             _gemm(1, 0, f_in, M_out, n, x, f_in, dz_rows, M_out, dw_ext, M_out)
             if need_dx:
                 _gemm(0, 1, n, f_in, M_out, dz_rows, M_out, w_ext, M_out, dx, f_in)
         else:
-            xh = torch.empty_like(x)
-            dxh = torch.empty_like(x) if need_dx else None
+            xh = _mem.empty_like(x)
+            dxh = _mem.empty_like(x) if need_dx else None
             if need_dx:
                 dx.zero_()
             for h in range(H):
@@ -251,15 +251,15 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         x = x.contiguous()
         w_full = w_full.contiguous()
         st = _stream()
-        z = torch.empty(n, Mz, dtype=torch.float32, device=dev)
+        z = _mem.empty(n, Mz, dtype=torch.float32, device=dev)
         _gemm(0, 0, n, Mz, f_in, x, f_in, w_full, Mz, z, Mz)
         f_ptr = z.data_ptr() + 4 * M_out
         g_ptr = f_ptr + 4 * H
         need_grad = any(ctx.needs_input_grad[:2])
-        out = torch.empty(n, HD, dtype=torch.float32, device=dev)
+        out = _mem.empty(n, HD, dtype=torch.float32, device=dev)
         separate_hagg = need_grad and (has_skip or act_elu)
-        hagg = torch.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
-        lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        hagg = _mem.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
+        lse = _mem.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
         hubs = graph.hubs
         scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, z.data_ptr(), Mz,
@@ -288,14 +288,14 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         f_ptr = z.data_ptr() + 4 * M_out
         g_ptr = f_ptr + 4 * H
 
-        dz_rows = torch.empty(n, Mz, dtype=torch.float32, device=dev)   # [dWh | dSkip | df | dg | pad]
+        dz_rows = _mem.empty(n, Mz, dtype=torch.float32, device=dev)   # [dWh | dSkip | df | dg | pad]
         if Mz > M_out + 2 * H:
             dz_rows[:, M_out + 2 * H:].zero_()
         df_ptr = dz_rows.data_ptr() + 4 * M_out
         dg_ptr = df_ptr + 4 * H
         ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
-        rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
-        edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        rec = _mem.empty(n, ldrec, dtype=torch.float32, device=dev)
+        edge_dz = _mem.empty(graph.nnz, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if (act_elu and has_skip) else None, HD,
                   int(act_elu), hagg.data_ptr(), HD, f_ptr, Mz, lse.data_ptr(), rec.data_ptr(), ldrec,
                   dz_rows.data_ptr() + 4 * HD if has_skip else None, Mz, st)
@@ -310,11 +310,11 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), None,
                   None, 1.0, None, 0, df_ptr, Mz, *hubs.args(scratch), st)
         del edge_dz
-        dw_full = torch.empty(f_in, Mz, dtype=torch.float32, device=dev)
+        dw_full = _mem.empty(f_in, Mz, dtype=torch.float32, device=dev)
         _gemm(1, 0, f_in, Mz, n, x, f_in, dz_rows, Mz, dw_full, Mz)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty(n, f_in, dtype=torch.float32, device=dev)
+            dx = _mem.empty(n, f_in, dtype=torch.float32, device=dev)
             _gemm(0, 1, n, f_in, Mz, dz_rows, Mz, w_full, Mz, dx, f_in)
         return dx, dw_full, None, None, None, None, None, None
 
@@ -358,19 +358,19 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         w_uv = w_uv.contiguous()
         st = _stream()
         P = _lib.query("gatk_xg_pitch", Fp, H)
-        xg = torch.empty(n, P, dtype=torch.float32, device=dev)
-        f = torch.empty(n, H, dtype=torch.float32, device=dev)
+        xg = _mem.empty(n, P, dtype=torch.float32, device=dev)
+        f = _mem.empty(n, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_logits_pack", n, f_in, H, x.data_ptr(), f_in, w_uv.data_ptr(), Muv, xg.data_ptr(), P,
                   f.data_ptr(), H, st)
         need_grad = any(ctx.needs_input_grad[1:3])
-        xagg = torch.empty(n, H * Fp, dtype=torch.float32, device=dev)
-        lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        xagg = _mem.empty(n, H * Fp, dtype=torch.float32, device=dev)
+        lse = _mem.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
         hubs = graph.hubs
         scratch = _x_scratch(0, H, Fp, hubs.n_seg, dev)
         _lib.call("gatk_attn_x_fwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
                   f.data_ptr(), H, float(alpha), xagg.data_ptr(), H * Fp, _ptr(lse),
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
-        out = torch.empty(n, HD, dtype=torch.float32, device=dev)
+        out = _mem.empty(n, HD, dtype=torch.float32, device=dev)
         fuse_elu = act_elu and not has_skip  # ELU rides in the projection's epilogue unless a skip term is added first
         _gemm_batched(0, 0, n, Dp, f_in, H, xagg, H * Fp, Fp, w_ext, M_out, Dp, out, HD, Dp, epilogue=int(fuse_elu),
                       label="gemm:project")
@@ -396,20 +396,20 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         st = _stream()
         gout = gout.contiguous()
         if act_elu:
-            dhp = torch.empty(n, HD, dtype=torch.float32, device=dev)
+            dhp = _mem.empty(n, HD, dtype=torch.float32, device=dev)
             _lib.call("gatk_elu_bwd", n, HD, gout.data_ptr(), HD, out.data_ptr(), HD, dhp.data_ptr(), HD, st)
         else:
             dhp = gout
         # value path: dW_h = xagg_h^T dh'_h, dS = x^T dh';  dxagg_h = dh'_h W_h^T feeds the softmax backward
-        dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
-        dxagg = (torch.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
+        dw_ext = _mem.empty(f_in, M_out, dtype=torch.float32, device=dev)
+        dxagg = (_mem.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
         _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp, label="gemm:dW")
         _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp, label="gemm:dxagg")
         if has_skip:
             _gemm(1, 0, f_in, HD, n, xg, P, dhp, HD, dw_ext, M_out, c_off=HD, label="gemm:dskip")
         # logit path: ds per stored entry, df per destination, dg per source (transposed sum of ds)
-        ds = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
-        dfg = (torch.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
+        ds = _mem.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        dfg = (_mem.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
         hubs = graph.hubs
         scratch = _x_scratch(1, H, Fp, hubs.n_seg, dev)
         _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
@@ -419,7 +419,7 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         tptr, _trow, perm, thubs = graph.transpose()[:4]
         _lib.call("gatk_edge_tsum", graph.n_src, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(),
                   dfg.data_ptr() + 4 * H, Muv, thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
-        dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
+        dw_uv = _mem.empty(f_in, Muv, dtype=torch.float32, device=dev)
         _gemm_batched(1, 0, f_in, Muv, n, 1, xg, P, 0, dfg, Muv, 0, dw_uv, Muv, 0, label="gemm:dlogits")  # one "head": the TMEM-A TN kernel
         return None, dw_ext, dw_uv, None, None, None, None, None, None
 
@@ -427,7 +427,7 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
 def _x_scratch(which: int, H: int, Fp: int, n_seg: int, dev):
     if not n_seg:
         return None
-    return torch.empty(_lib.query("gatk_attn_x_scratch_floats", which, H, Fp, n_seg), dtype=torch.float32, device=dev)
+    return _mem.empty(_lib.query("gatk_attn_x_scratch_floats", which, H, Fp, n_seg), dtype=torch.float32, device=dev)
 
 
 class HeadCombineFunction(torch.autograd.Function):
@@ -438,7 +438,7 @@ class HeadCombineFunction(torch.autograd.Function):
     def forward(ctx, rows, H: int, D: int, Dp: int, mode: int):
         rows = rows.contiguous()
         n = rows.shape[0]
-        out = torch.empty(n, H * D if mode == 0 else D, dtype=torch.float32, device=rows.device)
+        out = _mem.empty(n, H * D if mode == 0 else D, dtype=torch.float32, device=rows.device)
         _lib.call("gatk_head_combine", n, H, D, Dp, rows.data_ptr(), H * Dp, mode, out.data_ptr(), _stream())
         ctx.cfg = (n, H, D, Dp, mode)
         return out
@@ -447,7 +447,7 @@ class HeadCombineFunction(torch.autograd.Function):
     def backward(ctx, gout):
         n, H, D, Dp, mode = ctx.cfg
         gout = gout.contiguous()
-        gin = torch.empty(n, H * Dp, dtype=torch.float32, device=gout.device)
+        gin = _mem.empty(n, H * Dp, dtype=torch.float32, device=gout.device)
         _lib.call("gatk_head_combine_bwd", n, H, D, Dp, gout.data_ptr(), mode, gin.data_ptr(), H * Dp, _stream())
         return gin, None, None, None, None
 

@@ -9,7 +9,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _lib
+from . import _lib, _mem
 
 RULE_NONZERO = 0   # SpGraphAttentionLayer: every entry != 0 (layers.py:129)
 RULE_POSITIVE = 1  # GraphAttentionLayer:   entries > 0   (layers.py:41)
@@ -101,14 +101,14 @@ class Graph:
         if adj.dtype != torch.float32:
             adj = adj.float()
         n = adj.shape[0]
-        rowptr = torch.empty(n + 1, dtype=torch.int64, device=adj.device)
+        rowptr = _mem.empty(n + 1, dtype=torch.int64, device=adj.device)
         ws_bytes = _lib.query("gatk_scan_workspace_bytes", n)
-        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=adj.device)
+        ws = _mem.empty(max(ws_bytes, 1), dtype=torch.uint8, device=adj.device)
         rs, cs = adj.stride()
         _lib.call("gatk_csr_from_dense_rowptr", adj.data_ptr(), n, rs, cs, rule, rowptr.data_ptr(),
                   ws.data_ptr(), ws_bytes, _stream())
         e = int(rowptr[-1].item())  # the one host sync of the graph build (the reference syncs per head)
-        col = torch.empty(e, dtype=torch.int32, device=adj.device)
+        col = _mem.empty(e, dtype=torch.int32, device=adj.device)
         _lib.call("gatk_csr_from_dense_fill", adj.data_ptr(), n, rs, cs, rule, rowptr.data_ptr(),
                   col.data_ptr(), _stream())
         return Graph(rowptr, col, seg_len=seg_len)
@@ -119,10 +119,10 @@ class Graph:
         _require_cuda(edge, "edge")
         edge = edge.contiguous()
         e = edge.shape[1]
-        rowptr = torch.empty(n + 1, dtype=torch.int64, device=edge.device)
-        col = torch.empty(e, dtype=torch.int32, device=edge.device)
+        rowptr = _mem.empty(n + 1, dtype=torch.int64, device=edge.device)
+        col = _mem.empty(e, dtype=torch.int32, device=edge.device)
         ws_bytes = _lib.query("gatk_scan_workspace_bytes", n)
-        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=edge.device)
+        ws = _mem.empty(max(ws_bytes, 1), dtype=torch.uint8, device=edge.device)
         _lib.call("gatk_csr_from_coo", edge[0].data_ptr(), edge[1].data_ptr(), e, n, rowptr.data_ptr(),
                   col.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
         return Graph(rowptr, col, seg_len=seg_len)
@@ -135,11 +135,11 @@ class Graph:
     # ------------------------------------------------------------------ transpose (backward only)
     def transpose(self):
         if self._t is None:
-            tptr = torch.empty(self.n_src + 1, dtype=torch.int64, device=self.device)
-            trow = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
-            perm = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            tptr = _mem.empty(self.n_src + 1, dtype=torch.int64, device=self.device)
+            trow = _mem.empty(self.nnz, dtype=torch.int32, device=self.device)
+            perm = _mem.empty(self.nnz, dtype=torch.int32, device=self.device)
             ws_bytes = _lib.query("gatk_transpose_workspace_bytes", self.n_dst, self.n_src, self.nnz)
-            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=self.device)
+            ws = _mem.empty(max(ws_bytes, 1), dtype=torch.uint8, device=self.device)
             _lib.call("gatk_csr_transpose", self.n_dst, self.n_src, self.nnz, self.rowptr.data_ptr(),
                       _ptr(self.col), tptr.data_ptr(), _ptr(trow), _ptr(perm), ws.data_ptr(), ws_bytes, _stream())
             del ws
@@ -150,7 +150,7 @@ class Graph:
         """int32 [E]: CSR entry -> its position in the transposed pattern (inverse of transpose()[2])."""
         if self._iperm is None:
             perm = self.transpose()[2]
-            ip = torch.empty_like(perm)
+            ip = _mem.empty_like(perm)
             ip[perm.long()] = torch.arange(self.nnz, dtype=torch.int32, device=self.device)
             self._iperm = ip
         return self._iperm

@@ -18,7 +18,7 @@ from typing import List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, _mem
 from . import functional as Fn
 from .functional import (HeadCombineFunction, LayerMasks, _gemm, _gemm_batched, _hub_scratch, _x_scratch,
                          agg_first_geometry, pack_heads)
@@ -50,7 +50,7 @@ class ShardPlan:
         same_buf = c is not None and tuple(c[1].shape) == tuple(shape) and c[1].device == dev
         if same_buf and _same_input(c[0], key):
             return c[1], True
-        buf = c[1] if same_buf else torch.empty(*shape, dtype=torch.float32, device=dev)
+        buf = c[1] if same_buf else _mem.empty(*shape, dtype=torch.float32, device=dev)
         self._xg_cache = (key, buf)
         return buf, False
 
@@ -149,7 +149,7 @@ def reduce_rows(partial: torch.Tensor, plan: ShardPlan) -> torch.Tensor:
     if plan.world == 1:
         return plan.rows(partial)
     if _uneven_ok(plan.group):
-        out = torch.empty_like(plan.rows(partial))
+        out = _mem.empty_like(plan.rows(partial))
         dist.reduce_scatter(out, [plan.rows(partial, r) for r in range(plan.world)], group=plan.group)
         return out
     for r in range(plan.world):
@@ -163,7 +163,7 @@ def reduce_rows_async(partial: torch.Tensor, plan: ShardPlan):
     caller calls work.wait() (a stream-side wait, no host sync) before it reads the rows."""
     if plan.world == 1 or not _uneven_ok(plan.group):
         return reduce_rows(partial, plan), None
-    out = torch.empty_like(plan.rows(partial))
+    out = _mem.empty_like(plan.rows(partial))
     work = dist.reduce_scatter(out, [plan.rows(partial, r) for r in range(plan.world)], group=plan.group, async_op=True)
     return out, work
 
@@ -203,28 +203,28 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         M_out = w_ext.shape[1]
         st = _stream()
         if plan.world > 1:
-            x_full = torch.empty(N, f_in, dtype=torch.float32, device=dev)
+            x_full = _mem.empty(N, f_in, dtype=torch.float32, device=dev)
             plan.rows(x_full).copy_(x)
             gather_rows(x_full, plan)
         else:
             x_full = x
-        wh_full = torch.empty(N, HD, dtype=torch.float32, device=dev)
+        wh_full = _mem.empty(N, HD, dtype=torch.float32, device=dev)
         _gemm(0, 0, N, HD, f_in, x_full, f_in, w_ext, M_out, wh_full, HD)
         skipv = None
         if has_skip:
-            skipv = torch.empty(n, HD, dtype=torch.float32, device=dev)
+            skipv = _mem.empty(n, HD, dtype=torch.float32, device=dev)
             _gemm(0, 0, n, HD, f_in, x, f_in, w_ext, M_out, skipv, HD, b_off=HD)
-        f = torch.empty(n, H, dtype=torch.float32, device=dev)
-        g_full = torch.empty(N, H, dtype=torch.float32, device=dev)
+        f = _mem.empty(n, H, dtype=torch.float32, device=dev)
+        g_full = _mem.empty(N, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_logits_fwd", n, H, Dp, plan.rows(wh_full).data_ptr(), HD, None, 1.0, a_src.data_ptr(),
                   a_dst.data_ptr(), f.data_ptr(), plan.rows(g_full).data_ptr(), st)
         gather_rows(g_full, plan)
 
         need_grad = any(ctx.needs_input_grad[:4])
-        out = torch.empty(n, HD, dtype=torch.float32, device=dev)
+        out = _mem.empty(n, HD, dtype=torch.float32, device=dev)
         separate_hagg = need_grad and (has_skip or act_elu)
-        hagg = torch.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
-        lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        hagg = _mem.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
+        lse = _mem.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
         hubs = graph.hubs
         scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_full.data_ptr(), HD,
@@ -253,16 +253,16 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         tptr, trow, perm, thubs = graph.transpose()
 
         ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
-        rec = torch.empty(n, ldrec, dtype=torch.float32, device=dev)
-        dskip = torch.empty(n, HD, dtype=torch.float32, device=dev) if has_skip else None
+        rec = _mem.empty(n, ldrec, dtype=torch.float32, device=dev)
+        dskip = _mem.empty(n, HD, dtype=torch.float32, device=dev) if has_skip else None
         _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if (act_elu and has_skip) else None, HD,
                   int(act_elu), hagg.data_ptr(), HD, f.data_ptr(), H, lse.data_ptr(), rec.data_ptr(), ldrec,
                   _ptr(dskip), HD, st)
 
         # partial dWh / dg for EVERY source from this rank's destination rows
-        dwh_part = torch.empty(N, HD, dtype=torch.float32, device=dev)
-        dg_part = torch.empty(N, H, dtype=torch.float32, device=dev)
-        edge_dz = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        dwh_part = _mem.empty(N, HD, dtype=torch.float32, device=dev)
+        dg_part = _mem.empty(N, H, dtype=torch.float32, device=dev)
+        edge_dz = _mem.empty(graph.nnz, H, dtype=torch.float32, device=dev)
         scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, wh_full.data_ptr(), HD,
                   g_full.data_ptr(), H, rec.data_ptr(), ldrec, None, 1.0, alpha,
@@ -271,7 +271,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         del rec
         dg_loc = reduce_rows(dg_part, plan).contiguous()
         # owned rows: df = segmented sum of dz, dWh_i += df_i a_src (added once, on the owner's partial rows)
-        df = torch.empty(n, H, dtype=torch.float32, device=dev)
+        df = _mem.empty(n, H, dtype=torch.float32, device=dev)
         hubs = graph.hubs
         scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
         dwh_own = plan.rows(dwh_part)
@@ -279,13 +279,13 @@ class ShardedGatLayerFunction(torch.autograd.Function):
                   None, 1.0, dwh_own.data_ptr(), HD, df.data_ptr(), H, *hubs.args(scratch), st)
         del edge_dz
 
-        da_src = torch.empty(H, Dp, dtype=torch.float32, device=dev)
-        da_dst = torch.empty(H, Dp, dtype=torch.float32, device=dev)
-        ws = torch.empty(_lib.query("gatk_da_workspace_floats", H, Dp), dtype=torch.float32, device=dev)
+        da_src = _mem.empty(H, Dp, dtype=torch.float32, device=dev)
+        da_dst = _mem.empty(H, Dp, dtype=torch.float32, device=dev)
+        ws = _mem.empty(_lib.query("gatk_da_workspace_floats", H, Dp), dtype=torch.float32, device=dev)
         _lib.call("gatk_da_reduce", n, H, Dp, plan.rows(wh_full).data_ptr(), HD, df.data_ptr(), dg_loc.data_ptr(),
                   da_src.data_ptr(), da_dst.data_ptr(), ws.data_ptr(), st)
 
-        dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
+        dw_ext = _mem.empty(f_in, M_out, dtype=torch.float32, device=dev)
         dx = None
         if not need_dx:
             # dW = sum over ranks of x_full^T dWh_partial: no row exchange, only the F x H*D all-reduce below
@@ -295,7 +295,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         else:
             dwh_loc = reduce_rows(dwh_part, plan)
             _gemm(1, 0, f_in, HD, n, x, f_in, dwh_loc, HD, dw_ext, M_out)
-            dx = torch.empty(n, f_in, dtype=torch.float32, device=dev)
+            dx = _mem.empty(n, f_in, dtype=torch.float32, device=dev)
             _gemm(0, 1, n, f_in, HD, dwh_loc, HD, w_ext, M_out, dx, f_in)
             if has_skip:
                 _gemm(1, 0, f_in, HD, n, x, f_in, dskip, HD, dw_ext, M_out, c_off=HD)
@@ -335,7 +335,7 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         # dataset's feature matrix: constant across training steps, so its all-gather is done once and kept
         # (keyed on the input tensor's storage and version counter: any in-place update or a new tensor
         # gathers again).  Per step only the source logits g [N, H] cross NVLink.
-        f = torch.empty(n, H, dtype=torch.float32, device=dev)
+        f = _mem.empty(n, H, dtype=torch.float32, device=dev)
         peer = plan.peer_rows((N, P), dev) if plan.world > 1 else None
         if peer is not None:
             # fused pack + exchange: the pack kernel writes every row (or, when the peers already hold this
@@ -353,13 +353,13 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         else:
             cached = plan.cached_xg(x_key, (N, P), dev) if x_key is not None else None
             hit = cached is not None and cached[1]
-            xg_full = cached[0] if cached is not None else torch.empty(N, P, dtype=torch.float32, device=dev)
+            xg_full = cached[0] if cached is not None else _mem.empty(N, P, dtype=torch.float32, device=dev)
             xg_loc = plan.rows(xg_full)
             _lib.call("gatk_logits_pack", n, f_in, H, x.data_ptr(), f_in, w_uv.data_ptr(), Muv, xg_loc.data_ptr(), P,
                       f.data_ptr(), H, st)
             if hit and plan.world > 1:
                 with _lib.timed("comm:allgather_g"):
-                    g_all = torch.empty(N, H, dtype=torch.float32, device=dev)
+                    g_all = _mem.empty(N, H, dtype=torch.float32, device=dev)
                     plan.rows(g_all).copy_(xg_loc[:, Fp:Fp + H])
                     gather_rows(g_all, plan)
                     xg_full[:, Fp:Fp + H].copy_(g_all)
@@ -367,14 +367,14 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
                 with _lib.timed("comm:allgather_xg"):
                     gather_rows(xg_full, plan)
         need_grad = any(ctx.needs_input_grad[1:3])
-        xagg = torch.empty(n, H * Fp, dtype=torch.float32, device=dev)
-        lse = torch.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        xagg = _mem.empty(n, H * Fp, dtype=torch.float32, device=dev)
+        lse = _mem.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
         hubs = graph.hubs
         scratch = _x_scratch(0, H, Fp, hubs.n_seg, dev)
         _lib.call("gatk_attn_x_fwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg_full.data_ptr(), P,
                   f.data_ptr(), H, float(alpha), xagg.data_ptr(), H * Fp, _ptr(lse),
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
-        out = torch.empty(n, HD, dtype=torch.float32, device=dev)
+        out = _mem.empty(n, HD, dtype=torch.float32, device=dev)
         fuse_elu = act_elu and not has_skip
         _gemm_batched(0, 0, n, Dp, f_in, H, xagg, H * Fp, Fp, w_ext, M_out, Dp, out, HD, Dp, epilogue=int(fuse_elu),
                       label="gemm:project")
@@ -402,15 +402,15 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         gout = gout.contiguous()
         xg_loc = plan.rows(xg_full)
         if act_elu:
-            dhp = torch.empty(n, HD, dtype=torch.float32, device=dev)
+            dhp = _mem.empty(n, HD, dtype=torch.float32, device=dev)
             _lib.call("gatk_elu_bwd", n, HD, gout.data_ptr(), HD, out.data_ptr(), HD, dhp.data_ptr(), HD, st)
         else:
             dhp = gout
-        dw_ext = torch.empty(f_in, M_out, dtype=torch.float32, device=dev)
-        dxagg = (torch.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
+        dw_ext = _mem.empty(f_in, M_out, dtype=torch.float32, device=dev)
+        dxagg = (_mem.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
         _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp, label="gemm:dxagg")
-        ds = torch.empty(graph.nnz, H, dtype=torch.float32, device=dev)
-        dfg = (torch.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
+        ds = _mem.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        dfg = (_mem.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
         hubs = graph.hubs
         scratch = _x_scratch(1, H, Fp, hubs.n_seg, dev)
         _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg_full.data_ptr(), P,
@@ -419,7 +419,7 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         # dg: partial sums for EVERY source from this rank's stored entries, reduced to the rows' owners
         tptr, _trow, perm, thubs = graph.transpose()[:4]
-        dg_part = torch.empty(N, H, dtype=torch.float32, device=dev)
+        dg_part = _mem.empty(N, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_edge_tsum", N, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(), dg_part.data_ptr(), H,
                   thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
         # the reduce-scatter runs on NCCL's stream while the value-path products (which need nothing from it)
@@ -432,7 +432,7 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
             if work is not None:
                 work.wait()
             dfg[:, H:2 * H] = dg_own
-        dw_uv = torch.empty(f_in, Muv, dtype=torch.float32, device=dev)
+        dw_uv = _mem.empty(f_in, Muv, dtype=torch.float32, device=dev)
         _gemm_batched(1, 0, f_in, Muv, n, 1, xg_loc, P, 0, dfg, Muv, 0, dw_uv, Muv, 0, label="gemm:dlogits")  # one "head": the TMEM-A TN kernel
         if plan.world > 1:
             with _lib.timed("comm:allreduce_dw"):
@@ -586,7 +586,7 @@ class ShardedLayerBench:
         _lib.timer = old
         t = sum(v["ms_total"] for k, v in kern.items() if not k.startswith("comm:")) / steps
         mine = torch.tensor([float(self.plan.n_local), float(self.graph.nnz), t], dtype=torch.float64, device=self.dev)
-        allr = [torch.empty_like(mine) for _ in range(self.world)]
+        allr = [_mem.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(allr, mine)
         m = torch.stack(allr).cpu()
         return fit_row_cost(m[:, 0], m[:, 1], m[:, 2])
