@@ -337,6 +337,11 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         # gathers again).  Per step only the source logits g [N, H] cross NVLink.
         f = _mem.empty(n, H, dtype=torch.float32, device=dev)
         peer = plan.peer_rows((N, P), dev) if plan.world > 1 else None
+        persistent = peer is not None or x_key is not None
+        if persistent:
+            # the gathered rows live in a plan-wide buffer that the NEXT forward rewrites through raw pointers (no
+            # autograd version counter sees that): every forward takes a new generation and backward checks it
+            plan.xg_generation = getattr(plan, "xg_generation", 0) + 1
         if peer is not None:
             # fused pack + exchange: the pack kernel writes every row (or, when the peers already hold this
             # input's x columns, just its g columns) into all the other GPUs' copies over NVLink; two device-side
@@ -385,6 +390,7 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         if need_grad:
             ctx.graph, ctx.plan = graph, plan
             ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu), f_in, Fp, Muv)
+            ctx.xg_generation = plan.xg_generation if persistent else None
             ctx.save_for_backward(xg_full, w_ext, f, lse, xagg, out)
         return out
 
@@ -392,6 +398,12 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
     def backward(ctx, gout):
         xg_full, w_ext, f, lse, xagg, out = ctx.saved_tensors
         graph, plan = ctx.graph, ctx.plan
+        if ctx.xg_generation is not None and ctx.xg_generation != plan.xg_generation:
+            raise RuntimeError(
+                "pygat_b200.sharded: the gathered rows saved by this forward were overwritten by a later forward on the "
+                "same ShardPlan (generation %d, now %d).  Run backward before the next forward of this layer, or give "
+                "the second call its own ShardPlan / pass cache_input_gather=False with GATK_PEER_PUSH=0."
+                % (ctx.xg_generation, plan.xg_generation))
         H, Dp, has_skip, alpha, act_elu, f_in, Fp, Muv = ctx.cfg
         dev = xg_full.device
         N, P = xg_full.shape

@@ -170,6 +170,16 @@ def run_nccl(rank, world):
                 assert rel(got, want) < 2e-5, (variant, rel(got, want))
             for got, want in zip([a.grad for a in a_s + a_d], ref["da"]):
                 assert rel(got, want) < 2e-5, (variant, rel(got, want))
+        # a second forward on the same plan rewrites the kept rows: the first forward's backward must refuse loudly
+        # (raised before any collective, on every rank alike) instead of returning gradients of the wrong rows
+        ya = sharded_gat_layer(xs, graph, plan, Ws, a_s, a_d, Ss, 0.2, concat)
+        yb = sharded_gat_layer(xs, graph, plan, Ws, a_s, a_bad, Ss, 0.2, concat)
+        try:
+            ya.backward(plan.rows(gout))
+            raise AssertionError("stale gathered rows were not detected")
+        except RuntimeError as exc:
+            assert "overwritten by a later forward" in str(exc)
+        yb.backward(plan.rows(gout))
         # and the project-first sharded kernels on the same no-gradient input
         for p in Ws + a_s + a_d + (Ss or []):
             p.grad = None

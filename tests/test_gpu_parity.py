@@ -389,12 +389,13 @@ def test_power_law_layer_matches_oracle(H, D, f_in):
     assert (rowptr[1:] - rowptr[:-1]).max().item() > 300
     x, Ws, As, gout = _layer_inputs(n, f_in, H, D, 1)
     adj = O.PatternAdj(rowptr, col)
-    xo = x.clone().requires_grad_(True)
-    Wo = [w.clone().requires_grad_(True) for w in Ws]
-    Ao = [a.clone().requires_grad_(True) for a in As]
+    # oracle evaluated in fp64 (same functions, double inputs): independent of the host BLAS's fp32 code paths
+    xo = x.double().requires_grad_(True)
+    Wo = [w.double().requires_grad_(True) for w in Ws]
+    Ao = [a.double().requires_grad_(True) for a in As]
     edge = adj.nonzero().t()
     yo = torch.cat([O.sparse_head(xo, w, a, edge, 0.2, True, None, 0.0, faithful=False) for w, a in zip(Wo, Ao)], 1)
-    yo.backward(gout)
+    yo.backward(gout.double())
 
     graph = Graph.from_csr(rowptr.to(DEV), col.to(DEV), seg_len=128)
     assert graph.hubs.n_hub > 0
@@ -428,12 +429,12 @@ def test_aggregate_first_form_matches_oracle(H, D, f_in, skip, concat, seg_len):
     g = torch.Generator().manual_seed(9)
     Ss = [torch.randn(f_in, D, generator=g) * O.xavier_std(f_in, D) for _ in range(H)] if skip else None
     adj = O.PatternAdj(rowptr, col)
-    Wo = [w.clone().requires_grad_(True) for w in Ws]
-    Ao = [a.clone().requires_grad_(True) for a in As]
-    So = [s.clone().requires_grad_(True) for s in Ss] if skip else [None] * H
+    Wo = [w.double().requires_grad_(True) for w in Ws]
+    Ao = [a.double().requires_grad_(True) for a in As]
+    So = [s.double().requires_grad_(True) for s in Ss] if skip else [None] * H
     edge = adj.nonzero().t()
-    yo = torch.cat([O.sparse_head(x, w, a, edge, 0.2, concat, s, 0.0, faithful=False) for w, a, s in zip(Wo, Ao, So)], 1)
-    yo.backward(gout)
+    yo = torch.cat([O.sparse_head(x.double(), w, a, edge, 0.2, concat, s, 0.0, faithful=False) for w, a, s in zip(Wo, Ao, So)], 1)
+    yo.backward(gout.double())
 
     graph = Graph.from_csr(rowptr.to(DEV), col.to(DEV), seg_len=seg_len)
     assert (graph.hubs.n_hub > 0) == (seg_len < 1000)
@@ -551,3 +552,37 @@ def test_sparse_v2_heads_match_reference_golden(name):
     if "skip" in d:
         errs["dskip"] = rel_err(head.skip_projection.grad, d["dskip"])
     assert all(v < 1e-5 for v in errs.values()), errs
+
+
+def test_integration_md_binding_example_runs_on_the_gpu():
+    """The ctypes stub documented in INTEGRATION.md, executed as written, against the oracle's attention."""
+    import os
+    from tests.test_abi import ROOT, integration_snippet
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        exec(compile(integration_snippet(), "INTEGRATION.md", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    n, H, D = 3000, 4, 16
+    rowptr, col = power_law_csr(n, 9.0, seed=2, exponent=0.7)
+    g = torch.Generator().manual_seed(1)
+    wh = torch.randn(n, H * D, generator=g)
+    f = torch.randn(n, H, generator=g)
+    gg = torch.randn(n, H, generator=g)
+    edge = O.PatternAdj(rowptr, col).nonzero().t()
+    ref = []
+    for h in range(H):  # layers.py:144-160 per head, in fp64
+        s = (f[edge[0], h] + gg[edge[1], h]).double()
+        e = torch.exp(torch.where(s > 0, s, 0.2 * s))
+        den = torch.zeros(n, dtype=torch.float64).index_add_(0, edge[0], e)
+        num = torch.zeros(n, D, dtype=torch.float64).index_add_(0, edge[0], e[:, None] * wh[edge[1], h * D:(h + 1) * D].double())
+        ref.append(num / den[:, None])
+    ref = torch.cat(ref, 1)
+    out = torch.empty(n, H * D, device=DEV)
+    lse = torch.empty(n, H, device=DEV)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ns["sp_attention_forward"](rowptr.to(DEV), col.to(DEV).int(), wh.to(DEV), f.to(DEV), gg.to(DEV), 0.2, out, lse, counter)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < TOL

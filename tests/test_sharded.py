@@ -73,6 +73,32 @@ def test_sharded_layer_world1_equals_single_gpu():
 
 
 @pytest.mark.gpu
+def test_second_forward_before_backward_is_refused():
+    """The aggregate-first sharded layer keeps its gathered rows in a plan-wide buffer; a later forward rewrites it
+    behind autograd's back, so the earlier forward's backward must raise rather than use the wrong rows."""
+    from pygat_b200.sharded import ShardPlan, sharded_gat_layer
+    from pygat_b200.synth import init_layer_params, power_law_csr
+    dev = "cuda"
+    n, H, D, f_in = 2000, 4, 32, 20
+    rowptr, col = power_law_csr(n, 8.0, seed=2, exponent=0.7, device=dev)
+    x = torch.randn(n, f_in, device=dev)
+    gout = torch.randn(n, H * D, device=dev)
+    Ws, a_s, a_d = init_layer_params(f_in, H, D, dev)
+    plan = ShardPlan([0, n], 0)
+    graph = plan.local_graph(rowptr, col, seg_len=128)
+    ya = sharded_gat_layer(x, graph, plan, Ws, a_s, a_d, None, 0.2, True)
+    yb = sharded_gat_layer(x, graph, plan, Ws, a_s, [a * 2 for a in a_d], None, 0.2, True)
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        ya.backward(gout)
+    yb.backward(gout)
+    # without the kept rows every call owns its buffer: both backwards are fine
+    yc = sharded_gat_layer(x, graph, plan, Ws, a_s, a_d, None, 0.2, True, cache_input_gather=False)
+    yd = sharded_gat_layer(x, graph, plan, Ws, a_s, a_d, None, 0.2, True, cache_input_gather=False)
+    yc.backward(gout)
+    yd.backward(gout)
+
+
+@pytest.mark.gpu
 def test_sharded_layer_matches_single_gpu_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
