@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib, _mem
-from .graph import Graph, _ptr, _require_cuda, _stream
+from .graph import Graph, _ptr, _require_cuda, _stream, on_device
 
 
 import os
@@ -481,6 +481,14 @@ def gat_layer(x: torch.Tensor, graph: Graph, Ws, a_srcs, a_dsts, skips, alpha: f
     form: "auto" picks among the three algebraically equal forms of the layer -- "explicit" (projection,
     logits pass, attention; the only one valid with dropout), "folded" (logits as projection columns) and
     "agg_first" (neighbour sum before the projection; narrow inputs that need no gradient)."""
+    _require_cuda(x, "input features")
+    if graph.device != x.device:
+        raise RuntimeError(f"pygat_b200: the graph lives on {graph.device} but the input features are on {x.device}")
+    with on_device(x):
+        return _gat_layer(x, graph, Ws, a_srcs, a_dsts, skips, alpha, concat, p, training, masks, combine, form)
+
+
+def _gat_layer(x, graph, Ws, a_srcs, a_dsts, skips, alpha, concat, p, training, masks, combine, form):
     H = len(Ws)
     if x.dtype != torch.float32:
         x = x.float()

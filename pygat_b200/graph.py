@@ -26,9 +26,26 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_process_device = None  # the one GPU this process drives (per-device kernel attributes are configured once)
+
+
 def _require_cuda(t: torch.Tensor, what: str):
+    """No CPU path, and one process per GPU (the library caches per-device launch configuration): a tensor on a
+    second GPU of the same process is refused instead of launching with the first device's settings."""
+    global _process_device
     if not t.is_cuda:
         raise RuntimeError(f"pygat_b200: {what} must be a CUDA tensor (the engine has no CPU path); got {t.device}")
+    if _process_device is None:
+        _process_device = t.device.index
+    elif t.device.index != _process_device:
+        raise RuntimeError(f"pygat_b200: {what} is on {t.device}, but this process already drives cuda:{_process_device} "
+                           "(one process per GPU: launch with torchrun, one rank per device)")
+
+
+def on_device(t: torch.Tensor):
+    """Context manager making t's GPU the current device, so launches and the stream query go to the device the
+    operands live on even when the caller's current device is another one."""
+    return torch.cuda.device(t.device)
 
 
 class HubPartition:
@@ -135,6 +152,12 @@ class Graph:
     # ------------------------------------------------------------------ transpose (backward only)
     def transpose(self):
         if self._t is None:
+            with on_device(self.rowptr):
+                self._build_transpose()
+        return self._t
+
+    def _build_transpose(self):
+        if self._t is None:
             tptr = _mem.empty(self.n_src + 1, dtype=torch.int64, device=self.device)
             trow = _mem.empty(self.nnz, dtype=torch.int32, device=self.device)
             perm = _mem.empty(self.nnz, dtype=torch.int32, device=self.device)
@@ -145,6 +168,13 @@ class Graph:
             del ws
             self._t = (tptr, trow, perm, HubPartition(tptr, self.seg_len))
         return self._t
+
+    def empty_rows(self) -> Optional[torch.Tensor]:
+        """int64 ids of destination rows without a stored entry, or None (cached; one host read on first use)."""
+        if not hasattr(self, "_empty_rows"):
+            rows = torch.nonzero(self.rowptr[1:] == self.rowptr[:-1]).flatten()
+            self._empty_rows = rows if rows.numel() else None
+        return self._empty_rows
 
     def inverse_perm(self) -> torch.Tensor:
         """int32 [E]: CSR entry -> its position in the transposed pattern (inverse of transpose()[2])."""
@@ -178,13 +208,15 @@ def graph_of(adj, rule: int = RULE_NONZERO) -> Graph:
     sig = (adj._version, adj.data_ptr() if not adj.is_sparse else 0, tuple(adj.shape), adj.layout)
     if hit is not None and hit[0]() is adj and hit[1] == sig:
         return hit[2]
-    if adj.layout == torch.strided:
-        g = Graph.from_dense(adj, rule)
-    else:
-        coo = adj.coalesce() if adj.layout == torch.sparse_coo else adj.to_sparse_coo().coalesce()
-        idx, val = coo.indices(), coo.values()
-        sel = val != 0 if rule == RULE_NONZERO else val > 0
-        g = Graph.from_coo(idx[:, sel], adj.shape[0])
+    _require_cuda(adj, "adj")
+    with on_device(adj):
+        if adj.layout == torch.strided:
+            g = Graph.from_dense(adj, rule)
+        else:
+            coo = adj.coalesce() if adj.layout == torch.sparse_coo else adj.to_sparse_coo().coalesce()
+            idx, val = coo.indices(), coo.values()
+            sel = val != 0 if rule == RULE_NONZERO else val > 0
+            g = Graph.from_coo(idx[:, sel], adj.shape[0])
     ref = weakref.ref(adj, lambda _r, k=key: _cache.pop(k, None))
     _cache[key] = (ref, sig, g)
     return g

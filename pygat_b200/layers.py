@@ -95,8 +95,37 @@ def fused_heads(heads, x, adj, combine="cat", masks=None):
     graph = graph_of(adj, h0.PATTERN_RULE)
     vecs = [h.attention_vectors() for h in heads]
     skips = [h.skip_projection for h in heads] if h0.skip_connection else None
-    return gat_layer(x, graph, [h.W for h in heads], [v[0] for v in vecs], [v[1] for v in vecs], skips,
-                     h0.alpha, h0.concat, p=h0.dropout, training=h0.training, masks=masks, combine=combine)
+    out = gat_layer(x, graph, [h.W for h in heads], [v[0] for v in vecs], [v[1] for v in vecs], skips,
+                    h0.alpha, h0.concat, p=h0.dropout, training=h0.training, masks=masks, combine=combine)
+    if h0.PATTERN_RULE == RULE_POSITIVE:
+        empty = graph.empty_rows()
+        if empty is not None:
+            out = _dense_rows_without_neighbours(out, empty, heads, x, skips, combine)
+    return out
+
+
+def _dense_rows_without_neighbours(out, empty, heads, x, skips, combine):
+    """Dense class only: a row with no `adj > 0` entry is all -9e15 before the softmax (layers.py:40-42), so the
+    reference attends UNIFORMLY to all N nodes and h'_i is the mean of Wh over every node (+ skip, ELU).  The CSR
+    engine leaves such rows at 0 (+ skip); they are patched here with parameter-sized torch ops (the mean is linear:
+    mean_j(x_j W) = mean_j(x_j) W), which also routes their gradients.  Evaluated without dropout -- the reference's
+    random masks cannot be reproduced anyway.  Every loader of the reference adds self-loops, so this is rare."""
+    h0 = heads[0]
+    x = x.float()
+    xm = x.mean(0, keepdim=True)
+    per_head = []
+    for k, h in enumerate(heads):
+        v = (xm @ h.W).expand(empty.numel(), -1)
+        if skips is not None:
+            v = v + x[empty] @ skips[k]
+        per_head.append(torch.nn.functional.elu(v) if h0.concat else v)
+    if combine == "mean":
+        repl = torch.stack(per_head, dim=1).mean(dim=1)
+    elif combine == "cat":
+        repl = torch.cat(per_head, dim=1)
+    else:
+        raise RuntimeError("rows without neighbours are only patched for combine='cat' / 'mean'")
+    return out.index_copy(0, empty, repl)
 
 
 # ---------------------------------------------------------------------- SpecialSpmm (layers.py:70-95)

@@ -139,9 +139,30 @@ def v2_cases():
     head_case("de2_head_skip_last", de2, 96, 24, 7, a96, False, True, 45)
 
 
+def isolated_graph(n, seed):
+    """Rows without any `adj > 0` entry (no self-loop either): the dense class attends uniformly to ALL nodes there
+    (softmax of an all -9e15 row, layers.py:40-42).  Row 9 keeps only negative entries."""
+    adj = rand_graph(n, 3.0, seed)
+    for r in (5, 17, n - 1):
+        adj[r, :] = 0.0
+    adj[9, :] = 0.0
+    adj[9, 2] = adj[9, 40] = -0.7
+    return adj
+
+
+def isolated_cases():
+    de = ref_layers.GraphAttentionLayer
+    iso = isolated_graph(96, 9)
+    head_case("de_head_isolated", de, 96, 24, 8, iso, True, True, 51)
+    head_case("de_head_isolated_last", de, 96, 24, 7, iso, False, False, 52)
+    gat_case("gat_de_isolated", [12, 8, 5], [4, 3], de, iso, True, 53, 0.6, False)
+
+
 def main():
     if os.environ.get("GOLDEN_ONLY") == "v2":  # add the GATv2 fixtures without rewriting the others
         return v2_cases()
+    if os.environ.get("GOLDEN_ONLY") == "isolated":
+        return isolated_cases()
     sp, de = ref_layers.SpGraphAttentionLayer, ref_layers.GraphAttentionLayer
     a96 = rand_graph(96, 3.0, 1)
     head_case("sp_head_basic", sp, 96, 24, 8, a96, True, False, 11)
@@ -163,6 +184,7 @@ def main():
     gat_case("gat_sp_ppi_like", [10, 32, 32, 11], [4, 4, 6], sp, blk, True, 34, 0.0, True)
     gat_case("gat_sp_cora_topology", [16, 8, 7], [8, 1], sp, cora_adj(), False, 72, 0.6, False)
     v2_cases()
+    isolated_cases()
 
 
 if __name__ == "__main__":
