@@ -31,6 +31,8 @@ WORKLOADS = {
     "products": dict(n=2_449_029, avg_deg=25.26, f_in=100, H=8, D=64, exponent=0.5),
     "pubmed": dict(n=19_717, avg_deg=5.5, f_in=500, H=8, D=8, exponent=0.5),
     "papers_shard": dict(n=13_882_495, avg_deg=14.55, f_in=128, H=4, D=32, exponent=0.5),
+    # the products graph as a HIDDEN layer: the 8 x 64 output of layer 1 is the input, and it needs a gradient
+    "products_hidden": dict(n=2_449_029, avg_deg=25.26, f_in=512, H=8, D=64, exponent=0.5, needs_dx=True),
 }
 # reference backward is O(N^2) memory (layers.py:85): 1 GiB per product at 16384 nodes (the environment
 # variable only exists so that the contract test can run the arm in a second)
@@ -61,19 +63,23 @@ def algorithmic_bytes(n, e, H, D, f_in, need_dx=False):
     x_fwd = e * (4 * P + 4) + n * (4 * H * Fp + 8 * H + 8)                       # xg_j, col; xagg write, f, lse
     x_bwd = e * (4 * P + 4 + 4 * H) + n * (8 * H * Fp + 12 * H + 8)              # xg_j, col, ds write; xagg, dxagg, f, lse, df
     tsum = e * (4 * H + 4) + n * (4 * H + 8)                                     # ds through perm; dg write
-    elu_b = 12 * n * HD
+    elu_b = 12 * n * HD                                                          # separate ELU' pass (only when not fused)
     g_proj = 4 * n * H * Fp + 4 * n * HD                                         # out_h = ELU(xagg_h W_h)
-    g_dw = 4 * n * H * Fp + 4 * n * HD                                           # dW_h = xagg_h^T dh'_h
-    g_dx = 4 * n * HD + 4 * n * H * Fp                                           # dxagg_h = dh'_h W_h^T
+    # backward products with dh' = gout * ELU'(out) formed inside the kernel: each reads gout AND out (8 n HD)
+    g_dw = 4 * n * H * Fp + 8 * n * HD                                           # dW_h = xagg_h^T dh'_h
+    g_dx = 8 * n * HD + 4 * n * H * Fp                                           # dxagg_h = dh'_h W_h^T
     g_dl = 4 * n * f_in + 8 * n * H                                              # d[u|v] = x^T [df|dg]
-    agg = pack + x_fwd + x_bwd + tsum + elu_b + g_proj + g_dw + g_dx + g_dl
+    # x_bwd keeps its 4H bytes per entry: the ds values now travel to L2 as red.global.add operands instead of a store;
+    # the transposed segmented sum (tsum) only runs on the bit-reproducible route (GATK_DETERMINISTIC=1)
+    agg = pack + x_fwd + x_bwd + g_proj + g_dw + g_dx + g_dl
     return {"gatk_attn_fwd": k2, "gatk_attn_bwd_prep": prep, "gatk_attn_bwd_fused": fused,
             "gatk_attn_bwd_finish": finish, "projection_fwd": k1, "projection_bwd": k5,
             "gatk_logits_pack": pack, "gatk_attn_x_fwd": x_fwd, "gatk_attn_x_bwd": x_bwd, "gatk_edge_tsum": tsum,
             "gatk_elu_bwd": elu_b, "gemm:project": g_proj, "gemm:dW": g_dw, "gemm:dxagg": g_dx, "gemm:dlogits": g_dl,
             "layer_survey": k2 + k3_survey + k4_survey + k1 + k5,
             "layer_project_first": k2 + prep + fused + finish + k1 + k5,
-            "layer_agg_first": agg}
+            "layer_agg_first": agg, "layer_agg_first_deterministic": agg + tsum,
+            "layer_agg_first_r01": agg + tsum + elu_b - 8 * n * HD}  # round 1: separate ELU' pass, dh' read twice
 
 
 def measured_peak():
@@ -175,14 +181,79 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------ our arm
-def run_ours(args):
+def make_runner(cfg, rank, world, dev):
+    from benchmarks.layer import ShardedLayerBench, SingleGpuLayerBench
+    return ShardedLayerBench(cfg, rank, world, dev) if world > 1 else SingleGpuLayerBench(cfg, dev)
+
+
+def time_layer(runner, steps, warmup, rank, world, dev, sample_clocks=False):
+    """W warm-up steps, then exactly `steps` steps between barrier + synchronize on both sides, timed with CUDA
+    events on the launching stream; max over ranks.  Returns ms/step, per-entry-point kernel times, launch counts,
+    clocks (rank 0) and every rank's per-call times."""
     import torch
     import torch.distributed as dist
 
     from pygat_b200 import _lib
-    from pygat_b200.functional import gat_layer
-    from pygat_b200.graph import Graph
-    from pygat_b200.synth import power_law_csr
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        runner.step()
+    barrier()
+    clocks = ClockSampler(dev.index) if (sample_clocks and rank == 0) else None
+    if clocks:
+        clocks.start()
+    _lib.timer = _lib.KernelTimer()
+    calls0 = _lib.call_count
+    launches0 = _lib.query("gatk_launch_count")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        runner.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / steps
+    kern = _lib.timer.summary()
+    _lib.timer = None
+    out = {"launches": _lib.query("gatk_launch_count") - launches0, "calls": _lib.call_count - calls0,
+           "clocks": clocks.stop() if clocks else None, "per_rank": None}
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # every rank's per-call times (rank 0's alone hide the load balance: a "comm:" wait is mostly skew)
+        mine = {k: round(v["ms_total"] / steps, 4) for k, v in kern.items()}
+        mine["rows"], mine["entries"] = runner.plan.n_local, runner.graph.nnz
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        out["per_rank"] = {k: [g.get(k) for g in gathered] for k in mine}
+    out["ms"], out["kern"] = ms, kern
+    return out
+
+
+KERNEL_NAMES = ("gatk_attn_fwd", "gatk_attn_bwd_fused", "gatk_attn_bwd_prep", "gatk_attn_bwd_finish",
+                "gatk_logits_pack", "gatk_attn_x_fwd", "gatk_attn_x_bwd", "gatk_edge_tsum", "gatk_elu_bwd",
+                "gemm:project", "gemm:dW", "gemm:dxagg", "gemm:dlogits")
+
+
+def kernel_table(kern, ab, world, steps, peak):
+    per_kernel = {}
+    for name in KERNEL_NAMES:
+        if name in kern and name in ab:
+            gbs = ab[name] / world / (kern[name]["ms_avg"] * 1e-3) / 1e9
+            per_kernel[name] = {"ms": round(kern[name]["ms_avg"], 4), "algorithmic_GB": round(ab[name] / world / 1e9, 3),
+                                "achieved_GBs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    other = {k: round(v["ms_total"] / steps, 4) for k, v in kern.items() if k not in per_kernel}
+    return per_kernel, other
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,51 +265,10 @@ def run_ours(args):
     cfg = WORKLOADS[args.workload]
     n, H, D, f_in = cfg["n"], cfg["H"], cfg["D"], cfg["f_in"]
 
-    if world > 1:
-        from pygat_b200.sharded import ShardedLayerBench
-        runner = ShardedLayerBench(cfg, rank, world, dev)
-    else:
-        runner = SingleGpuLayerBench(cfg, dev)
+    runner = make_runner(cfg, rank, world, dev)
     e_total = runner.e_total
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        runner.step()
-    barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    _lib.timer = _lib.KernelTimer()
-    calls0 = _lib.call_count
-    launches0 = _lib.query("gatk_launch_count")
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        runner.step()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1) / args.steps
-    kern = _lib.timer.summary()
-    _lib.timer = None
-    launches = _lib.query("gatk_launch_count") - launches0
-    calls = _lib.call_count - calls0
-    clk = clocks.stop() if rank == 0 else None
-    per_rank = None
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        # every rank's per-call times (rank 0's alone hide the load balance: a "comm:" wait is mostly skew)
-        mine = {k: round(v["ms_total"] / args.steps, 4) for k, v in kern.items()}
-        mine["rows"], mine["entries"] = runner.plan.n_local, runner.graph.nnz
-        gathered = [None] * world
-        dist.all_gather_object(gathered, mine)
-        per_rank = {k: [g.get(k) for g in gathered] for k in mine}
+    res = time_layer(runner, args.steps, args.warmup, rank, world, dev, sample_clocks=True)
+    ms, kern = res["ms"], res["kern"]
 
     # ---- end-to-end through the public API with host buffers (pinned H2D of the step's input
     # features, D2H of the step's results: parameter gradients + a checksum of the output)
@@ -249,6 +279,59 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
 
+    # ---- N > 1: the sharded step against a single-GPU run of the same step (rank 0 holds the whole graph for it)
+    check = None
+    if world > 1 and not args.no_check:
+        from benchmarks.layer import parity_check
+        try:
+            check = parity_check(runner, rank, world, dev)
+        except Exception as exc:  # the headline line must still be printed; a failed check is reported, not hidden
+            check = {"parity_ok": False, "error": repr(exc)[:300]}
+    row_cost = runner.row_cost
+    del runner
+    torch.cuda.empty_cache()
+
+    # ---- the same layer as a HIDDEN layer (wide input that needs a gradient): the project-first kernels that
+    # layer 2 of models.GAT and every PPI layer run (models.py:29-35)
+    hidden = None
+    if not args.no_hidden and args.workload == "products":
+        hcfg = WORKLOADS["products_hidden"]
+        try:
+            hrun = make_runner(hcfg, rank, world, dev)
+            hres = time_layer(hrun, max(3, min(args.steps, 5)), 3, rank, world, dev)
+            if rank == 0:
+                peak, _ = measured_peak()
+                hab = algorithmic_bytes(hcfg["n"], hrun.e_total, hcfg["H"], hcfg["D"], hcfg["f_in"], need_dx=True)
+                hk, hother = kernel_table(hres["kern"], hab, world, max(3, min(args.steps, 5)), peak)
+                hidden = {"workload": "products-shape graph, hidden layer: F_in=512 (needs dx), 8 heads x 64, fwd+bwd",
+                          "ms_per_step": round(hres["ms"], 3), "value": hrun.e_total * hcfg["H"] / (hres["ms"] * 1e-3),
+                          "unit": "head-edges/s", "form": "project_first",
+                          "layer_frac": round(hab["layer_project_first"] / world / (hres["ms"] * 1e-3) / 1e9 / peak, 4),
+                          "layer_algorithmic_GB": round(hab["layer_project_first"] / 1e9, 2),
+                          "kernels": hk, "other_ms_per_step": hother, "per_rank_ms_per_step": hres["per_rank"]}
+            del hrun
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            hidden = {"error": repr(exc)[:300]}
+
+    # ---- epoch workloads: Pubmed (replicas only: one GPU) and PPI (graph-level data parallel over the ranks)
+    epochs = None
+    if not args.no_epochs:
+        epochs = {}
+        try:
+            from benchmarks import epochs as epoch_bench
+            if world == 1:
+                ms_e, info = epoch_bench.pubmed_epoch_ms(dev)
+                epochs["pubmed_GAT_sparse_train_plus_eval"] = {"ms_per_epoch": round(ms_e, 3), **info}
+            ms_e, info = epoch_bench.ppi_epoch_ms(dev, rank=rank, world=world)
+            if world > 1:
+                t = torch.tensor([ms_e], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_e = float(t.item())
+            epochs["ppi_GAT_dense_class_train"] = {"ms_per_epoch": round(ms_e, 3), "n_gpus": world, **info}
+        except Exception as exc:  # the headline metric must still be printed
+            epochs["error"] = repr(exc)[:300]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -256,15 +339,7 @@ def run_ours(args):
 
     peak, peak_src = measured_peak()
     ab = algorithmic_bytes(n, e_total, H, D, f_in)
-    per_kernel = {}
-    for name in ("gatk_attn_fwd", "gatk_attn_bwd_fused", "gatk_attn_bwd_prep", "gatk_attn_bwd_finish",
-                 "gatk_logits_pack", "gatk_attn_x_fwd", "gatk_attn_x_bwd", "gatk_edge_tsum", "gatk_elu_bwd",
-                 "gemm:project", "gemm:dW", "gemm:dxagg", "gemm:dlogits"):
-        if name in kern:
-            gbs = ab[name] / world / (kern[name]["ms_avg"] * 1e-3) / 1e9
-            per_kernel[name] = {"ms": round(kern[name]["ms_avg"], 4), "algorithmic_GB": round(ab[name] / world / 1e9, 3),
-                                "achieved_GBs": round(gbs, 1), "frac": round(gbs / peak, 4)}
-    other = {k: round(v["ms_total"] / args.steps, 4) for k, v in kern.items() if k not in per_kernel}
+    per_kernel, other = kernel_table(kern, ab, world, args.steps, peak)
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"]) if per_kernel else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -283,134 +358,30 @@ def run_ours(args):
                     "layer_survey_model_GB": round(ab["layer_survey"] / 1e9, 2)}
 
     cpu = cpu_reference_rate(cfg, steps=1, warmup=1)
-    epochs = None
-    if not args.no_epochs and world == 1:  # epoch workloads are single-GPU (Pubmed: replicas only; PPI: DESIGN.md 5)
-        epochs = {}
-        try:
-            from pygat_b200 import epoch_bench
-            ms_e, info = epoch_bench.pubmed_epoch_ms(dev)
-            epochs["pubmed_GAT_sparse_train_plus_eval"] = {"ms_per_epoch": round(ms_e, 3), **info}
-            ms_e, info = epoch_bench.ppi_epoch_ms(dev)
-            epochs["ppi_GAT_dense_class_train"] = {"ms_per_epoch": round(ms_e, 3), **info}
-        except Exception as exc:  # the headline metric must still be printed
-            epochs["error"] = repr(exc)[:300]
     line = {
         "metric": "gat_layer_fwd_bwd_head_edges_per_s", "value": e_total * H / (ms * 1e-3), "unit": "head-edges/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}-shape power-law graph, one hidden GAT layer fwd+bwd",
                    "nodes": n, "edges": e_total, "f_in": f_in, "heads": H, "head_dim": D, "dropout": 0.0,
-                   "parallelism": (f"dst-row shards x{world} (cost-balanced, row_cost={runner.row_cost:.1f} entries); layer-1 "
+                   "parallelism": (f"dst-row shards x{world} (cost-balanced, row_cost={row_cost:.1f} entries); layer-1 "
                                    "features are static, their all-gather is kept across steps; per step g [N,H] is "
                                    "all-gathered, dg reduce-scattered, dW all-reduced") if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (Wh alone is %.1f GB)" % (n * H * D * 4 / 1e9)},
         "e2e": {"value": e_total * H / (e2e_ms * 1e-3), "unit": "head-edges/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "input_pipeline": "pinned host -> device copy of step k+1 overlaps step k (double buffered)"},
-        "gpu_launches": launches, "abi_calls": calls, "clocks": clk, "roofline": roofline,
-        "kernels": per_kernel, "other_ms_per_step": other, "per_rank_ms_per_step": per_rank,
+                "input_pipeline": "pinned host -> device copy of step k+1 overlaps step k (double buffered)",
+                "result": "D2H = every parameter gradient + an output checksum; the layer output (%.1f GB) stays on the "
+                          "device as the next layer's input" % (n * H * D * 4 / 1e9)},
+        "gpu_launches": res["launches"], "abi_calls": res["calls"], "clocks": res["clocks"], "roofline": roofline,
+        "kernels": per_kernel, "other_ms_per_step": other, "per_rank_ms_per_step": res["per_rank"],
+        "check": check, "hidden_layer": hidden,
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "epoch_times": epochs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-class SingleGpuLayerBench:
-    """Whole graph on one GPU; the layer is driven through the public functional API."""
-
-    def __init__(self, cfg, dev):
-        import torch
-
-        from pygat_b200.graph import Graph
-        from pygat_b200.synth import init_layer_params, power_law_csr
-        self.torch = torch
-        n, H, D, f_in = cfg["n"], cfg["H"], cfg["D"], cfg["f_in"]
-        rowptr, col = power_law_csr(n, cfg["avg_deg"], seed=72, exponent=cfg["exponent"], device=dev)
-        self.graph = Graph.from_csr(rowptr, col)
-        self.graph.transpose()  # cached per adjacency, like the CSR itself; not part of a step
-        self.e_total = self.graph.nnz
-        g = torch.Generator(device=dev).manual_seed(72)
-        self.x = torch.randn(n, f_in, generator=g, device=dev)
-        self.gout = torch.randn(n, H * D, generator=g, device=dev)
-        self.Ws, self.a_src, self.a_dst = init_layer_params(f_in, H, D, dev, seed=72)
-        self.params = self.Ws + self.a_src + self.a_dst
-        self.cfg = cfg
-        hubs = 2 if self.graph.hubs.n_seg else 0
-        thubs = 2 if self.graph.transpose()[3].n_seg else 0
-        # gemm fwd 2 (weight split + tcgen05), attn fwd 1(+2), prep 1, fused 1(+2), finish 1(+2),
-        # gemm dW 2 (tcgen05 split-K + reduce)
-        self.launches_per_step = 2 + (1 + hubs) + 1 + (1 + thubs) + (1 + hubs) + 2
-        self.x_host = None
-
-    def _layer(self, x):
-        from pygat_b200.functional import gat_layer
-        return gat_layer(x, self.graph, self.Ws, self.a_src, self.a_dst, None, 0.2, concat=True)
-
-    def step(self):
-        for p in self.params:
-            p.grad = None
-        y = self._layer(self.x)
-        y.backward(self.gout)
-        return y
-
-    def e2e(self, steps):
-        return pipelined_e2e(self, steps)
-
-
-def pipelined_e2e(runner, steps, barrier=None):
-    """End to end through the public API with HOST inputs: every step copies its input features from
-    pinned host memory (double buffered on a copy stream, so step k+1's copy overlaps step k's compute,
-    as a training input pipeline would) and reads the step's results (all parameter gradients + an
-    output checksum) back to pinned host memory.  Returns (ms per step, H2D bytes, D2H bytes)."""
-    import torch
-    dev = runner.x.device
-    if runner.x_host is None:
-        runner.x_host = runner.x.cpu().pin_memory()
-    n_par = sum(p.numel() for p in runner.params)
-    host_out = torch.empty(n_par + 1, dtype=torch.float32).pin_memory()
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [torch.empty_like(runner.x), torch.empty_like(runner.x)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def issue_copy(k):
-        b = k & 1
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[b])  # the step that last used this buffer is done with it
-            bufs[b].copy_(runner.x_host, non_blocking=True)
-            ready[b].record(copy_stream)
-
-    def run(n_steps):
-        main = torch.cuda.current_stream()
-        for b in (0, 1):
-            freed[b].record(main)
-        issue_copy(0)
-        for k in range(n_steps):
-            b = k & 1
-            main.wait_event(ready[b])
-            if k + 1 < n_steps:
-                issue_copy(k + 1)
-            for p in runner.params:
-                p.grad = None
-            y = runner._layer(bufs[b])
-            y.backward(runner.gout)
-            freed[b].record(main)
-            flat = torch.cat([p.grad.reshape(-1) for p in runner.params] +
-                             [y[:: max(1, y.shape[0] // 1024)].sum().reshape(1)])
-            host_out.copy_(flat, non_blocking=True)
-
-    run(1)
-    if barrier is not None:
-        barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run(steps)
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps, runner.x_host.numel() * 4, host_out.numel() * 4
 
 
 def main():
@@ -421,6 +392,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
     ap.add_argument("--no-epochs", action="store_true", help="skip the Pubmed / PPI epoch-time add-on measurements")
+    ap.add_argument("--no-hidden", action="store_true", help="skip the hidden-layer (project-first) add-on measurement")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the comparison with a single-GPU run of the same step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

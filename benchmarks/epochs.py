@@ -27,7 +27,7 @@ def pubmed_epoch_ms(device, epochs: int = 20, warmup: int = 3, seed: int = 72):
     one epoch = train step + eval forward (train.py:154-170)."""
     import layers
     import models
-    from .synth import power_law_csr
+    from pygat_b200.synth import power_law_csr
     n, f_in, classes = 19717, 500, 3
     torch.manual_seed(seed)
     rowptr, col = power_law_csr(n, 5.5, seed=seed, device=device)
@@ -74,8 +74,8 @@ def ppi_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup:
     with node-count weights."""
     import layers
     import models
-    from .sharded import allreduce_gradients
-    from .synth import power_law_csr
+    from pygat_b200.sharded import allreduce_gradients
+    from pygat_b200.synth import power_law_csr
     torch.manual_seed(seed)
     graphs = []
     for k, n in enumerate(PPI_TRAIN_GRAPH_NODES):
@@ -91,7 +91,7 @@ def ppi_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup:
                        layer_type=layers.GraphAttentionLayer, skip_connection=True).to(device)
     opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0)
     loss_fn = torch.nn.BCEWithLogitsLoss(reduction="mean")
-    from .sharded import rank_batch_schedule
+    from pygat_b200.sharded import rank_batch_schedule
     mine = [batches[i] if i is not None else None for i in rank_batch_schedule(len(batches), rank, world)]
 
     def epoch():

@@ -91,11 +91,19 @@ GATK_API int gatk_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, 
  * (A operand split into tensor memory, fp32 parity through the 3xTF32 scheme) covers all batches when
  *   !transA:           M >= 1024, K <= 512 and (N <= 64 or K <= 128), pitches / batch strides multiples of 4 floats;
  *   transA, !transB:   K >= 2048, 8 <= M, N <= 512 (deterministic split-K over all SMs);
- * other shapes run one gatk_gemm per batch. */
+ * other shapes run one gatk_gemm per batch.
+ * elu_out (optional): the backward products of a layer with an ELU take dh' = gout * ELU'(v) as an operand (A of the
+ * NT product dxagg_h = dh'_h W_h^T, B of the TN product dW_h = xagg_h^T dh'_h).  With elu_out = ELU(v) (the layer's
+ * activated output, same shape and batch stride as that operand, row pitch ld_elu) the kernels load both tiles and
+ * form the product while they split the operand, so dh' is never written to memory (F.elu's autograd, layers.py:51,170).
+ * Only on the tensor-core paths: gatk_gemm_batched_fuses_elu_grad(...) == 1 for the shape; an error otherwise. */
 GATK_API size_t gatk_gemm_batched_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches);
+GATK_API int gatk_gemm_batched_fuses_elu_grad(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches,
+                                              int64_t lda, int64_t a_bs, int64_t ldb, int64_t b_bs, int64_t ldc, int64_t c_bs);
 GATK_API int gatk_gemm_batched(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A,
                                int64_t lda, int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, float* C, int64_t ldc,
-                               int64_t c_bs, int epilogue, void* ws, size_t ws_bytes, void* stream);
+                               int64_t c_bs, int epilogue, const float* elu_out, int64_t ld_elu, void* ws, size_t ws_bytes,
+                               void* stream);
 
 /* Attention-logit halves f_i = Wh_i . a[:D], g_j = Wh_j . a[D:] (layers.py:60-61, :141-144),
  * after the post-projection dropout (layers.py:37,136) applied IN PLACE to wh when
@@ -198,6 +206,10 @@ GATK_API int gatk_da_reduce(int64_t n, int H, int Dp, const float* wh, int64_t l
  *          inverse of gatk_csr_transpose's perm) ds is written in TRANSPOSED order, so that edge_tsum streams
  *          it (perm = NULL there) instead of gathering 32-byte pieces.  (dW_h = xagg_h^T dh'_h is a gatk_gemm;
  *          dx is not produced: the form is for layers whose input needs no gradient.)
+ *          With dg_acc (float [n_src, lddg_acc], ZERO-INITIALISED by the caller) the kernel adds every ds_ijh
+ *          straight into dg_acc[j, h] with red.global.add (vector reductions into an L2-resident array): ds may
+ *          then be NULL and gatk_edge_tsum is not needed.  The sum order is then scheduling dependent (fp32
+ *          rounding differences of ~1e-7 in dg); ds + gatk_edge_tsum is the bit-reproducible route.
  *  edge_tsum  dg[j,h] = sum_i ds_ijh: segmented sum along the transposed pattern (tptr, perm from
  *          gatk_csr_transpose; perm = NULL when ds is already in transposed order); sources with more than long_len entries are listed in long_rows.
  * n_src: rows of xg (sources; col indexes them), n_dst: destination rows of this shard.
@@ -226,7 +238,8 @@ GATK_API int gatk_attn_x_fwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr
 GATK_API int gatk_attn_x_bwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
                              const float* xg, int64_t ldxg, const float* f, int64_t ldf, const float* lse, float alpha,
                              const float* xagg, int64_t ldxa, const float* dxagg, int64_t ldd, float* ds,
-                             const int32_t* iperm, float* df, int64_t lddf, int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
+                             const int32_t* iperm, float* dg_acc, int64_t lddg_acc, float* df, int64_t lddf, int seg_len,
+                             const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                              int n_hub_seg, float* hub_scratch, int32_t* counter, const int32_t* item_ptr,
                              int n_items, void* stream);
 GATK_API int gatk_edge_tsum(int64_t n_src, const int64_t* tptr, const int32_t* perm, int H, const float* ds,

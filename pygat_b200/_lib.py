@@ -33,8 +33,10 @@ PROTOTYPES = {
     "gatk_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int,
                           P, c_size_t, P]),
     "gatk_gemm_batched_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int64, c_int64, c_int]),
+    "gatk_gemm_batched_fuses_elu_grad": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int64, c_int64, c_int64,
+                                                 c_int64, c_int64, c_int64]),
     "gatk_gemm_batched": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int, P, c_int64, c_int64, P, c_int64, c_int64,
-                                  P, c_int64, c_int64, c_int, P, c_size_t, P]),
+                                  P, c_int64, c_int64, c_int, P, c_int64, P, c_size_t, P]),
     "gatk_logits_fwd": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_float, P, P, P, P, P]),
     "gatk_hub_scratch_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gatk_attn_fwd": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, P, c_int64, P, c_float, c_float,
@@ -57,7 +59,7 @@ PROTOTYPES = {
     "gatk_attn_x_fwd": (c_int, [c_int64, c_int64, P, P, c_int, c_int, P, c_int64, P, c_int64, c_float, P, c_int64, P,
                                 c_int, P, P, c_int, c_int, P, P, P, c_int, P]),
     "gatk_attn_x_bwd": (c_int, [c_int64, c_int64, P, P, c_int, c_int, P, c_int64, P, c_int64, P, c_float, P, c_int64, P,
-                                c_int64, P, P, P, c_int64, c_int, P, P, c_int, c_int, P, P, P, c_int, P]),
+                                c_int64, P, P, P, c_int64, P, c_int64, c_int, P, P, c_int, c_int, P, P, P, c_int, P]),
     "gatk_edge_tsum": (c_int, [c_int64, P, P, c_int, P, P, c_int64, c_int, P, c_int, P]),
     "gatk_elu_fwd": (c_int, [c_int64, c_int64, P, c_int64, P]),
     "gatk_elu_bwd": (c_int, [c_int64, c_int64, P, c_int64, P, c_int64, P, c_int64, P]),

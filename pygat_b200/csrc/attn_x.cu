@@ -55,6 +55,9 @@ struct alignas(64) XArgs {
   int64_t ldd;
   float* ds;
   const int32_t* iperm;  // CSR entry -> position in the transposed pattern (NULL: ds stays in CSR order)
+  float* dgacc;          // NULL, or [n_src, lddgacc] zero-initialised: dg_j += ds_ij accumulated here with red.global.add
+  int64_t lddgacc;       //       (replaces the ds write + the transposed segmented sum gatk_edge_tsum)
+  int dg_vec4;           // H == 8 and 16-byte aligned rows: two red.global.add.v4.f32 per stored entry
   float* df;
   int64_t lddf;
   int seg_len;
@@ -131,6 +134,25 @@ __device__ __forceinline__ void fma4_pp(float4& acc, const float2 pp, const floa
   const float2 lo = __ffma2_rn(pp, make_float2(x.x, x.y), make_float2(acc.x, acc.y));
   const float2 hi = __ffma2_rn(pp, make_float2(x.z, x.w), make_float2(acc.z, acc.w));
   acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// dg accumulation: fire-and-forget vector reductions into the (L2-resident) [n_src, H] array
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// the same with an L2 evict_last policy: the dg array (N*H floats) is touched ~degree times per row at random,
+// between gigabytes of streamed gather rows
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void red_add_v4_pol(float* p, float a, float b, float c, float d, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
 struct Chunk {
@@ -531,7 +553,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const __grid_consta
       const float v = al * ((acc2[h].x + acc2[h].y) - cv[h]) * (z > 0.f ? 1.f : a.alpha);
       dsv[h] = (valid && h < H) ? v : 0.f;
     }
-    if (valid) {
+    if (valid && a.ds) {
       float* dp = a.ds + (a.iperm ? (int64_t)__ldg(a.iperm + c.base + lane) : c.base + lane) * H;
       if (HP >= 4 && H == HP) {
 #pragma unroll
@@ -540,6 +562,17 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_kernel(const __grid_consta
 #pragma unroll
         for (int h = 0; h < HP; ++h)
           if (h < H) dp[h] = dsv[h];
+      }
+    }
+    if (valid && a.dgacc) {
+      float* gp = a.dgacc + (int64_t)j * a.lddgacc;
+      if (HP >= 4 && a.dg_vec4) {
+#pragma unroll
+        for (int h = 0; h < HP; h += 4) red_add_v4(gp + h, dsv[h], dsv[h + 1], dsv[h + 2], dsv[h + 3]);
+      } else {
+#pragma unroll
+        for (int h = 0; h < HP; ++h)
+          if (h < H) red_add_f32(gp + h, dsv[h]);
       }
     }
     butterfly_scatter<HP>(dsv, lane);  // dsv[0]: this chunk's sum of head hq
@@ -651,7 +684,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
 #pragma unroll
     for (int q = 0; q < 2 * MT; ++q) {
       const int e = 16 * (q >> 1) + g + 8 * (q & 1);
-      npos[q] = (ch.ok && e < ch.cnt) ? (a.iperm ? (int64_t)__ldg(a.iperm + ch.base + e) : ch.base + e) : 0;
+      npos[q] = (a.ds && ch.ok && e < ch.cnt) ? (a.iperm ? (int64_t)__ldg(a.iperm + ch.base + e) : ch.base + e) : 0;
     }
   };
   auto prefetch_fl = [&](const Chunk& ch) {
@@ -669,6 +702,8 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
     prefetch_fl(c);
     prefetch_pos(c);
   }
+  int jc = cols_of(c);  // column ids of the chunk being computed (lane e holds entry e's source)
+  const uint64_t dg_pol = l2_policy_evict_last();
   Chunk n = it.next(a, lane);
   int jn = cols_of(n);
   int p = 0;
@@ -755,20 +790,38 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int e = 16 * mt + g + 8 * half;
-        if (e < c.cnt) {
+        const bool ev = e < c.cnt;
+        float v0 = 0.f, v1 = 0.f;
+        if (ev) {
           const float2 gq = *reinterpret_cast<const float2*>(rows + e * RS + Fp + h0);
           const float z0 = f0 + gq.x, z1 = f1 + gq.y;
           const float s0 = z0 > 0.f ? z0 : a.alpha * z0, s1 = z1 > 0.f ? z1 : a.alpha * z1;
-          const float v0 = expf(s0 - l0) * (acc[mt][0][2 * half] - c0) * (z0 > 0.f ? 1.f : a.alpha);
-          const float v1 = expf(s1 - l1) * (acc[mt][0][2 * half + 1] - c1) * (z1 > 0.f ? 1.f : a.alpha);
-          float* dp = a.ds + ipos[2 * mt + half] * H + h0;
-          if (h1 < H && (H & 1) == 0) {
-            *reinterpret_cast<float2*>(dp) = make_float2(v0, v1);
-            df0 += v0;
-            df1 += v1;
-          } else {
-            if (h0 < H) { dp[0] = v0; df0 += v0; }
-            if (h1 < H) { dp[1] = v1; df1 += v1; }
+          v0 = h0 < H ? expf(s0 - l0) * (acc[mt][0][2 * half] - c0) * (z0 > 0.f ? 1.f : a.alpha) : 0.f;
+          v1 = h1 < H ? expf(s1 - l1) * (acc[mt][0][2 * half + 1] - c1) * (z1 > 0.f ? 1.f : a.alpha) : 0.f;
+          df0 += v0;
+          df1 += v1;
+          if (a.ds) {
+            float* dp = a.ds + ipos[2 * mt + half] * H + h0;
+            if (h1 < H && (H & 1) == 0) {
+              *reinterpret_cast<float2*>(dp) = make_float2(v0, v1);
+            } else {
+              if (h0 < H) dp[0] = v0;
+              if (h1 < H) dp[1] = v1;
+            }
+          }
+        }
+        if (a.dgacc) {  // dg_j += ds_ij, straight into the per-source array (warp-uniform branch)
+          const int je = __shfl_sync(FULL, jc, e & 31);
+          float* gp = a.dgacc + (int64_t)je * a.lddgacc + h0;
+          if (a.dg_vec4) {  // lanes tg = 0, 2 of a group send heads 0..3 / 4..7 of the group's entry
+            const float q0 = __shfl_xor_sync(FULL, v0, 1), q1 = __shfl_xor_sync(FULL, v1, 1);
+            if (ev && !(tg & 1)) {
+              if (a.dg_vec4 == 2) red_add_v4_pol(gp, v0, v1, q0, q1, dg_pol);
+              else red_add_v4(gp, v0, v1, q0, q1);
+            }
+          } else if (ev) {
+            if (h0 < H) red_add_f32(gp, v0);
+            if (h1 < H) red_add_f32(gp + 1, v1);
           }
         }
       }
@@ -788,6 +841,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
     }
     __syncwarp();
     c = n;
+    jc = jn;
     n = nn;
     jn = jnn;
     p ^= 1;
@@ -970,6 +1024,136 @@ __global__ void __launch_bounds__(256) logits_pack_kernel(int64_t n, int F, int 
           const float val = t < H ? gval : 0.f;
           xg[row * P + Fp + t] = val;
           for (int q = 0; q < peers.n; ++q) peers.base[q][row * P + Fp + t] = val;
+        }
+      }
+    }
+  }
+}
+
+// The same pack on the tensor cores (Fp <= 128, 16-byte aligned rows): [16 rows x Fp] x [Fp x 16 columns (u | v)] per
+// warp tile with mma.sync m16n8k8 tf32 and the 3xTF32 split (fp32 parity).  The lane that loads a 16-byte piece of
+// an input row for the A fragment also stores it into the gather row, so x is read once and xg written once with
+// full 32-byte sectors; the split [u|v] fragments sit pre-packed per lane in shared memory (one LDS.128 per MMA
+// pair).  k is permuted inside each 16-feature block so that a lane's four k values are adjacent in memory
+// (k-step 2kp: logical k = tg -> feature 16kp+4tg, tg+4 -> +1; k-step 2kp+1: +2, +3), as in attn_x_bwd_mma_kernel.
+// The SIMT kernel above needed 16 dot products per row on the FMA pipe (66 % issue-active at 0.31 of the byte floor).
+template <int KPMAX>
+__global__ void __launch_bounds__(256) logits_pack_mma_kernel(int64_t n, int F, int H, const float* __restrict__ x, int64_t ldx,
+                                                              const float* __restrict__ uv, int64_t lduv, int Fp, int P,
+                                                              float* __restrict__ xg, float* __restrict__ f, int64_t ldf,
+                                                              const PackPeers peers) {
+  extern __shared__ __align__(16) float4 bfrag[];  // [KP][ks 2][nt 2][lane 32] = {b0 hi, b1 hi, b0 lo, b1 lo}
+  const int KP = (Fp + 15) >> 4;
+  for (int i = threadIdx.x; i < KP * 128; i += blockDim.x) {
+    const int ln = i & 31, nt = (i >> 5) & 1, ks = (i >> 6) & 1, kp = i >> 7;
+    const int gq = ln >> 2, tq = ln & 3;
+    const int f0 = 16 * kp + 4 * tq + 2 * ks;
+    const int colq = nt == 0 ? gq : H + gq;
+    const float b0 = (gq < H && f0 < F) ? uv[(int64_t)f0 * lduv + colq] : 0.f;
+    const float b1 = (gq < H && f0 + 1 < F) ? uv[(int64_t)(f0 + 1) * lduv + colq] : 0.f;
+    uint32_t h0, l0, h1, l1;
+    split_tf32(b0, h0, l0);
+    split_tf32(b1, h1, l1);
+    bfrag[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, tg = lane & 3;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 16; row0 < n; row0 += warps * 16) {
+    const int64_t ra = row0 + g, rb = row0 + g + 8;
+    const bool va = ra < n, vb = rb < n;
+    float4 xa[KPMAX], xb[KPMAX];
+#pragma unroll
+    for (int kp = 0; kp < KPMAX; ++kp) {
+      const int c = 16 * kp + 4 * tg;
+      const bool in = kp < KP && c < Fp;
+      xa[kp] = (in && va) ? ldg4_stream(x + ra * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xb[kp] = (in && vb) ? ldg4_stream(x + rb * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (F != Fp) {  // F % 4 != 0 never takes this kernel; kept for clarity: the pad columns of xg are zeros
+    }
+    // the input columns of the gather rows (and of the peers' copies when whole rows are pushed)
+#pragma unroll
+    for (int kp = 0; kp < KPMAX; ++kp) {
+      const int c = 16 * kp + 4 * tg;
+      if (kp < KP && c < Fp) {
+        if (va) stg4(xg + ra * P + c, xa[kp]);
+        if (vb) stg4(xg + rb * P + c, xb[kp]);
+        if (peers.rows)
+          for (int q = 0; q < peers.n; ++q) {
+            if (va) stg4(peers.base[q] + ra * P + c, xa[kp]);
+            if (vb) stg4(peers.base[q] + rb * P + c, xb[kp]);
+          }
+      }
+    }
+    float acc[2][2][4];  // [n-tile: u, v][main, compensation][fragment]
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[nt][t][q] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < KPMAX; ++kp) {
+      if (kp < KP) {
+        uint32_t ah[4], al[4], bh[4], bl[4];
+        split_tf32(xa[kp].x, ah[0], al[0]); split_tf32(xa[kp].y, ah[1], al[1]);
+        split_tf32(xa[kp].z, ah[2], al[2]); split_tf32(xa[kp].w, ah[3], al[3]);
+        split_tf32(xb[kp].x, bh[0], bl[0]); split_tf32(xb[kp].y, bh[1], bl[1]);
+        split_tf32(xb[kp].z, bh[2], bl[2]); split_tf32(xb[kp].w, bh[3], bl[3]);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            const float4 bq = bfrag[((kp * 2 + ks) * 2 + nt) * 32 + lane];
+            const uint32_t b0h = __float_as_uint(bq.x), b1h = __float_as_uint(bq.y);
+            const uint32_t b0l = __float_as_uint(bq.z), b1l = __float_as_uint(bq.w);
+            mma_tf32(acc[nt][0], ah[2 * ks], bh[2 * ks], ah[2 * ks + 1], bh[2 * ks + 1], b0h, b1h);
+            mma_tf32(acc[nt][1], al[2 * ks], bl[2 * ks], al[2 * ks + 1], bl[2 * ks + 1], b0h, b1h);
+            mma_tf32(acc[nt][1], ah[2 * ks], bh[2 * ks], ah[2 * ks + 1], bh[2 * ks + 1], b0l, b1l);
+          }
+        }
+      }
+    }
+    // fragment: [0] = (row g, col 2tg), [1] = (g, 2tg+1), [2] = (g+8, 2tg), [3] = (g+8, 2tg+1)
+    const int h0 = 2 * tg;
+    float fu[4], gv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      fu[q] = acc[0][0][q] + acc[0][1][q];
+      gv[q] = acc[1][0][q] + acc[1][1][q];
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int64_t row = half ? rb : ra;
+      if (half ? vb : va) {
+        if (h0 < H) f[row * ldf + h0] = fu[2 * half];
+        if (h0 + 1 < H) f[row * ldf + h0 + 1] = fu[2 * half + 1];
+        // g behind the input row, zeros up to the pitch
+        const float g0 = h0 < H ? gv[2 * half] : 0.f, g1 = h0 + 1 < H ? gv[2 * half + 1] : 0.f;
+        float* tail = xg + row * P + Fp;
+        if (Fp + h0 + 1 < P) {
+          *reinterpret_cast<float2*>(tail + h0) = make_float2(g0, g1);
+        } else if (Fp + h0 < P) {
+          tail[h0] = g0;
+        }
+        for (int t = 8 + h0; t < P - Fp; t += 8) {
+          tail[t] = 0.f;
+          if (t + 1 < P - Fp) tail[t + 1] = 0.f;
+        }
+        for (int q = 0; q < peers.n; ++q) {
+          float* pt = peers.base[q] + row * P + Fp;
+          if (Fp + h0 + 1 < P) {
+            *reinterpret_cast<float2*>(pt + h0) = make_float2(g0, g1);
+          } else if (Fp + h0 < P) {
+            pt[h0] = g0;
+          }
+          if (peers.rows)
+            for (int t = 8 + h0; t < P - Fp; t += 8) {
+              pt[t] = 0.f;
+              if (t + 1 < P - Fp) pt[t + 1] = 0.f;
+            }
         }
       }
     }
@@ -1165,6 +1349,20 @@ static int logits_pack_launch(int64_t n, int F, int H, const float* x, int64_t l
   int64_t blocks = (n + 31) / 32;  // 8 warps x 4 rows per iteration
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
+  static const bool pack_simt = getenv("GATK_PACK_SIMT") != nullptr;
+  if (vec && Fp <= 128 && (ldxg & 3) == 0 && !pack_simt) {  // tensor-core pack
+    const int kp = (Fp + 15) >> 4;
+    const size_t sm = (size_t)kp * 128 * sizeof(float4);
+    int64_t blk = (n + 127) / 128;  // 8 warps x 16 rows
+    const int64_t capm = (int64_t)sm_count() * 4;
+    if (blk > capm) blk = capm;
+    if (kp <= 4)
+      logits_pack_mma_kernel<4><<<(unsigned)blk, 256, sm, st>>>(n, F, H, x, ldx, uv, lduv, Fp, (int)ldxg, xg, f, ldf, peers);
+    else
+      logits_pack_mma_kernel<8><<<(unsigned)blk, 256, sm, st>>>(n, F, H, x, ldx, uv, lduv, Fp, (int)ldxg, xg, f, ldf, peers);
+    GATK_CHECK_LAUNCH();
+    return 0;
+  }
 #define PACK_LAUNCH(HPV, V) logits_pack_kernel<HPV, V><<<(unsigned)blocks, 256, smem, st>>>(n, F, H, x, ldx, uv, lduv, Fp, (int)ldxg, xg, f, ldf, peers)
   if (vec) {
     HP_DISPATCH(hp, PACK_LAUNCH(HP, true));
@@ -1240,7 +1438,8 @@ extern "C" int gatk_attn_x_fwd(int64_t n_src, int64_t n_dst, const int64_t* rowp
 extern "C" int gatk_attn_x_bwd(int64_t n_src, int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Fp,
                                const float* xg, int64_t ldxg, const float* f, int64_t ldf, const float* lse, float alpha,
                                const float* xagg, int64_t ldxa, const float* dxagg, int64_t ldd, float* ds,
-                               const int32_t* iperm, float* df, int64_t lddf, int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
+                               const int32_t* iperm, float* dg_acc, int64_t lddg_acc, float* df, int64_t lddf, int seg_len,
+                               const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                                int n_hub_seg, float* hub_scratch, int32_t* counter, const int32_t* item_ptr,
                                int n_items, void* stream) {
   int hp, ns, sx;
@@ -1249,12 +1448,17 @@ extern "C" int gatk_attn_x_bwd(int64_t n_src, int64_t n_dst, const int64_t* rowp
   if (int rc = fill_xargs(a, n_src, n_dst, rowptr, col, H, Fp, sx, xg, ldxg, f, ldf, alpha, seg_len, hub_rows, hub_seg_ptr,
                           n_hub, n_hub_seg, hub_scratch, counter, item_ptr, n_items))
     return rc;
-  GATK_REQUIRE(lse && xagg && dxagg && ds && df, "null pointer argument");
+  GATK_REQUIRE(lse && xagg && dxagg && (ds || dg_acc) && df, "null pointer argument (ds and dg_acc cannot both be NULL)");
   GATK_REQUIRE(ldxa % 4 == 0 && ldxa >= (int64_t)H * Fp && ldd % 4 == 0 && ldd >= (int64_t)H * Fp && lddf >= H &&
                    ((uintptr_t)xagg & 15) == 0 && ((uintptr_t)dxagg & 15) == 0 && ((uintptr_t)ds & 15) == 0,
                "xagg / dxagg: 16-byte aligned, pitch >= H*Fp (multiple of 4 floats); ds 16-byte aligned; lddf >= H");
+  GATK_REQUIRE(!dg_acc || lddg_acc >= H, "lddg_acc must be >= H");
   a.xagg = const_cast<float*>(xagg); a.ldxa = ldxa; a.lse = const_cast<float*>(lse);
   a.dxagg = dxagg; a.ldd = ldd; a.ds = ds; a.iperm = iperm; a.df = df; a.lddf = lddf;
+  a.dgacc = dg_acc; a.lddgacc = lddg_acc;
+  a.dg_vec4 = (dg_acc && H == 8 && lddg_acc % 4 == 0 && ((uintptr_t)dg_acc & 15) == 0) ? 1 : 0;
+  static const bool dg_plain = getenv("GATK_DG_NO_POLICY") != nullptr;  // measured: evict_last on the reds is worth ~0.1 ms
+  if (a.dg_vec4 && !dg_plain) a.dg_vec4 = 2;
   cudaStream_t st = (cudaStream_t)stream;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
   static const bool simt_only = getenv("GATK_XBWD_SIMT") != nullptr;

@@ -157,7 +157,8 @@ int gemm_batched_path(int transA, int transB, int64_t M, int64_t N, int64_t K, i
                       int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, const float* C, int64_t ldc, int64_t c_bs);
 int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A, int64_t lda,
                            int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, float* C, int64_t ldc, int64_t c_bs,
-                           int epilogue, void* ws, size_t ws_bytes, cudaStream_t st);
+                           int epilogue, const float* elu_out, int64_t ld_elu, void* ws, size_t ws_bytes, cudaStream_t st);
+bool gemm_batched_fuses_elu_grad(int path, int64_t N);
 
 static bool tc_enabled() {
   static int v = -1;
@@ -246,9 +247,17 @@ extern "C" size_t gatk_gemm_batched_workspace_bytes(int transA, int transB, int6
   return one > bat ? one : bat;
 }
 
+extern "C" int gatk_gemm_batched_fuses_elu_grad(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches, int64_t lda,
+                                                int64_t a_bs, int64_t ldb, int64_t b_bs, int64_t ldc, int64_t c_bs) {
+  if (!tc_enabled() || transA == transB) return 0;  // NT (dh' = A) and TN (dh' = B) products only
+  const int path = gemm_batched_path(transA, transB, M, N, K, batches, nullptr, lda, a_bs, nullptr, ldb, b_bs, nullptr, ldc, c_bs);
+  return (path && gemm_batched_fuses_elu_grad(path, N)) ? 1 : 0;
+}
+
 extern "C" int gatk_gemm_batched(int transA, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A,
                                  int64_t lda, int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, float* C, int64_t ldc,
-                                 int64_t c_bs, int epilogue, void* ws, size_t ws_bytes, void* stream) {
+                                 int64_t c_bs, int epilogue, const float* elu_out, int64_t ld_elu, void* ws, size_t ws_bytes,
+                                 void* stream) {
   GATK_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batches >= 0, "negative GEMM size");
   GATK_REQUIRE(epilogue == 0 || epilogue == 1, "epilogue must be 0 (none) or 1 (ELU)");
   if (M == 0 || N == 0 || batches == 0) return 0;
@@ -256,8 +265,9 @@ extern "C" int gatk_gemm_batched(int transA, int transB, int64_t M, int64_t N, i
   cudaStream_t st = (cudaStream_t)stream;
   const int path = tc_enabled() ? gemm_batched_path(transA, transB, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs) : 0;
   if (path && ws && ws_bytes >= gemm_batched_tc_workspace_bytes(transA, transB, M, N, K, batches))
-    return gemm_batched_tc_launch(path, transB, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, epilogue, ws,
-                                  ws_bytes, st);
+    return gemm_batched_tc_launch(path, transB, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, epilogue,
+                                  transA != transB ? elu_out : nullptr, ld_elu, ws, ws_bytes, st);
+  GATK_REQUIRE(!elu_out, "elu_out needs the batched tensor-core kernels (gatk_gemm_batched_fuses_elu_grad says when)");
   for (int b = 0; b < batches; ++b) {  // shapes the batched tensor-core kernels do not take: one product per batch
     if (int rc = gatk_gemm(transA, transB, M, N, K, A + b * a_bs, lda, B + b * b_bs, ldb, C + b * c_bs, ldc, 0, ws, ws_bytes, stream))
       return rc;

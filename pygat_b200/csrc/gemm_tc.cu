@@ -719,6 +719,21 @@ struct RingN {
   }
 };
 
+struct RingRT {  // depth chosen at run time (the fused dh' = gout * ELU'(out) mode pairs the raw A slots)
+  int n;
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ explicit RingRT(int depth) : n(depth) {}
+  __device__ __forceinline__ void advance() {
+    if (++stage == n) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+// d/dv ELU(v) from out = ELU(v) (F.elu, layers.py:51,170): 1 for v > 0, exp(v) = out + 1 otherwise
+__device__ __forceinline__ float elu_grad_from_out(float o) { return o > 0.f ? 1.f : o + 1.f; }
+
 constexpr int BT_THREADS = 512;  // warps 0-2 producer / MMA / TMEM, 4-7 splitter, 8-15 two epilogue warpgroups
 
 // configuration of the shared-memory-operand TN kernel (only the 128-wide tile still uses it: its accumulators
@@ -783,8 +798,13 @@ template <int BN>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                            const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c,
-                           int m_tiles, int n_tiles, int batches, int k_blocks, int npad, int epilogue, int contiguous, int box_n) {
+                           int m_tiles, int n_tiles, int batches, int k_blocks, int npad, int epilogue, int contiguous, int box_n,
+                           const __grid_constant__ CUtensorMap map_a2, int fuse_elu_grad) {
   using C = CfgTA<BN>;
+  // fuse_elu_grad: the A operand is dh' = A * ELU'(A2) (A = upstream gradient, A2 = the layer's activated output):
+  // both raw tiles land in one ring stage (two adjacent 16 KiB slots), the splitter multiplies while it splits
+  const int nsa = fuse_elu_grad ? C::NSA / 2 : C::NSA;
+  const int a_stride = fuse_elu_grad ? 2 * C::TILE_A : C::TILE_A;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* cstage = smem + C::OFF_C;
@@ -849,14 +869,16 @@ gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
   if (warp == 0) {
     // ---- A producer: the HBM stream
     if (elect_one()) {
-      RingN<C::NSA> r;
+      RingRT r(nsa);
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         int m0, n0, b;
         decode(tile, m0, n0, b);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(a_empty(r.stage), r.phase ^ 1);
-          mbar_expect_tx(a_full(r.stage), C::TILE_A);
-          tma_load_3d(smem_base + r.stage * C::TILE_A, &map_a, a_full(r.stage), kb * BLOCK_K, m0, b);
+          mbar_expect_tx(a_full(r.stage), fuse_elu_grad ? 2 * C::TILE_A : C::TILE_A);
+          tma_load_3d(smem_base + r.stage * a_stride, &map_a, a_full(r.stage), kb * BLOCK_K, m0, b);
+          if (fuse_elu_grad)
+            tma_load_3d(smem_base + r.stage * a_stride + C::TILE_A, &map_a2, a_full(r.stage), kb * BLOCK_K, m0, b);
           r.advance();
         }
       }
@@ -924,18 +946,28 @@ gemm_batched_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
     }
   } else if (warp >= 4 && warp < 8) {
     // ---- splitter: thread `row` owns row `row` of the tile = TMEM lane `row` (warp w may touch lanes 32 (w % 4) ...)
-    RingN<C::NSA> ra;
+    RingRT ra(nsa);
     RingN<C::NTA> rt;
     const int row = threadIdx.x - 128;
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::TMEM_A;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(a_full(ra.stage), ra.phase);
-        const uint8_t* src = smem + ra.stage * C::TILE_A + row * 128;
+        const uint8_t* src = smem + ra.stage * a_stride + row * 128;
         float4 v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)  // 16-byte chunk j of the 128-byte row is stored at j ^ (row & 7)
           v[j] = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
+        if (fuse_elu_grad) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 o = *reinterpret_cast<const float4*>(src + C::TILE_A + ((j ^ (row & 7)) << 4));
+            v[j].x *= elu_grad_from_out(o.x);
+            v[j].y *= elu_grad_from_out(o.y);
+            v[j].z *= elu_grad_from_out(o.z);
+            v[j].w *= elu_grad_from_out(o.w);
+          }
+        }
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -1292,7 +1324,10 @@ struct CfgTNA {
 __global__ void __launch_bounds__(tn::TN_THREADS, 1)
 gemm_tn_batched_ta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                           float* __restrict__ part, int Mo, int No, int m_tiles, int n_tiles, int batches, int splits,
-                          int kb_total, int kb_per_split, int box_m) {
+                          int kb_total, int kb_per_split, int box_m, const __grid_constant__ CUtensorMap map_b2,
+                          int fuse_elu_grad) {
+  // fuse_elu_grad: the B operand is dh' = B * ELU'(B2); the B2 tile lands in the slot that will hold Blo and the
+  // splitter multiplies before it splits in place
   using C = CfgTNA;
   constexpr int BN = C::BN;
   using tn::BOX_BYTES;
@@ -1377,9 +1412,14 @@ gemm_tn_batched_ta_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(s_empty(r.stage), r.phase ^ 1);
           const uint32_t st = smem_base + C::OFF_B + r.stage * 2 * C::TILE_B;
-          mbar_expect_tx(b_full(r.stage), C::TILE_B);
+          mbar_expect_tx(b_full(r.stage), fuse_elu_grad ? 2 * C::TILE_B : C::TILE_B);
 #pragma unroll
           for (int q = 0; q < BN / 32; ++q) tma_load_3d(st + q * BOX_BYTES, &map_b, b_full(r.stage), n0 + q * 32, kb * BLOCK_K, b);
+          if (fuse_elu_grad) {
+#pragma unroll
+            for (int q = 0; q < BN / 32; ++q)
+              tma_load_3d(st + C::TILE_B + q * BOX_BYTES, &map_b2, b_full(r.stage), n0 + q * 32, kb * BLOCK_K, b);
+          }
           r.advance();
         }
       }
@@ -1454,6 +1494,13 @@ gemm_tn_batched_ta_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         for (int i = 0; i < C::TILE_B / 16 / 128; ++i) {
           const int idx = t + i * 128;
           float4 v = bh[idx];
+          if (fuse_elu_grad) {
+            const float4 o = bl[idx];
+            v.x *= elu_grad_from_out(o.x);
+            v.y *= elu_grad_from_out(o.y);
+            v.z *= elu_grad_from_out(o.z);
+            v.w *= elu_grad_from_out(o.w);
+          }
           float4 h;
           h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
           h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
@@ -1625,10 +1672,17 @@ size_t gemm_batched_tc_workspace_bytes(int transA, int transB, int64_t M, int64_
   return (size_t)batches * sp * M * N * sizeof(float);
 }
 
+// elu_out != NULL: the dh' operand (A of the NT product, B of the TN product) is multiplied by ELU'(v) taken from
+// elu_out = ELU(v), same shape / batch stride as that operand, row pitch ld_elu
+bool gemm_batched_fuses_elu_grad(int path, int64_t N) { return path == 1 || (path == 2 && N <= 64); }
+
 int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K, int batches, const float* A, int64_t lda,
                            int64_t a_bs, const float* B, int64_t ldb, int64_t b_bs, float* C, int64_t ldc, int64_t c_bs,
-                           int epilogue, void* ws, size_t ws_bytes, cudaStream_t st) {
+                           int epilogue, const float* elu_out, int64_t ld_elu, void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace bt;
+  GATK_REQUIRE(!elu_out || (gemm_batched_fuses_elu_grad(path, N) && (ld_elu & 3) == 0 && aligned16(elu_out)),
+               "elu_out: unsupported shape for the fused ELU' operand (query gatk_gemm_batched_fuses_elu_grad)");
+  const int fuse = elu_out ? 1 : 0;
   GATK_REQUIRE(ws && ws_bytes >= gemm_batched_tc_workspace_bytes(path == 2, transB, M, N, K, batches),
                "batched GEMM workspace too small");
   const int bn = N <= 64 ? 64 : 128;
@@ -1641,8 +1695,10 @@ int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K
     split_transpose_b_batched_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, ldb, b_bs, (int)K, (int)N, Kpad, Npad,
                                                                                        batches, transB ? 1 : 0, bhi, blo);
     GATK_CHECK_LAUNCH();
-    CUtensorMap map_a, map_bhi, map_blo, map_c;
+    CUtensorMap map_a, map_a2, map_bhi, map_blo, map_c;
     if (int rc = make_map_3d(&map_a, A, K, M, batches, lda, a_bs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_3d(&map_a2, fuse ? elu_out : A, K, M, batches, fuse ? ld_elu : lda, a_bs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
     if (int rc = make_map_b(&map_bhi, bhi, (int64_t)batches * Npad, Kpad, bn)) return rc;
     if (int rc = make_map_b(&map_blo, blo, (int64_t)batches * Npad, Kpad, bn)) return rc;
     const int box_n = bn == 64 ? 32 : (int)(N >= 128 ? 128 : (N + 3) / 4 * 4);  // wide tile: one dense store box per tile
@@ -1666,7 +1722,7 @@ int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K
         configured = true;
       }
       gemm_batched_tf32x3_kernel<64><<<grid, BT_THREADS, CfgTA<64>::SMEM, st>>>(map_a, map_bhi, map_blo, map_c, m_tiles, n_tiles,
-                                                                               batches, k_blocks, Npad, epilogue, order, box_n);
+                                                                               batches, k_blocks, Npad, epilogue, order, box_n, map_a2, fuse);
     } else {
       static bool configured = false;
       if (!configured) {
@@ -1674,7 +1730,7 @@ int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K
         configured = true;
       }
       gemm_batched_tf32x3_kernel<128><<<grid, BT_THREADS, CfgTA<128>::SMEM, st>>>(map_a, map_bhi, map_blo, map_c, m_tiles, n_tiles,
-                                                                                 batches, k_blocks, Npad, epilogue, order, box_n);
+                                                                                 batches, k_blocks, Npad, epilogue, order, box_n, map_a2, fuse);
     }
     GATK_CHECK_LAUNCH();
     return 0;
@@ -1682,8 +1738,10 @@ int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K
   // TN: here M = Mo (columns of A_b), N = No (columns of B_b), K = rows
   int mt, nt, sp, kbt, kbs;
   tn_plan(M, N, K, batches, bn, &mt, &nt, &sp, &kbt, &kbs);
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_b2;
   if (int rc = make_map_3d(&map_b, B, N, K, batches, ldb, b_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_map_3d(&map_b2, fuse ? elu_out : B, N, K, batches, fuse ? ld_elu : ldb, b_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+    return rc;
   const int items = mt * nt * sp * batches;
   int grid = sm_count();
   if (items < grid) grid = items;
@@ -1697,7 +1755,8 @@ int gemm_batched_tc_launch(int path, int transB, int64_t M, int64_t N, int64_t K
       GATK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_batched_ta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgTNA::SMEM));
       configured = true;
     }
-    gemm_tn_batched_ta_kernel<<<grid, tn::TN_THREADS, CfgTNA::SMEM, st>>>(map_a, map_b, part, (int)M, (int)N, mt, nt, batches, sp, kbt, kbs, box_m);
+    gemm_tn_batched_ta_kernel<<<grid, tn::TN_THREADS, CfgTNA::SMEM, st>>>(map_a, map_b, part, (int)M, (int)N, mt, nt, batches, sp, kbt, kbs,
+                                                                          box_m, map_b2, fuse);
   } else {
     if (int rc = make_map_3d(&map_a, A, M, K, batches, lda, a_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     static bool configured = false;

@@ -28,6 +28,12 @@ FOLD_LOGITS = os.environ.get("GATK_FOLD", "1") != "0"
 # The aggregate-first form (neighbour sum before the projection) for narrow first-layer inputs; GATK_AGG_FIRST=0
 # keeps the project-first kernels (the tests compare the forms).
 AGG_FIRST = os.environ.get("GATK_AGG_FIRST", "1") != "0"
+# Aggregate-first backward: dg_j = sum_i ds_ij is accumulated with red.global.add inside the edge pass (default), or --
+# GATK_DETERMINISTIC=1 -- by writing ds and summing it along the transposed pattern in a fixed order (bit-reproducible;
+# one more kernel and 2.3 GB more traffic at the products shape).
+DETERMINISTIC = os.environ.get("GATK_DETERMINISTIC", "0") not in ("", "0")
+# ELU' folded into the operand paths of the backward products (GATK_FUSE_ELU_GRAD=0: separate gatk_elu_bwd pass)
+FUSE_ELU_GRAD = os.environ.get("GATK_FUSE_ELU_GRAD", "1") != "0"
 
 
 def padded_width(d: int) -> int:
@@ -56,12 +62,22 @@ def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=0, a_off=0, b_off=
               C.data_ptr() + 4 * c_off, ldc, accumulate, _ptr(ws), ws_bytes, _stream(), label=label)
 
 
-def _gemm_batched(ta, tb, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, epilogue=0, label=None):
-    """C_b = op(A_b) op(B_b) for the `batches` column blocks A_b = A + b*a_bs, ... (one launch for all heads)."""
+def _gemm_batched(ta, tb, M, N, K, batches, A, lda, a_bs, B, ldb, b_bs, C, ldc, c_bs, epilogue=0, label=None,
+                  elu_out=None, ld_elu=0):
+    """C_b = op(A_b) op(B_b) for the `batches` column blocks A_b = A + b*a_bs, ... (one launch for all heads).
+    elu_out: the dh' operand (A of an NT product, B of a TN product) is gout * ELU'(.) formed inside the kernel."""
     ws_bytes = _lib.query("gatk_gemm_batched_workspace_bytes", ta, tb, M, N, K, batches)
     ws = _mem.empty(ws_bytes, dtype=torch.uint8, device=C.device) if ws_bytes else None
     _lib.call("gatk_gemm_batched", ta, tb, M, N, K, batches, A.data_ptr(), lda, a_bs, B.data_ptr(), ldb, b_bs,
-              C.data_ptr(), ldc, c_bs, epilogue, _ptr(ws), ws_bytes, _stream(), label=label)
+              C.data_ptr(), ldc, c_bs, epilogue, _ptr(elu_out), ld_elu, _ptr(ws), ws_bytes, _stream(), label=label)
+
+
+def _elu_grad_fusable(n, f_in, H, Dp, Fp, M_out, HD) -> bool:
+    """True when both backward products of the aggregate-first form (dW_h = xagg_h^T dh'_h, dxagg_h = dh'_h W_h^T)
+    take the batched tensor-core kernels that form dh' = gout * ELU'(out) on the fly."""
+    tn = _lib.query("gatk_gemm_batched_fuses_elu_grad", 1, 0, f_in, Dp, n, H, H * Fp, Fp, HD, Dp, M_out, Dp)
+    nt = _lib.query("gatk_gemm_batched_fuses_elu_grad", 0, 1, n, f_in, Dp, H, HD, Dp, M_out, Dp, H * Fp, Fp)
+    return bool(tn and nt)
 
 
 def _hub_scratch(which: int, H: int, Dp: int, n_seg: int, dev):
@@ -395,30 +411,44 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
         M_out = HD * (2 if has_skip else 1)
         st = _stream()
         gout = gout.contiguous()
-        if act_elu:
+        # dh' = gout * ELU'(out): formed inside the two products that consume it when both run on the batched
+        # tensor-core kernels (no separate pass, dh' never written); a skip projection needs dh' for a third product
+        fuse = act_elu and not has_skip and FUSE_ELU_GRAD and _elu_grad_fusable(n, f_in, H, Dp, Fp, M_out, HD)
+        if act_elu and not fuse:
             dhp = _mem.empty(n, HD, dtype=torch.float32, device=dev)
             _lib.call("gatk_elu_bwd", n, HD, gout.data_ptr(), HD, out.data_ptr(), HD, dhp.data_ptr(), HD, st)
         else:
             dhp = gout
+        eo, ldeo = (out, HD) if fuse else (None, 0)
         # value path: dW_h = xagg_h^T dh'_h, dS = x^T dh';  dxagg_h = dh'_h W_h^T feeds the softmax backward
         dw_ext = _mem.empty(f_in, M_out, dtype=torch.float32, device=dev)
         dxagg = (_mem.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
-        _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp, label="gemm:dW")
-        _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp, label="gemm:dxagg")
+        _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp, label="gemm:dW",
+                      elu_out=eo, ld_elu=ldeo)
+        _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp, label="gemm:dxagg",
+                      elu_out=eo, ld_elu=ldeo)
         if has_skip:
             _gemm(1, 0, f_in, HD, n, xg, P, dhp, HD, dw_ext, M_out, c_off=HD, label="gemm:dskip")
         # logit path: ds per stored entry, df per destination, dg per source (transposed sum of ds)
-        ds = _mem.empty(graph.nnz, H, dtype=torch.float32, device=dev)
-        dfg = (_mem.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
         hubs = graph.hubs
         scratch = _x_scratch(1, H, Fp, hubs.n_seg, dev)
-        _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
-                  f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
-                  dxagg.data_ptr(), H * Fp, ds.data_ptr(), None, dfg.data_ptr(), Muv,
-                  *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
-        tptr, _trow, perm, thubs = graph.transpose()[:4]
-        _lib.call("gatk_edge_tsum", graph.n_src, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(),
-                  dfg.data_ptr() + 4 * H, Muv, thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
+        if DETERMINISTIC:
+            ds = _mem.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+            dfg = (_mem.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
+            _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
+                      f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
+                      dxagg.data_ptr(), H * Fp, ds.data_ptr(), None, None, 0, dfg.data_ptr(), Muv,
+                      *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+            tptr, _trow, perm, thubs = graph.transpose()[:4]
+            _lib.call("gatk_edge_tsum", graph.n_src, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(),
+                      dfg.data_ptr() + 4 * H, Muv, thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
+        else:
+            # dg_j is accumulated by the edge pass itself (vector reductions into the zeroed dg columns of dfg)
+            dfg = torch.zeros(n, Muv, dtype=torch.float32, device=dev)
+            _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
+                      f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
+                      dxagg.data_ptr(), H * Fp, None, None, dfg.data_ptr() + 4 * H, Muv, dfg.data_ptr(), Muv,
+                      *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         dw_uv = _mem.empty(f_in, Muv, dtype=torch.float32, device=dev)
         _gemm_batched(1, 0, f_in, Muv, n, 1, xg, P, 0, dfg, Muv, 0, dw_uv, Muv, 0, label="gemm:dlogits")  # one "head": the TMEM-A TN kernel
         return None, dw_ext, dw_uv, None, None, None, None, None, None

@@ -413,31 +413,42 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
         st = _stream()
         gout = gout.contiguous()
         xg_loc = plan.rows(xg_full)
-        if act_elu:
+        fuse = act_elu and not has_skip and Fn.FUSE_ELU_GRAD and Fn._elu_grad_fusable(n, f_in, H, Dp, Fp, M_out, HD)
+        if act_elu and not fuse:
             dhp = _mem.empty(n, HD, dtype=torch.float32, device=dev)
             _lib.call("gatk_elu_bwd", n, HD, gout.data_ptr(), HD, out.data_ptr(), HD, dhp.data_ptr(), HD, st)
         else:
             dhp = gout
+        eo, ldeo = (out, HD) if fuse else (None, 0)
         dw_ext = _mem.empty(f_in, M_out, dtype=torch.float32, device=dev)
         dxagg = (_mem.empty if Fp == f_in else torch.zeros)(n, H * Fp, dtype=torch.float32, device=dev)
-        _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp, label="gemm:dxagg")
-        ds = _mem.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+        _gemm_batched(0, 1, n, f_in, Dp, H, dhp, HD, Dp, w_ext, M_out, Dp, dxagg, H * Fp, Fp, label="gemm:dxagg",
+                      elu_out=eo, ld_elu=ldeo)
         dfg = (_mem.empty if Muv == 2 * H else torch.zeros)(n, Muv, dtype=torch.float32, device=dev)
         hubs = graph.hubs
         scratch = _x_scratch(1, H, Fp, hubs.n_seg, dev)
-        _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg_full.data_ptr(), P,
-                  f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
-                  dxagg.data_ptr(), H * Fp, ds.data_ptr(), None, dfg.data_ptr(), Muv,
-                  *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         # dg: partial sums for EVERY source from this rank's stored entries, reduced to the rows' owners
-        tptr, _trow, perm, thubs = graph.transpose()[:4]
-        dg_part = _mem.empty(N, H, dtype=torch.float32, device=dev)
-        _lib.call("gatk_edge_tsum", N, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(), dg_part.data_ptr(), H,
-                  thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
+        if Fn.DETERMINISTIC:
+            ds = _mem.empty(graph.nnz, H, dtype=torch.float32, device=dev)
+            _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg_full.data_ptr(), P,
+                      f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
+                      dxagg.data_ptr(), H * Fp, ds.data_ptr(), None, None, 0, dfg.data_ptr(), Muv,
+                      *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+            tptr, _trow, perm, thubs = graph.transpose()[:4]
+            dg_part = _mem.empty(N, H, dtype=torch.float32, device=dev)
+            _lib.call("gatk_edge_tsum", N, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(), dg_part.data_ptr(), H,
+                      thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
+        else:  # the edge pass accumulates them itself (red.global.add into the zeroed [N, H] array)
+            dg_part = torch.zeros(N, H, dtype=torch.float32, device=dev)
+            _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg_full.data_ptr(), P,
+                      f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
+                      dxagg.data_ptr(), H * Fp, None, None, dg_part.data_ptr(), H, dfg.data_ptr(), Muv,
+                      *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         # the reduce-scatter runs on NCCL's stream while the value-path products (which need nothing from it)
         # keep this stream busy
         dg_own, work = reduce_rows_async(dg_part, plan)
-        _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp, label="gemm:dW")
+        _gemm_batched(1, 0, f_in, Dp, n, H, xagg, H * Fp, Fp, dhp, HD, Dp, dw_ext, M_out, Dp, label="gemm:dW",
+                      elu_out=eo, ld_elu=ldeo)
         if has_skip:
             _gemm(1, 0, f_in, HD, n, xg_loc, P, dhp, HD, dw_ext, M_out, c_off=HD)
         with _lib.timed("comm:reduce_dg_wait"):
@@ -536,83 +547,3 @@ def fit_row_cost(rows: torch.Tensor, entries: torch.Tensor, t: torch.Tensor):
     if not (a > 0 and b > 0):
         return None
     return min(max(a / b, 0.0), 1000.0)
-
-
-# ---------------------------------------------------------------------- bench harness (bench.py --gpus N)
-ROW_COST = 25  # measured on one GPU at the products shape: row-proportional kernels ~7.0 ns/row, edge passes ~0.275 ns/entry
-
-
-class ShardedLayerBench:
-    """The bench.py workload on `world` GPUs: the whole synthetic graph is generated identically on
-    every rank (same seed) and each rank keeps its destination-row shard.
-
-    Shard boundaries equalise cost(row range) = stored entries + row_cost * rows.  row_cost starts from the
-    single-GPU measurement and, with calibrate=True, is re-fitted once from what the ranks actually measure:
-    a few untimed steps give every rank's kernel time t_r (collective waits excluded), least squares over the
-    ranks gives t = a * rows + b * entries, and the shards are cut again with row_cost = a / b.  This is setup
-    work, like the CSR build: it happens before the timed region."""
-
-    def __init__(self, cfg, rank: int, world: int, dev, calibrate: bool = True):
-        from .synth import init_layer_params, power_law_csr
-        n, H, D, f_in = cfg["n"], cfg["H"], cfg["D"], cfg["f_in"]
-        self.rank, self.world, self.dev = rank, world, dev
-        rowptr, col = power_law_csr(n, cfg["avg_deg"], seed=72, exponent=cfg["exponent"], device=dev)
-        self.e_total = int(col.numel())
-        g = torch.Generator(device=dev).manual_seed(72)
-        x = torch.randn(n, f_in, generator=g, device=dev)
-        gout = torch.randn(n, H * D, generator=g, device=dev)
-        self.Ws, self.a_src, self.a_dst = init_layer_params(f_in, H, D, dev, seed=72)
-        self.params = self.Ws + self.a_src + self.a_dst
-        self.row_cost = float(ROW_COST)
-        self._cut(rowptr, col, x, gout)
-        if calibrate and world > 1:
-            fitted = self._fit_row_cost()
-            if fitted is not None and abs(fitted - self.row_cost) > 0.5:
-                self.row_cost = fitted
-                self._cut(rowptr, col, x, gout)
-        del rowptr, col, x, gout
-        torch.cuda.empty_cache()
-        hubs = 2 if self.graph.hubs.n_seg else 0
-        thubs = 2 if self.graph.transpose()[3].n_seg else 0
-        self.launches_per_step = 2 + 1 + (1 + hubs) + 1 + (1 + thubs) + (1 + hubs) + 2 + 2
-        self.x_host = None
-
-    def _cut(self, rowptr, col, x, gout):
-        self.plan = ShardPlan(shard_rows_by_cost(rowptr, self.world, self.row_cost), self.rank)
-        self.graph = self.plan.local_graph(rowptr, col)
-        self.graph.transpose()
-        self.x = self.plan.rows(x).clone()
-        self.gout = self.plan.rows(gout).clone()
-
-    def _fit_row_cost(self, steps: int = 3):
-        """Least-squares (a, b) of t_r = a * rows_r + b * entries_r over the ranks -> a / b, or None when the
-        fit is unusable (fewer than 2 distinct shard shapes, non-positive coefficients)."""
-        for _ in range(2):
-            self.step()
-        torch.cuda.synchronize()
-        old = _lib.timer
-        _lib.timer = _lib.KernelTimer()
-        for _ in range(steps):
-            self.step()
-        kern = _lib.timer.summary()
-        _lib.timer = old
-        t = sum(v["ms_total"] for k, v in kern.items() if not k.startswith("comm:")) / steps
-        mine = torch.tensor([float(self.plan.n_local), float(self.graph.nnz), t], dtype=torch.float64, device=self.dev)
-        allr = [_mem.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(allr, mine)
-        m = torch.stack(allr).cpu()
-        return fit_row_cost(m[:, 0], m[:, 1], m[:, 2])
-
-    def _layer(self, x):
-        return sharded_gat_layer(x, self.graph, self.plan, self.Ws, self.a_src, self.a_dst, None, 0.2, concat=True)
-
-    def step(self):
-        for p in self.params:
-            p.grad = None
-        y = self._layer(self.x)
-        y.backward(self.gout)
-        return y
-
-    def e2e(self, steps: int):
-        import bench  # the harness lives with the benchmark driver
-        return bench.pipelined_e2e(self, steps, barrier=dist.barrier)

@@ -108,7 +108,11 @@ def test_poisoned_workspaces_change_nothing_models(name, monkeypatch):
                                                          ("folded", 6, 121, 64, True, True),
                                                          ("explicit", 4, 32, 128, False, True)])
 def test_poisoned_workspaces_change_nothing_layer_forms(form, H, D, f_in, skip, needs_dx, monkeypatch):
-    """Every form of the layer on a power-law graph with hub rows; twice clean (bit-equal), once poisoned."""
+    """Every form of the layer on a power-law graph with hub rows; twice clean (bit-equal), once poisoned.
+    The aggregate-first form is run on its bit-reproducible route (GATK_DETERMINISTIC: ds + transposed segmented sum);
+    its default route accumulates dg with floating-point atomics, see test_atomic_dg_route_matches_the_deterministic_one."""
+    import pygat_b200.functional as Fn
+    monkeypatch.setattr(Fn, "DETERMINISTIC", True)
     n = 5000
     rowptr, col = power_law_csr(n, 18.0, seed=11, exponent=0.7, device=DEV)
     g = torch.Generator().manual_seed(3)
@@ -137,3 +141,36 @@ def test_poisoned_workspaces_change_nothing_layer_forms(form, H, D, f_in, skip, 
         res.append(out)
     _all_equal_and_finite(res[0], res[1])
     _all_equal_and_finite(res[0], res[2])
+
+
+@pytest.mark.parametrize("H,D,f_in,skip", [(8, 64, 100, False), (4, 256, 50, True), (3, 8, 20, False), (1, 40, 12, False),
+                                           (4, 64, 200, False)])
+def test_atomic_dg_route_matches_the_deterministic_one(H, D, f_in, skip, monkeypatch):
+    """Default aggregate-first backward (dg_j accumulated with red.global.add inside the edge pass) against the
+    bit-reproducible route (ds written, gatk_edge_tsum): outputs and dW identical bits (they do not depend on dg),
+    the attention-vector gradients equal up to the order of fp32 additions."""
+    import pygat_b200.functional as Fn
+    n = 5000
+    rowptr, col = power_law_csr(n, 18.0, seed=11, exponent=0.7, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, f_in, generator=g).to(DEV)
+    Ws = [(torch.randn(f_in, D, generator=g) * 0.2).to(DEV) for _ in range(H)]
+    As = [(torch.randn(2 * D, generator=g) * 0.2).to(DEV) for _ in range(H)]
+    Ss = [(torch.randn(f_in, D, generator=g) * 0.2).to(DEV) for _ in range(H)] if skip else None
+    gout = torch.randn(n, H * D, generator=g).to(DEV)
+    res = {}
+    for det in (True, False):
+        monkeypatch.setattr(Fn, "DETERMINISTIC", det)
+        graph = Graph.from_csr(rowptr, col, seg_len=128)
+        Wd = [w.clone().requires_grad_(True) for w in Ws]
+        Ad = [a.clone().requires_grad_(True) for a in As]
+        Sd = [s.clone().requires_grad_(True) for s in Ss] if skip else None
+        y = gat_layer(x, graph, Wd, [a[:D] for a in Ad], [a[D:] for a in Ad], Sd, 0.2, True, form="agg_first")
+        y.backward(gout)
+        torch.cuda.synchronize()
+        res[det] = (y.detach().clone(), [w.grad.clone() for w in Wd], [a.grad.clone() for a in Ad])
+    assert torch.equal(res[True][0], res[False][0])
+    for a, b in zip(res[True][2], res[False][2]):
+        assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item()
+    for a, b in zip(res[True][1], res[False][1]):   # dW = dvalue path + da-dependent logit path
+        assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item()

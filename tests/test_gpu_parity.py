@@ -201,12 +201,52 @@ def test_batched_per_head_gemms(kind, M, N, K, batches, elu):
     outs = []
     for _ in range(2):
         _lib.call("gatk_gemm_batched", ta, tb, M, N, K, batches, dA.data_ptr(), lda, a_bs, dB.data_ptr(), ldb, b_bs,
-                  C.data_ptr(), batches * N + 4, N, int(elu), ws.data_ptr(), ws_bytes, _stream())
+                  C.data_ptr(), batches * N + 4, N, int(elu), None, 0, ws.data_ptr(), ws_bytes, _stream())
         torch.cuda.synchronize()
         outs.append(C.clone())
     assert rel_err(C[:, :batches * N], ref) < 3e-6
     assert torch.all(C[:, batches * N:] == 7.0)
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("kind,M,N,K,batches", [
+    ("nt", 5000, 100, 64, 8),      # dxagg_h = (gout_h * ELU'(out_h)) W_h^T            (products shape, wide tile)
+    ("nt", 3000, 36, 32, 4),       # narrow tile
+    ("tn", 100, 64, 30000, 8),     # dW_h = xagg_h^T (gout_h * ELU'(out_h))
+    ("tn", 52, 32, 9000, 4),
+])
+def test_batched_gemms_with_fused_elu_gradient(kind, M, N, K, batches):
+    """gatk_gemm_batched with elu_out: the dh' operand is formed inside the kernel from the upstream gradient and the
+    layer's activated output (F.elu's autograd, layers.py:51,170) -- against fp64 products of the explicit dh'."""
+    g = torch.Generator().manual_seed(M + N + K + batches)
+    if kind == "tn":   # A [K, batches*M] (xagg), B = gout [K, batches*N], elu_out [K, batches*N (+pad)]
+        A = torch.randn(K, batches * M, generator=g)
+        G = torch.randn(K, batches * N, generator=g)
+        O_ = torch.nn.functional.elu(torch.randn(K, batches * N + 8, generator=g))
+        dhp = G.double() * torch.where(O_[:, :batches * N] > 0, 1.0, O_[:, :batches * N].double() + 1.0)
+        ref = torch.cat([A[:, b * M:(b + 1) * M].double().t() @ dhp[:, b * N:(b + 1) * N] for b in range(batches)], 1)
+        ta, tb, lda, a_bs, ldb, b_bs = 1, 0, batches * M, M, batches * N, N
+        dA, dB = A.to(DEV), G.to(DEV)
+        q = _lib.query("gatk_gemm_batched_fuses_elu_grad", ta, tb, M, N, K, batches, lda, a_bs, ldb, b_bs, batches * N + 4, N)
+    else:              # A = gout [M, batches*K], elu_out [M, batches*K (+pad)], B [N, batches*K]
+        G = torch.randn(M, batches * K, generator=g)
+        O_ = torch.nn.functional.elu(torch.randn(M, batches * K + 8, generator=g))
+        B = torch.randn(N, batches * K, generator=g) * 0.2
+        dhp = G.double() * torch.where(O_[:, :batches * K] > 0, 1.0, O_[:, :batches * K].double() + 1.0)
+        ref = torch.cat([dhp[:, b * K:(b + 1) * K] @ B[:, b * K:(b + 1) * K].double().t() for b in range(batches)], 1)
+        ta, tb, lda, a_bs, ldb, b_bs = 0, 1, batches * K, K, batches * K, K
+        dA, dB = G.to(DEV), B.to(DEV)
+        q = _lib.query("gatk_gemm_batched_fuses_elu_grad", ta, tb, M, N, K, batches, lda, a_bs, ldb, b_bs, batches * N + 4, N)
+    assert q == 1
+    dO = O_.to(DEV)
+    C = torch.full((M, batches * N + 4), 7.0, device=DEV)
+    ws_bytes = _lib.query("gatk_gemm_batched_workspace_bytes", ta, tb, M, N, K, batches)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=DEV)
+    _lib.call("gatk_gemm_batched", ta, tb, M, N, K, batches, dA.data_ptr(), lda, a_bs, dB.data_ptr(), ldb, b_bs,
+              C.data_ptr(), batches * N + 4, N, 0, dO.data_ptr(), dO.shape[1], ws.data_ptr(), ws_bytes, _stream())
+    torch.cuda.synchronize()
+    assert rel_err(C[:, :batches * N], ref) < 3e-6
+    assert torch.all(C[:, batches * N:] == 7.0)
 
 
 # ------------------------------------------------------------------------------ heads
