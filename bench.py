@@ -128,9 +128,27 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ reference / CPU arm
+def _load_true_reference():
+    """The UNMODIFIED reference's layers.py from baseline/_ref (copied there by __graft_entry__.build() where
+    /root/reference exists; git-ignored, travels with the snapshot), or None.  Its one un-vendored dependency,
+    torch_scatter.scatter_max, comes from the shim the golden vectors were generated with."""
+    path = os.path.join(ROOT, "baseline", "_ref", "layers.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    shim = os.path.join(ROOT, "tests", "golden", "shims")
+    if shim not in sys.path:
+        sys.path.insert(0, shim)
+    spec = importlib.util.spec_from_file_location("pygat_reference_layers", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def cpu_reference_rate(cfg, steps: int, warmup: int, nodes: int = CPU_SAMPLE_NODES):
-    """head-edges/s of the reference's sparse CPU path on a bounded sample (oracle port, faithful
-    dense N x N backward of layers.py:85 included), all host threads."""
+    """head-edges/s of the reference's sparse CPU path on a bounded sample, all host threads: the reference's own
+    SpGraphAttentionLayer modules (layers.py:98-176, dense N x N adjacency in, its dense N x N backward) when
+    baseline/_ref is present (kind "reference"), else the oracle port of the same lines (kind "port")."""
     import torch
     from oracle import gat_oracle as O
     cores = os.cpu_count() or 1
@@ -140,16 +158,30 @@ def cpu_reference_rate(cfg, steps: int, warmup: int, nodes: int = CPU_SAMPLE_NOD
     adj = O.PatternAdj(rowptr, col)
     e = int(col.numel())
     torch.manual_seed(72)
-    heads = [O.init_head(f_in, D, "sparse", False) for _ in range(H)]
     x = torch.randn(nodes, f_in)
     gout = torch.randn(nodes, H * D)
+    ref = _load_true_reference() if os.environ.get("BENCH_REFERENCE_PORT", "0") == "0" else None
+    if ref is not None:
+        kind = "reference"
+        heads = [ref.SpGraphAttentionLayer(f_in, D, dropout=0.0, alpha=0.2, concat=True) for _ in range(H)]
+        edge = adj.nonzero()
+        dense = torch.zeros(nodes, nodes)
+        dense[edge[:, 0], edge[:, 1]] = 1.0   # what utils.load_data hands the model: a dense N x N float matrix (utils.py:55)
 
-    def step():
-        xs = x.clone().requires_grad_(True)
-        ps = [{k: v.clone().requires_grad_(True) for k, v in hp.items()} for hp in heads]
-        edge = adj.nonzero().t()  # layers.py:129 (the duck-typed adj makes this free)
-        outs = [O.sparse_head(xs, hp["W"], hp["a"], edge, 0.2, True, None, 0.0, faithful=True) for hp in ps]
-        torch.cat(outs, dim=1).backward(gout)
+        def step():
+            for h in heads:
+                h.zero_grad(set_to_none=True)
+            torch.cat([h(x, dense) for h in heads], dim=1).backward(gout)   # models.py:32 over the reference's heads
+    else:
+        kind = "port"
+        heads = [O.init_head(f_in, D, "sparse", False) for _ in range(H)]
+
+        def step():
+            xs = x.clone().requires_grad_(True)
+            ps = [{k: v.clone().requires_grad_(True) for k, v in hp.items()} for hp in heads]
+            edge = adj.nonzero().t()  # layers.py:129 (the duck-typed adj makes this free)
+            outs = [O.sparse_head(xs, hp["W"], hp["a"], edge, 0.2, True, None, 0.0, faithful=True) for hp in ps]
+            torch.cat(outs, dim=1).backward(gout)
 
     for _ in range(warmup):
         step()
@@ -157,9 +189,11 @@ def cpu_reference_rate(cfg, steps: int, warmup: int, nodes: int = CPU_SAMPLE_NOD
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return {"value": e * H / dt, "unit": "head-edges/s", "cores": cores, "kind": "port",
+    what = ("the unmodified reference's SpGraphAttentionLayer x%d (baseline/_ref/layers.py), dense adj in" % H
+            if kind == "reference" else "oracle port")
+    return {"value": e * H / dt, "unit": "head-edges/s", "cores": cores, "kind": kind,
             "sample": f"power-law N={nodes} E={e} F={f_in} H={H} D={D}, fwd+bwd incl. the reference's dense "
-                      f"N x N backward, {steps} step(s) of {dt:.2f} s", "ms_per_step": dt * 1e3, "edges": e}
+                      f"N x N backward, {what}, {steps} step(s) of {dt:.2f} s", "ms_per_step": dt * 1e3, "edges": e}
 
 
 def run_reference_arm(args):

@@ -250,6 +250,24 @@ GATK_API int gatk_elu_fwd(int64_t n, int64_t cols, float* buf, int64_t ld, void*
 GATK_API int gatk_elu_bwd(int64_t n, int64_t cols, const float* gout, int64_t ldg, const float* out, int64_t ldo,
                           float* dhp, int64_t ldd, void* stream);
 
+/* ------------------------------------------------------------------ GATv2 flavour: SpGraphAttentionLayerV2 (layers.py:255-313)
+ * z [n_src, ldz] = [Whi | Whj | (skip)] (H*Dp columns each: the two projections of the input, layers.py:265-266, and the
+ * optional skip projection :301), a [H, Dp].  Per stored entry (i, j):  s_ij = a . LeakyReLU(Whi_i + Whj_j)
+ * (layers.py:275-278), softmax over the row (scatter_max / exp / rowsum, :280-288), attention dropout through
+ * keep_att [E, H] (:289), h'_i = sum_j alpha~_ij Whi_j (:291-295), + skip, ELU (:301-305).  One fused CSR pass per
+ * destination row; hagg (pre-skip, pre-ELU) and lse are saved for backward.
+ * Backward (one destination-major pass): dz [n_src, ldz] and da [H, Dp] must be ZERO-INITIALISED; source-side
+ * gradients are accumulated with vector reductions (fp32 addition order is scheduling dependent, ~1e-7). */
+GATK_API int gatk_attn_v2_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp, const float* z,
+                              int64_t ldz, const float* a, const uint8_t* keep_att, float inv_keep, float alpha,
+                              int has_skip, int act_elu, float* hagg, float* out, int64_t ldo, float* lse,
+                              int32_t* counter, void* stream);
+GATK_API int gatk_attn_v2_bwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp, const float* z,
+                              int64_t ldz, const float* a, const uint8_t* keep_att, float inv_keep, float alpha,
+                              int has_skip, int act_elu, const float* hagg, const float* out, int64_t ldo,
+                              const float* lse, const float* gout, int64_t ldgo, float* dz, float* da, int32_t* counter,
+                              void* stream);
+
 /* ------------------------------------------------------------------ K6: head combine (models.py:32-34)
  * mode 0: strip the Dp padding -> out [n, H*D] (torch.cat);  mode 1: mean over heads ->
  * out [n, D] (torch.mean(torch.stack)).  The backward scatters gout back to [n, H*Dp]. */
@@ -257,6 +275,22 @@ GATK_API int gatk_head_combine(int64_t n, int H, int D, int Dp, const float* in,
                       float* out, void* stream);
 GATK_API int gatk_head_combine_bwd(int64_t n, int H, int D, int Dp, const float* gout, int mode,
                           float* gin, int64_t ldi, void* stream);
+
+/* ------------------------------------------------------------------ loss heads + metrics of the callers' step
+ * Citation scripts (train.py:151-160): loss = nll_loss(log_softmax(elu(logits))[idx], labels[idx]), accuracy of the
+ * same rows (utils.py:92-96).  fwd adds into stats (double[2], zeroed by the caller): [0] the SUM of the per-row
+ * losses, [1] the number of correct predictions.  bwd ADDS scale * gscale[0] * dloss/dlogits for the selected rows into
+ * dlogits (zero-initialised; gscale: optional device scalar, the upstream gradient of the mean loss).
+ * idx: int64 [n_idx] row ids or NULL for rows 0..n_idx-1; labels: int64 [N].
+ * PPI script (train_ppi.py:106-120): BCEWithLogits + micro-F1 of (logits > 0): stats (double[4]) += [sum of the
+ * element losses, TP, FP, FN]; micro-F1 = 2TP / (2TP + FP + FN).  Nothing here synchronises or leaves the device. */
+GATK_API int gatk_nll_head_fwd(int64_t n_idx, const int64_t* idx, const float* logits, int64_t ld, const int64_t* labels,
+                               int C, double* stats, void* stream);
+GATK_API int gatk_nll_head_bwd(int64_t n_idx, const int64_t* idx, const float* logits, int64_t ld, const int64_t* labels,
+                               int C, const float* gscale, float scale, float* dlogits, int64_t ldd, void* stream);
+GATK_API int gatk_bce_f1_fwd(int64_t total, const float* logits, const float* labels, double* stats, void* stream);
+GATK_API int gatk_bce_bwd(int64_t total, const float* logits, const float* labels, const float* gscale, float scale,
+                          float* dlogits, void* stream);
 
 /* ------------------------------------------------------------------ SpecialSpmm (layers.py:70-95)
  * out[n_rows, k] = COO(row, col, val) @ b ; grad_val[e] = gout[row_e] . b[col_e] ;

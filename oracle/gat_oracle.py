@@ -316,3 +316,28 @@ class PatternAdj:
 
 def xavier_std(fan_in: int, fan_out: int, gain: float = 1.414) -> float:
     return gain * math.sqrt(2.0 / (fan_in + fan_out))
+
+
+# --------------------------------------------------------------------------- loss heads of the callers
+def citation_loss_acc(logits: torch.Tensor, labels: torch.Tensor, idx: torch.Tensor):
+    """train.py:151-152,159-160 and utils.py:92-96: nll_loss(log_softmax(elu(logits))[idx], labels[idx]) and the
+    accuracy of the same rows."""
+    out = torch.log_softmax(torch.nn.functional.elu(logits), dim=1)
+    loss = torch.nn.functional.nll_loss(out[idx], labels[idx])
+    preds = out[idx].max(1)[1].type_as(labels)
+    acc = preds.eq(labels[idx]).sum() / len(labels[idx])
+    return loss, acc
+
+
+def ppi_loss_f1(logits: torch.Tensor, labels: torch.Tensor):
+    """train_ppi.py:106-110,114,119-120: BCEWithLogitsLoss(mean) and sklearn's f1_score(gt, logits > 0, average='micro'),
+    which for multilabel indicator input is 2 TP / (2 TP + FP + FN) over all (node, label) cells (0 when undefined)."""
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction="mean")
+    pred = logits > 0
+    pos = labels > 0.5
+    tp = (pred & pos).sum().double()
+    fp = (pred & ~pos).sum().double()
+    fn = (~pred & pos).sum().double()
+    denom = 2 * tp + fp + fn
+    f1 = 2 * tp / denom if denom > 0 else torch.zeros((), dtype=torch.float64)
+    return loss, f1

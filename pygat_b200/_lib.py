@@ -63,8 +63,16 @@ PROTOTYPES = {
     "gatk_edge_tsum": (c_int, [c_int64, P, P, c_int, P, P, c_int64, c_int, P, c_int, P]),
     "gatk_elu_fwd": (c_int, [c_int64, c_int64, P, c_int64, P]),
     "gatk_elu_bwd": (c_int, [c_int64, c_int64, P, c_int64, P, c_int64, P, c_int64, P]),
+    "gatk_attn_v2_fwd": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, P, c_float, c_float, c_int, c_int, P, P, c_int64, P,
+                                 P, P]),
+    "gatk_attn_v2_bwd": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, P, c_float, c_float, c_int, c_int, P, P, c_int64,
+                                 P, P, c_int64, P, P, P, P]),
     "gatk_head_combine": (c_int, [c_int64, c_int, c_int, c_int, P, c_int64, c_int, P, P]),
     "gatk_head_combine_bwd": (c_int, [c_int64, c_int, c_int, c_int, P, c_int, P, c_int64, P]),
+    "gatk_nll_head_fwd": (c_int, [c_int64, P, P, c_int64, P, c_int, P, P]),
+    "gatk_nll_head_bwd": (c_int, [c_int64, P, P, c_int64, P, c_int, P, c_float, P, c_int64, P]),
+    "gatk_bce_f1_fwd": (c_int, [c_int64, P, P, P, P]),
+    "gatk_bce_bwd": (c_int, [c_int64, P, P, P, c_float, P, P]),
     "gatk_spmm_coo_fwd": (c_int, [P, P, P, c_int64, c_int64, P, P, P]),
     "gatk_spmm_coo_bwd": (c_int, [P, P, P, c_int64, c_int64, P, P, P, P, P]),
 }

@@ -565,3 +565,115 @@ def pack_masks(keep_in: Optional[List[torch.Tensor]], keep_wh: Optional[List[tor
     if keep_att is not None:
         m.keep_att = torch.stack([k.to(torch.uint8) for k in keep_att], dim=1).contiguous()
     return m
+
+
+# ====================================================================== GATv2 flavour (layers.py:234-316)
+class EngineMatmul(torch.autograd.Function):
+    """x @ w through gatk_gemm (and its autograd: dW = x^T dZ, dx = dZ w^T)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        _require_cuda(x, "input features")
+        x, w = x.contiguous().float(), w.contiguous().float()
+        n, k = x.shape
+        m = w.shape[1]
+        z = _mem.empty(n, m, dtype=torch.float32, device=x.device)
+        _gemm(0, 0, n, m, k, x, k, w, m, z, m)
+        ctx.save_for_backward(x, w)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, w = ctx.saved_tensors
+        dz = dz.contiguous()
+        n, k = x.shape
+        m = w.shape[1]
+        dw = dx = None
+        if ctx.needs_input_grad[1]:
+            dw = _mem.empty(k, m, dtype=torch.float32, device=x.device)
+            _gemm(1, 0, k, m, n, x, k, dz, m, dw, m)
+        if ctx.needs_input_grad[0]:
+            dx = _mem.empty(n, k, dtype=torch.float32, device=x.device)
+            _gemm(0, 1, n, k, m, dz, m, w, m, dx, k)
+        return dx, dw
+
+
+class GatV2AttnFunction(torch.autograd.Function):
+    """out[N, H*Dp] = act( sum_j softmax_j(a . LeakyReLU(Whi_i + Whj_j)) Whi_j (+ skip_i) ) from z = [Whi | Whj | (skip)]:
+    the fused attention of SpGraphAttentionLayerV2 (layers.py:275-305), csrc/attn_v2.cu."""
+
+    @staticmethod
+    def forward(ctx, z, a, graph: Graph, H: int, Dp: int, has_skip: bool, alpha: float, act_elu: bool, keep_att, inv_keep: float):
+        _require_cuda(z, "projected features")
+        dev = z.device
+        z, a = z.contiguous(), a.contiguous()
+        n, ldz = z.shape
+        if graph.n_dst != n or graph.n_src != n:
+            raise RuntimeError(f"adjacency is {graph.n_dst}x{graph.n_src} but the input has {n} rows")
+        HD = H * Dp
+        assert ldz == HD * (3 if has_skip else 2) and a.shape == (H, Dp)
+        need_grad = any(ctx.needs_input_grad[:2])
+        out = _mem.empty(n, HD, dtype=torch.float32, device=dev)
+        hagg = _mem.empty(n, HD, dtype=torch.float32, device=dev) if need_grad else None
+        lse = _mem.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        _lib.call("gatk_attn_v2_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, z.data_ptr(), ldz, a.data_ptr(),
+                  _ptr(keep_att), float(inv_keep), float(alpha), int(has_skip), int(act_elu), _ptr(hagg), out.data_ptr(), HD,
+                  _ptr(lse), graph.counter.data_ptr(), _stream())
+        if need_grad:
+            ctx.graph, ctx.keep = graph, keep_att
+            ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu), float(inv_keep))
+            ctx.save_for_backward(z, a, hagg, out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        z, a, hagg, out, lse = ctx.saved_tensors
+        H, Dp, has_skip, alpha, act_elu, inv_keep = ctx.cfg
+        graph = ctx.graph
+        n, ldz = z.shape
+        HD = H * Dp
+        gout = gout.contiguous()
+        dz = torch.zeros_like(z)
+        da = torch.zeros_like(a)
+        _lib.call("gatk_attn_v2_bwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, z.data_ptr(), ldz, a.data_ptr(),
+                  _ptr(ctx.keep), inv_keep, alpha, int(has_skip), int(act_elu), hagg.data_ptr(), out.data_ptr(), HD,
+                  lse.data_ptr(), gout.data_ptr(), HD, dz.data_ptr(), da.data_ptr(), graph.counter.data_ptr(), _stream())
+        return dz, da, None, None, None, None, None, None, None, None
+
+
+def gat_v2_layer(x: torch.Tensor, graph: Graph, Ws, a_vecs, skips, alpha: float, concat: bool, p: float = 0.0,
+                 training: bool = False, combine: str = "cat") -> torch.Tensor:
+    """All heads of one SpGraphAttentionLayerV2 layer.  Ws: per head (2*F_in, D) with rows [:F_in] = the Whi projection and
+    [F_in:] = Whj (layers.py:265-266); a_vecs: per head (D,).  Training-mode dropout follows the reference's sites: the
+    input and both projections (layers.py:262-269) with torch's generator, the attention through a keep mask."""
+    _require_cuda(x, "input features")
+    with on_device(x):
+        H = len(Ws)
+        x = x.float()
+        f_in = x.shape[1]
+        D = Ws[0].shape[1]
+        Dp = padded_width(D)
+        p_eff = float(p) if training else 0.0
+        left = [_pad_cols(w[:f_in], Dp) for w in Ws]
+        right = [_pad_cols(w[f_in:], Dp) for w in Ws]
+        cols = left + right + ([_pad_cols(s, Dp) for s in skips] if skips is not None else [])
+        w_ext = torch.cat(cols, dim=1)
+        a = torch.stack([_pad_cols(v.reshape(-1), Dp) for v in a_vecs])
+        keep_att, inv_keep = None, 1.0
+        if p_eff > 0.0:
+            # every head of the reference drops the input with its own mask; a batched layer call shares one mask
+            # between the heads it fuses (same distribution, different draws)
+            h = torch.nn.functional.dropout(x, p_eff, training=True)
+            z = EngineMatmul.apply(h, w_ext)
+            HD = H * Dp
+            z = torch.cat([torch.nn.functional.dropout(z[:, :2 * HD], p_eff, training=True), z[:, 2 * HD:]], dim=1)
+            keep_att = (torch.rand(graph.nnz, H, device=x.device) >= p_eff).to(torch.uint8)
+            inv_keep = 1.0 / (1.0 - p_eff)
+        else:
+            z = EngineMatmul.apply(x, w_ext)
+        rows = GatV2AttnFunction.apply(z, a, graph, H, Dp, skips is not None, float(alpha), bool(concat), keep_att, inv_keep)
+        if combine == "none":
+            return rows
+        if combine == "mean":
+            return HeadCombineFunction.apply(rows, H, D, Dp, 1)
+        return rows if D == Dp else HeadCombineFunction.apply(rows, H, D, Dp, 0)

@@ -1,8 +1,10 @@
-"""GATv2 flavours of the reference (layers.py:179-316), kept importable because train.py:17 and
-train_ppi.py:18 import all four layer names.  They are NOT on the accelerated path (SURVEY.md
-section 8(f) ranks a fused GATv2 kernel as the next row): the math below is plain torch ops on the
-caller's device, with the sparse variant using the engine's cached CSR edge list and O(E*D)
-segment ops instead of the reference's per-call adj.nonzero() and dense N x N backward."""
+"""GATv2 flavours of the reference (layers.py:179-316; train.py:17 and train_ppi.py:18 import all four layer names).
+
+SpGraphAttentionLayerV2 runs on the engine: one projection GEMM for [Whi | Whj | skip] and the fused CSR attention
+kernels of csrc/attn_v2.cu (gatk_attn_v2_fwd / _bwd) instead of the reference's per-call adj.nonzero(), E x 2D
+gathers and dense N x N backward.  The dense GraphAttentionLayerV2 is degenerate as shipped (its score is a per-node
+column, so attention is uniform over a node's neighbours, layers.py:212-217): it is kept as plain torch ops for
+import compatibility."""
 from __future__ import annotations
 
 import torch
@@ -67,15 +69,26 @@ class SpGraphAttentionLayerV2(_V2Base):
         self._setup(in_features, out_features, dropout, alpha, concat, skip_connection, (1, out_features), True)
 
     def forward(self, input, adj):
-        n = input.shape[0]
-        dst, src = graph_of(adj, RULE_NONZERO).edge_index()
-        h, left, right = self._project(input)
-        score = self.leakyrelu(left[dst] + right[src]) @ self.a.reshape(-1)
-        top = torch.zeros(n, dtype=score.dtype, device=score.device).scatter_reduce(
-            0, dst, score.detach(), reduce="amax", include_self=False)
-        ex = torch.exp(score - top[dst])
-        denom = torch.zeros(n, dtype=ex.dtype, device=ex.device).index_add(0, dst, ex)
-        ex = F.dropout(ex, self.dropout, training=self.training)
-        agg = torch.zeros(n, self.out_features, dtype=ex.dtype, device=ex.device).index_add(
-            0, dst, ex.unsqueeze(1) * left[src])
-        return self._finish(agg / denom.unsqueeze(1), h)
+        return fused_heads_v2([self], input, adj, combine="cat")
+
+
+def can_fuse_v2(heads) -> bool:
+    h0 = heads[0]
+    if not isinstance(h0, SpGraphAttentionLayerV2):
+        return False
+    key = (h0.in_features, h0.out_features, h0.dropout, h0.alpha, h0.concat, h0.skip_connection, h0.training)
+    return all(isinstance(h, SpGraphAttentionLayerV2) and
+               (h.in_features, h.out_features, h.dropout, h.alpha, h.concat, h.skip_connection, h.training) == key
+               for h in heads)
+
+
+def fused_heads_v2(heads, x, adj, combine="cat"):
+    """Every SpGraphAttentionLayerV2 head of a layer in one engine call (models.py:29-35 loops over them)."""
+    from .functional import gat_v2_layer
+    from .graph import _require_cuda
+    h0 = heads[0]
+    _require_cuda(x, "input features")
+    graph = graph_of(adj, RULE_NONZERO)
+    skips = [h.skip_projection for h in heads] if h0.skip_connection else None
+    return gat_v2_layer(x, graph, [h.W for h in heads], [h.a.reshape(-1) for h in heads], skips, h0.alpha, h0.concat,
+                        p=h0.dropout, training=h0.training, combine=combine)

@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from .layers import GraphAttentionLayer, can_fuse, fused_heads
+from .layers_v2 import can_fuse_v2, fused_heads_v2
 
 
 class GAT(nn.Module):
@@ -29,6 +30,8 @@ class GAT(nn.Module):
         for i, heads in enumerate(self.gat_layers):
             if can_fuse(heads):
                 x = fused_heads(heads, x, adj, combine="mean" if i == last else "cat")
+            elif can_fuse_v2(heads):
+                x = fused_heads_v2(heads, x, adj, combine="mean" if i == last else "cat")
             elif i < last:
                 x = torch.cat([att(x, adj) for att in heads], dim=1)
             else:

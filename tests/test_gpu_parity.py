@@ -569,10 +569,10 @@ def test_products_shape_invariants_at_full_size():
 # ------------------------------------------------------------------------------ GATv2 flavours
 @pytest.mark.parametrize("name", ["sp2_head_basic", "sp2_head_skip_last", "sp2_head_hub"])
 def test_sparse_v2_heads_match_reference_golden(name):
-    """SpGraphAttentionLayerV2 (layers.py:234-316) is not on the accelerated path yet: torch ops on the device over
-    the engine's cached CSR (O(E*D) instead of the reference's per-call adj.nonzero() and dense N x N backward).
-    Outputs and gradients against the unmodified reference.  (The dense GATv2 class is device-agnostic torch code
+    """SpGraphAttentionLayerV2 (layers.py:234-316) through the fused kernels of csrc/attn_v2.cu (gatk_attn_v2_fwd/_bwd):
+    outputs and gradients against the unmodified reference.  (The dense GATv2 class is device-agnostic torch code
     and is checked against its golden vectors on CPU, tests/test_modules_cpu.py.)"""
+    before = _lib.call_count
     d = load(name)
     cls = layers.SpGraphAttentionLayerV2 if name.startswith("sp2_") else layers.GraphAttentionLayerV2
     two_f, dd = d["W"].shape
@@ -592,6 +592,69 @@ def test_sparse_v2_heads_match_reference_golden(name):
     if "skip" in d:
         errs["dskip"] = rel_err(head.skip_projection.grad, d["dskip"])
     assert all(v < 1e-5 for v in errs.values()), errs
+    if name.startswith("sp2_"):
+        assert _lib.call_count >= before + 4  # projection, attention forward, attention backward, dW / dx products
+
+
+@pytest.mark.parametrize("H,D,f_in,skip,concat", [(4, 64, 40, False, True), (8, 8, 100, True, True), (3, 7, 20, True, False),
+                                                  (2, 121, 30, False, False), (1, 256, 16, False, True)])
+def test_sparse_v2_layer_matches_oracle_on_a_power_law_graph(H, D, f_in, skip, concat):
+    """Batched GATv2 layer (all heads in one call, head widths that need padding, hub rows) against the oracle's
+    restatement of layers.py:255-313 evaluated in fp64."""
+    from pygat_b200.functional import gat_v2_layer
+    n = 4000
+    rowptr, col = power_law_csr(n, 12.0, seed=21, exponent=0.7)
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(n, f_in, generator=g)
+    Ws = [torch.randn(2 * f_in, D, generator=g) * O.xavier_std(2 * f_in, D) for _ in range(H)]
+    As = [torch.randn(1, D, generator=g) * O.xavier_std(1, D) for _ in range(H)]
+    Ss = [torch.randn(f_in, D, generator=g) * O.xavier_std(f_in, D) for _ in range(H)] if skip else None
+    gout = torch.randn(n, H * D, generator=g)
+    edge = O.PatternAdj(rowptr, col).nonzero().t()
+    xo = x.double().requires_grad_(True)
+    Wo = [w.double().requires_grad_(True) for w in Ws]
+    Ao = [a.double().requires_grad_(True) for a in As]
+    So = [s.double().requires_grad_(True) for s in Ss] if skip else [None] * H
+    yo = torch.cat([O.sparse_head_v2(xo, w, a, edge, 0.2, concat, s, faithful=False) for w, a, s in zip(Wo, Ao, So)], 1)
+    yo.backward(gout.double())
+    graph = Graph.from_csr(rowptr.to(DEV), col.to(DEV))
+    xd = x.to(DEV).requires_grad_(True)
+    Wd = [w.to(DEV).requires_grad_(True) for w in Ws]
+    Ad = [a.to(DEV).requires_grad_(True) for a in As]
+    Sd = [s.to(DEV).requires_grad_(True) for s in Ss] if skip else None
+    y = gat_v2_layer(xd, graph, Wd, [a.reshape(-1) for a in Ad], Sd, 0.2, concat)
+    y.backward(gout.to(DEV))
+    assert rel_err(y, yo) < TOL
+    assert rel_err(xd.grad, xo.grad) < TOL
+    for k in range(H):
+        assert rel_err(Wd[k].grad, Wo[k].grad) < TOL, k
+        assert rel_err(Ad[k].grad, Ao[k].grad) < TOL, k
+        if skip:
+            assert rel_err(Sd[k].grad, So[k].grad) < TOL, k
+
+
+def test_sparse_v2_model_runs_batched_and_trains():
+    """models.GAT with layer_type=SpGraphAttentionLayerV2 (train.py:117: --model GATv2_sparse): the heads of a layer
+    run as one engine call and equal the per-head loop; training-mode dropout draws are seeded by torch."""
+    d = load("sp2_head_basic")
+    adj = dense_adj(d).to(DEV)
+    n, f_in = d["x"].shape
+    torch.manual_seed(3)
+    model = models.GAT(nfeat=[f_in, 8, 5], nheads=[4, 2], nlayers=2, dropout=0.5, alpha=0.2,
+                       layer_type=layers.SpGraphAttentionLayerV2, skip_connection=True).to(DEV).eval()
+    x = d["x"].to(DEV)
+    y = model(x, adj)
+    hid = torch.cat([h(x, adj) for h in model.gat_layers[0]], dim=1)
+    looped = torch.mean(torch.stack([h(hid, adj) for h in model.gat_layers[1]], dim=1), dim=1)
+    assert y.shape == (n, 5) and rel_err(y, looped) < 1e-6
+    model.train()
+    torch.manual_seed(11)
+    y1 = model(x, adj)
+    torch.manual_seed(11)
+    y2 = model(x, adj)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y)
+    y1.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
 
 
 def test_integration_md_binding_example_runs_on_the_gpu():
