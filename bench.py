@@ -357,6 +357,10 @@ def run_ours(args):
             if world == 1:
                 ms_e, info = epoch_bench.pubmed_epoch_ms(dev)
                 epochs["pubmed_GAT_sparse_train_plus_eval"] = {"ms_per_epoch": round(ms_e, 3), **info}
+                ms_e, info = epoch_bench.pubmed_epoch_sync_free_ms(dev)
+                epochs["pubmed_GAT_sparse_fused_loss_head"] = {"ms_per_epoch": round(ms_e, 3), **info}
+                ms_e, info = epoch_bench.ppi_epoch_graphed_ms(dev)
+                epochs["ppi_GAT_dense_class_fused_head_cuda_graphs"] = {"ms_per_epoch": round(ms_e, 3), **info}
             ms_e, info = epoch_bench.ppi_epoch_ms(dev, rank=rank, world=world)
             if world > 1:
                 t = torch.tensor([ms_e], device=dev)

@@ -66,15 +66,9 @@ def pubmed_epoch_ms(device, epochs: int = 20, warmup: int = 3, seed: int = 72):
     return e0.elapsed_time(e1) / epochs, {"nodes": n, "stored_entries": int(col.numel()), "epochs": epochs}
 
 
-def ppi_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup: int = 1, seed: int = 72):
-    """`python train_ppi.py` shape: 20 training graphs, batches of 2 merged by block_diag
-    (load_data_ppi.py:84-86), 3 layers 50 -> 4x256 -> 4x256 -> 6x121 (mean), skip connections, dense
-    class (the script's default), BCEWithLogits, Adam lr 0.005.  With world > 1 the batches of an epoch
-    are dealt round-robin to the ranks (graph-level data parallelism) and gradients are all-reduced
-    with node-count weights."""
+def _ppi_setup(device, seed):
     import layers
     import models
-    from pygat_b200.sharded import allreduce_gradients
     from pygat_b200.synth import power_law_csr
     torch.manual_seed(seed)
     graphs = []
@@ -89,9 +83,32 @@ def ppi_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup:
                 torch.block_diag(graphs[i][2], graphs[i + 1][2])) for i in range(0, len(graphs), 2)]
     model = models.GAT(nfeat=[50, 256, 256, 121], nheads=[4, 4, 6], nlayers=3, dropout=0.0, alpha=0.2,
                        layer_type=layers.GraphAttentionLayer, skip_connection=True).to(device)
+    return graphs, batches, model
+
+
+def _time_epochs(epoch, epochs, warmup):
+    for _ in range(warmup):
+        epoch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(epochs):
+        epoch()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / epochs
+
+
+def ppi_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup: int = 1, seed: int = 72):
+    """`python train_ppi.py` shape: 20 training graphs, batches of 2 merged by block_diag
+    (load_data_ppi.py:84-86), 3 layers 50 -> 4x256 -> 4x256 -> 6x121 (mean), skip connections, dense
+    class (the script's default), BCEWithLogits, Adam lr 0.005; driven as train_ppi.py:112-132 drives it, including
+    its per-batch host read of the loss.  With world > 1 the batches of an epoch are dealt round-robin to the ranks
+    (graph-level data parallelism) and gradients are all-reduced with node-count weights."""
+    from pygat_b200.sharded import allreduce_gradients, rank_batch_schedule
+    graphs, batches, model = _ppi_setup(device, seed)
     opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0)
     loss_fn = torch.nn.BCEWithLogitsLoss(reduction="mean")
-    from pygat_b200.sharded import rank_batch_schedule
     mine = [batches[i] if i is not None else None for i in rank_batch_schedule(len(batches), rank, world)]
 
     def epoch():
@@ -111,14 +128,77 @@ def ppi_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup:
             opt.step()
         return tot
 
-    for _ in range(warmup):
-        epoch()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(epochs):
-        epoch()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / epochs, {"graphs": len(graphs), "batches_per_rank": sum(m is not None for m in mine), "epochs": epochs,
-                                          "nodes": sum(PPI_TRAIN_GRAPH_NODES)}
+    ms = _time_epochs(epoch, epochs, warmup)
+    return ms, {"graphs": len(graphs), "batches_per_rank": sum(m is not None for m in mine), "epochs": epochs,
+                "nodes": sum(PPI_TRAIN_GRAPH_NODES)}
+
+
+def ppi_epoch_graphed_ms(device, epochs: int = 5, warmup: int = 1, seed: int = 72):
+    """The same epoch with the caller's side widened: fused BCE + on-device micro-F1
+    (pygat_b200.heads.ppi_head) instead of the per-batch .cpu().numpy() + sklearn, no per-batch .item(), and every
+    batch's whole step (forward, loss, backward, Adam) replayed from a CUDA graph (pygat_b200.graphed).  One host
+    read per EPOCH (the summed loss).  Single GPU."""
+    from pygat_b200.graphed import GraphedStep
+    from pygat_b200.heads import ppi_head
+    graphs, batches, model = _ppi_setup(device, seed)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0, capturable=True)
+    steps, pool = [], None
+
+    def make(feats, labels, adj):
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss, f1 = ppi_head(model(feats, adj), labels)
+            loss.backward()
+            opt.step()
+            return loss.detach(), f1
+        return step
+
+    for feats, labels, adj in batches:
+        gs = GraphedStep(model, opt, make(feats, labels, adj), pool=pool)
+        pool = pool or gs.pool()
+        steps.append(gs)
+    tot = torch.zeros((), device=device)
+
+    def epoch():
+        tot.zero_()
+        for gs in steps:
+            loss, _f1 = gs()
+            tot.add_(loss)
+        return tot.item()  # one host read per epoch
+
+    ms = _time_epochs(epoch, epochs, warmup)
+    return ms, {"graphs": len(graphs), "batches": len(batches), "epochs": epochs, "nodes": sum(PPI_TRAIN_GRAPH_NODES),
+                "cuda_graphs": len(steps)}
+
+
+def pubmed_epoch_sync_free_ms(device, epochs: int = 20, warmup: int = 3, seed: int = 72):
+    """pubmed_epoch_ms with the caller's side widened: the fused loss head (heads.citation_epoch) and one host read
+    per 10 epochs instead of four .item() calls per epoch.  Dropout 0.6 is active, so the step is not graph-captured."""
+    import layers
+    import models
+    from pygat_b200.heads import citation_epoch
+    from pygat_b200.synth import power_law_csr
+    n, f_in, classes = 19717, 500, 3
+    torch.manual_seed(seed)
+    rowptr, col = power_law_csr(n, 5.5, seed=seed, device=device)
+    adj = _dense_from_csr(rowptr, col, n, device, column_major=True)
+    x = torch.rand(n, f_in, device=device)
+    x = x / x.sum(1, keepdim=True)
+    labels = torch.randint(0, classes, (n,), device=device)
+    idx_train = torch.arange(60, device=device)
+    idx_val = torch.arange(200, 700, device=device)
+    model = models.GAT(nfeat=[f_in, 8, classes], nheads=[8, 8], nlayers=2, dropout=0.6, alpha=0.2,
+                       layer_type=layers.SpGraphAttentionLayer, skip_connection=False).to(device)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0.001)
+    k = [0]
+
+    def epoch():
+        lt, at, lv, av = citation_epoch(model, opt, x, adj, labels, idx_train, idx_val)
+        k[0] += 1
+        if k[0] % 10 == 0:
+            return lv.item()
+        return None
+
+    ms = _time_epochs(epoch, epochs, warmup)
+    return ms, {"nodes": n, "stored_entries": int(col.numel()), "epochs": epochs, "host_reads": "1 per 10 epochs"}

@@ -49,35 +49,43 @@ def on_device(t: torch.Tensor):
 
 
 class HubPartition:
-    """Rows longer than seg_len, cut into segments (see gatk_attn_fwd in include/gatk.h)."""
+    """Rows longer than seg_len, cut into segments (see gatk_attn_fwd in include/gatk.h), and the edge-balanced work
+    items of the dynamic scheduler.  Built on the HOST from one copy of the row pointers (`ptr_host`: the caller's
+    single device->host read per pattern; a fresh PPI batch used to cost eight small syncs here) and uploaded."""
 
-    def __init__(self, ptr: torch.Tensor, seg_len: int):
-        deg = ptr[1:] - ptr[:-1]
-        rows = torch.nonzero(deg > seg_len).flatten()
+    def __init__(self, ptr: torch.Tensor, seg_len: int, ptr_host=None):
+        import numpy as np
+        dev = ptr.device
+        ph = (ptr.cpu() if ptr_host is None else ptr_host).numpy()
+        deg = ph[1:] - ph[:-1]
+        rows = np.nonzero(deg > seg_len)[0]
         self.seg_len = int(seg_len)
-        self.n_hub = int(rows.numel())
+        self.n_hub = int(rows.size)
         if self.n_hub:
             nseg = (deg[rows] + seg_len - 1) // seg_len
-            seg_ptr = torch.zeros(self.n_hub + 1, dtype=torch.int64, device=ptr.device)
-            seg_ptr[1:] = torch.cumsum(nseg, 0)
-            self.rows = rows.to(torch.int32)
-            self.seg_ptr = seg_ptr.to(torch.int32)
-            self.n_seg = int(seg_ptr[-1].item())
+            seg_ptr = np.zeros(self.n_hub + 1, dtype=np.int64)
+            np.cumsum(nseg, out=seg_ptr[1:])
+            self.rows = torch.from_numpy(rows.astype(np.int32)).to(dev)
+            self.seg_ptr = torch.from_numpy(seg_ptr.astype(np.int32)).to(dev)
+            self.n_seg = int(seg_ptr[-1])
         else:
             self.rows = self.seg_ptr = None
             self.n_seg = 0
         # edge-balanced work items for the dynamic scheduler of the gather kernels: consecutive rows are
         # grouped until they hold ~ITEM_EDGES stored entries (hub rows are skipped by those kernels)
-        n, e = ptr.numel() - 1, int(ptr[-1].item()) if ptr.numel() > 1 else 0
+        n, e = ph.size - 1, int(ph[-1]) if ph.size > 1 else 0
         if n > 0 and e > 0:
-            cuts = torch.searchsorted(ptr[:-1].contiguous(), torch.arange(0, e, ITEM_EDGES, device=ptr.device))
-            bounds = torch.unique_consecutive(torch.cat([cuts, torch.tensor([n], device=ptr.device)]))
-            if int(bounds[0].item()) != 0:
-                bounds = torch.cat([torch.zeros(1, dtype=bounds.dtype, device=ptr.device), bounds])
-            self.items = bounds.to(torch.int32).contiguous()
-            self.n_items = int(self.items.numel()) - 1
+            cuts = np.searchsorted(ph[:-1], np.arange(0, e, ITEM_EDGES, dtype=np.int64), side="left")
+            bounds = np.concatenate([cuts, np.array([n], dtype=cuts.dtype)])
+            bounds = bounds[np.concatenate([[True], bounds[1:] != bounds[:-1]])]  # unique_consecutive
+            if bounds[0] != 0:
+                bounds = np.concatenate([np.zeros(1, dtype=bounds.dtype), bounds])
+            self.items = torch.from_numpy(bounds.astype(np.int32)).to(dev)
+            self.n_items = int(bounds.size) - 1
         else:
             self.items, self.n_items = None, 0
+        self.n_empty = int((deg == 0).sum()) if n > 0 else 0
+        self.empty_rows_host = np.nonzero(deg == 0)[0] if self.n_empty else None
 
     def args(self, scratch: Optional[torch.Tensor]):
         return (self.seg_len, _ptr(self.rows), _ptr(self.seg_ptr), self.n_hub, self.n_seg, _ptr(scratch))
@@ -93,7 +101,7 @@ class Graph:
     """
 
     def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, n_src: Optional[int] = None,
-                 seg_len: Optional[int] = None):
+                 seg_len: Optional[int] = None, rowptr_host: Optional[torch.Tensor] = None):
         _require_cuda(rowptr, "rowptr")
         _require_cuda(col, "col")
         assert rowptr.dtype == torch.int64 and col.dtype == torch.int32
@@ -104,7 +112,7 @@ class Graph:
         self.nnz = int(col.numel())
         self.device = rowptr.device
         self.seg_len = int(seg_len or DEFAULT_SEG_LEN)
-        self.hubs = HubPartition(self.rowptr, self.seg_len)
+        self.hubs = HubPartition(self.rowptr, self.seg_len, rowptr_host)
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._t: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, HubPartition]] = None
         self._iperm: Optional[torch.Tensor] = None
@@ -124,11 +132,12 @@ class Graph:
         rs, cs = adj.stride()
         _lib.call("gatk_csr_from_dense_rowptr", adj.data_ptr(), n, rs, cs, rule, rowptr.data_ptr(),
                   ws.data_ptr(), ws_bytes, _stream())
-        e = int(rowptr[-1].item())  # the one host sync of the graph build (the reference syncs per head)
+        rowptr_host = rowptr.cpu()  # the ONE host read of the graph build (the reference syncs per head, per call)
+        e = int(rowptr_host[-1])
         col = _mem.empty(e, dtype=torch.int32, device=adj.device)
         _lib.call("gatk_csr_from_dense_fill", adj.data_ptr(), n, rs, cs, rule, rowptr.data_ptr(),
                   col.data_ptr(), _stream())
-        return Graph(rowptr, col, seg_len=seg_len)
+        return Graph(rowptr, col, seg_len=seg_len, rowptr_host=rowptr_host)
 
     @staticmethod
     def from_coo(edge: torch.Tensor, n: int, seg_len: Optional[int] = None) -> "Graph":
@@ -171,9 +180,9 @@ class Graph:
 
     def empty_rows(self) -> Optional[torch.Tensor]:
         """int64 ids of destination rows without a stored entry, or None (cached; one host read on first use)."""
-        if not hasattr(self, "_empty_rows"):
-            rows = torch.nonzero(self.rowptr[1:] == self.rowptr[:-1]).flatten()
-            self._empty_rows = rows if rows.numel() else None
+        if not hasattr(self, "_empty_rows"):  # found on the host copy of the row pointers: no device sync here
+            h = self.hubs.empty_rows_host
+            self._empty_rows = None if h is None else torch.from_numpy(h).to(self.device)
         return self._empty_rows
 
     def inverse_perm(self) -> torch.Tensor:

@@ -602,15 +602,26 @@ def test_sparse_v2_layer_matches_oracle_on_a_power_law_graph(H, D, f_in, skip, c
     """Batched GATv2 layer (all heads in one call, head widths that need padding, hub rows) against the oracle's
     restatement of layers.py:255-313 evaluated in fp64."""
     from pygat_b200.functional import gat_v2_layer
-    n = 4000
-    rowptr, col = power_law_csr(n, 12.0, seed=21, exponent=0.7)
-    g = torch.Generator().manual_seed(13)
-    x = torch.randn(n, f_in, generator=g)
-    Ws = [torch.randn(2 * f_in, D, generator=g) * O.xavier_std(2 * f_in, D) for _ in range(H)]
-    As = [torch.randn(1, D, generator=g) * O.xavier_std(1, D) for _ in range(H)]
-    Ss = [torch.randn(f_in, D, generator=g) * O.xavier_std(f_in, D) for _ in range(H)] if skip else None
-    gout = torch.randn(n, H * D, generator=g)
+    n = 700
+    rowptr, col = power_law_csr(n, 9.0, seed=21, exponent=0.7)
+    assert (rowptr[1:] - rowptr[:-1]).max().item() > 100
     edge = O.PatternAdj(rowptr, col).nonzero().t()
+    # LeakyReLU is applied to u_ij = Whi_i + Whj_j per (entry, dimension): a u within fp32 rounding of 0 takes the other
+    # slope in fp32 than in the fp64 oracle, and that one entry's gradient jumps by (1 - alpha) ds a.  Draw inputs
+    # whose |u| stays clear of the kink (at n = 4000, seed 13 had one entry at |u| ~ 1e-8 for 4 x 64: the only error it
+    # caused was on the two rows of that entry, in one head, 3e-4).
+    for seed in range(13, 80):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(n, f_in, generator=g)
+        Ws = [torch.randn(2 * f_in, D, generator=g) * O.xavier_std(2 * f_in, D) for _ in range(H)]
+        As = [torch.randn(1, D, generator=g) * O.xavier_std(1, D) for _ in range(H)]
+        Ss = [torch.randn(f_in, D, generator=g) * O.xavier_std(f_in, D) for _ in range(H)] if skip else None
+        gout = torch.randn(n, H * D, generator=g)
+        umin = min(((x.double() @ w[:f_in].double())[edge[0]] + (x.double() @ w[f_in:].double())[edge[1]]).abs().min().item()
+                   for w in Ws)
+        if umin > 2e-6:
+            break
+    assert umin > 2e-6
     xo = x.double().requires_grad_(True)
     Wo = [w.double().requires_grad_(True) for w in Ws]
     Ao = [a.double().requires_grad_(True) for a in As]

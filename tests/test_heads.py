@@ -128,3 +128,52 @@ def test_sync_free_epochs_equal_the_reference_steps():
     assert abs(l1.item() - l2.item()) < 1e-6 and abs(f1.item() - f2) < 1e-6
     for a, b in zip(p1.parameters(), p2.parameters()):
         assert (a - b).abs().max().item() < 1e-5
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replays_equal_eager_steps():
+    """pygat_b200.graphed.GraphedStep: the whole PPI-like training step (3 layers with skip, fused BCE head, backward,
+    Adam) captured once; three replays leave the parameters where three eager steps leave them."""
+    import copy
+
+    import layers
+    import models
+    from pygat_b200.graphed import GraphedStep
+    from pygat_b200.heads import ppi_head
+    from tests.golden_io import dense_adj, load
+    d = load("gat_de_ppi_like")
+    adj = dense_adj(d).cuda()
+    x = d["x"].cuda()
+    g = torch.Generator().manual_seed(0)
+    yl = (torch.rand(x.shape[0], 11, generator=g) < 0.3).float().cuda()
+    torch.manual_seed(2)
+    m1 = models.GAT(nfeat=[10, 32, 32, 11], nheads=[4, 4, 6], nlayers=3, dropout=0.0, alpha=0.2,
+                    layer_type=layers.GraphAttentionLayer, skip_connection=True).cuda().train()
+    m2 = copy.deepcopy(m1)
+    o1 = torch.optim.Adam(m1.parameters(), lr=0.005, capturable=True)
+    o2 = torch.optim.Adam(m2.parameters(), lr=0.005)
+
+    def step():
+        o1.zero_grad(set_to_none=True)
+        loss, f1 = ppi_head(m1(x, adj), yl)
+        loss.backward()
+        o1.step()
+        return loss.detach(), f1
+
+    gs = GraphedStep(m1, o1, step)
+    for a, b in zip(m1.parameters(), m2.parameters()):   # the warm-up steps were undone
+        assert torch.equal(a, b)
+    losses = []
+    for _ in range(3):
+        loss, _ = gs()
+        losses.append(loss.item())
+        o2.zero_grad()
+        l2 = torch.nn.BCEWithLogitsLoss()(m2(x, adj), yl)
+        l2.backward()
+        o2.step()
+        assert abs(losses[-1] - l2.item()) < 1e-5
+    assert losses[2] < losses[0]
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        assert (a - b).abs().max().item() < 1e-5
+    with pytest.raises(RuntimeError, match="capture-safe"):
+        GraphedStep(m2, o2, lambda: None)

@@ -104,3 +104,34 @@ def test_graph_handles_equal_dense_build_and_run_the_model():
     y_dense = model(x, adj.to(dev))
     y_graph = model(x, g)
     assert torch.equal(y_dense, y_graph)
+
+
+def test_hub_partition_host_build_matches_the_definition():
+    """HubPartition (rows longer than seg_len cut into segments; edge-balanced work items) is built on the host from one
+    copy of the row pointers; check it against the plain definition on skewed and degenerate patterns."""
+    import torch
+    from pygat_b200 import graph as G
+    from pygat_b200.synth import power_law_csr
+    cases = [power_law_csr(3000, 14.0, seed=3, exponent=0.7)[0], torch.zeros(8, dtype=torch.int64),
+             torch.tensor([0, 0, 5, 5, 5, 700, 700, 1300], dtype=torch.int64), torch.arange(0, 4001, 4, dtype=torch.int64)]
+    for ptr in cases:
+        for seg_len in (16, 64, 512):
+            hp = G.HubPartition(ptr, seg_len)
+            deg = ptr[1:] - ptr[:-1]
+            rows = torch.nonzero(deg > seg_len).flatten()
+            assert hp.n_hub == rows.numel()
+            if hp.n_hub:
+                assert torch.equal(hp.rows.long(), rows)
+                nseg = (deg[rows] + seg_len - 1) // seg_len
+                assert torch.equal(hp.seg_ptr.long(), torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(nseg, 0)]))
+                assert hp.n_seg == int(nseg.sum())
+            n, e = ptr.numel() - 1, int(ptr[-1])
+            if e == 0:
+                assert hp.items is None and hp.n_items == 0
+            else:
+                it = hp.items.long()
+                assert it[0] == 0 and it[-1] == n and torch.all(it[1:] > it[:-1]) and hp.n_items == it.numel() - 1
+                # every item starts at the first row whose first entry is >= a multiple of ITEM_EDGES
+                starts = torch.searchsorted(ptr[:-1].contiguous(), torch.arange(0, e, G.ITEM_EDGES))
+                assert set(it[:-1].tolist()) == (set(starts.tolist()) - {n}) | {0}
+            assert hp.n_empty == int((deg == 0).sum())
