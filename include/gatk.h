@@ -131,7 +131,7 @@ GATK_API int gatk_logits_fwd(int64_t n, int H, int Dp, float* wh, int64_t ldw, c
  * 1 (attn_bwd_fused), 2 (attn_bwd_finish). */
 GATK_API size_t gatk_hub_scratch_floats(int which, int H, int Dp, int n_hub_seg);
 GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp,
-                  const float* wh, int64_t ldw, const float* f, const float* g, int64_t ldfg,
+                  const float* wh, int64_t ldw, const float* f, int64_t ldf, const float* g, int64_t ldg,
                   const uint8_t* keep_att, float inv_keep, float alpha,
                   const float* skipv, int64_t lds, int act_elu,
                   float* hagg, float* out, int64_t ldo, float* lse,

@@ -39,7 +39,7 @@ PROTOTYPES = {
                                   P, c_int64, c_int64, c_int, P, c_int64, P, c_size_t, P]),
     "gatk_logits_fwd": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_float, P, P, P, P, P]),
     "gatk_hub_scratch_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "gatk_attn_fwd": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, P, c_int64, P, c_float, c_float,
+    "gatk_attn_fwd": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, c_int64, P, c_int64, P, c_float, c_float,
                               P, c_int64, c_int, P, P, c_int64, P,
                               c_int, P, P, c_int, c_int, P, P, P, c_int, P]),
     "gatk_attn_bwd_record_ld": (c_int64, [c_int, c_int]),

@@ -24,7 +24,7 @@ struct FwdArgs {
   int64_t ldw;
   const float* f;
   const float* g;
-  int64_t ldfg;  // row pitch of f and g (floats): H when they are dense [N,H] arrays
+  int64_t ldf, ldg;  // row pitches of f and g (floats): H when they are dense [N,H] arrays
   const uint8_t* keep;
   float inv_keep, alpha;
   const float* skipv;
@@ -53,7 +53,7 @@ __device__ __forceinline__ void fwd_segment(const FwdArgs& a, int row, int64_t b
   constexpr int U = NV >= 8 ? 1 : 8 / NV;
   const int H = a.H, WS = lay.WS, lph = a.lph;
   const int q = lph >= 32 ? lph >> 5 : 1;
-  float f_reg = lane < H ? __ldg(a.f + (int64_t)row * a.ldfg + lane) : 0.f;
+  float f_reg = lane < H ? __ldg(a.f + (int64_t)row * a.ldf + lane) : 0.f;
   m_reg = -INFINITY;
   l_reg = 0.f;
 #pragma unroll
@@ -65,7 +65,7 @@ __device__ __forceinline__ void fwd_segment(const FwdArgs& a, int row, int64_t b
     const int64_t e = base + lane;
     const int j = valid ? __ldg(a.col + e) : 0;
     col_s[lane] = j;
-    const float* gj = a.g + (int64_t)j * a.ldfg;
+    const float* gj = a.g + (int64_t)j * a.ldg;
     const uint8_t* kp = a.keep ? a.keep + e * H : nullptr;
     for (int h = 0; h < H; ++h) {
       float fi = __shfl_sync(FULL, f_reg, h);
@@ -264,7 +264,7 @@ static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
 using namespace gatk;
 
 extern "C" int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* col, int H, int Dp,
-                             const float* wh, int64_t ldw, const float* f, const float* g, int64_t ldfg,
+                             const float* wh, int64_t ldw, const float* f, int64_t ldf, const float* g, int64_t ldg,
                              const uint8_t* keep_att, float inv_keep, float alpha,
                              const float* skipv, int64_t lds, int act_elu,
                              float* hagg, float* out, int64_t ldo, float* lse,
@@ -277,12 +277,12 @@ extern "C" int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t
   GATK_REQUIRE(n_dst < (1LL << 31), "n_dst too large for one shard");
   GATK_REQUIRE(ldw % 4 == 0 && ldo % 4 == 0 && (!skipv || lds % 4 == 0), "leading dims must be multiples of 4 floats");
   GATK_REQUIRE(rowptr && col && wh && f && g && out && counter, "null pointer argument");
-  GATK_REQUIRE(ldfg >= H, "ldfg must be >= H");
+  GATK_REQUIRE(ldf >= H && ldg >= H, "ldf / ldg must be >= H");
   cudaStream_t st = (cudaStream_t)stream;
   FwdArgs a;
   a.n_dst = n_dst; a.rowptr = rowptr; a.col = col; a.H = H; a.Dp = Dp; a.lph = Dp / 4; a.V = H * (Dp / 4);
   a.HP = H | 1;
-  a.wh = wh; a.ldw = ldw; a.f = f; a.g = g; a.ldfg = ldfg; a.keep = keep_att; a.inv_keep = inv_keep; a.alpha = alpha;
+  a.wh = wh; a.ldw = ldw; a.f = f; a.g = g; a.ldf = ldf; a.ldg = ldg; a.keep = keep_att; a.inv_keep = inv_keep; a.alpha = alpha;
   a.skipv = skipv; a.lds = lds; a.act_elu = act_elu; a.hagg = hagg; a.out = out; a.ldo = ldo; a.lse = lse;
   a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub; a.n_hub_seg = n_hub_seg;
   a.scratch = hub_scratch; a.counter = counter; a.item_ptr = item_ptr; a.n_items = n_items;

@@ -152,7 +152,7 @@ class GatLayerFunction(torch.autograd.Function):
         hubs = graph.hubs
         scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_ptr, M_out,
-                  f.data_ptr(), g.data_ptr(), H, _ptr(masks.keep_att), inv_keep, float(alpha),
+                  f.data_ptr(), H, g.data_ptr(), H, _ptr(masks.keep_att), inv_keep, float(alpha),
                   skip_ptr, M_out, int(act_elu), _ptr(hagg), out.data_ptr(), HD, _ptr(lse),
                   *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
 
@@ -279,7 +279,7 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         hubs = graph.hubs
         scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, z.data_ptr(), Mz,
-                  f_ptr, g_ptr, Mz, None, 1.0, float(alpha),
+                  f_ptr, Mz, g_ptr, Mz, None, 1.0, float(alpha),
                   z.data_ptr() + 4 * HD if has_skip else None, Mz, int(act_elu), _ptr(hagg), out.data_ptr(), HD,
                   _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         if need_grad:

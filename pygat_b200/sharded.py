@@ -228,7 +228,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         hubs = graph.hubs
         scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_full.data_ptr(), HD,
-                  f.data_ptr(), g_full.data_ptr(), H, None, 1.0, float(alpha), _ptr(skipv), HD, int(act_elu),
+                  f.data_ptr(), H, g_full.data_ptr(), H, None, 1.0, float(alpha), _ptr(skipv), HD, int(act_elu),
                   _ptr(hagg), out.data_ptr(), HD, _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
         if need_grad:
             ctx.graph, ctx.plan = graph, plan
@@ -303,6 +303,161 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         if plan.world > 1:
             allreduce_([dw_ext, da_src, da_dst], plan)
         return dx, dw_ext, da_src, da_dst, None, None, None, None, None, None, None
+
+
+def gather_rows_async(full: torch.Tensor, plan: ShardPlan):
+    """gather_rows without blocking the launching stream: returns a work handle (None when nothing is in flight);
+    work.wait() is a stream-side wait."""
+    if plan.world == 1:
+        return None
+    if _uneven_ok(plan.group):
+        return dist.all_gather([plan.rows(full, r) for r in range(plan.world)], plan.rows(full), group=plan.group, async_op=True)
+    gather_rows(full, plan)
+    return None
+
+
+def head_chunks(H: int) -> int:
+    """Heads per exchange chunk of the hidden-layer form: up to four chunks, so that chunk k+1's rows cross NVLink
+    while chunk k's attention runs (GATK_SHARD_CHUNKS overrides the number of chunks)."""
+    want = int(os.environ.get("GATK_SHARD_CHUNKS", "4"))
+    c = max(1, min(want, H))
+    while H % c:
+        c -= 1
+    return H // c
+
+
+class ShardedGatLayerWhFunction(torch.autograd.Function):
+    """A HIDDEN layer on a destination-row shard (wide input that needs a gradient; no dropout): every rank projects
+    only ITS OWN rows and the projected rows cross NVLink, in head chunks that overlap with the attention kernels
+    (north_star: "all-gather of Wh/g and reduce-scatter of dWh, overlapped with local-edge compute").
+
+    Per chunk c of Hc heads (columns of one [N, Pc] buffer, Pc = Hc*Dp + 4*ceil(Hc/4)):
+      forward   own rows of [Wh_c | g_c] = x_own [W_c | W_c a_dst] (one GEMM straight into the gathered buffer: the
+                logits are linear in the input, as in functional.GatLayerFoldedFunction) -> async all-gather -> K2 on the
+                chunk's heads as soon as ITS rows have landed, while the next chunks are still in flight;
+      backward  K3/K4 on the chunk give the partial [dWh_c | dg_c] of EVERY source from this rank's destination rows
+                -> async reduce-scatter to the owners, overlapped with the next chunk's kernels and with the
+                skip / f-side products; dW = x_own^T dZ_own and dx = dZ_own W^T on own rows; one all-reduce of the
+                parameter-sized gradients.
+    The previous version all-gathered the INPUT rows and projected all N rows on every rank (G-fold redundant GEMM
+    work) and blocked on both reduce-scatters."""
+
+    @staticmethod
+    def forward(ctx, x, w_a, w_b, graph: Graph, plan: ShardPlan, H: int, Dp: int, Hc: int, has_skip: bool, alpha: float,
+                act_elu: bool):
+        dev = x.device
+        n, f_in = x.shape
+        assert n == plan.n_local == graph.n_dst and graph.n_src == plan.n_total
+        N, HD, C = plan.n_total, H * Dp, H // Hc
+        HDc = Hc * Dp
+        Pc = HDc + 4 * ((Hc + 3) // 4)
+        Mb = w_b.shape[1]                      # [S (HD, if skip) | W a_src (H) | pad]
+        off_f = HD if has_skip else 0
+        assert w_a.shape == (f_in, C * Pc) and Mb >= off_f + H and Mb % 4 == 0
+        x, w_a, w_b = x.contiguous(), w_a.contiguous(), w_b.contiguous()
+        st = _stream()
+        whg, works = [], []
+        for c in range(C):
+            buf = _mem.empty(N, Pc, dtype=torch.float32, device=dev)
+            _gemm(0, 0, n, Pc, f_in, x, f_in, w_a, C * Pc, buf, Pc, b_off=c * Pc, c_off=plan.lo * Pc, label="gemm:project_own")
+            with _lib.timed("comm:allgather_whg_issue"):
+                works.append(gather_rows_async(buf, plan))
+            whg.append(buf)
+        z2 = _mem.empty(n, Mb, dtype=torch.float32, device=dev)
+        _gemm(0, 0, n, Mb, f_in, x, f_in, w_b, Mb, z2, Mb, label="gemm:project_own")
+        need_grad = any(ctx.needs_input_grad[:3])
+        out = _mem.empty(n, HD, dtype=torch.float32, device=dev)
+        separate_hagg = need_grad and (has_skip or act_elu)
+        haggs = [(_mem.empty(n, HDc, dtype=torch.float32, device=dev) if separate_hagg else None) for _ in range(C)]
+        lses = [(_mem.empty(n, Hc, dtype=torch.float32, device=dev) if need_grad else None) for _ in range(C)]
+        hubs = graph.hubs
+        for c in range(C):
+            if works[c] is not None:
+                with _lib.timed("comm:allgather_whg_wait"):
+                    works[c].wait()
+            scratch = _hub_scratch(0, Hc, Dp, hubs.n_seg, dev)
+            _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), Hc, Dp, whg[c].data_ptr(), Pc,
+                      z2.data_ptr() + 4 * (off_f + c * Hc), Mb, whg[c].data_ptr() + 4 * HDc, Pc, None, 1.0, float(alpha),
+                      z2.data_ptr() + 4 * c * HDc if has_skip else None, Mb, int(act_elu), _ptr(haggs[c]),
+                      out.data_ptr() + 4 * c * HDc, HD, _ptr(lses[c]), *hubs.args(scratch), graph.counter.data_ptr(),
+                      *hubs.item_args(), st)
+        if need_grad:
+            ctx.graph, ctx.plan = graph, plan
+            ctx.cfg = (H, Dp, Hc, has_skip, float(alpha), bool(act_elu), separate_hagg)
+            ctx.n_chunk_saved = C
+            ctx.save_for_backward(x, w_a, w_b, z2, out, *whg, *[h for h in haggs if h is not None], *lses)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        H, Dp, Hc, has_skip, alpha, act_elu, separate_hagg = ctx.cfg
+        C = ctx.n_chunk_saved
+        saved = ctx.saved_tensors
+        x, w_a, w_b, z2, out = saved[:5]
+        whg = saved[5:5 + C]
+        haggs = saved[5 + C:5 + 2 * C] if separate_hagg else None
+        lses = saved[-C:]
+        graph, plan = ctx.graph, ctx.plan
+        dev = x.device
+        n, f_in = x.shape
+        N, HD = plan.n_total, H * Dp
+        HDc = Hc * Dp
+        Pc = HDc + 4 * ((Hc + 3) // 4)
+        Mb = w_b.shape[1]
+        off_f = HD if has_skip else 0
+        st = _stream()
+        gout = gout.contiguous()
+        tptr, trow, perm, thubs = graph.transpose()
+        hubs = graph.hubs
+        dzb = torch.zeros(n, Mb, dtype=torch.float32, device=dev)   # [dSkip | df | pad]
+        ldrec = _lib.query("gatk_attn_bwd_record_ld", Hc, Dp)
+        owned, works = [], []
+        for c in range(C):
+            hagg_c = haggs[c] if separate_hagg else None
+            rec = _mem.empty(n, ldrec, dtype=torch.float32, device=dev)
+            # without a separate hagg (no skip, no ELU) the layer output IS the aggregation
+            _lib.call("gatk_attn_bwd_prep", n, Hc, Dp, gout.data_ptr() + 4 * c * HDc, HD,
+                      out.data_ptr() + 4 * c * HDc if (act_elu and has_skip) else None, HD, int(act_elu),
+                      hagg_c.data_ptr() if hagg_c is not None else out.data_ptr() + 4 * c * HDc, HDc if hagg_c is not None else HD,
+                      z2.data_ptr() + 4 * (off_f + c * Hc), Mb, lses[c].data_ptr(), rec.data_ptr(), ldrec,
+                      dzb.data_ptr() + 4 * c * HDc if has_skip else None, Mb, st)
+            part = _mem.empty(N, Pc, dtype=torch.float32, device=dev)
+            if Pc > HDc + Hc:
+                part[:, HDc + Hc:].zero_()   # pad columns behind dg meet zero weight columns in the products below
+            edge_dz = _mem.empty(graph.nnz, Hc, dtype=torch.float32, device=dev)
+            scratch_t = _hub_scratch(1, Hc, Dp, thubs.n_seg, dev)
+            _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), Hc, Dp, whg[c].data_ptr(), Pc,
+                      whg[c].data_ptr() + 4 * HDc, Pc, rec.data_ptr(), ldrec, None, 1.0, alpha, None,
+                      part.data_ptr(), Pc, part.data_ptr() + 4 * HDc, Pc, edge_dz.data_ptr(),
+                      *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), st)
+            with _lib.timed("comm:reduce_dwh_issue"):
+                own, work = reduce_rows_async(part, plan)
+            owned.append(own)
+            works.append(work)
+            scratch = _hub_scratch(2, Hc, Dp, hubs.n_seg, dev)
+            _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), Hc, Dp, edge_dz.data_ptr(), None, None, 1.0, None, 0,
+                      dzb.data_ptr() + 4 * (off_f + c * Hc), Mb, *hubs.args(scratch), st)
+            del rec, edge_dz
+        # own-row products; the f-side / skip block first (needs nothing from the exchange)
+        dw_a = _mem.empty(f_in, C * Pc, dtype=torch.float32, device=dev)
+        dw_b = _mem.empty(f_in, Mb, dtype=torch.float32, device=dev)
+        need_dx = ctx.needs_input_grad[0]
+        dx = _mem.empty(n, f_in, dtype=torch.float32, device=dev) if need_dx else None
+        _gemm(1, 0, f_in, Mb, n, x, f_in, dzb, Mb, dw_b, Mb, label="gemm:dW_own")
+        if need_dx:
+            _gemm(0, 1, n, f_in, Mb, dzb, Mb, w_b, Mb, dx, f_in, label="gemm:dx_own")
+        for c in range(C):
+            if works[c] is not None:
+                with _lib.timed("comm:reduce_dwh_wait"):
+                    works[c].wait()
+            dza = owned[c].contiguous()
+            _gemm(1, 0, f_in, Pc, n, x, f_in, dza, Pc, dw_a, C * Pc, c_off=c * Pc, label="gemm:dW_own")
+            if need_dx:
+                _gemm(0, 1, n, f_in, Pc, dza, Pc, w_a, C * Pc, dx, f_in, accumulate=1, b_off=c * Pc, label="gemm:dx_own")
+        if plan.world > 1:
+            with _lib.timed("comm:allreduce_dw"):
+                allreduce_([dw_a, dw_b], plan)
+        return dx, dw_a, dw_b, None, None, None, None, None, None, None, None
 
 
 class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
@@ -482,6 +637,27 @@ def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, 
         x_key = _input_key(x_local) if cache_input_gather else None
         rows = ShardedGatLayerAggFirstFunction.apply(x_local, w_ext, torch.cat(uv, dim=1), graph, plan, H, Dp,
                                                      skips is not None, float(alpha), bool(concat), x_key)
+    elif form in ("auto", "exchange_wh") and (x_local.requires_grad and torch.is_grad_enabled() or form == "exchange_wh"):
+        # hidden layer: project own rows, exchange [Wh | g] in head chunks (ShardedGatLayerWhFunction)
+        f_in = x_local.shape[1]
+        Hc = head_chunks(H)
+        C = H // Hc
+        HDc, gp = Hc * Dp, 4 * ((Hc + 3) // 4)
+        w3 = w_ext[:, : H * Dp].reshape(f_in, H, Dp)
+        u, v = (w3 * a_src).sum(-1), (w3 * a_dst).sum(-1)            # f = x (W a_src), g = x (W a_dst)
+        blocks = []
+        for c in range(C):
+            blocks.append(w_ext[:, c * HDc:(c + 1) * HDc])
+            blocks.append(v[:, c * Hc:(c + 1) * Hc])
+            if gp > Hc:
+                blocks.append(w_ext.new_zeros(f_in, gp - Hc))
+        w_a = torch.cat(blocks, dim=1)
+        bcols = ([w_ext[:, H * Dp:]] if skips is not None else []) + [u]
+        if (-H) % 4:
+            bcols.append(w_ext.new_zeros(f_in, (-H) % 4))
+        w_b = torch.cat(bcols, dim=1)
+        rows = ShardedGatLayerWhFunction.apply(x_local, w_a, w_b, graph, plan, H, Dp, Hc, skips is not None,
+                                               float(alpha), bool(concat))
     else:
         rows = ShardedGatLayerFunction.apply(x_local, w_ext, a_src, a_dst, graph, plan, H, Dp, skips is not None,
                                              float(alpha), bool(concat))

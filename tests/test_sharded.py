@@ -73,6 +73,42 @@ def test_sharded_layer_world1_equals_single_gpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("H,D,f_in,skip,concat", [(8, 64, 96, False, True), (6, 121, 64, True, False), (4, 32, 128, True, True),
+                                                  (1, 16, 40, False, True), (3, 8, 20, False, False)])
+def test_sharded_hidden_layer_world1_equals_single_gpu(H, D, f_in, skip, concat):
+    """The hidden-layer form (own-row projection, [Wh | g] exchanged in head chunks, ShardedGatLayerWhFunction) on a
+    one-rank plan against functional.gat_layer: outputs, input gradient and every parameter gradient."""
+    from pygat_b200.functional import gat_layer
+    from pygat_b200.graph import Graph
+    from pygat_b200.sharded import ShardPlan, sharded_gat_layer
+    from pygat_b200.synth import init_layer_params, power_law_csr
+    dev = "cuda"
+    n = 3000
+    rowptr, col = power_law_csr(n, 12.0, seed=5, exponent=0.7, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(n, f_in, generator=g, device=dev)
+    gout = torch.randn(n, H * D if concat or True else D, generator=g, device=dev)
+    Ws, a_s, a_d = init_layer_params(f_in, H, D, dev)
+    Ss = [w.detach().clone().flip(0).requires_grad_(True) for w in Ws] if skip else None
+    params = Ws + a_s + a_d + (Ss or [])
+    x0 = x.clone().requires_grad_(True)
+    y0 = gat_layer(x0, Graph.from_csr(rowptr, col, seg_len=128), Ws, a_s, a_d, Ss, 0.2, concat)
+    y0.backward(gout)
+    g0 = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    plan = ShardPlan([0, n], 0)
+    x1 = x.clone().requires_grad_(True)
+    y1 = sharded_gat_layer(x1, plan.local_graph(rowptr, col, seg_len=128), plan, Ws, a_s, a_d, Ss, 0.2, concat)
+    y1.backward(gout)
+    rel = lambda a, b: (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+    assert rel(y1, y0) < 3e-6
+    assert rel(x1.grad, x0.grad) < 5e-6
+    for a, b in zip([p.grad for p in params], g0):
+        assert rel(a, b) < 5e-6
+
+
+@pytest.mark.gpu
 def test_second_forward_before_backward_is_refused():
     """The aggregate-first sharded layer keeps its gathered rows in a plan-wide buffer; a later forward rewrites it
     behind autograd's back, so the earlier forward's backward must raise rather than use the wrong rows."""
