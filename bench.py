@@ -25,6 +25,24 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; stdout carries ONE JSON line
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle to the real stdout for it and point file descriptor 1
+    at stderr, so that whatever a library prints (the NCCL banner still appears with some launchers) cannot precede it."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
+def emit(line: dict):
+    out = _claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 WORKLOADS = {
     # name: nodes, average stored entries per row, in-features, heads, per-head width, zipf exponent
@@ -211,7 +229,7 @@ def run_reference_arm(args):
                        "edges": r["edges"], "f_in": cfg["f_in"], "heads": cfg["H"], "head_dim": cfg["D"]},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "head-edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -417,7 +435,7 @@ def run_ours(args):
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "epoch_times": epochs,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -433,6 +451,7 @@ def main():
     ap.add_argument("--no-hidden", action="store_true", help="skip the hidden-layer (project-first) add-on measurement")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the comparison with a single-GPU run of the same step")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -317,9 +317,10 @@ def gather_rows_async(full: torch.Tensor, plan: ShardPlan):
 
 
 def head_chunks(H: int) -> int:
-    """Heads per exchange chunk of the hidden-layer form: up to four chunks, so that chunk k+1's rows cross NVLink
-    while chunk k's attention runs (GATK_SHARD_CHUNKS overrides the number of chunks)."""
-    want = int(os.environ.get("GATK_SHARD_CHUNKS", "4"))
+    """Heads per exchange chunk of the hidden-layer form: two chunks by default, so that chunk 1's rows cross NVLink
+    while chunk 0's attention runs (measured at the products shape on 2 GPUs: four chunks of two heads made the
+    attention kernels ~1.5x slower per byte than they won in overlap; GATK_SHARD_CHUNKS overrides the count)."""
+    want = int(os.environ.get("GATK_SHARD_CHUNKS", "2"))
     c = max(1, min(want, H))
     while H % c:
         c -= 1
@@ -331,19 +332,19 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
     only ITS OWN rows and the projected rows cross NVLink, in head chunks that overlap with the attention kernels
     (north_star: "all-gather of Wh/g and reduce-scatter of dWh, overlapped with local-edge compute").
 
-    Per chunk c of Hc heads (columns of one [N, Pc] buffer, Pc = Hc*Dp + 4*ceil(Hc/4)):
-      forward   own rows of [Wh_c | g_c] = x_own [W_c | W_c a_dst] (one GEMM straight into the gathered buffer: the
-                logits are linear in the input, as in functional.GatLayerFoldedFunction) -> async all-gather -> K2 on the
-                chunk's heads as soon as ITS rows have landed, while the next chunks are still in flight;
+    One projection of the own rows, Z = x_own [W_0 | W_0 a_dst | .. | W_{C-1} | W_{C-1} a_dst | S | W a_src] (the
+    logits are linear in the input, as in functional.GatLayerFoldedFunction).  Per chunk c of Hc heads (Pc = Hc*Dp +
+    4*ceil(Hc/4) columns [Wh_c | g_c]):
+      forward   own rows copied into the chunk's [N, Pc] buffer -> async all-gather -> K2 on the chunk's heads as soon
+                as ITS rows have landed, while the next chunks are still in flight;
       backward  K3/K4 on the chunk give the partial [dWh_c | dg_c] of EVERY source from this rank's destination rows
-                -> async reduce-scatter to the owners, overlapped with the next chunk's kernels and with the
-                skip / f-side products; dW = x_own^T dZ_own and dx = dZ_own W^T on own rows; one all-reduce of the
-                parameter-sized gradients.
-    The previous version all-gathered the INPUT rows and projected all N rows on every rank (G-fold redundant GEMM
-    work) and blocked on both reduce-scatters."""
+                -> async reduce-scatter to the owners, overlapped with the next chunk's kernels.
+    Then dW = x_own^T dZ_own and dx = dZ_own W^T on own rows (one product each) and one all-reduce of the
+    parameter-sized gradients.  The previous version all-gathered the INPUT rows and projected all N rows on every
+    rank (G-fold redundant GEMM work) and blocked on both reduce-scatters."""
 
     @staticmethod
-    def forward(ctx, x, w_a, w_b, graph: Graph, plan: ShardPlan, H: int, Dp: int, Hc: int, has_skip: bool, alpha: float,
+    def forward(ctx, x, w_all, graph: Graph, plan: ShardPlan, H: int, Dp: int, Hc: int, has_skip: bool, alpha: float,
                 act_elu: bool):
         dev = x.device
         n, f_in = x.shape
@@ -351,21 +352,22 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
         N, HD, C = plan.n_total, H * Dp, H // Hc
         HDc = Hc * Dp
         Pc = HDc + 4 * ((Hc + 3) // 4)
-        Mb = w_b.shape[1]                      # [S (HD, if skip) | W a_src (H) | pad]
-        off_f = HD if has_skip else 0
-        assert w_a.shape == (f_in, C * Pc) and Mb >= off_f + H and Mb % 4 == 0
-        x, w_a, w_b = x.contiguous(), w_a.contiguous(), w_b.contiguous()
+        Mz = w_all.shape[1]                    # C*Pc | S (HD, if skip) | W a_src (H) | pad
+        off_s = C * Pc
+        off_f = off_s + (HD if has_skip else 0)
+        assert Mz >= off_f + H and Mz % 4 == 0
+        x, w_all = x.contiguous(), w_all.contiguous()
         st = _stream()
+        z = _mem.empty(n, Mz, dtype=torch.float32, device=dev)
+        _gemm(0, 0, n, Mz, f_in, x, f_in, w_all, Mz, z, Mz, label="gemm:project_own")
         whg, works = [], []
         for c in range(C):
             buf = _mem.empty(N, Pc, dtype=torch.float32, device=dev)
-            _gemm(0, 0, n, Pc, f_in, x, f_in, w_a, C * Pc, buf, Pc, b_off=c * Pc, c_off=plan.lo * Pc, label="gemm:project_own")
+            plan.rows(buf).copy_(z[:, c * Pc:(c + 1) * Pc])
             with _lib.timed("comm:allgather_whg_issue"):
                 works.append(gather_rows_async(buf, plan))
             whg.append(buf)
-        z2 = _mem.empty(n, Mb, dtype=torch.float32, device=dev)
-        _gemm(0, 0, n, Mb, f_in, x, f_in, w_b, Mb, z2, Mb, label="gemm:project_own")
-        need_grad = any(ctx.needs_input_grad[:3])
+        need_grad = any(ctx.needs_input_grad[:2])
         out = _mem.empty(n, HD, dtype=torch.float32, device=dev)
         separate_hagg = need_grad and (has_skip or act_elu)
         haggs = [(_mem.empty(n, HDc, dtype=torch.float32, device=dev) if separate_hagg else None) for _ in range(C)]
@@ -377,25 +379,24 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
                     works[c].wait()
             scratch = _hub_scratch(0, Hc, Dp, hubs.n_seg, dev)
             _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), Hc, Dp, whg[c].data_ptr(), Pc,
-                      z2.data_ptr() + 4 * (off_f + c * Hc), Mb, whg[c].data_ptr() + 4 * HDc, Pc, None, 1.0, float(alpha),
-                      z2.data_ptr() + 4 * c * HDc if has_skip else None, Mb, int(act_elu), _ptr(haggs[c]),
+                      z.data_ptr() + 4 * (off_f + c * Hc), Mz, whg[c].data_ptr() + 4 * HDc, Pc, None, 1.0, float(alpha),
+                      z.data_ptr() + 4 * (off_s + c * HDc) if has_skip else None, Mz, int(act_elu), _ptr(haggs[c]),
                       out.data_ptr() + 4 * c * HDc, HD, _ptr(lses[c]), *hubs.args(scratch), graph.counter.data_ptr(),
                       *hubs.item_args(), st)
         if need_grad:
             ctx.graph, ctx.plan = graph, plan
             ctx.cfg = (H, Dp, Hc, has_skip, float(alpha), bool(act_elu), separate_hagg)
-            ctx.n_chunk_saved = C
-            ctx.save_for_backward(x, w_a, w_b, z2, out, *whg, *[h for h in haggs if h is not None], *lses)
+            ctx.save_for_backward(x, w_all, z, out, *whg, *[h for h in haggs if h is not None], *lses)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         H, Dp, Hc, has_skip, alpha, act_elu, separate_hagg = ctx.cfg
-        C = ctx.n_chunk_saved
+        C = H // Hc
         saved = ctx.saved_tensors
-        x, w_a, w_b, z2, out = saved[:5]
-        whg = saved[5:5 + C]
-        haggs = saved[5 + C:5 + 2 * C] if separate_hagg else None
+        x, w_all, z, out = saved[:4]
+        whg = saved[4:4 + C]
+        haggs = saved[4 + C:4 + 2 * C] if separate_hagg else None
         lses = saved[-C:]
         graph, plan = ctx.graph, ctx.plan
         dev = x.device
@@ -403,13 +404,16 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
         N, HD = plan.n_total, H * Dp
         HDc = Hc * Dp
         Pc = HDc + 4 * ((Hc + 3) // 4)
-        Mb = w_b.shape[1]
-        off_f = HD if has_skip else 0
+        Mz = w_all.shape[1]
+        off_s = C * Pc
+        off_f = off_s + (HD if has_skip else 0)
         st = _stream()
         gout = gout.contiguous()
         tptr, trow, perm, thubs = graph.transpose()
         hubs = graph.hubs
-        dzb = torch.zeros(n, Mb, dtype=torch.float32, device=dev)   # [dSkip | df | pad]
+        dz = _mem.empty(n, Mz, dtype=torch.float32, device=dev)   # [dWh_c | dg_c | pad].. | dSkip | df | pad
+        if Mz > off_f + H:
+            dz[:, off_f + H:].zero_()
         ldrec = _lib.query("gatk_attn_bwd_record_ld", Hc, Dp)
         owned, works = [], []
         for c in range(C):
@@ -419,8 +423,8 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
             _lib.call("gatk_attn_bwd_prep", n, Hc, Dp, gout.data_ptr() + 4 * c * HDc, HD,
                       out.data_ptr() + 4 * c * HDc if (act_elu and has_skip) else None, HD, int(act_elu),
                       hagg_c.data_ptr() if hagg_c is not None else out.data_ptr() + 4 * c * HDc, HDc if hagg_c is not None else HD,
-                      z2.data_ptr() + 4 * (off_f + c * Hc), Mb, lses[c].data_ptr(), rec.data_ptr(), ldrec,
-                      dzb.data_ptr() + 4 * c * HDc if has_skip else None, Mb, st)
+                      z.data_ptr() + 4 * (off_f + c * Hc), Mz, lses[c].data_ptr(), rec.data_ptr(), ldrec,
+                      dz.data_ptr() + 4 * (off_s + c * HDc) if has_skip else None, Mz, st)
             part = _mem.empty(N, Pc, dtype=torch.float32, device=dev)
             if Pc > HDc + Hc:
                 part[:, HDc + Hc:].zero_()   # pad columns behind dg meet zero weight columns in the products below
@@ -436,28 +440,24 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
             works.append(work)
             scratch = _hub_scratch(2, Hc, Dp, hubs.n_seg, dev)
             _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), Hc, Dp, edge_dz.data_ptr(), None, None, 1.0, None, 0,
-                      dzb.data_ptr() + 4 * (off_f + c * Hc), Mb, *hubs.args(scratch), st)
+                      dz.data_ptr() + 4 * (off_f + c * Hc), Mz, *hubs.args(scratch), st)
             del rec, edge_dz
-        # own-row products; the f-side / skip block first (needs nothing from the exchange)
-        dw_a = _mem.empty(f_in, C * Pc, dtype=torch.float32, device=dev)
-        dw_b = _mem.empty(f_in, Mb, dtype=torch.float32, device=dev)
-        need_dx = ctx.needs_input_grad[0]
-        dx = _mem.empty(n, f_in, dtype=torch.float32, device=dev) if need_dx else None
-        _gemm(1, 0, f_in, Mb, n, x, f_in, dzb, Mb, dw_b, Mb, label="gemm:dW_own")
-        if need_dx:
-            _gemm(0, 1, n, f_in, Mb, dzb, Mb, w_b, Mb, dx, f_in, label="gemm:dx_own")
         for c in range(C):
             if works[c] is not None:
                 with _lib.timed("comm:reduce_dwh_wait"):
                     works[c].wait()
-            dza = owned[c].contiguous()
-            _gemm(1, 0, f_in, Pc, n, x, f_in, dza, Pc, dw_a, C * Pc, c_off=c * Pc, label="gemm:dW_own")
-            if need_dx:
-                _gemm(0, 1, n, f_in, Pc, dza, Pc, w_a, C * Pc, dx, f_in, accumulate=1, b_off=c * Pc, label="gemm:dx_own")
+            dz[:, c * Pc:(c + 1) * Pc].copy_(owned[c])
+        # own-row products (one each, as on a single GPU)
+        dw_all = _mem.empty(f_in, Mz, dtype=torch.float32, device=dev)
+        _gemm(1, 0, f_in, Mz, n, x, f_in, dz, Mz, dw_all, Mz, label="gemm:dW_own")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _mem.empty(n, f_in, dtype=torch.float32, device=dev)
+            _gemm(0, 1, n, f_in, Mz, dz, Mz, w_all, Mz, dx, f_in, label="gemm:dx_own")
         if plan.world > 1:
             with _lib.timed("comm:allreduce_dw"):
-                allreduce_([dw_a, dw_b], plan)
-        return dx, dw_a, dw_b, None, None, None, None, None, None, None, None
+                allreduce_([dw_all], plan)
+        return dx, dw_all, None, None, None, None, None, None, None, None
 
 
 class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
@@ -651,12 +651,12 @@ def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, 
             blocks.append(v[:, c * Hc:(c + 1) * Hc])
             if gp > Hc:
                 blocks.append(w_ext.new_zeros(f_in, gp - Hc))
-        w_a = torch.cat(blocks, dim=1)
-        bcols = ([w_ext[:, H * Dp:]] if skips is not None else []) + [u]
+        if skips is not None:
+            blocks.append(w_ext[:, H * Dp:])
+        blocks.append(u)
         if (-H) % 4:
-            bcols.append(w_ext.new_zeros(f_in, (-H) % 4))
-        w_b = torch.cat(bcols, dim=1)
-        rows = ShardedGatLayerWhFunction.apply(x_local, w_a, w_b, graph, plan, H, Dp, Hc, skips is not None,
+            blocks.append(w_ext.new_zeros(f_in, (-H) % 4))
+        rows = ShardedGatLayerWhFunction.apply(x_local, torch.cat(blocks, dim=1), graph, plan, H, Dp, Hc, skips is not None,
                                                float(alpha), bool(concat))
     else:
         rows = ShardedGatLayerFunction.apply(x_local, w_ext, a_src, a_dst, graph, plan, H, Dp, skips is not None,
