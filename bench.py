@@ -48,7 +48,9 @@ WORKLOADS = {
     # name: nodes, average stored entries per row, in-features, heads, per-head width, zipf exponent
     "products": dict(n=2_449_029, avg_deg=25.26, f_in=100, H=8, D=64, exponent=0.5),
     "pubmed": dict(n=19_717, avg_deg=5.5, f_in=500, H=8, D=8, exponent=0.5),
-    "papers_shard": dict(n=13_882_495, avg_deg=14.55, f_in=128, H=4, D=32, exponent=0.5),
+    # papers100M shape (config 5): n = rows PER RANK (111,059,956 / 8), sources span all ranks' rows; weak scaling
+    "papers_shard": dict(n=13_882_495, avg_deg=14.55, f_in=128, H=4, D=32, exponent=0.5, shard_only=True),
+    "papers_tiny": dict(n=200_000, avg_deg=14.55, f_in=128, H=4, D=32, exponent=0.5, shard_only=True),
     # the products graph as a HIDDEN layer: the 8 x 64 output of layer 1 is the input, and it needs a gradient
     "products_hidden": dict(n=2_449_029, avg_deg=25.26, f_in=512, H=8, D=64, exponent=0.5, needs_dx=True),
 }
@@ -234,7 +236,9 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------ our arm
 def make_runner(cfg, rank, world, dev):
-    from benchmarks.layer import ShardedLayerBench, SingleGpuLayerBench
+    from benchmarks.layer import ShardedLayerBench, ShardOnlyLayerBench, SingleGpuLayerBench
+    if cfg.get("shard_only"):
+        return ShardOnlyLayerBench(cfg, rank, world, dev)
     return ShardedLayerBench(cfg, rank, world, dev) if world > 1 else SingleGpuLayerBench(cfg, dev)
 
 
@@ -324,7 +328,7 @@ def run_ours(args):
 
     # ---- end-to-end through the public API with host buffers (pinned H2D of the step's input
     # features, D2H of the step's results: parameter gradients + a checksum of the output)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 10)) if not cfg.get("shard_only") else 2
     e2e_ms, h2d, d2h = runner.e2e(e2e_steps)
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
@@ -333,7 +337,7 @@ def run_ours(args):
 
     # ---- N > 1: the sharded step against a single-GPU run of the same step (rank 0 holds the whole graph for it)
     check = None
-    if world > 1 and not args.no_check:
+    if world > 1 and not args.no_check and not cfg.get("shard_only"):
         from benchmarks.layer import parity_check
         try:
             check = parity_check(runner, rank, world, dev)
@@ -346,7 +350,7 @@ def run_ours(args):
     # ---- the same layer as a HIDDEN layer (wide input that needs a gradient): the project-first kernels that
     # layer 2 of models.GAT and every PPI layer run (models.py:29-35)
     hidden = None
-    if not args.no_hidden and args.workload == "products":
+    if not args.no_hidden and args.workload == "products":  # (the papers shard has no hidden-layer add-on)
         hcfg = WORKLOADS["products_hidden"]
         try:
             hrun = make_runner(hcfg, rank, world, dev)
@@ -368,7 +372,7 @@ def run_ours(args):
 
     # ---- epoch workloads: Pubmed (replicas only: one GPU) and PPI (graph-level data parallel over the ranks)
     epochs = None
-    if not args.no_epochs:
+    if not args.no_epochs and not cfg.get("shard_only"):
         epochs = {}
         try:
             from benchmarks import epochs as epoch_bench
@@ -394,7 +398,8 @@ def run_ours(args):
         return
 
     peak, peak_src = measured_peak()
-    ab = algorithmic_bytes(n, e_total, H, D, f_in)
+    n_nodes = n * world if cfg.get("shard_only") else n
+    ab = algorithmic_bytes(n_nodes, e_total, H, D, f_in)
     per_kernel, other = kernel_table(kern, ab, world, args.steps, peak)
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"]) if per_kernel else None
     traffic = None
@@ -417,10 +422,14 @@ def run_ours(args):
     line = {
         "metric": "gat_layer_fwd_bwd_head_edges_per_s", "value": e_total * H / (ms * 1e-3), "unit": "head-edges/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak" if cfg.get("shard_only") else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}-shape power-law graph, one hidden GAT layer fwd+bwd",
-                   "nodes": n, "edges": e_total, "f_in": f_in, "heads": H, "head_dim": D, "dropout": 0.0,
-                   "parallelism": (f"dst-row shards x{world} (cost-balanced, row_cost={row_cost:.1f} entries); layer-1 "
+                   "nodes": n_nodes, "edges": e_total, "f_in": f_in, "heads": H, "head_dim": D, "dropout": 0.0,
+                   "parallelism": (f"dst-row shards x{world}, {n} rows each, generated per rank (the whole pattern never exists); "
+                                   "aggregate-first form; layer-1 features are static, their all-gather is kept across steps; "
+                                   "per step g [N,H] is pushed, dg reduce-scattered, dW all-reduced") if cfg.get("shard_only") else
+                                  (f"dst-row shards x{world} (cost-balanced, row_cost={row_cost:.1f} entries); layer-1 "
                                    "features are static, their all-gather is kept across steps; per step g [N,H] is "
                                    "all-gathered, dg reduce-scattered, dW all-reduced") if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (Wh alone is %.1f GB)" % (n * H * D * 4 / 1e9)},

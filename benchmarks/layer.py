@@ -130,6 +130,74 @@ class ShardedLayerBench:
         return pipelined_e2e(self, steps, barrier=dist.barrier)
 
 
+class ShardOnlyLayerBench:
+    """papers100M-shaped workload (BASELINE.json config 5): every rank generates and keeps ONLY its own destination-row
+    shard (cfg["n"] rows per rank, sources over all world * cfg["n"] nodes, synth.power_law_shard) -- the whole graph
+    (1.6 G entries at 8 ranks) and the N x N adjacency of the reference never exist anywhere.  First layer with a
+    static input, so the aggregate-first form is forced: the x columns of the gathered rows are exchanged once, a
+    step moves g [N, H] forward and dg [N, H] backward.  Weak scaling by construction (per-rank shard fixed)."""
+
+    def __init__(self, cfg, rank: int, world: int, dev):
+        from pygat_b200.synth import power_law_shard
+        self.rank, self.world, self.dev, self.cfg = rank, world, dev, cfg
+        n, H, D, f_in = cfg["n"], cfg["H"], cfg["D"], cfg["f_in"]
+        self.plan = ShardPlan([r * n for r in range(world + 1)], rank)
+        rowptr, col = power_law_shard(world * n, rank * n, (rank + 1) * n, cfg["avg_deg"], seed=72,
+                                      exponent=cfg["exponent"], device=dev)
+        self.graph = Graph(rowptr, col, n_src=world * n)
+        del rowptr, col
+        torch.cuda.empty_cache()
+        e = torch.tensor([self.graph.nnz], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(e)
+        self.e_total = int(e.item())
+        g = torch.Generator(device=dev).manual_seed(72 + rank)
+        self.x = torch.randn(n, f_in, generator=g, device=dev)
+        self.gout = torch.randn(n, H * D, generator=g, device=dev)
+        self.Ws, self.a_src, self.a_dst = init_layer_params(f_in, H, D, dev, seed=72)
+        self.params = self.Ws + self.a_src + self.a_dst
+        self.needs_dx = False
+        self.row_cost = float("nan")
+        self.x_host = None
+
+    def _layer(self, x):
+        return sharded_gat_layer(x, self.graph, self.plan, self.Ws, self.a_src, self.a_dst, None, 0.2, concat=True,
+                                 form="agg_first")
+
+    def step(self):
+        for p in self.params:
+            p.grad = None
+        y = self._layer(self.x)
+        y.backward(self.gout)
+        return y
+
+    def e2e(self, steps: int):
+        """Host buffers in, gradients out, SINGLE device buffer (the shard's working set leaves no room for a second
+        copy of the features at the papers shape): the copy of step k+1 waits for step k."""
+        if self.x_host is None:
+            self.x_host = self.x.cpu().pin_memory()
+        n_par = sum(p.numel() for p in self.params)
+        host_out = torch.empty(n_par + 1, dtype=torch.float32).pin_memory()
+
+        def run(k):
+            for _ in range(k):
+                self.x.copy_(self.x_host, non_blocking=True)   # in place: bumps the version counter, the kept rows go stale
+                y = self.step()
+                flat = torch.cat([p.grad.reshape(-1) for p in self.params] + [y.detach()[:: max(1, y.shape[0] // 1024)].sum().reshape(1)])
+                host_out.copy_(flat, non_blocking=True)
+                del y
+        run(1)
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, self.x_host.numel() * 4, host_out.numel() * 4
+
+
 def pipelined_e2e(runner, steps, barrier=None):
     """End to end through the public API with HOST inputs: every step copies its input features from
     pinned host memory (double buffered on a copy stream, so step k+1's copy overlaps step k's compute,

@@ -65,7 +65,11 @@ GATK_API int gatk_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t e, const
                        void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ dropout (F.dropout, layers.py:34,37,43 / :132,136,153)
- * keep[i] = 1 with probability 1-p (Philox4x32-10 keyed by seed, counter = offset + i/4). */
+ * keep[i] = 1 with probability 1-p (Philox4x32-10 keyed by seed, counter = offset + i/4).
+ * The layer kernels take a dropout site EITHER as a materialised keep mask (uint8, how the parity tests inject the
+ * masks the reference drew) OR as (seed, drop_offset, p_drop) with the mask pointer NULL: the kernel then evaluates
+ * exactly this stream where it consumes the decision (element index = the mask's flat index), so training with
+ * p > 0 never materialises a mask.  p_drop = 0 with a NULL mask: site not dropped. */
 GATK_API int gatk_dropout_keep_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
 /* y = keep ? x * scale : 0  (rows x cols with leading dims; keep dense rows*cols). */
 GATK_API int gatk_mask_scale(const float* x, int64_t ldx, const uint8_t* keep, float scale, float* y, int64_t ldy,
@@ -105,12 +109,33 @@ GATK_API int gatk_gemm_batched(int transA, int transB, int64_t M, int64_t N, int
                                int64_t c_bs, int epilogue, const float* elu_out, int64_t ld_elu, void* ws, size_t ws_bytes,
                                void* stream);
 
+/* Projection with the reference's PER-HEAD input dropout (every head module drops the layer input with its own mask,
+ * layers.py:34,132, and its skip projection uses the same dropped input, :48,166), all heads in ONE launch and
+ * without materialising masks: the keep decision of element (h, i, k) of the [H, n, F] site is evaluated from
+ * (seed, drop_offset) where x[i, k] is loaded.  W is [F, ldw] with the weight block of head h at columns
+ * [h*Dp, (h+1)*Dp) and, when has_skip, the skip block at [H*Dp + h*Dp, ...); z / dz use the same column layout.
+ *   fwd   z[i, blk_h] = sum_k x[i,k] m_h[i,k] inv_keep W[k, blk_h]
+ *   dW    dW[k, blk_h] = sum_i x[i,k] m_h[i,k] inv_keep dz[i, blk_h]           (deterministic two-stage reduction;
+ *         ws floats: gatk_gemm_heads_dropout_ws_floats)
+ *   dx    dx[i,k] = inv_keep sum_h m_h[i,k] sum_{c in blk_h} dz[i,c] W[k,c]
+ * fp32 SIMT kernels (exact products): the shapes that train with dropout are the citation graphs (n <= 2e4). */
+GATK_API size_t gatk_gemm_heads_dropout_ws_floats(int64_t n, int F, int H, int Dp, int has_skip);
+GATK_API int gatk_gemm_heads_dropout_fwd(int64_t n, int F, int H, int Dp, int has_skip, const float* x, int64_t ldx,
+                                         const float* W, int64_t ldw, float* z, int64_t ldz, uint64_t seed,
+                                         uint64_t drop_offset, float p_drop, void* stream);
+GATK_API int gatk_gemm_heads_dropout_dw(int64_t n, int F, int H, int Dp, int has_skip, const float* x, int64_t ldx,
+                                        const float* dz, int64_t ldz, float* dW, int64_t lddw, float* ws,
+                                        uint64_t seed, uint64_t drop_offset, float p_drop, void* stream);
+GATK_API int gatk_gemm_heads_dropout_dx(int64_t n, int F, int H, int Dp, int has_skip, const float* dz, int64_t ldz,
+                                        const float* W, int64_t ldw, float* dx, int64_t lddx, uint64_t seed,
+                                        uint64_t drop_offset, float p_drop, void* stream);
+
 /* Attention-logit halves f_i = Wh_i . a[:D], g_j = Wh_j . a[D:] (layers.py:60-61, :141-144),
  * after the post-projection dropout (layers.py:37,136) applied IN PLACE to wh when
  * keep_wh != NULL (keep_wh is [n, H*Dp] dense).  a_src / a_dst are [H, Dp]. */
 GATK_API int gatk_logits_fwd(int64_t n, int H, int Dp, float* wh, int64_t ldw, const uint8_t* keep_wh,
                     float inv_keep, const float* a_src, const float* a_dst, float* f, float* g,
-                    void* stream);
+                    uint64_t seed, uint64_t drop_offset, float p_drop, void* stream);
 
 /* ------------------------------------------------------------------ K2: fused attention forward
  * One pass per destination row over its CSR edges: LeakyReLU(f_i + g_j), online
@@ -137,7 +162,8 @@ GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* 
                   float* hagg, float* out, int64_t ldo, float* lse,
                   int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr,
                   int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter,
-                  const int32_t* item_ptr, int n_items, void* stream);
+                  const int32_t* item_ptr, int n_items, uint64_t seed, uint64_t drop_offset, float p_drop,
+                  void* stream);
 
 /* ------------------------------------------------------------------ K3/K4: backward of the fused attention
  * Autograd of layers.py:141-160, with the reference's dense N x N SpecialSpmmFunction.backward
@@ -174,12 +200,13 @@ GATK_API int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int32
                                  int64_t lddg, float* edge_dz,
                                  int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                                  int n_hub_seg, float* hub_scratch, int32_t* counter,
-                                 const int32_t* item_ptr, int n_items, void* stream);
+                                 const int32_t* item_ptr, int n_items, uint64_t seed, uint64_t drop_offset,
+                                 float p_drop, void* stream);
 GATK_API int gatk_attn_bwd_finish(int64_t n, const int64_t* rowptr, int H, int Dp, const float* edge_dz,
                                   const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
                                   int64_t lddwh, float* df, int64_t lddf, int seg_len, const int32_t* hub_rows,
                                   const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
-                                  void* stream);
+                                  uint64_t seed, uint64_t drop_offset, float p_drop, void* stream);
 
 /* da_src[h,:] = sum_i df[i,h] Wh[i,h,:],  da_dst[h,:] = sum_j dg[j,h] Wh[j,h,:]  (autograd of
  * layers.py:60-61 / :144).  ws floats: gatk_da_workspace_floats(H, Dp). Deterministic. */

@@ -37,19 +37,26 @@ PROTOTYPES = {
                                                  c_int64, c_int64, c_int64]),
     "gatk_gemm_batched": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int, P, c_int64, c_int64, P, c_int64, c_int64,
                                   P, c_int64, c_int64, c_int, P, c_int64, P, c_size_t, P]),
-    "gatk_logits_fwd": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_float, P, P, P, P, P]),
+    "gatk_logits_fwd": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_float, P, P, P, P, c_uint64, c_uint64, c_float, P]),
+    "gatk_gemm_heads_dropout_ws_floats": (c_size_t, [c_int64, c_int, c_int, c_int, c_int]),
+    "gatk_gemm_heads_dropout_fwd": (c_int, [c_int64, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, c_int64, c_uint64,
+                                            c_uint64, c_float, P]),
+    "gatk_gemm_heads_dropout_dw": (c_int, [c_int64, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, c_int64, P, c_uint64,
+                                           c_uint64, c_float, P]),
+    "gatk_gemm_heads_dropout_dx": (c_int, [c_int64, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, c_int64, c_uint64,
+                                           c_uint64, c_float, P]),
     "gatk_hub_scratch_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gatk_attn_fwd": (c_int, [c_int64, P, P, c_int, c_int, P, c_int64, P, c_int64, P, c_int64, P, c_float, c_float,
                               P, c_int64, c_int, P, P, c_int64, P,
-                              c_int, P, P, c_int, c_int, P, P, P, c_int, P]),
+                              c_int, P, P, c_int, c_int, P, P, P, c_int, c_uint64, c_uint64, c_float, P]),
     "gatk_attn_bwd_record_ld": (c_int64, [c_int, c_int]),
     "gatk_attn_bwd_prep": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_int64, c_int, P, c_int64, P, c_int64, P,
                                    P, c_int64, P, c_int64, P]),
     "gatk_attn_bwd_fused": (c_int, [c_int64, P, P, P, c_int, c_int, P, c_int64, P, c_int64, P, c_int64, P, c_float,
                                     c_float, P, P, c_int64, P, c_int64, P,
-                                    c_int, P, P, c_int, c_int, P, P, P, c_int, P]),
+                                    c_int, P, P, c_int, c_int, P, P, P, c_int, c_uint64, c_uint64, c_float, P]),
     "gatk_attn_bwd_finish": (c_int, [c_int64, P, c_int, c_int, P, P, P, c_float, P, c_int64, P, c_int64,
-                                     c_int, P, P, c_int, c_int, P, P]),
+                                     c_int, P, P, c_int, c_int, P, c_uint64, c_uint64, c_float, P]),
     "gatk_da_workspace_floats": (c_size_t, [c_int, c_int]),
     "gatk_da_reduce": (c_int, [c_int64, c_int, c_int, P, c_int64, P, P, P, P, P, P]),
     "gatk_xg_pitch": (c_int64, [c_int, c_int]),

@@ -41,3 +41,11 @@ def empty_like(ref: torch.Tensor) -> torch.Tensor:
     if trace is not None:
         trace.append(t)
     return t
+
+
+def zeros(*size, dtype=torch.float32, device=None) -> torch.Tensor:
+    """A buffer that must START at zero (accumulation targets of reductions); traced like the others."""
+    t = torch.zeros(*size, dtype=dtype, device=device)
+    if trace is not None:
+        trace.append(t)
+    return t

@@ -88,6 +88,8 @@ struct BwdFusedArgs {
   int64_t ldrec;
   const uint8_t* keep;
   float inv_keep, alpha;
+  uint64_t seed, drop_offset;  // keep == NULL and p_drop > 0: the forward's attention-dropout decisions, re-evaluated
+  float p_drop;
   const float* a_dst;
   float* dwh;
   int64_t lddwh;
@@ -173,7 +175,8 @@ __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, 
         const float s = z > 0.f ? z : a.alpha * z;
         const float al = expf(s - t4.y);
         const float slope = z > 0.f ? 1.f : a.alpha;
-        const float kv = kp ? (kp[h] ? a.inv_keep : 0.f) : 1.f;
+        const float kv = kp ? (kp[h] ? a.inv_keep : 0.f)
+                            : (a.p_drop > 0.f ? (drop_keep(a.seed, a.drop_offset, (int64_t)pe * H + h, a.p_drop) ? a.inv_keep : 0.f) : 1.f);
         at = al * kv;
         A = al * slope * kv;
         B = al * slope * t4.z;
@@ -322,6 +325,8 @@ struct FinishArgs {
   const float* a_src;
   const uint8_t* keep_wh;
   float inv_keep;
+  uint64_t seed, drop_offset;  // keep_wh == NULL and p_drop > 0: the post-projection dropout decisions, re-evaluated
+  float p_drop;
   float* dwh;
   int64_t lddwh;
   float* df;
@@ -368,6 +373,12 @@ __device__ __forceinline__ void finish_row(const FinishArgs& a, int64_t row, flo
         r.y = k.y ? r.y * a.inv_keep : 0.f;
         r.z = k.z ? r.z * a.inv_keep : 0.f;
         r.w = k.w ? r.w * a.inv_keep : 0.f;
+      } else if (a.p_drop > 0.f) {
+        const unsigned m = drop_keep4(a.seed, a.drop_offset, row * a.V + slot, a.p_drop);
+        r.x = (m & 1u) ? r.x * a.inv_keep : 0.f;
+        r.y = (m & 2u) ? r.y * a.inv_keep : 0.f;
+        r.z = (m & 4u) ? r.z * a.inv_keep : 0.f;
+        r.w = (m & 8u) ? r.w * a.inv_keep : 0.f;
       }
       stg4(p, r);
     }
@@ -495,7 +506,7 @@ extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int
                                    float* edge_dz,
                                    int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                                    int n_hub_seg, float* hub_scratch, int32_t* counter, const int32_t* item_ptr,
-                                   int n_items, void* stream) {
+                                   int n_items, uint64_t seed, uint64_t drop_offset, float p_drop, void* stream) {
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
   if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
@@ -508,6 +519,7 @@ extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int
   a.n_src = n_src; a.tptr = tptr; a.trow = trow; a.perm = perm; a.H = H; a.Dp = Dp; a.lph = Dp / 4;
   a.V = H * (Dp / 4);
   a.wh = wh; a.ldw = ldw; a.g = g; a.ldg = ldg; a.rec = rec; a.ldrec = ldrec; a.keep = keep_att; a.inv_keep = inv_keep;
+  a.seed = seed; a.drop_offset = drop_offset; a.p_drop = keep_att ? 0.f : p_drop;
   a.alpha = alpha; a.a_dst = a_dst; a.dwh = dwh; a.lddwh = lddwh; a.dg = dg; a.lddg = lddg;
   a.edge_dz = edge_dz; a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub;
   a.n_hub_seg = n_hub_seg; a.scratch = hub_scratch; a.counter = counter; a.item_ptr = item_ptr; a.n_items = n_items;
@@ -520,14 +532,16 @@ extern "C" int gatk_attn_bwd_finish(int64_t n, const int64_t* rowptr, int H, int
                                     const float* a_src, const uint8_t* keep_wh, float inv_keep, float* dwh,
                                     int64_t lddwh, float* df, int64_t lddf, int seg_len, const int32_t* hub_rows,
                                     const int32_t* hub_seg_ptr, int n_hub, int n_hub_seg, float* hub_scratch,
-                                    void* stream) {
+                                    uint64_t seed, uint64_t drop_offset, float p_drop, void* stream) {
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
   if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
   GATK_REQUIRE(rowptr && df && lddf >= H && (!a_src || (dwh && lddwh % 4 == 0)) && (a_src || !keep_wh), "bad arguments");
   FinishArgs a;
   a.n = n; a.rowptr = rowptr; a.H = H; a.lph = Dp / 4; a.V = H * (Dp / 4); a.edge_dz = edge_dz; a.a_src = a_src;
-  a.keep_wh = keep_wh; a.inv_keep = inv_keep; a.dwh = dwh; a.lddwh = lddwh; a.df = df; a.lddf = lddf; a.seg_len = seg_len;
+  a.keep_wh = keep_wh; a.inv_keep = inv_keep; a.seed = seed; a.drop_offset = drop_offset;
+  a.p_drop = (keep_wh || !a_src) ? 0.f : p_drop;
+  a.dwh = dwh; a.lddwh = lddwh; a.df = df; a.lddf = lddf; a.seg_len = seg_len;
   a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub; a.n_hub_seg = n_hub_seg; a.scratch = hub_scratch;
   cudaStream_t st = (cudaStream_t)stream;
   NV_DISPATCH(nv, return launch_finish<NV>(a, st));

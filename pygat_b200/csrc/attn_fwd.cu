@@ -27,6 +27,8 @@ struct FwdArgs {
   int64_t ldf, ldg;  // row pitches of f and g (floats): H when they are dense [N,H] arrays
   const uint8_t* keep;
   float inv_keep, alpha;
+  uint64_t seed, drop_offset;  // keep == NULL and p_drop > 0: attention-dropout decisions evaluated in the kernel
+  float p_drop;
   const float* skipv;
   int64_t lds;
   int act_elu;
@@ -85,6 +87,7 @@ __device__ __forceinline__ void fwd_segment(const FwdArgs& a, int row, int64_t b
         for (int k = 0; k < q; ++k) scale_s[pos + k] = sc;
       }
       if (kp) pe = (valid && kp[h]) ? pe * a.inv_keep : 0.f;
+      else if (a.p_drop > 0.f) pe = (valid && drop_keep(a.seed, a.drop_offset, e * H + h, a.p_drop)) ? pe * a.inv_keep : 0.f;
       for (int k = 0; k < q; ++k) p_s[lane * WS + pos + k] = pe;
     }
     __syncwarp();
@@ -270,7 +273,8 @@ extern "C" int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t
                              float* hagg, float* out, int64_t ldo, float* lse,
                              int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr,
                              int n_hub, int n_hub_seg, float* hub_scratch, int32_t* counter,
-                             const int32_t* item_ptr, int n_items, void* stream) {
+                             const int32_t* item_ptr, int n_items, uint64_t seed, uint64_t drop_offset, float p_drop,
+                             void* stream) {
   int nv;
   if (int rc = check_geom(H, Dp, &nv)) return rc;
   if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
@@ -283,6 +287,7 @@ extern "C" int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t
   a.n_dst = n_dst; a.rowptr = rowptr; a.col = col; a.H = H; a.Dp = Dp; a.lph = Dp / 4; a.V = H * (Dp / 4);
   a.HP = H | 1;
   a.wh = wh; a.ldw = ldw; a.f = f; a.g = g; a.ldf = ldf; a.ldg = ldg; a.keep = keep_att; a.inv_keep = inv_keep; a.alpha = alpha;
+  a.seed = seed; a.drop_offset = drop_offset; a.p_drop = keep_att ? 0.f : p_drop;
   a.skipv = skipv; a.lds = lds; a.act_elu = act_elu; a.hagg = hagg; a.out = out; a.ldo = ldo; a.lse = lse;
   a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub; a.n_hub_seg = n_hub_seg;
   a.scratch = hub_scratch; a.counter = counter; a.item_ptr = item_ptr; a.n_items = n_items;

@@ -101,6 +101,39 @@ __device__ __forceinline__ void head_reduce(float (&part)[NV], int lph) {
   }
 }
 
+// ------------------------------------------------------------------ dropout decisions (Philox4x32-10)
+// One stream of keep bits per dropout site, keyed by (seed, offset): element i of the site takes word (i & 3) of
+// Philox(seed)(offset + (i >> 2)) and is kept when its 24-bit uniform is >= p.  gatk_dropout_keep_mask materialises
+// exactly this stream (that is how the in-kernel decisions are tested: same seed and offset -> same mask); the
+// layer kernels evaluate it where the mask is consumed, so no mask ever exists in memory (F.dropout at
+// layers.py:34,37,43 / :132,136,153).
+__device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr) {
+  uint4 c = make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u);
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ a, lo1, hi0 ^ c.w ^ b, lo0);
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ bool keep_from_word(uint32_t w, float p) { return ((w >> 8) * (1.0f / 16777216.0f)) >= p; }
+// element i of the site
+__device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t offset, int64_t i, float p) {
+  const uint4 r = philox4(seed, offset + (uint64_t)(i >> 2));
+  const int k = (int)(i & 3);
+  return keep_from_word(k == 0 ? r.x : (k == 1 ? r.y : (k == 2 ? r.z : r.w)), p);
+}
+// the four elements 4q .. 4q+3 of the site (q = i >> 2), as a 4-bit mask
+__device__ __forceinline__ unsigned drop_keep4(uint64_t seed, uint64_t offset, int64_t q, float p) {
+  const uint4 r = philox4(seed, offset + (uint64_t)q);
+  return (keep_from_word(r.x, p) ? 1u : 0u) | (keep_from_word(r.y, p) ? 2u : 0u) | (keep_from_word(r.z, p) ? 4u : 0u) |
+         (keep_from_word(r.w, p) ? 8u : 0u);
+}
+
 inline int nv_for(int H, int Dp) {
   int V = H * (Dp / 4);
   int nv = (V + 31) / 32;

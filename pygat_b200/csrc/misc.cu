@@ -29,36 +29,15 @@ int sm_count() {
   return n;
 }
 
-// ------------------------------------------------------------------ Philox4x32-10
-struct Philox {
-  uint32_t k0, k1;
-  __device__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
-  __device__ uint4 operator()(uint64_t ctr) const {
-    uint4 c = make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u);
-    uint32_t a = k0, b = k1;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-      c = make_uint4(hi1 ^ c.y ^ a, lo1, hi0 ^ c.w ^ b, lo0);
-      a += 0x9E3779B9u;
-      b += 0xBB67AE85u;
-    }
-    return c;
-  }
-};
-
+// ------------------------------------------------------------------ dropout masks (Philox4x32-10, common.cuh)
 __global__ void dropout_keep_kernel(uint8_t* __restrict__ keep, int64_t n, float p, uint64_t seed, uint64_t offset) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 outputs
   if (q * 4 >= n) return;
-  Philox rng(seed);
-  const uint4 r = rng(offset + (uint64_t)q);
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  const unsigned m = drop_keep4(seed, offset, q, p);  // 24-bit uniforms in [0,1): keep with probability 1-p
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int64_t i = q * 4 + k;
-    // 24-bit uniform in [0,1): keep with probability 1-p
-    if (i < n) keep[i] = ((w[k] >> 8) * (1.0f / 16777216.0f)) >= p ? 1 : 0;
+    if (i < n) keep[i] = (m >> k) & 1u;
   }
 }
 
@@ -74,7 +53,8 @@ __global__ void mask_scale_kernel(const float* __restrict__ x, int64_t ldx, cons
 template <int NV>
 __global__ void logits_kernel(int64_t n, int H, int lph, int V, float* __restrict__ wh, int64_t ldw,
                               const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ a_src,
-                              const float* __restrict__ a_dst, float* __restrict__ f, float* __restrict__ g) {
+                              const float* __restrict__ a_dst, float* __restrict__ f, float* __restrict__ g,
+                              uint64_t seed, uint64_t offset, float p_drop) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -92,6 +72,13 @@ __global__ void logits_kernel(int64_t n, int H, int lph, int V, float* __restric
         w.y = k.y ? w.y * inv_keep : 0.f;
         w.z = k.z ? w.z * inv_keep : 0.f;
         w.w = k.w ? w.w * inv_keep : 0.f;
+        stg4(p, w);
+      } else if (p_drop > 0.f) {  // the same decisions, evaluated here: element (row, 4 slot + k) of the [n, H*Dp] site
+        const unsigned m = drop_keep4(seed, offset, row * V + slot, p_drop);
+        w.x = (m & 1u) ? w.x * inv_keep : 0.f;
+        w.y = (m & 2u) ? w.y * inv_keep : 0.f;
+        w.z = (m & 4u) ? w.z * inv_keep : 0.f;
+        w.w = (m & 8u) ? w.w * inv_keep : 0.f;
         stg4(p, w);
       }
       pf[v] = dot4(w, ldg4(a_src + slot * 4));
@@ -235,7 +222,8 @@ extern "C" int gatk_mask_scale(const float* x, int64_t ldx, const uint8_t* keep,
 }
 
 extern "C" int gatk_logits_fwd(int64_t n, int H, int Dp, float* wh, int64_t ldw, const uint8_t* keep_wh, float inv_keep,
-                               const float* a_src, const float* a_dst, float* f, float* g, void* stream) {
+                               const float* a_src, const float* a_dst, float* f, float* g, uint64_t seed, uint64_t offset,
+                               float p_drop, void* stream) {
   GATK_REQUIRE(H >= 1 && H <= 32 && dp_ok(Dp), "bad head geometry H=%d Dp=%d", H, Dp);
   const int nv = nv_for(H, Dp);
   GATK_REQUIRE(nv > 0, "row too wide");
@@ -245,11 +233,11 @@ extern "C" int gatk_logits_fwd(int64_t n, int H, int Dp, float* wh, int64_t ldw,
   const unsigned grid = (unsigned)((n + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
   switch (nv) {
-    case 1: logits_kernel<1><<<grid, 256, 0, st>>>(n, H, lph, V, wh, ldw, keep_wh, inv_keep, a_src, a_dst, f, g); break;
-    case 2: logits_kernel<2><<<grid, 256, 0, st>>>(n, H, lph, V, wh, ldw, keep_wh, inv_keep, a_src, a_dst, f, g); break;
-    case 4: logits_kernel<4><<<grid, 256, 0, st>>>(n, H, lph, V, wh, ldw, keep_wh, inv_keep, a_src, a_dst, f, g); break;
-    case 8: logits_kernel<8><<<grid, 256, 0, st>>>(n, H, lph, V, wh, ldw, keep_wh, inv_keep, a_src, a_dst, f, g); break;
-    default: logits_kernel<16><<<grid, 256, 0, st>>>(n, H, lph, V, wh, ldw, keep_wh, inv_keep, a_src, a_dst, f, g); break;
+    case 1: logits_kernel<1><<<grid, 256, 0, st>>>(n, H, lph, V, wh, ldw, keep_wh, inv_keep, a_src, a_dst, f, g, seed, offset, p_drop); break;
+    case 2: logits_kernel<2><<<grid, 256, 0, st>>>(n, H, lph, V, wh, ldw, keep_wh, inv_keep, a_src, a_dst, f, g, seed, offset, p_drop); break;
+    case 4: logits_kernel<4><<<grid, 256, 0, st>>>(n, H, lph, V, wh, ldw, keep_wh, inv_keep, a_src, a_dst, f, g, seed, offset, p_drop); break;
+    case 8: logits_kernel<8><<<grid, 256, 0, st>>>(n, H, lph, V, wh, ldw, keep_wh, inv_keep, a_src, a_dst, f, g, seed, offset, p_drop); break;
+    default: logits_kernel<16><<<grid, 256, 0, st>>>(n, H, lph, V, wh, ldw, keep_wh, inv_keep, a_src, a_dst, f, g, seed, offset, p_drop); break;
   }
   GATK_CHECK_LAUNCH();
   return 0;

@@ -52,6 +52,10 @@ class LayerMasks:
     keep_in: Optional[torch.Tensor] = None
     keep_wh: Optional[torch.Tensor] = None
     keep_att: Optional[torch.Tensor] = None
+    # seeded mode (training with p > 0 and no injected masks): nothing is materialised; the kernels evaluate the Philox
+    # stream (seed, offset of the site) where they consume a decision.  offsets = (input, projected, attention).
+    seed: Optional[int] = None
+    offsets: tuple = (0, 0, 0)
 
 
 def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, accumulate=0, a_off=0, b_off=0, c_off=0, label=None):
@@ -86,18 +90,37 @@ def _hub_scratch(which: int, H: int, Dp: int, n_seg: int, dev):
     return _mem.empty(_lib.query("gatk_hub_scratch_floats", which, H, Dp, n_seg), dtype=torch.float32, device=dev)
 
 
-def random_masks(n: int, f_in: int, H: int, Dp: int, nnz: int, p: float, device) -> LayerMasks:
-    """Draw the three masks with the in-library Philox generator.  The 64-bit seed comes from
-    torch's CPU generator, so torch.manual_seed (train.py:91-99) makes runs reproducible."""
-    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+def site_offsets(n: int, f_in: int, H: int, Dp: int, nnz: int):
+    """Philox counter offsets of the three dropout sites of a layer: consecutive, non-overlapping ranges of the
+    stream (a site of `sz` elements uses ceil(sz / 4) counters)."""
     sizes = (H * n * f_in, n * H * Dp, nnz * H)
-    bufs, off = [], 0
+    offs, off = [], 0
     for sz in sizes:
+        offs.append(off)
+        off += (sz + 3) // 4
+    return tuple(offs), sizes
+
+
+def random_masks(n: int, f_in: int, H: int, Dp: int, nnz: int, p: float, device, seed: Optional[int] = None) -> LayerMasks:
+    """MATERIALISE the three masks of a layer from the in-library Philox stream (debugging / tests: the seeded mode
+    of the layer consumes the same stream without ever building them)."""
+    if seed is None:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    offs, sizes = site_offsets(n, f_in, H, Dp, nnz)
+    bufs = []
+    for sz, off in zip(sizes, offs):
         t = _mem.empty(sz, dtype=torch.uint8, device=device)
         _lib.call("gatk_dropout_keep_mask", t.data_ptr(), sz, float(p), seed, off, _stream())
-        off += (sz + 3) // 4
         bufs.append(t)
     return LayerMasks(bufs[0].view(H, n, f_in), bufs[1].view(n, H * Dp), bufs[2].view(nnz, H))
+
+
+def seeded_masks(n: int, f_in: int, H: int, Dp: int, nnz: int, seed: Optional[int] = None) -> LayerMasks:
+    """Dropout sites as (seed, offsets): the 64-bit seed comes from torch's CPU generator, so torch.manual_seed
+    (train.py:91-99) makes runs reproducible; no mask is materialised."""
+    if seed is None:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    return LayerMasks(seed=seed & 0x7FFFFFFFFFFFFFFF, offsets=site_offsets(n, f_in, H, Dp, nnz)[0])
 
 
 class GatLayerFunction(torch.autograd.Function):
@@ -121,10 +144,17 @@ class GatLayerFunction(torch.autograd.Function):
         masks = masks if (masks is not None and p > 0.0) else LayerMasks()
         inv_keep = 1.0 / (1.0 - p) if p > 0.0 else 1.0
         st = _stream()
+        seeded = masks.seed is not None
+        seed = masks.seed if seeded else 0
+        o_in, o_wh, o_att = masks.offsets if seeded else (0, 0, 0)
+        pk = float(p) if seeded else 0.0   # p handed to the kernels: > 0 only in seeded mode
 
         # ---- K1: projection (+ skip columns) ---------------------------------------------
         z = _mem.empty(n, M_out, dtype=torch.float32, device=dev)
-        if masks.keep_in is None:
+        if seeded:   # every head drops the input with its own decisions (layers.py:34,132), all heads in one launch
+            _lib.call("gatk_gemm_heads_dropout_fwd", n, f_in, H, Dp, int(has_skip), x.data_ptr(), f_in, w_ext.data_ptr(), M_out,
+                      z.data_ptr(), M_out, seed, o_in, pk, st)
+        elif masks.keep_in is None:
             _gemm(0, 0, n, M_out, f_in, x, f_in, w_ext, M_out, z, M_out)
         else:
             xh = _mem.empty_like(x)
@@ -141,7 +171,7 @@ class GatLayerFunction(torch.autograd.Function):
         f = _mem.empty(n, H, dtype=torch.float32, device=dev)
         g = _mem.empty(n, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_logits_fwd", n, H, Dp, wh_ptr, M_out, _ptr(masks.keep_wh), inv_keep,
-                  a_src.data_ptr(), a_dst.data_ptr(), f.data_ptr(), g.data_ptr(), st)
+                  a_src.data_ptr(), a_dst.data_ptr(), f.data_ptr(), g.data_ptr(), seed, o_wh, pk, st)
 
         # ---- K2: fused attention -----------------------------------------------------------
         need_grad = any(ctx.needs_input_grad[:4])
@@ -154,7 +184,7 @@ class GatLayerFunction(torch.autograd.Function):
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_ptr, M_out,
                   f.data_ptr(), H, g.data_ptr(), H, _ptr(masks.keep_att), inv_keep, float(alpha),
                   skip_ptr, M_out, int(act_elu), _ptr(hagg), out.data_ptr(), HD, _ptr(lse),
-                  *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+                  *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), seed, o_att, pk, st)
 
         if need_grad:
             ctx.graph, ctx.masks = graph, masks
@@ -174,6 +204,10 @@ class GatLayerFunction(torch.autograd.Function):
         st = _stream()
         gout = gout.contiguous()
         tptr, trow, perm, thubs = graph.transpose()
+        seeded = masks.seed is not None
+        seed = masks.seed if seeded else 0
+        o_in, o_wh, o_att = masks.offsets if seeded else (0, 0, 0)
+        pk = float(p) if seeded else 0.0
 
         # dZ = [dWh | dSkip]; with a skip projection dL/dh' IS dSkip, so prep writes it there as well.
         dz_rows = _mem.empty(n, M_out, dtype=torch.float32, device=dev)
@@ -193,7 +227,7 @@ class GatLayerFunction(torch.autograd.Function):
         _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, z.data_ptr(), M_out,
                   g.data_ptr(), H, rec.data_ptr(), ldrec, _ptr(masks.keep_att), inv_keep, alpha,
                   a_dst.data_ptr(), dz_rows.data_ptr(), M_out, dg.data_ptr(), H, edge_dz.data_ptr(),
-                  *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), st)
+                  *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), seed, o_att, pk, st)
         del rec
 
         # ---- finish: df = segmented sum of dz, dWh += df a_src, Wh-dropout mask ------------------
@@ -201,7 +235,7 @@ class GatLayerFunction(torch.autograd.Function):
         scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), a_src.data_ptr(),
                   _ptr(masks.keep_wh), inv_keep, dz_rows.data_ptr(), M_out, df.data_ptr(), H,
-                  *hubs.args(scratch), st)
+                  *hubs.args(scratch), seed, o_wh, pk, st)
         del edge_dz
 
         # ---- da ------------------------------------------------------------------------------
@@ -215,7 +249,15 @@ class GatLayerFunction(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         dw_ext = _mem.empty(f_in, M_out, dtype=torch.float32, device=dev)
         dx = _mem.empty(n, f_in, dtype=torch.float32, device=dev) if need_dx else None
-        if masks.keep_in is None:
+        if seeded:   # the forward's per-head input decisions, re-evaluated inside one launch per product
+            ws2 = _mem.empty(_lib.query("gatk_gemm_heads_dropout_ws_floats", n, f_in, H, Dp, int(has_skip)),
+                             dtype=torch.float32, device=dev)
+            _lib.call("gatk_gemm_heads_dropout_dw", n, f_in, H, Dp, int(has_skip), x.data_ptr(), f_in, dz_rows.data_ptr(), M_out,
+                      dw_ext.data_ptr(), M_out, ws2.data_ptr(), seed, o_in, pk, st)
+            if need_dx:
+                _lib.call("gatk_gemm_heads_dropout_dx", n, f_in, H, Dp, int(has_skip), dz_rows.data_ptr(), M_out,
+                          w_ext.data_ptr(), M_out, dx.data_ptr(), f_in, seed, o_in, pk, st)
+        elif masks.keep_in is None:
             _gemm(1, 0, f_in, M_out, n, x, f_in, dz_rows, M_out, dw_ext, M_out)
             if need_dx:
                 _gemm(0, 1, n, f_in, M_out, dz_rows, M_out, w_ext, M_out, dx, f_in)
@@ -268,7 +310,7 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         w_full = w_full.contiguous()
         st = _stream()
         z = _mem.empty(n, Mz, dtype=torch.float32, device=dev)
-        _gemm(0, 0, n, Mz, f_in, x, f_in, w_full, Mz, z, Mz)
+        _gemm(0, 0, n, Mz, f_in, x, f_in, w_full, Mz, z, Mz, label="gemm:project_folded")
         f_ptr = z.data_ptr() + 4 * M_out
         g_ptr = f_ptr + 4 * H
         need_grad = any(ctx.needs_input_grad[:2])
@@ -281,7 +323,7 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, z.data_ptr(), Mz,
                   f_ptr, Mz, g_ptr, Mz, None, 1.0, float(alpha),
                   z.data_ptr() + 4 * HD if has_skip else None, Mz, int(act_elu), _ptr(hagg), out.data_ptr(), HD,
-                  _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+                  _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), 0, 0, 0.0, st)
         if need_grad:
             ctx.graph = graph
             ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu))
@@ -319,19 +361,19 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, z.data_ptr(), Mz,
                   g_ptr, Mz, rec.data_ptr(), ldrec, None, 1.0, alpha,
                   None, dz_rows.data_ptr(), Mz, dg_ptr, Mz, edge_dz.data_ptr(),
-                  *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), st)
+                  *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), 0, 0, 0.0, st)
         del rec
         hubs = graph.hubs
         scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), None,
-                  None, 1.0, None, 0, df_ptr, Mz, *hubs.args(scratch), st)
+                  None, 1.0, None, 0, df_ptr, Mz, *hubs.args(scratch), 0, 0, 0.0, st)
         del edge_dz
         dw_full = _mem.empty(f_in, Mz, dtype=torch.float32, device=dev)
-        _gemm(1, 0, f_in, Mz, n, x, f_in, dz_rows, Mz, dw_full, Mz)
+        _gemm(1, 0, f_in, Mz, n, x, f_in, dz_rows, Mz, dw_full, Mz, label="gemm:dW_folded")
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _mem.empty(n, f_in, dtype=torch.float32, device=dev)
-            _gemm(0, 1, n, f_in, Mz, dz_rows, Mz, w_full, Mz, dx, f_in)
+            _gemm(0, 1, n, f_in, Mz, dz_rows, Mz, w_full, Mz, dx, f_in, label="gemm:dx_folded")
         return dx, dw_full, None, None, None, None, None, None
 
 
@@ -444,7 +486,7 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
                       dfg.data_ptr() + 4 * H, Muv, thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
         else:
             # dg_j is accumulated by the edge pass itself (vector reductions into the zeroed dg columns of dfg)
-            dfg = torch.zeros(n, Muv, dtype=torch.float32, device=dev)
+            dfg = _mem.zeros(n, Muv, dtype=torch.float32, device=dev)
             _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
                       f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
                       dxagg.data_ptr(), H * Fp, None, None, dfg.data_ptr() + 4 * H, Muv, dfg.data_ptr(), Muv,
@@ -525,7 +567,7 @@ def _gat_layer(x, graph, Ws, a_srcs, a_dsts, skips, alpha, concat, p, training, 
     w_ext, a_src, a_dst, D, Dp = pack_heads(Ws, a_srcs, a_dsts, skips)
     p_eff = float(p) if training else 0.0
     if p_eff > 0.0 and masks is None:
-        masks = random_masks(x.shape[0], x.shape[1], H, Dp, graph.nnz, p_eff, x.device)
+        masks = seeded_masks(x.shape[0], x.shape[1], H, Dp, graph.nnz)   # nothing materialised: decisions live in the kernels
     use_agg_first = (p_eff == 0.0 and FOLD_LOGITS and AGG_FIRST and form in ("auto", "agg_first")
                      and not (x.requires_grad and torch.is_grad_enabled())
                      and (agg_first_geometry(x.shape[1], H, Dp)[1] or form == "agg_first"))

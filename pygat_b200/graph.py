@@ -74,8 +74,11 @@ class HubPartition:
         # edge-balanced work items for the dynamic scheduler of the gather kernels: consecutive rows are
         # grouped until they hold ~ITEM_EDGES stored entries (hub rows are skipped by those kernels)
         n, e = ph.size - 1, int(ph[-1]) if ph.size > 1 else 0
+        # small patterns (Pubmed: 1e5 entries) get finer items, or a 148-SM part would see only a few hundred warps:
+        # aim at ~32 items per SM, between 32 and ITEM_EDGES entries each
+        self.item_edges = int(min(ITEM_EDGES, max(32, e // (148 * 32)))) if e > 0 else ITEM_EDGES
         if n > 0 and e > 0:
-            cuts = np.searchsorted(ph[:-1], np.arange(0, e, ITEM_EDGES, dtype=np.int64), side="left")
+            cuts = np.searchsorted(ph[:-1], np.arange(0, e, self.item_edges, dtype=np.int64), side="left")
             bounds = np.concatenate([cuts, np.array([n], dtype=cuts.dtype)])
             bounds = bounds[np.concatenate([[True], bounds[1:] != bounds[:-1]])]  # unique_consecutive
             if bounds[0] != 0:

@@ -217,7 +217,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         f = _mem.empty(n, H, dtype=torch.float32, device=dev)
         g_full = _mem.empty(N, H, dtype=torch.float32, device=dev)
         _lib.call("gatk_logits_fwd", n, H, Dp, plan.rows(wh_full).data_ptr(), HD, None, 1.0, a_src.data_ptr(),
-                  a_dst.data_ptr(), f.data_ptr(), plan.rows(g_full).data_ptr(), st)
+                  a_dst.data_ptr(), f.data_ptr(), plan.rows(g_full).data_ptr(), 0, 0, 0.0, st)
         gather_rows(g_full, plan)
 
         need_grad = any(ctx.needs_input_grad[:4])
@@ -229,7 +229,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
         _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, wh_full.data_ptr(), HD,
                   f.data_ptr(), H, g_full.data_ptr(), H, None, 1.0, float(alpha), _ptr(skipv), HD, int(act_elu),
-                  _ptr(hagg), out.data_ptr(), HD, _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+                  _ptr(hagg), out.data_ptr(), HD, _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), 0, 0, 0.0, st)
         if need_grad:
             ctx.graph, ctx.plan = graph, plan
             ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu))
@@ -267,7 +267,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, wh_full.data_ptr(), HD,
                   g_full.data_ptr(), H, rec.data_ptr(), ldrec, None, 1.0, alpha,
                   a_dst.data_ptr(), dwh_part.data_ptr(), HD, dg_part.data_ptr(), H, edge_dz.data_ptr(),
-                  *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), st)
+                  *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), 0, 0, 0.0, st)
         del rec
         dg_loc = reduce_rows(dg_part, plan).contiguous()
         # owned rows: df = segmented sum of dz, dWh_i += df_i a_src (added once, on the owner's partial rows)
@@ -276,7 +276,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
         dwh_own = plan.rows(dwh_part)
         _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), a_src.data_ptr(),
-                  None, 1.0, dwh_own.data_ptr(), HD, df.data_ptr(), H, *hubs.args(scratch), st)
+                  None, 1.0, dwh_own.data_ptr(), HD, df.data_ptr(), H, *hubs.args(scratch), 0, 0, 0.0, st)
         del edge_dz
 
         da_src = _mem.empty(H, Dp, dtype=torch.float32, device=dev)
@@ -316,11 +316,13 @@ def gather_rows_async(full: torch.Tensor, plan: ShardPlan):
     return None
 
 
-def head_chunks(H: int) -> int:
-    """Heads per exchange chunk of the hidden-layer form: two chunks by default, so that chunk 1's rows cross NVLink
-    while chunk 0's attention runs (measured at the products shape on 2 GPUs: four chunks of two heads made the
-    attention kernels ~1.5x slower per byte than they won in overlap; GATK_SHARD_CHUNKS overrides the count)."""
-    want = int(os.environ.get("GATK_SHARD_CHUNKS", "2"))
+def head_chunks(H: int, world: int = 8) -> int:
+    """Heads per exchange chunk of the hidden-layer form.  Chunking lets chunk k+1's rows cross NVLink while chunk k's
+    attention runs, but the attention kernels lose efficiency on narrower rows (measured at the products shape on
+    2 GPUs, 8 x 64: one chunk 60.6 ms, two 62.4, four 64.6 per step -- the exposed exchange is only ~14 ms there).  So:
+    one chunk on up to two ranks, two beyond (the exchange grows with the rank count while the compute per rank
+    shrinks); GATK_SHARD_CHUNKS overrides the count."""
+    want = int(os.environ.get("GATK_SHARD_CHUNKS", "1" if world <= 2 else "2"))
     c = max(1, min(want, H))
     while H % c:
         c -= 1
@@ -382,7 +384,7 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
                       z.data_ptr() + 4 * (off_f + c * Hc), Mz, whg[c].data_ptr() + 4 * HDc, Pc, None, 1.0, float(alpha),
                       z.data_ptr() + 4 * (off_s + c * HDc) if has_skip else None, Mz, int(act_elu), _ptr(haggs[c]),
                       out.data_ptr() + 4 * c * HDc, HD, _ptr(lses[c]), *hubs.args(scratch), graph.counter.data_ptr(),
-                      *hubs.item_args(), st)
+                      *hubs.item_args(), 0, 0, 0.0, st)
         if need_grad:
             ctx.graph, ctx.plan = graph, plan
             ctx.cfg = (H, Dp, Hc, has_skip, float(alpha), bool(act_elu), separate_hagg)
@@ -433,14 +435,14 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
             _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), Hc, Dp, whg[c].data_ptr(), Pc,
                       whg[c].data_ptr() + 4 * HDc, Pc, rec.data_ptr(), ldrec, None, 1.0, alpha, None,
                       part.data_ptr(), Pc, part.data_ptr() + 4 * HDc, Pc, edge_dz.data_ptr(),
-                      *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), st)
+                      *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), 0, 0, 0.0, st)
             with _lib.timed("comm:reduce_dwh_issue"):
                 own, work = reduce_rows_async(part, plan)
             owned.append(own)
             works.append(work)
             scratch = _hub_scratch(2, Hc, Dp, hubs.n_seg, dev)
             _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), Hc, Dp, edge_dz.data_ptr(), None, None, 1.0, None, 0,
-                      dz.data_ptr() + 4 * (off_f + c * Hc), Mz, *hubs.args(scratch), st)
+                      dz.data_ptr() + 4 * (off_f + c * Hc), Mz, *hubs.args(scratch), 0, 0, 0.0, st)
             del rec, edge_dz
         for c in range(C):
             if works[c] is not None:
@@ -640,7 +642,7 @@ def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, 
     elif form in ("auto", "exchange_wh") and (x_local.requires_grad and torch.is_grad_enabled() or form == "exchange_wh"):
         # hidden layer: project own rows, exchange [Wh | g] in head chunks (ShardedGatLayerWhFunction)
         f_in = x_local.shape[1]
-        Hc = head_chunks(H)
+        Hc = head_chunks(H, plan.world)
         C = H // Hc
         HDc, gp = Hc * Dp, 4 * ((Hc + 3) // 4)
         w3 = w_ext[:, : H * Dp].reshape(f_in, H, Dp)

@@ -32,6 +32,37 @@ def power_law_csr(n: int, avg_deg: float, seed: int, exponent: float = 0.5, devi
     return rowptr, col
 
 
+def power_law_shard(n_total: int, lo: int, hi: int, avg_deg: float, seed: int, exponent: float = 0.5, device="cpu"):
+    """Destination rows [lo, hi) of a power-law pattern over n_total nodes, generated WITHOUT the rest of the graph
+    (papers100M-shaped shards: the whole pattern -- 1.6 G entries -- never exists on one device): rowptr int64
+    [hi-lo+1] (local), col int32 [E_local] (GLOBAL source ids), row-major sorted, one self-loop per row.
+    Half of the sampled entries take a Zipf(exponent) SOURCE over all n_total nodes and a uniform local row (hub
+    columns: rows that every shard gathers), half a Zipf row inside the shard and a uniform global source (hub
+    rows: the segment path).  Directed: the layer kernels never assume symmetry."""
+    dev = torch.device(device)
+    n = hi - lo
+    g = torch.Generator(device=dev).manual_seed(seed * 1000003 + lo % 999983)
+    m = int(n * max(avg_deg - 1.0, 0.0))
+    h = m // 2
+    u = torch.rand(h, generator=g, dtype=torch.float64, device=dev)
+    src_a = (u.pow(1.0 / (1.0 - exponent)) * n_total).long().clamp_(max=n_total - 1)
+    dst_a = torch.randint(0, n, (h,), generator=g, device=dev)
+    u = torch.rand(m - h, generator=g, dtype=torch.float64, device=dev)
+    dst_b = (u.pow(1.0 / (1.0 - exponent)) * n).long().clamp_(max=n - 1)
+    del u
+    src_b = torch.randint(0, n_total, (m - h,), generator=g, device=dev)
+    loops = torch.arange(n, device=dev)
+    key = torch.cat([dst_a * n_total + src_a, dst_b * n_total + src_b, loops * n_total + (loops + lo)])
+    del src_a, dst_a, src_b, dst_b
+    key = torch.unique(key)
+    row = key // n_total
+    col = (key - row * n_total).to(torch.int32)
+    del key
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    rowptr[1:] = torch.cumsum(torch.bincount(row, minlength=n), 0)
+    return rowptr, col
+
+
 def shard_rows_by_nnz(rowptr: torch.Tensor, world: int, row_cost: int = 0):
     """Contiguous destination-row ranges of ~equal COST, cost(row) = stored entries + row_cost (power-law
     graphs are balanced neither by row count nor, once per-row work matters, by entries alone: at the

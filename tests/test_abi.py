@@ -71,4 +71,4 @@ def test_integration_md_binding_example_matches_the_abi():
             elif isinstance(a.value, float):
                 assert t is ctypes.c_float
             else:
-                assert t in (ctypes.c_int, ctypes.c_int64)
+                assert t in (ctypes.c_int, ctypes.c_int64, ctypes.c_uint64)

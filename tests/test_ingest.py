@@ -132,6 +132,7 @@ def test_hub_partition_host_build_matches_the_definition():
                 it = hp.items.long()
                 assert it[0] == 0 and it[-1] == n and torch.all(it[1:] > it[:-1]) and hp.n_items == it.numel() - 1
                 # every item starts at the first row whose first entry is >= a multiple of ITEM_EDGES
-                starts = torch.searchsorted(ptr[:-1].contiguous(), torch.arange(0, e, G.ITEM_EDGES))
+                assert 32 <= hp.item_edges <= G.ITEM_EDGES
+                starts = torch.searchsorted(ptr[:-1].contiguous(), torch.arange(0, e, hp.item_edges))
                 assert set(it[:-1].tolist()) == (set(starts.tolist()) - {n}) | {0}
             assert hp.n_empty == int((deg == 0).sum())
