@@ -133,6 +133,37 @@ def ppi_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup:
                 "nodes": sum(PPI_TRAIN_GRAPH_NODES)}
 
 
+def ppi_epoch_sync_free_ms(device, rank: int = 0, world: int = 1, epochs: int = 3, warmup: int = 1, seed: int = 72):
+    """The PPI epoch with the caller's side widened but WITHOUT graph capture (works at any rank count): fused BCE +
+    on-device micro-F1 (heads.ppi_batch_step), the sync-free single-collective gradient all-reduce of
+    sharded.allreduce_gradients, one host read per epoch."""
+    from pygat_b200.heads import ppi_batch_step
+    from pygat_b200.sharded import allreduce_gradients, rank_batch_schedule
+    graphs, batches, model = _ppi_setup(device, seed)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0)
+    mine = [batches[i] if i is not None else None for i in rank_batch_schedule(len(batches), rank, world)]
+    tot = torch.zeros((), device=device)
+
+    def epoch():
+        tot.zero_()
+        for item in mine:
+            if item is not None:
+                feats, labels, adj = item
+                loss, _f1 = ppi_batch_step(model, opt, feats, labels, adj,
+                                           allreduce=(lambda ps, n: allreduce_gradients(ps, n)) if world > 1 else None)
+                tot.add_(loss)
+            else:   # this rank idles in the step but still takes part in the collective and the (zero) update
+                opt.zero_grad(set_to_none=True)
+                allreduce_gradients(model.parameters(), 0)
+                opt.step()
+        return tot.item()
+
+    ms = _time_epochs(epoch, epochs, warmup)
+    return ms, {"graphs": len(graphs), "batches_per_rank": sum(m is not None for m in mine), "epochs": epochs,
+                "nodes": sum(PPI_TRAIN_GRAPH_NODES), "host_reads": "1 per epoch"}
+
+
 def ppi_epoch_graphed_ms(device, epochs: int = 5, warmup: int = 1, seed: int = 72):
     """The same epoch with the caller's side widened: fused BCE + on-device micro-F1
     (pygat_b200.heads.ppi_head) instead of the per-batch .cpu().numpy() + sklearn, no per-batch .item(), and every

@@ -282,6 +282,27 @@ class GatLayerFunction(torch.autograd.Function):
         return dx, dw_ext, da_src, da_dst, None, None, None, None, None, None, None, None
 
 
+# Small graphs with wide rows (PPI: ~4.5 k nodes, 4 x 256 / 6 x 128 floats per row) are latency bound in the attention
+# kernels: a warp owns a whole H*Dp row, rows that wide need 8+ float4 accumulators per lane, which limits an SM to four
+# resident warps -- a few hundred warps chasing dependent gathers on a 148-SM part.  Below SMALL_GRAPH_ENTRIES stored
+# entries such layers are run one head group at a time (rows of <= 64 slots: 2 accumulators per lane, 16 resident warps
+# per SM and H/Hc times more work items).  MEASURED (PPI epoch, ncu launch list, 20 steps): once the work items are
+# sized for small patterns (graph.HubPartition.item_edges) the unsplit kernels take 13.9 ms and the split ones 15.3 ms,
+# and at the products scale the split is slower as well (bandwidth bound: narrower gathers lose efficiency) -- so the
+# split is OFF by default (GATK_SMALL_GRAPH_ENTRIES=<entries> turns it on below that many stored entries).
+SMALL_GRAPH_ENTRIES = int(os.environ.get("GATK_SMALL_GRAPH_ENTRIES", "0"))
+
+
+def small_graph_head_chunk(H: int, Dp: int, nnz: int) -> int:
+    """Heads per attention launch (H = no split)."""
+    if nnz >= SMALL_GRAPH_ENTRIES or H * Dp <= 512:
+        return H
+    hc = max(1, 256 // Dp)
+    while H % hc:
+        hc -= 1
+    return hc
+
+
 class GatLayerFoldedFunction(torch.autograd.Function):
     """The layer when no dropout sits between projection and logits (eval, or p == 0 as in train_ppi.py:49
     and the benchmark shapes).  The attention-logit halves are linear in the input,
@@ -293,7 +314,9 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         dx = dZ w_full^T                              dW_full back into dW, da_src, da_dst)
 
     which removes the logits pass, the da reduction over the nodes and the read-modify-write of dWh for
-    the df a_src / dg a_dst terms.  Same math as GatLayerFunction up to fp32 re-association."""
+    the df a_src / dg a_dst terms.  Same math as GatLayerFunction up to fp32 re-association.
+    The attention kernels run on all heads at once, or -- small graphs with wide rows, see
+    small_graph_head_chunk -- on head groups of Hc heads (column blocks of the same buffers)."""
 
     @staticmethod
     def forward(ctx, x, w_full, graph: Graph, H: int, Dp: int, has_skip: bool, alpha: float, act_elu: bool):
@@ -311,22 +334,27 @@ class GatLayerFoldedFunction(torch.autograd.Function):
         st = _stream()
         z = _mem.empty(n, Mz, dtype=torch.float32, device=dev)
         _gemm(0, 0, n, Mz, f_in, x, f_in, w_full, Mz, z, Mz, label="gemm:project_folded")
-        f_ptr = z.data_ptr() + 4 * M_out
-        g_ptr = f_ptr + 4 * H
+        zp = z.data_ptr()
         need_grad = any(ctx.needs_input_grad[:2])
         out = _mem.empty(n, HD, dtype=torch.float32, device=dev)
         separate_hagg = need_grad and (has_skip or act_elu)
-        hagg = _mem.empty(n, HD, dtype=torch.float32, device=dev) if separate_hagg else None
-        lse = _mem.empty(n, H, dtype=torch.float32, device=dev) if need_grad else None
+        Hc = small_graph_head_chunk(H, Dp, graph.nnz)
+        C, HDc = H // Hc, Hc * Dp
+        # per head group: hagg [C, n, Hc*Dp] and lse [C, n, Hc] (C == 1: the plain [n, H*Dp] / [n, H] layouts)
+        hagg = _mem.empty(C, n, HDc, dtype=torch.float32, device=dev) if separate_hagg else None
+        lse = _mem.empty(C, n, Hc, dtype=torch.float32, device=dev) if need_grad else None
         hubs = graph.hubs
-        scratch = _hub_scratch(0, H, Dp, hubs.n_seg, dev)
-        _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Dp, z.data_ptr(), Mz,
-                  f_ptr, Mz, g_ptr, Mz, None, 1.0, float(alpha),
-                  z.data_ptr() + 4 * HD if has_skip else None, Mz, int(act_elu), _ptr(hagg), out.data_ptr(), HD,
-                  _ptr(lse), *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), 0, 0, 0.0, st)
+        scratch = _hub_scratch(0, Hc, Dp, hubs.n_seg, dev)
+        for c in range(C):
+            _lib.call("gatk_attn_fwd", n, graph.rowptr.data_ptr(), _ptr(graph.col), Hc, Dp, zp + 4 * c * HDc, Mz,
+                      zp + 4 * (M_out + c * Hc), Mz, zp + 4 * (M_out + H + c * Hc), Mz, None, 1.0, float(alpha),
+                      zp + 4 * (HD + c * HDc) if has_skip else None, Mz, int(act_elu),
+                      hagg[c].data_ptr() if separate_hagg else None, out.data_ptr() + 4 * c * HDc, HD,
+                      lse[c].data_ptr() if need_grad else None, *hubs.args(scratch), graph.counter.data_ptr(),
+                      *hubs.item_args(), 0, 0, 0.0, st)
         if need_grad:
             ctx.graph = graph
-            ctx.cfg = (H, Dp, has_skip, float(alpha), bool(act_elu))
+            ctx.cfg = (H, Dp, Hc, has_skip, float(alpha), bool(act_elu), separate_hagg)
             ctx.save_for_backward(x, w_full, z, lse, out, hagg if separate_hagg else out)
         return out
 
@@ -334,40 +362,42 @@ class GatLayerFoldedFunction(torch.autograd.Function):
     def backward(ctx, gout):
         x, w_full, z, lse, out, hagg = ctx.saved_tensors
         graph = ctx.graph
-        H, Dp, has_skip, alpha, act_elu = ctx.cfg
+        H, Dp, Hc, has_skip, alpha, act_elu, separate_hagg = ctx.cfg
         dev = x.device
         n, f_in = x.shape
         HD = H * Dp
+        C, HDc = H // Hc, Hc * Dp
         M_out = HD * (2 if has_skip else 1)
         Mz = w_full.shape[1]
         st = _stream()
         gout = gout.contiguous()
         tptr, trow, perm, thubs = graph.transpose()[:4]
-        f_ptr = z.data_ptr() + 4 * M_out
-        g_ptr = f_ptr + 4 * H
+        zp = z.data_ptr()
 
         dz_rows = _mem.empty(n, Mz, dtype=torch.float32, device=dev)   # [dWh | dSkip | df | dg | pad]
         if Mz > M_out + 2 * H:
             dz_rows[:, M_out + 2 * H:].zero_()
-        df_ptr = dz_rows.data_ptr() + 4 * M_out
-        dg_ptr = df_ptr + 4 * H
-        ldrec = _lib.query("gatk_attn_bwd_record_ld", H, Dp)
+        dzp = dz_rows.data_ptr()
+        ldrec = _lib.query("gatk_attn_bwd_record_ld", Hc, Dp)
         rec = _mem.empty(n, ldrec, dtype=torch.float32, device=dev)
-        edge_dz = _mem.empty(graph.nnz, H, dtype=torch.float32, device=dev)
-        _lib.call("gatk_attn_bwd_prep", n, H, Dp, gout.data_ptr(), HD, out.data_ptr() if (act_elu and has_skip) else None, HD,
-                  int(act_elu), hagg.data_ptr(), HD, f_ptr, Mz, lse.data_ptr(), rec.data_ptr(), ldrec,
-                  dz_rows.data_ptr() + 4 * HD if has_skip else None, Mz, st)
-        scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
-        _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, z.data_ptr(), Mz,
-                  g_ptr, Mz, rec.data_ptr(), ldrec, None, 1.0, alpha,
-                  None, dz_rows.data_ptr(), Mz, dg_ptr, Mz, edge_dz.data_ptr(),
-                  *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), 0, 0, 0.0, st)
-        del rec
+        edge_dz = _mem.empty(graph.nnz, Hc, dtype=torch.float32, device=dev)
         hubs = graph.hubs
-        scratch = _hub_scratch(2, H, Dp, hubs.n_seg, dev)
-        _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), H, Dp, edge_dz.data_ptr(), None,
-                  None, 1.0, None, 0, df_ptr, Mz, *hubs.args(scratch), 0, 0, 0.0, st)
-        del edge_dz
+        scratch_t = _hub_scratch(1, Hc, Dp, thubs.n_seg, dev)
+        scratch = _hub_scratch(2, Hc, Dp, hubs.n_seg, dev)
+        for c in range(C):   # stream order lets the head groups share rec / edge_dz / the hub scratch
+            # without a separate hagg (no skip, no ELU) the layer output IS the aggregation
+            hp, ldh = (hagg[c].data_ptr(), HDc) if separate_hagg else (out.data_ptr() + 4 * c * HDc, HD)
+            _lib.call("gatk_attn_bwd_prep", n, Hc, Dp, gout.data_ptr() + 4 * c * HDc, HD,
+                      out.data_ptr() + 4 * c * HDc if (act_elu and has_skip) else None, HD, int(act_elu), hp, ldh,
+                      zp + 4 * (M_out + c * Hc), Mz, lse[c].data_ptr(), rec.data_ptr(), ldrec,
+                      dzp + 4 * (HD + c * HDc) if has_skip else None, Mz, st)
+            _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), Hc, Dp, zp + 4 * c * HDc, Mz,
+                      zp + 4 * (M_out + H + c * Hc), Mz, rec.data_ptr(), ldrec, None, 1.0, alpha,
+                      None, dzp + 4 * c * HDc, Mz, dzp + 4 * (M_out + H + c * Hc), Mz, edge_dz.data_ptr(),
+                      *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), 0, 0, 0.0, st)
+            _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), Hc, Dp, edge_dz.data_ptr(), None,
+                      None, 1.0, None, 0, dzp + 4 * (M_out + c * Hc), Mz, *hubs.args(scratch), 0, 0, 0.0, st)
+        del rec, edge_dz
         dw_full = _mem.empty(f_in, Mz, dtype=torch.float32, device=dev)
         _gemm(1, 0, f_in, Mz, n, x, f_in, dz_rows, Mz, dw_full, Mz, label="gemm:dW_folded")
         dx = None
@@ -532,16 +562,19 @@ def _pad_cols(t: torch.Tensor, Dp: int) -> torch.Tensor:
 def pack_heads(Ws: Sequence[torch.Tensor], a_srcs: Sequence[torch.Tensor], a_dsts: Sequence[torch.Tensor],
                skips: Optional[Sequence[torch.Tensor]]):
     """Per-head parameters (the reference's nn.Parameters, models.py:27) -> packed operands.
-    Plain torch ops on parameter-sized tensors, so autograd splits the packed gradients back."""
+    Plain torch ops on parameter-sized tensors, so autograd splits the packed gradients back; the heads are
+    stacked first and padded once (a handful of launches per layer instead of a pad + copy per head: the PPI
+    step spent a third of its launches here)."""
     D = Ws[0].shape[1]
     Dp = padded_width(D)
-    cols = [_pad_cols(w, Dp) for w in Ws]
+    f_in, H = Ws[0].shape[0], len(Ws)
+    blocks = [torch.stack(list(Ws), dim=1)]                      # [F, H, D]
     if skips is not None:
-        cols += [_pad_cols(s, Dp) for s in skips]
-    w_ext = torch.cat(cols, dim=1) if len(cols) > 1 else cols[0]
-    a_src = torch.stack([_pad_cols(a.reshape(-1), Dp) for a in a_srcs])
-    a_dst = torch.stack([_pad_cols(a.reshape(-1), Dp) for a in a_dsts])
-    return w_ext, a_src, a_dst, D, Dp
+        blocks.append(torch.stack(list(skips), dim=1))
+    w3 = torch.cat(blocks, dim=1) if len(blocks) > 1 else blocks[0]   # [F, (2)H, D]
+    w_ext = _pad_cols(w3, Dp).reshape(f_in, -1)                  # [F, (2)H*Dp]
+    a2 = _pad_cols(torch.stack([a.reshape(-1) for a in list(a_srcs) + list(a_dsts)]), Dp)   # [2H, Dp]
+    return w_ext, a2[:H], a2[H:], D, Dp
 
 
 def gat_layer(x: torch.Tensor, graph: Graph, Ws, a_srcs, a_dsts, skips, alpha: float, concat: bool,

@@ -680,21 +680,26 @@ def allreduce_gradients(params, n_local_nodes: int, group=None):
     if not params:
         return
     dev = params[0].device
-    cnt = torch.tensor([float(n_local_nodes)], device=dev)
-    dist.all_reduce(cnt, group=group)
-    total = float(cnt.item())
-    w = float(n_local_nodes) / total if total > 0 else 0.0
-    flat = torch.cat([(p.grad.reshape(-1) * w) if (p.grad is not None and n_local_nodes > 0)
-                      else torch.zeros(p.numel(), dtype=p.dtype, device=dev) for p in params])
+    # ONE collective and no host synchronisation: every rank contributes n_local * grad and, in the last slot, n_local;
+    # the sum of the first part divided by the summed count is the merged-batch gradient.  (The first version
+    # all-reduced the count separately and read it back with .item(): a device sync per training step, which
+    # serialised the launch-bound PPI step behind the GPU and erased the data-parallel gain.)
+    nl = float(n_local_nodes)
+    pieces = [(p.grad.reshape(-1) if (p.grad is not None and n_local_nodes > 0)
+               else torch.zeros(p.numel(), dtype=p.dtype, device=dev)) for p in params]
+    flat = torch.cat(pieces + [torch.ones(1, dtype=params[0].dtype, device=dev)])
+    flat.mul_(nl)
     dist.all_reduce(flat, group=group)
-    off = 0
+    total = flat[-1].clamp_min(1.0)
+    flat.div_(total)
+    views, off = [], 0
     for p in params:
-        g = flat[off:off + p.numel()].view_as(p)
-        if p.grad is None:
-            p.grad = g.clone()
-        else:
-            p.grad.copy_(g)
+        views.append(flat[off:off + p.numel()].view_as(p))
         off += p.numel()
+    missing = [i for i, p in enumerate(params) if p.grad is None]
+    for i in missing:
+        params[i].grad = torch.empty_like(params[i])
+    torch._foreach_copy_([p.grad for p in params], views)
 
 
 def rank_batch_schedule(n_batches: int, rank: int, world: int):
