@@ -90,7 +90,11 @@ class ShardedLayerBench:
     def _cut(self, rowptr, col, x, gout):
         self.plan = ShardPlan(shard_rows_by_cost(rowptr, self.world, self.row_cost), self.rank)
         self.graph = self.plan.local_graph(rowptr, col)
-        self.graph.transpose()
+        self.graph_t = None
+        if self.needs_dx:   # hidden layer: its backward walks this rank's SOURCE rows (sharded.SourceShard)
+            self.graph_t = self.plan.source_shard(rowptr, col)
+        else:
+            self.graph.transpose()
         self.x = self.plan.rows(x).clone()
         if self.needs_dx:
             self.x.requires_grad_(True)
@@ -116,7 +120,8 @@ class ShardedLayerBench:
         return fit_row_cost(m[:, 0], m[:, 1], m[:, 2])
 
     def _layer(self, x):
-        return sharded_gat_layer(x, self.graph, self.plan, self.Ws, self.a_src, self.a_dst, None, 0.2, concat=True)
+        return sharded_gat_layer(x, self.graph, self.plan, self.Ws, self.a_src, self.a_dst, None, 0.2, concat=True,
+                                 graph_t=self.graph_t)
 
     def step(self):
         for p in self.params:

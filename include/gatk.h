@@ -179,6 +179,10 @@ GATK_API int gatk_attn_fwd(int64_t n_dst, const int64_t* rowptr, const int32_t* 
  *          per edge and uses it for both  dz_ij = alpha_ij (keep/(1-p) dhp_i.Wh_j - c_i)
  *          LeakyReLU'(f_i+g_j)  and  dwh_j = sum_i alpha~_ij dhp_i + dg_j a_dst,  dg_j = sum_i
  *          dz_ij.  dz is written in CSR edge order (edge_dz [E,H]); keep_att is in CSR edge order.
+ *          With df_acc (float [n_dst, lddf_acc], ZERO-INITIALISED) the kernel adds dz_ij straight into df_acc[i, h]
+ *          (red.global.add) instead: edge_dz, perm and gatk_attn_bwd_finish are then not needed.  That is the form a
+ *          SOURCE-row shard uses (tptr / trow cover this rank's sources, rec holds every destination: the entries of
+ *          a destination row are spread over the ranks, their df partials are reduce-scattered by the caller).
  *          hub_* describe the TRANSPOSED pattern's long rows (scratch: which = 1).
  *  finish  per destination row: df_i = sum_j dz_ij (segmented sum over CSR rows), then
  *          dwh_i += df_i a_src and the post-projection dropout mask keep_wh (layers.py:37,136).
@@ -197,7 +201,7 @@ GATK_API int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int32
                                  int H, int Dp, const float* wh, int64_t ldw, const float* g, int64_t ldg,
                                  const float* rec, int64_t ldrec, const uint8_t* keep_att, float inv_keep,
                                  float alpha, const float* a_dst, float* dwh, int64_t lddwh, float* dg,
-                                 int64_t lddg, float* edge_dz,
+                                 int64_t lddg, float* edge_dz, float* df_acc, int64_t lddf_acc,
                                  int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                                  int n_hub_seg, float* hub_scratch, int32_t* counter,
                                  const int32_t* item_ptr, int n_items, uint64_t seed, uint64_t drop_offset,

@@ -53,7 +53,7 @@ PROTOTYPES = {
     "gatk_attn_bwd_prep": (c_int, [c_int64, c_int, c_int, P, c_int64, P, c_int64, c_int, P, c_int64, P, c_int64, P,
                                    P, c_int64, P, c_int64, P]),
     "gatk_attn_bwd_fused": (c_int, [c_int64, P, P, P, c_int, c_int, P, c_int64, P, c_int64, P, c_int64, P, c_float,
-                                    c_float, P, P, c_int64, P, c_int64, P,
+                                    c_float, P, P, c_int64, P, c_int64, P, P, c_int64,
                                     c_int, P, P, c_int, c_int, P, P, P, c_int, c_uint64, c_uint64, c_float, P]),
     "gatk_attn_bwd_finish": (c_int, [c_int64, P, c_int, c_int, P, P, P, c_float, P, c_int64, P, c_int64,
                                      c_int, P, P, c_int, c_int, P, c_uint64, c_uint64, c_float, P]),

@@ -96,6 +96,8 @@ struct BwdFusedArgs {
   float* dg;
   int64_t lddg;      // row pitch of dg (floats)
   float* edge_dz;
+  float* df_acc;     // NULL, or [n_dst, lddf_acc] zero-initialised: df_i += dz_ij accumulated here with red.global.add
+  int64_t lddf_acc;  //       (source-row shards: the entries of a destination row live on several ranks) instead of edge_dz
   int seg_len;
   const int32_t* hub_rows;
   const int32_t* hub_seg_ptr;
@@ -160,7 +162,7 @@ __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, 
     const int cnt = (end - base) < 32 ? (int)(end - base) : 32;
     const bool valid = lane < cnt;
     const int i = valid ? __ldg(a.trow + base + lane) : 0;
-    const int pe = valid ? __ldg(a.perm + base + lane) : 0;
+    const int pe = (valid && a.perm) ? __ldg(a.perm + base + lane) : 0;
     row_s[lane] = i;
     perm_s[lane] = pe;
     // ---- lanes = edges: softmax terms of every head, stored at the positions the slot lanes read
@@ -222,7 +224,10 @@ __device__ __forceinline__ void bwd_fused_segment(const BwdFusedArgs& a, int j, 
     for (int idx = lane; idx < cnt * H; idx += 32) {
       const int tt = idx / H, h = idx - tt * H;
       const int pos = lph < 32 ? (h % lay.G) * NV + h / lay.G : h * q;
-      a.edge_dz[(int64_t)perm_s[tt] * H + h] = dz_s[tt * WS + pos];
+      if (a.df_acc)
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(a.df_acc + (int64_t)row_s[tt] * a.lddf_acc + h), "f"(dz_s[tt * WS + pos]) : "memory");
+      else
+        a.edge_dz[(int64_t)perm_s[tt] * H + h] = dz_s[tt * WS + pos];
     }
     __syncwarp();
   }
@@ -503,7 +508,7 @@ extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int
                                    int Dp, const float* wh, int64_t ldw, const float* g, int64_t ldg, const float* rec,
                                    int64_t ldrec, const uint8_t* keep_att, float inv_keep, float alpha,
                                    const float* a_dst, float* dwh, int64_t lddwh, float* dg, int64_t lddg,
-                                   float* edge_dz,
+                                   float* edge_dz, float* df_acc, int64_t lddf_acc,
                                    int seg_len, const int32_t* hub_rows, const int32_t* hub_seg_ptr, int n_hub,
                                    int n_hub_seg, float* hub_scratch, int32_t* counter, const int32_t* item_ptr,
                                    int n_items, uint64_t seed, uint64_t drop_offset, float p_drop, void* stream) {
@@ -512,8 +517,10 @@ extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int
   if (int rc = check_hub(seg_len, n_hub, n_hub_seg, hub_rows, hub_seg_ptr, hub_scratch)) return rc;
   GATK_REQUIRE(n_src < (1LL << 31), "n_src too large for one shard");
   GATK_REQUIRE(ldw % 4 == 0 && ldrec % 4 == 0 && lddwh % 4 == 0, "leading dims must be multiples of 4 floats");
-  GATK_REQUIRE(tptr && wh && g && rec && dwh && dg && edge_dz && counter, "null pointer argument");
-  GATK_REQUIRE(ldg >= H && lddg >= H, "ldg / lddg must be >= H");
+  GATK_REQUIRE(tptr && wh && g && rec && dwh && dg && (edge_dz || df_acc) && counter, "null pointer argument");
+  GATK_REQUIRE(ldg >= H && lddg >= H && (!df_acc || lddf_acc >= H), "ldg / lddg / lddf_acc must be >= H");
+  GATK_REQUIRE(df_acc || perm, "perm is required when dz goes to edge_dz");
+  GATK_REQUIRE(!(df_acc && keep_att) && !(df_acc && p_drop > 0.f), "df_acc (source-row shards) does not take attention dropout");
   cudaStream_t st = (cudaStream_t)stream;
   BwdFusedArgs a;
   a.n_src = n_src; a.tptr = tptr; a.trow = trow; a.perm = perm; a.H = H; a.Dp = Dp; a.lph = Dp / 4;
@@ -521,7 +528,7 @@ extern "C" int gatk_attn_bwd_fused(int64_t n_src, const int64_t* tptr, const int
   a.wh = wh; a.ldw = ldw; a.g = g; a.ldg = ldg; a.rec = rec; a.ldrec = ldrec; a.keep = keep_att; a.inv_keep = inv_keep;
   a.seed = seed; a.drop_offset = drop_offset; a.p_drop = keep_att ? 0.f : p_drop;
   a.alpha = alpha; a.a_dst = a_dst; a.dwh = dwh; a.lddwh = lddwh; a.dg = dg; a.lddg = lddg;
-  a.edge_dz = edge_dz; a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub;
+  a.edge_dz = edge_dz; a.df_acc = df_acc; a.lddf_acc = lddf_acc; a.seg_len = seg_len; a.hub_rows = hub_rows; a.hub_seg_ptr = hub_seg_ptr; a.n_hub = n_hub;
   a.n_hub_seg = n_hub_seg; a.scratch = hub_scratch; a.counter = counter; a.item_ptr = item_ptr; a.n_items = n_items;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
   NV_DISPATCH(nv, return launch_fused<NV>(a, st));

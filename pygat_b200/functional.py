@@ -226,7 +226,7 @@ class GatLayerFunction(torch.autograd.Function):
         scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, z.data_ptr(), M_out,
                   g.data_ptr(), H, rec.data_ptr(), ldrec, _ptr(masks.keep_att), inv_keep, alpha,
-                  a_dst.data_ptr(), dz_rows.data_ptr(), M_out, dg.data_ptr(), H, edge_dz.data_ptr(),
+                  a_dst.data_ptr(), dz_rows.data_ptr(), M_out, dg.data_ptr(), H, edge_dz.data_ptr(), None, 0,
                   *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), seed, o_att, pk, st)
         del rec
 
@@ -393,7 +393,7 @@ class GatLayerFoldedFunction(torch.autograd.Function):
                       dzp + 4 * (HD + c * HDc) if has_skip else None, Mz, st)
             _lib.call("gatk_attn_bwd_fused", n, tptr.data_ptr(), _ptr(trow), _ptr(perm), Hc, Dp, zp + 4 * c * HDc, Mz,
                       zp + 4 * (M_out + H + c * Hc), Mz, rec.data_ptr(), ldrec, None, 1.0, alpha,
-                      None, dzp + 4 * c * HDc, Mz, dzp + 4 * (M_out + H + c * Hc), Mz, edge_dz.data_ptr(),
+                      None, dzp + 4 * c * HDc, Mz, dzp + 4 * (M_out + H + c * Hc), Mz, edge_dz.data_ptr(), None, 0,
                       *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), 0, 0, 0.0, st)
             _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), Hc, Dp, edge_dz.data_ptr(), None,
                       None, 1.0, None, 0, dzp + 4 * (M_out + c * Hc), Mz, *hubs.args(scratch), 0, 0, 0.0, st)

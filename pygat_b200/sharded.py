@@ -87,6 +87,32 @@ class ShardPlan:
                      n_src=self.n_total, seg_len=seg_len)
 
 
+class SourceShard:
+    """This rank's SOURCE rows of the transposed pattern: tptr int64 [n_local + 1] (local), trow int32 [E_src]
+    (GLOBAL destination ids), work items / hub segments over the source rows.  The backward of a hidden layer walks
+    it (ShardedGatLayerWhFunction): every rank then completes dWh_j / dg_j of ITS OWN sources from the all-gathered
+    destination records, instead of producing partial rows for all N sources (which does not shrink with the rank
+    count) and reduce-scattering them."""
+
+    def __init__(self, tptr: torch.Tensor, trow: torch.Tensor, seg_len: Optional[int] = None):
+        from .graph import DEFAULT_SEG_LEN, HubPartition
+        self.tptr, self.trow = tptr.contiguous(), trow.contiguous()
+        self.n_src = tptr.numel() - 1
+        self.nnz = int(trow.numel())
+        self.hubs = HubPartition(self.tptr, int(seg_len or DEFAULT_SEG_LEN))
+        self.counter = torch.zeros(1, dtype=torch.int32, device=tptr.device)
+
+
+def _plan_source_shard(self, rowptr: torch.Tensor, col: torch.Tensor, seg_len: Optional[int] = None) -> SourceShard:
+    """Source-row shard [lo, hi) of the GLOBAL pattern (setup work, like the CSR build: one transpose of the whole
+    pattern on this device, then a slice)."""
+    tptr_g, trow_g, _perm, _ = Graph(rowptr, col).transpose()
+    e0, e1 = int(tptr_g[self.lo].item()), int(tptr_g[self.hi].item())
+    return SourceShard((tptr_g[self.lo:self.hi + 1] - e0).contiguous(), trow_g[e0:e1].contiguous(), seg_len)
+
+
+ShardPlan.source_shard = _plan_source_shard
+
 MAX_PEERS = 15  # GATK_MAX_PEERS in include/gatk.h
 
 
@@ -266,7 +292,7 @@ class ShardedGatLayerFunction(torch.autograd.Function):
         scratch_t = _hub_scratch(1, H, Dp, thubs.n_seg, dev)
         _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), H, Dp, wh_full.data_ptr(), HD,
                   g_full.data_ptr(), H, rec.data_ptr(), ldrec, None, 1.0, alpha,
-                  a_dst.data_ptr(), dwh_part.data_ptr(), HD, dg_part.data_ptr(), H, edge_dz.data_ptr(),
+                  a_dst.data_ptr(), dwh_part.data_ptr(), HD, dg_part.data_ptr(), H, edge_dz.data_ptr(), None, 0,
                   *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), 0, 0, 0.0, st)
         del rec
         dg_loc = reduce_rows(dg_part, plan).contiguous()
@@ -347,7 +373,7 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_all, graph: Graph, plan: ShardPlan, H: int, Dp: int, Hc: int, has_skip: bool, alpha: float,
-                act_elu: bool):
+                act_elu: bool, graph_t: "Optional[SourceShard]" = None):
         dev = x.device
         n, f_in = x.shape
         assert n == plan.n_local == graph.n_dst and graph.n_src == plan.n_total
@@ -386,7 +412,7 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
                       out.data_ptr() + 4 * c * HDc, HD, _ptr(lses[c]), *hubs.args(scratch), graph.counter.data_ptr(),
                       *hubs.item_args(), 0, 0, 0.0, st)
         if need_grad:
-            ctx.graph, ctx.plan = graph, plan
+            ctx.graph, ctx.plan, ctx.graph_t = graph, plan, graph_t
             ctx.cfg = (H, Dp, Hc, has_skip, float(alpha), bool(act_elu), separate_hagg)
             ctx.save_for_backward(x, w_all, z, out, *whg, *[h for h in haggs if h is not None], *lses)
         return out
@@ -411,44 +437,85 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
         off_f = off_s + (HD if has_skip else 0)
         st = _stream()
         gout = gout.contiguous()
-        tptr, trow, perm, thubs = graph.transpose()
         hubs = graph.hubs
         dz = _mem.empty(n, Mz, dtype=torch.float32, device=dev)   # [dWh_c | dg_c | pad].. | dSkip | df | pad
         if Mz > off_f + H:
             dz[:, off_f + H:].zero_()
         ldrec = _lib.query("gatk_attn_bwd_record_ld", Hc, Dp)
-        owned, works = [], []
-        for c in range(C):
+        gt = ctx.graph_t
+
+        def prep(c, rec_ptr):
             hagg_c = haggs[c] if separate_hagg else None
-            rec = _mem.empty(n, ldrec, dtype=torch.float32, device=dev)
             # without a separate hagg (no skip, no ELU) the layer output IS the aggregation
             _lib.call("gatk_attn_bwd_prep", n, Hc, Dp, gout.data_ptr() + 4 * c * HDc, HD,
                       out.data_ptr() + 4 * c * HDc if (act_elu and has_skip) else None, HD, int(act_elu),
                       hagg_c.data_ptr() if hagg_c is not None else out.data_ptr() + 4 * c * HDc, HDc if hagg_c is not None else HD,
-                      z.data_ptr() + 4 * (off_f + c * Hc), Mz, lses[c].data_ptr(), rec.data_ptr(), ldrec,
+                      z.data_ptr() + 4 * (off_f + c * Hc), Mz, lses[c].data_ptr(), rec_ptr, ldrec,
                       dz.data_ptr() + 4 * (off_s + c * HDc) if has_skip else None, Mz, st)
-            part = _mem.empty(N, Pc, dtype=torch.float32, device=dev)
-            if Pc > HDc + Hc:
-                part[:, HDc + Hc:].zero_()   # pad columns behind dg meet zero weight columns in the products below
-            edge_dz = _mem.empty(graph.nnz, Hc, dtype=torch.float32, device=dev)
-            scratch_t = _hub_scratch(1, Hc, Dp, thubs.n_seg, dev)
-            _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), Hc, Dp, whg[c].data_ptr(), Pc,
-                      whg[c].data_ptr() + 4 * HDc, Pc, rec.data_ptr(), ldrec, None, 1.0, alpha, None,
-                      part.data_ptr(), Pc, part.data_ptr() + 4 * HDc, Pc, edge_dz.data_ptr(),
-                      *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), 0, 0, 0.0, st)
-            with _lib.timed("comm:reduce_dwh_issue"):
-                own, work = reduce_rows_async(part, plan)
-            owned.append(own)
-            works.append(work)
-            scratch = _hub_scratch(2, Hc, Dp, hubs.n_seg, dev)
-            _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), Hc, Dp, edge_dz.data_ptr(), None, None, 1.0, None, 0,
-                      dz.data_ptr() + 4 * (off_f + c * Hc), Mz, *hubs.args(scratch), 0, 0, 0.0, st)
-            del rec, edge_dz
-        for c in range(C):
-            if works[c] is not None:
-                with _lib.timed("comm:reduce_dwh_wait"):
-                    works[c].wait()
-            dz[:, c * Pc:(c + 1) * Pc].copy_(owned[c])
+
+        if gt is not None:
+            # ---- source-row shards: all-gather the destination records [dh' | f, lse, c], then every rank COMPLETES
+            # dWh_j / dg_j of its own sources (work and traffic shrink with the rank count); the per-destination
+            # df partials are accumulated with reds and reduce-scattered ([N, Hc] floats: small)
+            recs, works = [], []
+            for c in range(C):
+                rec_full = _mem.empty(N, ldrec, dtype=torch.float32, device=dev)
+                prep(c, rec_full.data_ptr() + 4 * plan.lo * ldrec)
+                with _lib.timed("comm:allgather_rec_issue"):
+                    works.append(gather_rows_async(rec_full, plan))
+                recs.append(rec_full)
+            df_owned, df_works = [], []
+            for c in range(C):
+                if works[c] is not None:
+                    with _lib.timed("comm:allgather_rec_wait"):
+                        works[c].wait()
+                if Pc > HDc + Hc:
+                    dz[:, c * Pc + HDc + Hc:(c + 1) * Pc].zero_()
+                df_part = torch.zeros(N, Hc, dtype=torch.float32, device=dev)
+                scratch_t = _hub_scratch(1, Hc, Dp, gt.hubs.n_seg, dev)
+                own_whg = whg[c].data_ptr() + 4 * plan.lo * Pc
+                _lib.call("gatk_attn_bwd_fused", n, gt.tptr.data_ptr(), _ptr(gt.trow), None, Hc, Dp, own_whg, Pc,
+                          own_whg + 4 * HDc, Pc, recs[c].data_ptr(), ldrec, None, 1.0, alpha, None,
+                          dz.data_ptr() + 4 * c * Pc, Mz, dz.data_ptr() + 4 * (c * Pc + HDc), Mz, None, df_part.data_ptr(), Hc,
+                          *gt.hubs.args(scratch_t), gt.counter.data_ptr(), *gt.hubs.item_args(), 0, 0, 0.0, st)
+                with _lib.timed("comm:reduce_df_issue"):
+                    own, work = reduce_rows_async(df_part, plan)
+                df_owned.append(own)
+                df_works.append(work)
+            for c in range(C):
+                if df_works[c] is not None:
+                    with _lib.timed("comm:reduce_df_wait"):
+                        df_works[c].wait()
+                dz[:, off_f + c * Hc:off_f + (c + 1) * Hc].copy_(df_owned[c])
+            del recs
+        else:
+            tptr, trow, perm, thubs = graph.transpose()
+            owned, works = [], []
+            for c in range(C):
+                rec = _mem.empty(n, ldrec, dtype=torch.float32, device=dev)
+                prep(c, rec.data_ptr())
+                part = _mem.empty(N, Pc, dtype=torch.float32, device=dev)
+                if Pc > HDc + Hc:
+                    part[:, HDc + Hc:].zero_()   # pad columns behind dg meet zero weight columns in the products below
+                edge_dz = _mem.empty(graph.nnz, Hc, dtype=torch.float32, device=dev)
+                scratch_t = _hub_scratch(1, Hc, Dp, thubs.n_seg, dev)
+                _lib.call("gatk_attn_bwd_fused", N, tptr.data_ptr(), _ptr(trow), _ptr(perm), Hc, Dp, whg[c].data_ptr(), Pc,
+                          whg[c].data_ptr() + 4 * HDc, Pc, rec.data_ptr(), ldrec, None, 1.0, alpha, None,
+                          part.data_ptr(), Pc, part.data_ptr() + 4 * HDc, Pc, edge_dz.data_ptr(), None, 0,
+                          *thubs.args(scratch_t), graph.counter.data_ptr(), *thubs.item_args(), 0, 0, 0.0, st)
+                with _lib.timed("comm:reduce_dwh_issue"):
+                    own, work = reduce_rows_async(part, plan)
+                owned.append(own)
+                works.append(work)
+                scratch = _hub_scratch(2, Hc, Dp, hubs.n_seg, dev)
+                _lib.call("gatk_attn_bwd_finish", n, graph.rowptr.data_ptr(), Hc, Dp, edge_dz.data_ptr(), None, None, 1.0, None, 0,
+                          dz.data_ptr() + 4 * (off_f + c * Hc), Mz, *hubs.args(scratch), 0, 0, 0.0, st)
+                del rec, edge_dz
+            for c in range(C):
+                if works[c] is not None:
+                    with _lib.timed("comm:reduce_dwh_wait"):
+                        works[c].wait()
+                dz[:, c * Pc:(c + 1) * Pc].copy_(owned[c])
         # own-row products (one each, as on a single GPU)
         dw_all = _mem.empty(f_in, Mz, dtype=torch.float32, device=dev)
         _gemm(1, 0, f_in, Mz, n, x, f_in, dz, Mz, dw_all, Mz, label="gemm:dW_own")
@@ -459,7 +526,7 @@ class ShardedGatLayerWhFunction(torch.autograd.Function):
         if plan.world > 1:
             with _lib.timed("comm:allreduce_dw"):
                 allreduce_([dw_all], plan)
-        return dx, dw_all, None, None, None, None, None, None, None, None
+        return dx, dw_all, None, None, None, None, None, None, None, None, None
 
 
 class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
@@ -621,7 +688,8 @@ class ShardedGatLayerAggFirstFunction(torch.autograd.Function):
 
 
 def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, a_srcs, a_dsts, skips, alpha: float,
-                      concat: bool, combine: str = "cat", form: str = "auto", cache_input_gather: bool = True) -> torch.Tensor:
+                      concat: bool, combine: str = "cat", form: str = "auto", cache_input_gather: bool = True,
+                      graph_t: "Optional[SourceShard]" = None) -> torch.Tensor:
     """All heads of one GAT layer on this rank's destination rows (see functional.gat_layer).
     cache_input_gather: keep the all-gathered input rows of the aggregate-first form while the input tensor is
     unchanged (same storage, same version counter): a first layer's features are static across steps."""
@@ -659,7 +727,7 @@ def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, 
         if (-H) % 4:
             blocks.append(w_ext.new_zeros(f_in, (-H) % 4))
         rows = ShardedGatLayerWhFunction.apply(x_local, torch.cat(blocks, dim=1), graph, plan, H, Dp, Hc, skips is not None,
-                                               float(alpha), bool(concat))
+                                               float(alpha), bool(concat), graph_t)
     else:
         rows = ShardedGatLayerFunction.apply(x_local, w_ext, a_src, a_dst, graph, plan, H, Dp, skips is not None,
                                              float(alpha), bool(concat))

@@ -119,21 +119,26 @@ def run_nccl(rank, world):
             p.grad = None
         plan = ShardPlan.by_nnz(rowptr, rank, world)
         graph = plan.local_graph(rowptr, col, seg_len=256)
-        xl = plan.rows(x).clone().requires_grad_(True)
-        y = sharded_gat_layer(xl, graph, plan, Ws, a_s, a_d, Ss, 0.2, concat)
-        y.backward(plan.rows(gout))
 
         def rel(a, b):
             return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
-        assert rel(y, plan.rows(y_ref)) < 1e-5, rel(y, plan.rows(y_ref))
-        assert rel(xl.grad, plan.rows(ref["dx"])) < 1e-5
-        for got, want in zip([w.grad for w in Ws], ref["dW"]):
-            assert rel(got, want) < 1e-5, rel(got, want)
-        for got, want in zip([a.grad for a in a_s + a_d], ref["da"]):
-            assert rel(got, want) < 1e-5, rel(got, want)
-        if skip:
-            for got, want in zip([s.grad for s in Ss], ref["dS"]):
-                assert rel(got, want) < 1e-5
+        # hidden layer (input needs a gradient): [Wh | g] exchanged forward; backward either by reduce-scattering the
+        # partial dWh rows (gt None) or on this rank's SOURCE rows from all-gathered destination records
+        for gt in (None, plan.source_shard(rowptr, col, seg_len=256)):
+            for p in Ws + a_s + a_d + (Ss or []):
+                p.grad = None
+            xl = plan.rows(x).clone().requires_grad_(True)
+            y = sharded_gat_layer(xl, graph, plan, Ws, a_s, a_d, Ss, 0.2, concat, graph_t=gt)
+            y.backward(plan.rows(gout))
+            assert rel(y, plan.rows(y_ref)) < 1e-5, rel(y, plan.rows(y_ref))
+            assert rel(xl.grad, plan.rows(ref["dx"])) < 1e-5
+            for got, want in zip([w.grad for w in Ws], ref["dW"]):
+                assert rel(got, want) < 1e-5, rel(got, want)
+            for got, want in zip([a.grad for a in a_s + a_d], ref["da"]):
+                assert rel(got, want) < 1e-5, rel(got, want)
+            if skip:
+                for got, want in zip([s.grad for s in Ss], ref["dS"]):
+                    assert rel(got, want) < 1e-5
         # first-layer case: the input needs no gradient, so no dWh rows are exchanged at all
         for p in Ws + a_s + a_d + (Ss or []):
             p.grad = None

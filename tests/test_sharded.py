@@ -73,9 +73,10 @@ def test_sharded_layer_world1_equals_single_gpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("source_shard", [False, True])
 @pytest.mark.parametrize("H,D,f_in,skip,concat", [(8, 64, 96, False, True), (6, 121, 64, True, False), (4, 32, 128, True, True),
                                                   (1, 16, 40, False, True), (3, 8, 20, False, False)])
-def test_sharded_hidden_layer_world1_equals_single_gpu(H, D, f_in, skip, concat):
+def test_sharded_hidden_layer_world1_equals_single_gpu(H, D, f_in, skip, concat, source_shard):
     """The hidden-layer form (own-row projection, [Wh | g] exchanged in head chunks, ShardedGatLayerWhFunction) on a
     one-rank plan against functional.gat_layer: outputs, input gradient and every parameter gradient."""
     from pygat_b200.functional import gat_layer
@@ -99,7 +100,9 @@ def test_sharded_hidden_layer_world1_equals_single_gpu(H, D, f_in, skip, concat)
         p.grad = None
     plan = ShardPlan([0, n], 0)
     x1 = x.clone().requires_grad_(True)
-    y1 = sharded_gat_layer(x1, plan.local_graph(rowptr, col, seg_len=128), plan, Ws, a_s, a_d, Ss, 0.2, concat)
+    # source_shard: the backward walks the rank's SOURCE rows (all-gathered destination records, df through reds)
+    gt = plan.source_shard(rowptr, col, seg_len=128) if source_shard else None
+    y1 = sharded_gat_layer(x1, plan.local_graph(rowptr, col, seg_len=128), plan, Ws, a_s, a_d, Ss, 0.2, concat, graph_t=gt)
     y1.backward(gout)
     rel = lambda a, b: (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
     assert rel(y1, y0) < 3e-6
