@@ -1461,6 +1461,10 @@ extern "C" int gatk_attn_x_bwd(int64_t n_src, int64_t n_dst, const int64_t* rowp
   if (a.dg_vec4 && !dg_plain) a.dg_vec4 = 2;
   cudaStream_t st = (cudaStream_t)stream;
   GATK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
+  // (A stream access-policy window that pins the dg accumulation array in the persisting part of L2 was measured: the
+  // edge pass itself went 10.6 -> 8.8 ms, but the device-wide set-aside it needs took the L2 away from every other
+  // kernel of the step -- 27.9 -> 38.5 ms per step -- so it is not used; an evict_first hint on the streamed row-state
+  // copies changed nothing measurable either.  What remains is the evict_last hint on the reductions themselves.)
   static const bool simt_only = getenv("GATK_XBWD_SIMT") != nullptr;
   if (Fp <= 128 && !simt_only) return launch_x_bwd_mma(a, st);
   HP_DISPATCH(hp, return (launch_x_bwd<HP>(a, st)));

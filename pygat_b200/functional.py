@@ -515,12 +515,15 @@ class GatLayerAggFirstFunction(torch.autograd.Function):
             _lib.call("gatk_edge_tsum", graph.n_src, tptr.data_ptr(), _ptr(perm), H, ds.data_ptr(),
                       dfg.data_ptr() + 4 * H, Muv, thubs.seg_len, _ptr(thubs.rows), thubs.n_hub, st)
         else:
-            # dg_j is accumulated by the edge pass itself (vector reductions into the zeroed dg columns of dfg)
+            # dg_j is accumulated by the edge pass itself: vector reductions into a COMPACT zeroed [N, H] array (half the
+            # footprint of the [df | dg] rows, so it fits the persisting L2 window the kernel sets up), merged afterwards
             dfg = _mem.zeros(n, Muv, dtype=torch.float32, device=dev)
+            dg = torch.zeros(graph.n_src, H, dtype=torch.float32, device=dev)
             _lib.call("gatk_attn_x_bwd", graph.n_src, n, graph.rowptr.data_ptr(), _ptr(graph.col), H, Fp, xg.data_ptr(), P,
                       f.data_ptr(), H, lse.data_ptr(), alpha, xagg.data_ptr(), H * Fp,
-                      dxagg.data_ptr(), H * Fp, None, None, dfg.data_ptr() + 4 * H, Muv, dfg.data_ptr(), Muv,
+                      dxagg.data_ptr(), H * Fp, None, None, dg.data_ptr(), H, dfg.data_ptr(), Muv,
                       *hubs.args(scratch), graph.counter.data_ptr(), *hubs.item_args(), st)
+            dfg[:, H:2 * H] = dg
         dw_uv = _mem.empty(f_in, Muv, dtype=torch.float32, device=dev)
         _gemm_batched(1, 0, f_in, Muv, n, 1, xg, P, 0, dfg, Muv, 0, dw_uv, Muv, 0, label="gemm:dlogits")  # one "head": the TMEM-A TN kernel
         return None, dw_ext, dw_uv, None, None, None, None, None, None
