@@ -233,3 +233,67 @@ def pubmed_epoch_sync_free_ms(device, epochs: int = 20, warmup: int = 3, seed: i
 
     ms = _time_epochs(epoch, epochs, warmup)
     return ms, {"nodes": n, "stored_entries": int(col.numel()), "epochs": epochs, "host_reads": "1 per 10 epochs"}
+
+
+def products_model_epoch_ms(device, rank: int = 0, world: int = 1, epochs: int = 5, warmup: int = 2, seed: int = 72):
+    """BASELINE.json metric (ii) at the products shape: one full-batch training epoch of a 2-layer models.GAT
+    (100 -> 8 x 64 -> 47 classes, ogbn-products' widths; SpGraphAttentionLayer, p = 0) = forward of both layers,
+    the fused loss head of train.py:151-160 on an 8 % training split, backward, Adam -- on one GPU through the
+    drop-in modules, on N GPUs through sharded.sharded_gat_forward (layer 1 aggregate-first with the kept input
+    rows, layer 2 hidden-layer form with the source-shard backward; every rank's loss term is weighted by its share of
+    the training nodes, the layers' backward all-reduces the parameter gradients)."""
+    import torch.distributed as dist
+
+    import layers
+    import models
+    from pygat_b200.graph import Graph
+    from pygat_b200.heads import citation_head
+    from pygat_b200.sharded import ShardPlan, shard_rows_by_cost, sharded_gat_forward
+    from pygat_b200.synth import power_law_csr
+    n, f_in, classes = 2_449_029, 100, 47
+    rowptr, col = power_law_csr(n, 25.26, seed=seed, exponent=0.5, device=device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn(n, f_in, generator=g, device=device)
+    labels = torch.randint(0, classes, (n,), generator=g, device=device)
+    is_train = torch.rand(n, generator=g, device=device) < 0.08
+    torch.manual_seed(seed)
+    model = models.GAT(nfeat=[f_in, 64, classes], nheads=[8, 1], nlayers=2, dropout=0.0, alpha=0.2,
+                       layer_type=layers.SpGraphAttentionLayer, skip_connection=False).to(device).train()
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0.0)
+    n_train = int(is_train.sum().item())
+    if world > 1:
+        plan = ShardPlan(shard_rows_by_cost(rowptr, world, 30.0), rank)
+        graph = plan.local_graph(rowptr, col)
+        graph_t = plan.source_shard(rowptr, col)
+        x_loc = plan.rows(x).clone()
+        lab_loc = plan.rows(labels).clone()
+        idx = torch.nonzero(plan.rows(is_train)).flatten()
+        del x, labels
+        weight = idx.numel() / max(n_train, 1)
+
+        def epoch():
+            opt.zero_grad(set_to_none=True)
+            out = sharded_gat_forward(model, x_loc, graph, plan, graph_t)
+            loss, _acc = citation_head(out, lab_loc, idx)
+            (loss * weight).backward()
+            opt.step()
+            return None
+    else:
+        graph = Graph.from_csr(rowptr, col)
+        graph.transpose()
+        idx = torch.nonzero(is_train).flatten()
+
+        def epoch():
+            opt.zero_grad(set_to_none=True)
+            out = model(x, graph)
+            loss, _acc = citation_head(out, labels, idx)
+            loss.backward()
+            opt.step()
+            return None
+    del rowptr, col
+    torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+    ms = _time_epochs(epoch, epochs, warmup)
+    return ms, {"nodes": n, "stored_entries": 61_861_615, "layers": "100 -> 8x64 -> 47 (mean of 1 head)", "train_nodes": n_train,
+                "epochs": epochs, "n_gpus": world}

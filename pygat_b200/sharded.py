@@ -736,6 +736,30 @@ def sharded_gat_layer(x_local: torch.Tensor, graph: Graph, plan: ShardPlan, Ws, 
     return HeadCombineFunction.apply(rows, H, D, Dp, 1 if combine == "mean" else 0)
 
 
+def sharded_gat_forward(model, x_local: torch.Tensor, graph: Graph, plan: ShardPlan,
+                        graph_t: "Optional[SourceShard]" = None) -> torch.Tensor:
+    """models.GAT.forward (models.py:29-35) on a destination-row shard: every layer runs through
+    sharded_gat_layer -- the first one in the aggregate-first form when its input is narrow and needs no gradient,
+    the following ones in the hidden-layer form (own-row projection, [Wh | g] exchange, source-shard backward when
+    graph_t is given); heads are concatenated, the last layer averaged.  The parameter gradients every layer's
+    backward leaves are already summed over the ranks.  Dropout must be inactive (the sharded kernels train the
+    large shapes, which use p = 0)."""
+    from .layers import _EngineHead
+    last = len(model.gat_layers) - 1
+    x = x_local
+    for i, heads in enumerate(model.gat_layers):
+        h0 = heads[0]
+        if not all(isinstance(h, _EngineHead) for h in heads):
+            raise RuntimeError("sharded_gat_forward: only GraphAttentionLayer / SpGraphAttentionLayer heads are sharded")
+        if h0.training and h0.dropout > 0.0:
+            raise RuntimeError("sharded_gat_forward: dropout is active; the sharded layers have no dropout path")
+        vecs = [h.attention_vectors() for h in heads]
+        skips = [h.skip_projection for h in heads] if h0.skip_connection else None
+        x = sharded_gat_layer(x, graph, plan, [h.W for h in heads], [v[0] for v in vecs], [v[1] for v in vecs], skips,
+                              h0.alpha, h0.concat, combine="mean" if i == last else "cat", graph_t=graph_t)
+    return x
+
+
 # ---------------------------------------------------------------------- graph-level data parallelism (PPI)
 def allreduce_gradients(params, n_local_nodes: int, group=None):
     """Make per-rank mean-loss gradients equal the gradient of the mean over ALL ranks' nodes: the
