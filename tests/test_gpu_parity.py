@@ -92,7 +92,8 @@ def test_gemm_matches_fp64(ta, tb, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K,pad", [(4096, 512, 100, 0), (5000, 136, 76, 4), (2449, 1024, 512, 0),
-                                       (100_000, 512, 128, 0), (1500, 64, 500, 0), (1025, 8, 4, 0)])
+                                       (100_000, 512, 128, 0), (1500, 64, 500, 0), (1025, 8, 4, 0),
+                                       (5000, 528, 512, 0), (3000, 100, 544, 4), (2048, 576, 576, 0)])
 def test_tensor_core_gemm_is_fp32_accurate(M, N, K, pad):
     """tcgen05 kind::tf32 with the hi/lo split (3 MMAs per product) against an fp64 product."""
     assert _lib.query("gatk_gemm_uses_tensor_cores", 0, 0, M, N, K, K, N + pad, 0) == 1
@@ -115,7 +116,8 @@ def test_tensor_core_gemm_is_fp32_accurate(M, N, K, pad):
 
 
 @pytest.mark.parametrize("tb,M,N,K,ldc_pad,acc", [(0, 4500, 2048, 1024, 0, 0), (1, 4500, 1024, 2048, 0, 0),
-                                                  (1, 3000, 100, 1536, 3, 1), (0, 2449, 1024, 1024, 1, 1)])
+                                                  (1, 3000, 100, 1536, 3, 1), (0, 2449, 1024, 1024, 1, 1),
+                                                  (1, 5000, 512, 528, 0, 0), (1, 3000, 200, 300, 4, 0)])
 def test_tensor_core_long_k_projection(tb, M, N, K, ldc_pad, acc):
     """PPI-sized products (K up to 2048, dx = dZ W^T with the weights already K-major): the promoted
     tcgen05 kernel drains its TMEM accumulators every 16 k-blocks, so accuracy does not degrade with K."""
