@@ -110,7 +110,78 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------ clocks
+class NvmlClockSampler:
+    """SM clock, power and clock-event reasons read through NVML on a thread, every ~2 ms, so that even the
+    ~40 ms timed region of an 8-GPU run holds samples taken under load (`nvidia-smi -lms` needs ~0.5 s to
+    deliver its first line).  Raises from __init__ when NVML is not usable; ClockSampler then takes over."""
+    PERIOD_S = 0.002
+
+    def __init__(self, dev):
+        import pynvml
+        import torch
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        handle = None
+        uuid = getattr(torch.cuda.get_device_properties(dev), "uuid", None)
+        if uuid is not None:
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except pynvml.NVMLError:
+                handle = None
+        if handle is None:   # no uuid on this torch: the visible-device list, then the plain index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip()]
+            idx = int(ids[dev.index]) if ids and all(v.strip().isdigit() for v in ids) else dev.index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.handle = handle
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        self.rows = []
+        self.stop_flag = False
+        self.thread = None
+
+    def _read(self):
+        nv = self.nv
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except (nv.NVMLError, AttributeError):
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)),
+                          nv.nvmlDeviceGetPowerUsage(self.handle) / 1e3, int(mask)))
+
+    def _loop(self):
+        while not self.stop_flag:
+            self._read()
+            time.sleep(self.PERIOD_S)
+
+    def start(self):
+        import threading
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def sample_now(self):
+        """One read from the calling thread (the benchmark takes it with the last step still in flight)."""
+        self._read()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        rows = self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "source": "nvml"}
+        reasons = sorted(nm for nm, bit in names.items() if any(r[2] & bit for r in rows))
+        return {"sm_mhz": statistics.median(r[0] for r in rows), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(r[1] for r in rows), "source": "nvml"}
+
+
 class ClockSampler:
+    """`nvidia-smi -lms 100` beside the timed region (the profiling recipe's clocks line); used when NVML cannot
+    be loaded in-process."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -127,6 +198,9 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def sample_now(self):
+        pass
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -139,12 +213,20 @@ class ClockSampler:
         rows = [r.split(",") for r in open(self.tmp.name).read().strip().splitlines() if r.count(",") >= 8]
         os.unlink(self.tmp.name)
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "source": "nvidia-smi"}
         sm = [float(r[1]) for r in rows]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({nm for r in rows for nm, v in zip(names, r[5:9]) if "Active" in v and "Not" not in v})
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
-                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows), "source": "nvidia-smi"}
+
+
+def make_clock_sampler(dev):
+    try:
+        return NvmlClockSampler(dev)
+    except Exception as exc:   # NVML missing or refusing: fall back to the nvidia-smi loop
+        sys.stderr.write(f"[bench] NVML clock sampling unavailable ({type(exc).__name__}: {exc}); using nvidia-smi -lms\n")
+        return ClockSampler(dev.index)
 
 
 # ------------------------------------------------------------------------------ reference / CPU arm
@@ -259,18 +341,20 @@ def time_layer(runner, steps, warmup, rank, world, dev, sample_clocks=False):
     for _ in range(max(warmup, 3)):
         runner.step()
     barrier()
-    clocks = ClockSampler(dev.index) if (sample_clocks and rank == 0) else None
-    if clocks:
-        clocks.start()
+    clocks = make_clock_sampler(dev) if (sample_clocks and rank == 0) else None
     _lib.timer = _lib.KernelTimer()
     calls0 = _lib.call_count
     launches0 = _lib.query("gatk_launch_count")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if clocks:
+        clocks.start()
     ev0.record()
     for _ in range(steps):
         runner.step()
     ev1.record()
+    if clocks:
+        clocks.sample_now()   # the host runs ahead of the device: the last steps are still executing
     barrier()
     ms = ev0.elapsed_time(ev1) / steps
     kern = _lib.timer.summary()
@@ -365,6 +449,11 @@ def run_ours(args):
                           "layer_frac": round(hab["layer_project_first"] / world / (hres["ms"] * 1e-3) / 1e9 / peak, 4),
                           "layer_algorithmic_GB": round(hab["layer_project_first"] / 1e9, 2),
                           "kernels": hk, "other_ms_per_step": hother, "per_rank_ms_per_step": hres["per_rank"]}
+                if world > 1:
+                    hidden["note"] = ("per-kernel bytes are the single-GPU model / N: every gathered row is counted as "
+                                      "moved, so a shard whose hub rows stay in L2 can read above 1.0, and the source-"
+                                      "shard backward's prep kernel writes only the destination records (its model does "
+                                      "not apply); ms_per_step and layer_frac are the figures to read at N > 1")
             del hrun
             torch.cuda.empty_cache()
         except Exception as exc:

@@ -116,9 +116,19 @@ class Graph:
         self.device = rowptr.device
         self.seg_len = int(seg_len or DEFAULT_SEG_LEN)
         self.hubs = HubPartition(self.rowptr, self.seg_len, rowptr_host)
-        self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._counters = {}   # one scheduler counter per (graph, stream): see `counter`
         self._t: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, HubPartition]] = None
         self._iperm: Optional[torch.Tensor] = None
+
+    @property
+    def counter(self) -> torch.Tensor:
+        """int32 scratch word of the dynamic row scheduler.  One per CUDA stream that uses this graph: a kernel zeroes
+        and consumes it in stream order, so two streams working on the same pattern must not share it."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        c = self._counters.get(key)
+        if c is None:
+            c = self._counters[key] = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return c
 
     # ------------------------------------------------------------------ constructors
     @staticmethod
