@@ -537,7 +537,8 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (Wh alone is %.1f GB)" % (n * H * D * 4 / 1e9)},
         "e2e": {"value": e_total * H / (e2e_ms * 1e-3), "unit": "head-edges/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "input_pipeline": "pinned host -> device copy of step k+1 overlaps step k (double buffered)",
+                "input_pipeline": "pinned host -> device copy of step k+1 overlaps step k (double buffered), timed in steady "
+                                  "state: `steps` copies and `steps` steps inside the region, which ends when the last copy has landed",
                 "result": "D2H = every parameter gradient + an output checksum; the layer output (%.1f GB) stays on the "
                           "device as the next layer's input" % (n * H * D * 4 / 1e9)},
         "gpu_launches": res["launches"], "abi_calls": res["calls"], "clocks": res["clocks"], "roofline": roofline,

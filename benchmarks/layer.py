@@ -208,7 +208,10 @@ def pipelined_e2e(runner, steps, barrier=None):
     pinned host memory (double buffered on a copy stream, so step k+1's copy overlaps step k's compute,
     as a training input pipeline would) and reads the step's results (all parameter gradients + an
     output checksum; the layer output itself stays on the device for the next layer) back to pinned host
-    memory.  Returns (ms per step, H2D bytes, D2H bytes)."""
+    memory.  The pipeline is timed in steady state: the input of the first timed step was copied while the
+    last warm-up step ran, every timed step issues the copy for the step after it (the last one included) and
+    the region ends only when that copy has landed -- `steps` copies and `steps` steps inside the region.
+    Returns (ms per step, H2D bytes, D2H bytes)."""
     dev = runner.x.device
     if runner.x_host is None:
         runner.x_host = runner.x.detach().cpu().pin_memory()
@@ -221,6 +224,8 @@ def pipelined_e2e(runner, steps, barrier=None):
             b.requires_grad_(True)
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
+    main = torch.cuda.current_stream()
+    done = [0]
 
     def issue_copy(k):
         b = k & 1
@@ -230,15 +235,11 @@ def pipelined_e2e(runner, steps, barrier=None):
             ready[b].record(copy_stream)
 
     def run(n_steps):
-        main = torch.cuda.current_stream()
-        for b in (0, 1):
-            freed[b].record(main)
-        issue_copy(0)
-        for k in range(n_steps):
+        for _ in range(n_steps):
+            k = done[0]
             b = k & 1
             main.wait_event(ready[b])
-            if k + 1 < n_steps:
-                issue_copy(k + 1)
+            issue_copy(k + 1)
             for p in runner.params:
                 p.grad = None
             bufs[b].grad = None
@@ -248,8 +249,13 @@ def pipelined_e2e(runner, steps, barrier=None):
             flat = torch.cat([p.grad.reshape(-1) for p in runner.params] +
                              [y.detach()[:: max(1, y.shape[0] // 1024)].sum().reshape(1)])
             host_out.copy_(flat, non_blocking=True)
+            done[0] = k + 1
+        main.wait_event(ready[done[0] & 1])  # the copy the last step issued
 
-    run(1)
+    for b in (0, 1):
+        freed[b].record(main)
+    issue_copy(0)
+    run(2)
     if barrier is not None:
         barrier()
     torch.cuda.synchronize()
