@@ -59,7 +59,7 @@ WORKLOADS = {
 CPU_SAMPLE_NODES = int(os.environ.get("BENCH_CPU_SAMPLE_NODES", "16384"))
 
 
-def algorithmic_bytes(n, e, H, D, f_in, need_dx=False):
+def algorithmic_bytes(n, e, H, D, f_in, need_dx=False, n_long=None):
     """Bytes each kernel's algorithm must move (no-reuse gather model: every stored entry moves its
     neighbour row once per pass; fp32, 4-byte col ids, 8-byte rowptr).
 
@@ -81,7 +81,10 @@ def algorithmic_bytes(n, e, H, D, f_in, need_dx=False):
     HD = H * D
     pack = n * (4 * f_in + 4 * P + 4 * H)                                        # x read; xg, f written
     x_fwd = e * (4 * P + 4) + n * (4 * H * Fp + 8 * H + 8)                       # xg_j, col; xagg write, f, lse
-    x_bwd = e * (4 * P + 4 + 4 * H) + n * (8 * H * Fp + 12 * H + 8)              # xg_j, col, ds write; xagg, dxagg, f, lse, df
+    # xg_j, col, ds write; dxagg, f, lse, df per row; xagg_i only for rows of more than 32 stored entries (n_long: the
+    # others take c_i = sum_j alpha_ij dalpha_ij from their own entries, csrc/attn_x.cu; None = every row, the R1/R2a kernel)
+    n_xagg = n if n_long is None else n_long
+    x_bwd = e * (4 * P + 4 + 4 * H) + n * (4 * H * Fp + 12 * H + 8) + n_xagg * 4 * H * Fp
     tsum = e * (4 * H + 4) + n * (4 * H + 8)                                     # ds through perm; dg write
     elu_b = 12 * n * HD                                                          # separate ELU' pass (only when not fused)
     g_proj = 4 * n * H * Fp + 4 * n * HD                                         # out_h = ELU(xagg_h W_h)
@@ -407,6 +410,8 @@ def run_ours(args):
 
     runner = make_runner(cfg, rank, world, dev)
     e_total = runner.e_total
+    # rows whose xagg_i the backward edge pass reads: all of them, unless the opt-in short-row variant runs
+    n_long = runner.n_long_rows if os.environ.get("GATK_XBWD_SHORT_C") == "1" else None
     res = time_layer(runner, args.steps, args.warmup, rank, world, dev, sample_clocks=True)
     ms, kern = res["ms"], res["kern"]
 
@@ -501,7 +506,7 @@ def run_ours(args):
 
     peak, peak_src = measured_peak()
     n_nodes = n * world if cfg.get("shard_only") else n
-    ab = algorithmic_bytes(n_nodes, e_total, H, D, f_in)
+    ab = algorithmic_bytes(n_nodes, e_total, H, D, f_in, n_long=n_long)
     per_kernel, other = kernel_table(kern, ab, world, args.steps, peak)
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"]) if per_kernel else None
     traffic = None

@@ -12,6 +12,13 @@ from pygat_b200.graph import Graph
 from pygat_b200.sharded import ShardPlan, fit_row_cost, shard_rows_by_cost, sharded_gat_layer
 from pygat_b200.synth import init_layer_params, power_law_csr
 
+XBWD_SHORT_ROW = 32  # rows up to two 16-entry chunks: the aggregate-first backward does not read their xagg_i (csrc/attn_x.cu)
+
+
+def long_rows(rowptr: torch.Tensor) -> int:
+    return int(((rowptr[1:] - rowptr[:-1]) > XBWD_SHORT_ROW).sum().item())
+
+
 ROW_COST = 25  # measured on one GPU at the products shape: row-proportional kernels ~7.0 ns/row, edge passes ~0.275 ns/entry
 
 
@@ -35,6 +42,7 @@ class SingleGpuLayerBench:
         self.graph = Graph.from_csr(rowptr, col)
         self.graph.transpose()  # cached per adjacency, like the CSR itself; not part of a step
         self.e_total = self.graph.nnz
+        self.n_long_rows = long_rows(rowptr)
         self.needs_dx = bool(cfg.get("needs_dx", False))
         if self.needs_dx:
             self.x.requires_grad_(True)
@@ -73,6 +81,7 @@ class ShardedLayerBench:
         self.rank, self.world, self.dev, self.cfg = rank, world, dev, cfg
         rowptr, col, x, gout = _inputs(cfg, dev)
         self.e_total = int(col.numel())
+        self.n_long_rows = long_rows(rowptr)
         self.needs_dx = bool(cfg.get("needs_dx", False))
         self.Ws, self.a_src, self.a_dst = init_layer_params(cfg["f_in"], cfg["H"], cfg["D"], dev, seed=72)
         self.params = self.Ws + self.a_src + self.a_dst
@@ -150,12 +159,12 @@ class ShardOnlyLayerBench:
         rowptr, col = power_law_shard(world * n, rank * n, (rank + 1) * n, cfg["avg_deg"], seed=72,
                                       exponent=cfg["exponent"], device=dev)
         self.graph = Graph(rowptr, col, n_src=world * n)
+        e = torch.tensor([self.graph.nnz, long_rows(rowptr)], dtype=torch.int64, device=dev)
         del rowptr, col
         torch.cuda.empty_cache()
-        e = torch.tensor([self.graph.nnz], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(e)
-        self.e_total = int(e.item())
+        self.e_total, self.n_long_rows = int(e[0].item()), int(e[1].item())
         g = torch.Generator(device=dev).manual_seed(72 + rank)
         self.x = torch.randn(n, f_in, generator=g, device=dev)
         self.gout = torch.randn(n, H * D, generator=g, device=dev)

@@ -58,6 +58,7 @@ struct alignas(64) XArgs {
   float* dgacc;          // NULL, or [n_src, lddgacc] zero-initialised: dg_j += ds_ij accumulated here with red.global.add
   int64_t lddgacc;       //       (replaces the ds write + the transposed segmented sum gatk_edge_tsum)
   int dg_vec4;           // H == 8 and 16-byte aligned rows: two red.global.add.v4.f32 per stored entry
+  int short_c;           // backward: rows of <= 2 chunks sum c_i over their own entries instead of staging xagg_i
   float* df;
   int64_t lddf;
   int seg_len;
@@ -117,8 +118,10 @@ __host__ __device__ __forceinline__ int xfwd_warp_floats(int RS, int HP, int chu
 // backward (tensor-core kernel): row pitch = 16 (mod 32) floats, so the two rows a quarter-warp touches per
 // 128-bit fragment load sit in different bank halves
 __host__ __device__ __forceinline__ int xmma_row_pitch(int Sx) { return (4 * Sx + 15) / 32 * 32 + 16; }
+__host__ __device__ __forceinline__ int xmma_pend_floats(int chunk) { return (4 * (chunk / 16) * 2 + 3) * 32; }
 __host__ __device__ __forceinline__ int xmma_warp_floats(int RS, int H, int Fp, int chunk) {
-  return 2 * chunk * RS + (2 * H * Fp + 31) / 32 * 32 + 32;  // every piece a multiple of 128 bytes
+  // two row buffers | dxagg_i, xagg_i | barriers | held-back first chunk of a two-chunk row (w, dalpha, col, c sums per lane)
+  return 2 * chunk * RS + (2 * H * Fp + 31) / 32 * 32 + 32 + xmma_pend_floats(chunk);  // every piece a multiple of 128 bytes
 }
 __host__ __device__ __forceinline__ int xbwd_warp_floats(int RS, int H, int Fp, int chunk) { return chunk * RS + H * Fp + 4; }
 
@@ -159,6 +162,7 @@ struct Chunk {
   int row, cnt;
   int64_t base;
   bool first, last, ok;
+  bool two;  // the whole destination row fits in two chunks (never set for hub segments)
 };
 
 // Enumerates the chunks a warp processes, one chunk AHEAD of the compute (warp-uniform state).  HUB: the
@@ -192,10 +196,11 @@ struct ChunkIter {
   __device__ __forceinline__ Chunk next(const XArgs& a, int lane) {
     Chunk c;
     c.ok = false;
-    c.row = 0; c.cnt = 0; c.base = 0; c.first = c.last = false;
+    c.row = 0; c.cnt = 0; c.base = 0; c.first = c.last = c.two = false;
     while (true) {
       if (open) {
         const int64_t rem = end - base;
+        c.two = !HUB && a.short_c && end - beg <= 2 * (int64_t)chunk;
         c.row = row;
         c.base = base;
         c.cnt = rem < chunk ? (int)rem : chunk;
@@ -606,14 +611,20 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
-template <int KPMAX, int MT, bool HUB>  // MT: 16-edge MMA tiles per chunk (chunk = 16*MT stored entries)
-__global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_constant__ XArgs a) {
+// Five CTAs per SM (shared memory allows them at MT = 1): the kernel is latency bound, at four it measured 11.0 ms
+// instead of 8.8 ms alone -- ten warps are three on one scheduler, 16384 / 3 / 32 = 170 registers per thread at most
+// (the SC variant is held there by its launch bounds; the plain one needs 167 on its own).
+// SC: rows of at most two chunks take c_i from their own entries (see below); hub segments never do.
+// KX: the row has exactly KPMAX pairs of k-steps, so the k loop carries no run-time bound (no predicate, no
+// reconvergence point per step, and the fragment loads of the next step can be scheduled across the MMAs).
+template <int KPMAX, int MT, bool HUB, bool SC = false, bool KX = false>  // MT: 16-edge MMA tiles per chunk (chunk = 16*MT stored entries)
+__global__ void __launch_bounds__(XW * 32, (SC && MT == 1) ? 5 : 0) attn_x_bwd_mma_kernel(const __grid_constant__ XArgs a) {
   constexpr int CH = 16 * MT;
   extern __shared__ __align__(128) float x_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tg = lane & 3;
   const int H = a.H, Fp = a.Fp, RS = a.RS;
-  const int KP = (Fp + 15) >> 4;  // pairs of k-steps
+  const int KP = KX ? KPMAX : (Fp + 15) >> 4;  // pairs of k-steps
   const int h0 = 2 * tg, h1 = 2 * tg + 1;
   // per warp: two row buffers (the next chunk's rows land while this chunk is computed), one staging area for
   // the row state (dxagg_i, xagg_i) of the next destination row, two mbarriers
@@ -641,7 +652,7 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
     if (ch.cnt > 0) {
       const unsigned bar = bar0 + 8 * buf;
       float* rb = rowbuf + buf * CH * RS;
-      const unsigned st_tx = ch.first ? 2 * st_bytes : 0u;
+      const unsigned st_tx = ch.first ? ((SC && ch.two) ? st_bytes : 2 * st_bytes) : 0u;
       if (a.use_g4) {
         const int ngrp = (ch.cnt + 3) >> 2;
         const int r0 = __shfl_sync(FULL, jcol, (4 * lane) & 31), r1 = __shfl_sync(FULL, jcol, (4 * lane + 1) & 31);
@@ -665,7 +676,9 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
                        : "memory");
         }
       }
-      if (ch.first && lane >= 30) {  // the row state rides on the same barrier (lanes that issue no row copies)
+      // the row state rides on the same barrier (lanes that issue no row copies): dxagg_i always, xagg_i only for
+      // rows of more than two chunks (shorter rows get c_i = sum_j alpha_ij dalpha_ij from their own entries)
+      if (ch.first && (lane == 30 || (lane == 31 && !(SC && ch.two)))) {
         const float* src = lane == 30 ? a.dxagg + (int64_t)ch.row * a.ldd : a.xagg + (int64_t)ch.row * a.ldxa;
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          smem_u32(lane == 30 ? dxs : xas)),
@@ -680,6 +693,9 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
   float f0 = 0.f, f1 = 0.f, l0 = 0.f, l1 = 0.f, c0 = 0.f, c1 = 0.f, df0 = 0.f, df1 = 0.f;
   float nf0 = 0.f, nf1 = 0.f, nl0 = 0.f, nl1 = 0.f;  // f, lse of the NEXT destination row (prefetched)
   int64_t ipos[2 * MT], npos[2 * MT];              // where this lane's ds entries go (this chunk / the next one)
+  // rows of at most two chunks: c_ih = sum_j alpha_ij dalpha_ij is summed over the row's own entries (cs0, cs1),
+  // so the first chunk of a two-chunk row is held back until c is known -- in shared memory (weights, dalpha,
+  // column ids): the kernel needs <= 168 registers to keep five CTAs on an SM
   auto prefetch_pos = [&](const Chunk& ch) {
 #pragma unroll
     for (int q = 0; q < 2 * MT; ++q) {
@@ -722,14 +738,15 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
       df0 = df1 = 0.f;
       if (c.cnt > 0) {
         // row state from the staging area: B fragments of dxagg_i (head g, features 16kp + 4tg .. +3),
-        // c_ih = dxagg_ih . xagg_ih
+        // c_ih = dxagg_ih . xagg_ih (rows of more than two chunks; the others sum it over their entries below)
         float cp = 0.f;
+        const bool staged_c = !(SC && c.two);
 #pragma unroll
         for (int kp = 0; kp < KPMAX; ++kp) {
           float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
           if (kp < KP && g < H && 16 * kp + 4 * tg < Fp) {
             d = *reinterpret_cast<const float4*>(dxs + g * Fp + 16 * kp + 4 * tg);
-            cp += dot4(d, *reinterpret_cast<const float4*>(xas + g * Fp + 16 * kp + 4 * tg));
+            if (staged_c) cp += dot4(d, *reinterpret_cast<const float4*>(xas + g * Fp + 16 * kp + 4 * tg));
           }
           split_tf32(d.x, bhi[kp][0], blo[kp][0]);
           split_tf32(d.y, bhi[kp][1], blo[kp][1]);
@@ -784,46 +801,161 @@ __global__ void __launch_bounds__(XW * 32) attn_x_bwd_mma_kernel(const __grid_co
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[mt][0][q] += acc[mt][1][q] + acc[mt][2][q];
-    // ---- ds for this lane's (edge, head) pairs: acc[mt][0][0..1] = edge 16mt+g, heads h0,h1; [2..3] = edge 16mt+g+8
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int e = 16 * mt + g + 8 * half;
-        const bool ev = e < c.cnt;
-        float v0 = 0.f, v1 = 0.f;
-        if (ev) {
-          const float2 gq = *reinterpret_cast<const float2*>(rows + e * RS + Fp + h0);
-          const float z0 = f0 + gq.x, z1 = f1 + gq.y;
-          const float s0 = z0 > 0.f ? z0 : a.alpha * z0, s1 = z1 > 0.f ? z1 : a.alpha * z1;
-          v0 = h0 < H ? expf(s0 - l0) * (acc[mt][0][2 * half] - c0) * (z0 > 0.f ? 1.f : a.alpha) : 0.f;
-          v1 = h1 < H ? expf(s1 - l1) * (acc[mt][0][2 * half + 1] - c1) * (z1 > 0.f ? 1.f : a.alpha) : 0.f;
-          df0 += v0;
-          df1 += v1;
-          if (a.ds) {
-            float* dp = a.ds + ipos[2 * mt + half] * H + h0;
-            if (h1 < H && (H & 1) == 0) {
-              *reinterpret_cast<float2*>(dp) = make_float2(v0, v1);
-            } else {
-              if (h0 < H) dp[0] = v0;
-              if (h1 < H) dp[1] = v1;
+    if constexpr (!SC) {
+      // ---- ds for this lane's (edge, head) pairs: acc[mt][0][0..1] = edge 16mt+g, heads h0,h1; [2..3] = edge 16mt+g+8
+  #pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+  #pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int e = 16 * mt + g + 8 * half;
+          const bool ev = e < c.cnt;
+          float v0 = 0.f, v1 = 0.f;
+          if (ev) {
+            const float2 gq = *reinterpret_cast<const float2*>(rows + e * RS + Fp + h0);
+            const float z0 = f0 + gq.x, z1 = f1 + gq.y;
+            const float s0 = z0 > 0.f ? z0 : a.alpha * z0, s1 = z1 > 0.f ? z1 : a.alpha * z1;
+            v0 = h0 < H ? expf(s0 - l0) * (acc[mt][0][2 * half] - c0) * (z0 > 0.f ? 1.f : a.alpha) : 0.f;
+            v1 = h1 < H ? expf(s1 - l1) * (acc[mt][0][2 * half + 1] - c1) * (z1 > 0.f ? 1.f : a.alpha) : 0.f;
+            df0 += v0;
+            df1 += v1;
+            if (a.ds) {
+              float* dp = a.ds + ipos[2 * mt + half] * H + h0;
+              if (h1 < H && (H & 1) == 0) {
+                *reinterpret_cast<float2*>(dp) = make_float2(v0, v1);
+              } else {
+                if (h0 < H) dp[0] = v0;
+                if (h1 < H) dp[1] = v1;
+              }
+            }
+          }
+          if (a.dgacc) {  // dg_j += ds_ij, straight into the per-source array (warp-uniform branch)
+            const int je = __shfl_sync(FULL, jc, e & 31);
+            float* gp = a.dgacc + (int64_t)je * a.lddgacc + h0;
+            if (a.dg_vec4) {  // lanes tg = 0, 2 of a group send heads 0..3 / 4..7 of the group's entry
+              const float q0 = __shfl_xor_sync(FULL, v0, 1), q1 = __shfl_xor_sync(FULL, v1, 1);
+              if (ev && !(tg & 1)) {
+                if (a.dg_vec4 == 2) red_add_v4_pol(gp, v0, v1, q0, q1, dg_pol);
+                else red_add_v4(gp, v0, v1, q0, q1);
+              }
+            } else if (ev) {
+              if (h0 < H) red_add_f32(gp, v0);
+              if (h1 < H) red_add_f32(gp + 1, v1);
             }
           }
         }
-        if (a.dgacc) {  // dg_j += ds_ij, straight into the per-source array (warp-uniform branch)
-          const int je = __shfl_sync(FULL, jc, e & 31);
-          float* gp = a.dgacc + (int64_t)je * a.lddgacc + h0;
-          if (a.dg_vec4) {  // lanes tg = 0, 2 of a group send heads 0..3 / 4..7 of the group's entry
-            const float q0 = __shfl_xor_sync(FULL, v0, 1), q1 = __shfl_xor_sync(FULL, v1, 1);
-            if (ev && !(tg & 1)) {
-              if (a.dg_vec4 == 2) red_add_v4_pol(gp, v0, v1, q0, q1, dg_pol);
-              else red_add_v4(gp, v0, v1, q0, q1);
+      }
+    } else {
+      // ---- ds for this lane's (edge, head) pairs: acc[mt][0][0..1] = edge 16mt+g, heads h0,h1; [2..3] = edge 16mt+g+8
+      // w = alpha_ij LeakyReLU'(z_ij), da = dalpha_ij; ds_ij = w (da - c_i)
+      float wv[MT][2][2], dav[MT][2][2];
+      float cs0 = 0.f, cs1 = 0.f;  // this chunk's part of c_i = sum_j alpha_ij dalpha_ij
+  #pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+  #pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int e = 16 * mt + g + 8 * half;
+          float w0 = 0.f, w1 = 0.f;
+          if (e < c.cnt) {
+            const float2 gq = *reinterpret_cast<const float2*>(rows + e * RS + Fp + h0);
+            const float z0 = f0 + gq.x, z1 = f1 + gq.y;
+            const float s0 = z0 > 0.f ? z0 : a.alpha * z0, s1 = z1 > 0.f ? z1 : a.alpha * z1;
+            const float p0 = h0 < H ? expf(s0 - l0) : 0.f, p1 = h1 < H ? expf(s1 - l1) : 0.f;
+            cs0 += p0 * acc[mt][0][2 * half];
+            cs1 += p1 * acc[mt][0][2 * half + 1];
+            w0 = p0 * (z0 > 0.f ? 1.f : a.alpha);
+            w1 = p1 * (z1 > 0.f ? 1.f : a.alpha);
+          }
+          wv[mt][half][0] = w0;
+          wv[mt][half][1] = w1;
+          dav[mt][half][0] = acc[mt][0][2 * half];
+          dav[mt][half][1] = acc[mt][0][2 * half + 1];
+        }
+      }
+      auto emit = [&](const float (&w)[MT][2][2], const float (&da)[MT][2][2], const int64_t (&pos)[2 * MT], int jcol, int cnt) {
+  #pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+  #pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int e = 16 * mt + g + 8 * half;
+            const bool ev = e < cnt;
+            const float v0 = ev ? w[mt][half][0] * (da[mt][half][0] - c0) : 0.f;
+            const float v1 = ev ? w[mt][half][1] * (da[mt][half][1] - c1) : 0.f;
+            if (ev) {
+              df0 += v0;
+              df1 += v1;
+              if (a.ds) {
+                float* dp = a.ds + pos[2 * mt + half] * H + h0;
+                if (h1 < H && (H & 1) == 0) {
+                  *reinterpret_cast<float2*>(dp) = make_float2(v0, v1);
+                } else {
+                  if (h0 < H) dp[0] = v0;
+                  if (h1 < H) dp[1] = v1;
+                }
+              }
             }
-          } else if (ev) {
-            if (h0 < H) red_add_f32(gp, v0);
-            if (h1 < H) red_add_f32(gp + 1, v1);
+            if (a.dgacc) {  // dg_j += ds_ij, straight into the per-source array (warp-uniform branch)
+              const int je = __shfl_sync(FULL, jcol, e & 31);
+              float* gp = a.dgacc + (int64_t)je * a.lddgacc + h0;
+              if (a.dg_vec4) {  // lanes tg = 0, 2 of a group send heads 0..3 / 4..7 of the group's entry
+                const float q0 = __shfl_xor_sync(FULL, v0, 1), q1 = __shfl_xor_sync(FULL, v1, 1);
+                if (ev && !(tg & 1)) {
+                  if (a.dg_vec4 == 2) red_add_v4_pol(gp, v0, v1, q0, q1, dg_pol);
+                  else red_add_v4(gp, v0, v1, q0, q1);
+                }
+              } else if (ev) {
+                if (h0 < H) red_add_f32(gp, v0);
+                if (h1 < H) red_add_f32(gp + 1, v1);
+              }
+            }
           }
         }
+      };
+      // [4 MT w | 4 MT dalpha | col | cs0 | cs1][32 lanes], behind the barriers
+      float* pend = dxs + (2 * H * Fp + 31) / 32 * 32 + 32 + lane;
+      if (c.two && !c.last) {  // first chunk of a two-chunk row: held back until the second one has completed c
+  #pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+  #pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            pend[(4 * mt + q) * 32] = wv[mt][q >> 1][q & 1];
+            pend[(4 * MT + 4 * mt + q) * 32] = dav[mt][q >> 1][q & 1];
+          }
+        pend[8 * MT * 32] = __int_as_float(jc);
+        pend[(8 * MT + 1) * 32] = cs0;
+        pend[(8 * MT + 2) * 32] = cs1;
+      } else {
+        if (c.two) {
+          if (!c.first) {
+            cs0 += pend[(8 * MT + 1) * 32];
+            cs1 += pend[(8 * MT + 2) * 32];
+          }
+  #pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {  // lanes of one tg hold the same heads: sum over the 8 entry groups
+            cs0 += __shfl_xor_sync(FULL, cs0, o);
+            cs1 += __shfl_xor_sync(FULL, cs1, o);
+          }
+          c0 = cs0;
+          c1 = cs1;
+          if (!c.first) {  // the held-back chunk (a non-last chunk is always full)
+            float pw[MT][2][2], pda[MT][2][2];
+            int64_t ppos[2 * MT];
+            const int64_t pbase = c.base - CH;  // the second chunk starts CH entries after the first
+  #pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+  #pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                pw[mt][q >> 1][q & 1] = pend[(4 * mt + q) * 32];
+                pda[mt][q >> 1][q & 1] = pend[(4 * MT + 4 * mt + q) * 32];
+              }
+  #pragma unroll
+            for (int q = 0; q < 2 * MT; ++q) {
+              const int e = 16 * (q >> 1) + g + 8 * (q & 1);
+              ppos[q] = a.ds ? (a.iperm ? (int64_t)__ldg(a.iperm + pbase + e) : pbase + e) : 0;
+            }
+            emit(pw, pda, ppos, __float_as_int(pend[8 * MT * 32]), CH);
+          }
+        }
+        emit(wv, dav, ipos, jc, c.cnt);
       }
     }
     if (c.last) {
@@ -1281,12 +1413,37 @@ static int launch_x_bwd_mma(XArgs a, cudaStream_t st) {
   make_xg_map(a);
   static const int mt_env = getenv("GATK_XBWD_MT") ? atoi(getenv("GATK_XBWD_MT")) : 1;
   const int mt = mt_env == 2 ? 2 : 1;
+  // GATK_XBWD_SHORT_C=1 (read per call, so a test can switch it): rows of at most two chunks sum c_i over their own
+  // entries instead of reading xagg_i.  Measured at the products shape (profiles/r02c_xbwd_short_c.md): DRAM traffic
+  // 50.7 -> 43.6 GB, but 4.35 -> 4.94 G instructions at the same issue rate (the kernel is bound by dependent-issue
+  // latency at 2.5 warps per scheduler, not by bytes): 8.73 -> 10.27 ms alone, 10.3 -> 11.6 ms in the step.  Off.
+  const char* sc_env = getenv("GATK_XBWD_SHORT_C");
+  a.short_c = (sc_env && atoi(sc_env) == 1) ? 1 : 0;
   const size_t smem = (size_t)XW * xmma_warp_floats(a.RS, a.H, a.Fp, 16 * mt) * sizeof(float);
   int rc;
-  if (a.Fp <= 64) {
+  if (!a.short_c && mt == 1) {  // the default: one instantiation per k extent
+    switch ((a.Fp + 15) >> 4) {
+#define GATK_XBWD_KX(K)                                                                                                  \
+  case K:                                                                                                                \
+    rc = launch_x_mma(attn_x_bwd_mma_kernel<K, 1, true, false, true>, attn_x_bwd_mma_kernel<K, 1, false, false, true>, a, \
+                      smem, st);                                                                                         \
+    break;
+      GATK_XBWD_KX(1) GATK_XBWD_KX(2) GATK_XBWD_KX(3) GATK_XBWD_KX(4) GATK_XBWD_KX(5) GATK_XBWD_KX(6) GATK_XBWD_KX(7)
+      GATK_XBWD_KX(8)
+#undef GATK_XBWD_KX
+      default:
+        set_error("Fp=%d too wide for the tensor-core backward", a.Fp);
+        return 3;
+    }
+  } else if (a.short_c && mt == 1) {  // (the hub segments always stage xagg_i)
+    rc = a.Fp <= 64 ? launch_x_mma(attn_x_bwd_mma_kernel<4, 1, true>, attn_x_bwd_mma_kernel<4, 1, false, true>, a, smem, st)
+                    : launch_x_mma(attn_x_bwd_mma_kernel<8, 1, true>, attn_x_bwd_mma_kernel<8, 1, false, true>, a, smem, st);
+  } else if (a.Fp <= 64) {
+    a.short_c = 0;
     rc = mt == 2 ? launch_x_mma(attn_x_bwd_mma_kernel<4, 2, true>, attn_x_bwd_mma_kernel<4, 2, false>, a, smem, st)
                  : launch_x_mma(attn_x_bwd_mma_kernel<4, 1, true>, attn_x_bwd_mma_kernel<4, 1, false>, a, smem, st);
   } else {
+    a.short_c = 0;
     rc = mt == 2 ? launch_x_mma(attn_x_bwd_mma_kernel<8, 2, true>, attn_x_bwd_mma_kernel<8, 2, false>, a, smem, st)
                  : launch_x_mma(attn_x_bwd_mma_kernel<8, 1, true>, attn_x_bwd_mma_kernel<8, 1, false>, a, smem, st);
   }

@@ -496,6 +496,41 @@ def test_aggregate_first_form_matches_oracle(H, D, f_in, skip, concat, seg_len):
             assert rel_err(Sd[k].grad, So[k].grad) < TOL, k
 
 
+@pytest.mark.parametrize("short_c", ["0", "1"])
+@pytest.mark.parametrize("H,f_in", [(8, 100), (4, 36)])
+def test_aggregate_first_backward_at_the_chunk_boundaries(H, f_in, short_c, monkeypatch):
+    """The aggregate-first backward walks a destination row in 16-entry chunks; its opt-in variant
+    (GATK_XBWD_SHORT_C=1, csrc/attn_x.cu) takes c_i = sum_j alpha_ij dalpha_ij from the row's own entries when the
+    row fits in two chunks and from the staged xagg_i otherwise.  Rows of exactly 1, 15, 16, 17, 31, 32, 33, 47, 48,
+    49 and 100 entries in a directed pattern, every route in one launch, both variants, against the oracle."""
+    monkeypatch.setenv("GATK_XBWD_SHORT_C", short_c)
+    D = 16
+    degs = [1, 15, 16, 17, 31, 32, 33, 47, 48, 49, 100]
+    n = 40 * len(degs)
+    g = torch.Generator().manual_seed(21)
+    deg = torch.tensor([degs[(i * 7) % len(degs)] for i in range(n)])
+    rowptr = torch.zeros(n + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(deg, 0)
+    col = torch.cat([torch.randperm(n, generator=g)[:d].sort().values for d in deg.tolist()]).to(torch.int32)
+    x, Ws, As, gout = _layer_inputs(n, f_in, H, D, 8)
+    adj = O.PatternAdj(rowptr, col)
+    Wo = [w.double().requires_grad_(True) for w in Ws]
+    Ao = [a.double().requires_grad_(True) for a in As]
+    edge = adj.nonzero().t()
+    yo = torch.cat([O.sparse_head(x.double(), w, a, edge, 0.2, True, None, 0.0, faithful=False) for w, a in zip(Wo, Ao)], 1)
+    yo.backward(gout.double())
+    graph = Graph.from_csr(rowptr.to(DEV), col.to(DEV), seg_len=64)   # the 100-entry rows are hub segments
+    assert graph.hubs.n_hub > 0
+    Wd = [w.to(DEV).requires_grad_(True) for w in Ws]
+    Ad = [a.to(DEV).requires_grad_(True) for a in As]
+    y = gat_layer(x.to(DEV), graph, Wd, [a[0, :D] for a in Ad], [a[0, D:] for a in Ad], None, 0.2, True, form="agg_first")
+    y.backward(gout.to(DEV))
+    assert rel_err(y, yo) < TOL
+    for k in range(H):
+        assert rel_err(Wd[k].grad, Wo[k].grad) < TOL, k
+        assert rel_err(Ad[k].grad, Ao[k].grad) < TOL, k
+
+
 def test_aggregate_first_is_the_default_for_narrow_first_layers(monkeypatch):
     """gat_layer picks the aggregate-first form only when it is valid (no dropout, input without gradient)
     and pays (input row narrower than the projected row); it agrees with the folded form to fp32 rounding."""
