@@ -174,3 +174,45 @@ def test_atomic_dg_route_matches_the_deterministic_one(H, D, f_in, skip, monkeyp
         assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item()
     for a, b in zip(res[True][1], res[False][1]):   # dW = dvalue path + da-dependent logit path
         assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item()
+
+
+@pytest.mark.parametrize("form,needs_dx", [("folded", True), ("agg_first", False)])
+def test_two_streams_share_a_graph_but_not_its_scheduler_word(form, needs_dx, monkeypatch):
+    """Graph.counter (the dynamic row scheduler's scratch word) is per CUDA stream: one pattern driven from two
+    streams at the same time -- forward + backward, different inputs -- gives the bits of the same two runs done
+    one after the other on the default stream."""
+    import pygat_b200.functional as Fn
+    monkeypatch.setattr(Fn, "DETERMINISTIC", True)
+    n, H, D, f_in = 30000, 8, 64, 100
+    rowptr, col = power_law_csr(n, 18.0, seed=5, exponent=0.7, device=DEV)
+    graph = Graph.from_csr(rowptr, col, seg_len=128)
+    graph.transpose()
+    cases = []
+    for seed in (1, 2):
+        g = torch.Generator().manual_seed(seed)
+        cases.append((torch.randn(n, f_in, generator=g).to(DEV),
+                      [(torch.randn(f_in, D, generator=g) * 0.2).to(DEV) for _ in range(H)],
+                      [(torch.randn(2 * D, generator=g) * 0.2).to(DEV) for _ in range(H)],
+                      torch.randn(n, H * D, generator=g).to(DEV)))
+
+    def run(case):
+        x, Ws, As, gout = case
+        xi = x.clone().requires_grad_(needs_dx)
+        Wd = [w.clone().requires_grad_(True) for w in Ws]
+        Ad = [a.clone().requires_grad_(True) for a in As]
+        y = gat_layer(xi, graph, Wd, [a[:D] for a in Ad], [a[D:] for a in Ad], None, 0.2, True, form=form)
+        y.backward(gout)
+        return [y.detach()] + [w.grad for w in Wd] + [a.grad for a in Ad] + ([xi.grad] if needs_dx else [])
+
+    one_after_the_other = [run(c) for c in cases]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    together = []
+    for s, c in zip(streams, cases):
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            together.append(run(c))
+    torch.cuda.synchronize()
+    assert len(graph._counters) == 3
+    for a, b in zip(one_after_the_other, together):
+        _all_equal_and_finite(a, b)
