@@ -128,3 +128,32 @@ def test_dense_v2_head_matches_reference_golden(name):
     if "skip" in d:
         errs["dskip"] = rel_err(head.skip_projection.grad, d["dskip"])
     assert all(v < 1e-5 for v in errs.values()), errs
+
+
+def test_dropout_site_offsets_do_not_overlap():
+    """The three dropout sites of a layer draw from disjoint counter ranges of one Philox stream
+    (functional.site_offsets): a site of sz elements owns ceil(sz / 4) counters."""
+    from pygat_b200.functional import site_offsets
+    for n, f_in, H, Dp, nnz in [(7, 5, 3, 8, 19), (2708, 1433, 8, 8, 13264), (1, 1, 1, 4, 1)]:
+        offs, sizes = site_offsets(n, f_in, H, Dp, nnz)
+        assert sizes == (H * n * f_in, n * H * Dp, nnz * H) and offs[0] == 0
+        ends = [o + (s + 3) // 4 for o, s in zip(offs, sizes)]
+        assert offs[1] == ends[0] and offs[2] == ends[1]
+
+
+def test_head_chunks_divide_the_heads(monkeypatch):
+    """sharded.head_chunks: heads per exchange chunk; one chunk up to two ranks, two beyond, the override clipped to
+    a divisor of H."""
+    from pygat_b200.sharded import head_chunks
+    monkeypatch.delenv("GATK_SHARD_CHUNKS", raising=False)
+    assert head_chunks(8, 2) == 8 and head_chunks(8, 8) == 4 and head_chunks(1, 8) == 1 and head_chunks(3, 8) == 3
+    monkeypatch.setenv("GATK_SHARD_CHUNKS", "4")
+    assert head_chunks(8, 2) == 2 and head_chunks(6, 8) == 2 and head_chunks(2, 8) == 1
+    monkeypatch.setenv("GATK_SHARD_CHUNKS", "100")
+    assert head_chunks(8, 8) == 1
+
+
+def test_long_row_count_of_the_byte_model():
+    from benchmarks.layer import XBWD_SHORT_ROW, long_rows
+    rowptr = torch.tensor([0, 1, 1 + XBWD_SHORT_ROW, 2 + 2 * XBWD_SHORT_ROW, 2 + 2 * XBWD_SHORT_ROW])
+    assert long_rows(rowptr) == 1   # rows of 1, 32, 33 and 0 entries
