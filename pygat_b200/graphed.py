@@ -1,4 +1,6 @@
-"""CUDA-graph capture of a whole training step (forward, loss head, backward, optimizer) on a FIXED batch.
+"""CUDA-graph capture of a whole training step (forward, loss head, backward, optimizer) on a FIXED batch: the body of
+the reference's per-batch loop, train_ppi.py:117-124 (zero_grad, model(features, adj), BCE loss, backward,
+optimizer.step), and of its full-batch step, train.py:154-162.
 
 A PPI batch is ~4.5 k nodes: its 3-layer step is a few hundred small launches (the reference: ~25 ATen launches per
 head and direction; this engine: one projection + one attention kernel per layer and direction plus the
